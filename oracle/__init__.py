@@ -1,0 +1,259 @@
+"""CPU ORACLE -- test infrastructure, never a product path.
+
+numpy front-end over oracle/p3d_oracle.c (see that file's header for the
+reference citations and the pinned / unpinned status of every operator).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` legs may import this package.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_LIB = None
+
+_F = ctypes.POINTER(ctypes.c_float)
+_L = ctypes.POINTER(ctypes.c_int64)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = _build.OUT
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(_build.SRC):
+            path = _build.build()
+        _LIB = ctypes.CDLL(path)
+        _LIB.orc_radius_csr.restype = ctypes.c_int64
+        _LIB.orc_num_threads.restype = ctypes.c_int
+    return _LIB
+
+
+def num_threads() -> int:
+    return int(lib().orc_num_threads())
+
+
+def set_num_threads(n: int) -> None:
+    lib().orc_set_num_threads(ctypes.c_int(int(n)))
+
+
+def _f(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, a.ctypes.data_as(_F)
+
+
+def _l(a):
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    return a, a.ctypes.data_as(_L)
+
+
+def batch_to_ptr(batch, num_clouds=None):
+    """sorted batch vector -> CSR ptr [C+1] (int64)."""
+    batch = np.asarray(batch, dtype=np.int64)
+    if num_clouds is None:
+        num_clouds = int(batch.max()) + 1 if batch.size else 0
+    counts = np.bincount(batch, minlength=num_clouds).astype(np.int64)
+    ptr = np.zeros(num_clouds + 1, dtype=np.int64)
+    np.cumsum(counts, out=ptr[1:])
+    return ptr
+
+
+# ------------------------------------------------------------------ FPS ----
+def fps_dense(xyz, npoint):
+    xyz, p = _f(xyz)
+    B, N, _ = xyz.shape
+    if npoint > N:
+        raise ValueError("npoint > N")
+    idx = np.zeros((B, npoint), dtype=np.int64)
+    lib().orc_fps_dense(p, B, N, npoint, idx.ctypes.data_as(_L))
+    return idx
+
+
+def fps_counts(ptr, ratio):
+    """per-cloud sample count = ceil(ratio * N_c) (torch_cluster 1.5.x)."""
+    n = np.diff(np.asarray(ptr, dtype=np.int64))
+    return np.ceil(np.float32(ratio) * n.astype(np.float32)).astype(np.int64)
+
+
+def fps_csr(xyz, ptr, counts):
+    xyz, p = _f(xyz)
+    ptr, pp = _l(ptr)
+    C = ptr.shape[0] - 1
+    out_ptr = np.zeros(C + 1, dtype=np.int64)
+    np.cumsum(np.asarray(counts, dtype=np.int64), out=out_ptr[1:])
+    idx = np.zeros(int(out_ptr[-1]), dtype=np.int64)
+    lib().orc_fps_csr(p, pp, C, out_ptr.ctypes.data_as(_L), idx.ctypes.data_as(_L))
+    return idx
+
+
+# ----------------------------------------------------------- ball query ----
+def ball_query_dense(radius, nsample, x, y, strict=True):
+    x, px = _f(x)
+    y, py = _f(y)
+    B, N, _ = x.shape
+    S = y.shape[1]
+    idx = np.zeros((B, S, nsample), dtype=np.int64)
+    d2 = np.zeros((B, S, nsample), dtype=np.float32)
+    lib().orc_ball_query_dense(px, py, B, N, S, ctypes.c_float(radius), nsample, int(strict),
+                               idx.ctypes.data_as(_L), d2.ctypes.data_as(_F))
+    return idx, d2
+
+
+def ball_query_csr(radius, nsample, x, y, ptr_x, ptr_y, strict=False, shadow=None):
+    x, px = _f(x)
+    y, py = _f(y)
+    ptr_x, ppx = _l(ptr_x)
+    ptr_y, ppy = _l(ptr_y)
+    C = ptr_x.shape[0] - 1
+    n = y.shape[0]
+    if shadow is None:
+        shadow = x.shape[0]
+    idx = np.zeros((n, nsample), dtype=np.int64)
+    d2 = np.zeros((n, nsample), dtype=np.float32)
+    lib().orc_ball_query_csr(px, py, ppx, ppy, C, ctypes.c_float(radius), nsample, int(strict),
+                             ctypes.c_int64(shadow), idx.ctypes.data_as(_L), d2.ctypes.data_as(_F))
+    return idx, d2
+
+
+def radius_csr(x, y, r, ptr_x, ptr_y, max_num_neighbors=32, strict=False):
+    x, px = _f(x)
+    y, py = _f(y)
+    ptr_x, ppx = _l(ptr_x)
+    ptr_y, ppy = _l(ptr_y)
+    C = ptr_x.shape[0] - 1
+    cap = y.shape[0] * max_num_neighbors
+    row = np.zeros(cap, dtype=np.int64)
+    col = np.zeros(cap, dtype=np.int64)
+    e = lib().orc_radius_csr(px, py, ppx, ppy, C, ctypes.c_float(r), max_num_neighbors, int(strict),
+                             row.ctypes.data_as(_L), col.ctypes.data_as(_L))
+    return np.stack([row[:e], col[:e]])
+
+
+# ------------------------------------------------------------- grouping ----
+def group_fwd(feat, idx):
+    feat, pf = _f(feat)
+    idx, pi = _l(idx)
+    B, C, N = feat.shape
+    _, S, K = idx.shape
+    out = np.zeros((B, C, S, K), dtype=np.float32)
+    lib().orc_group_fwd(pf, pi, B, C, N, S, K, out.ctypes.data_as(_F))
+    return out
+
+
+def group_bwd(dout, idx, N):
+    dout, pg = _f(dout)
+    idx, pi = _l(idx)
+    B, C, S, K = dout.shape
+    d = np.zeros((B, C, N), dtype=np.float32)
+    lib().orc_group_bwd(pg, pi, B, C, N, S, K, d.ctypes.data_as(_F))
+    return d
+
+
+# ------------------------------------------------ three_nn / interpolate ----
+def three_nn(unknown, known):
+    unknown, pu = _f(unknown)
+    known, pk = _f(known)
+    B, n, _ = unknown.shape
+    m = known.shape[1]
+    if m < 3:
+        raise ValueError("three_nn needs at least 3 known points")
+    dist = np.zeros((B, n, 3), dtype=np.float32)
+    idx = np.zeros((B, n, 3), dtype=np.int64)
+    lib().orc_three_nn(pu, pk, B, n, m, dist.ctypes.data_as(_F), idx.ctypes.data_as(_L))
+    return dist, idx
+
+
+def three_interpolate_fwd(feat, idx, weight):
+    feat, pf = _f(feat)
+    idx, pi = _l(idx)
+    weight, pw = _f(weight)
+    B, C, m = feat.shape
+    n = idx.shape[1]
+    out = np.zeros((B, C, n), dtype=np.float32)
+    lib().orc_three_interp_fwd(pf, pi, pw, B, C, m, n, out.ctypes.data_as(_F))
+    return out
+
+
+def three_interpolate_bwd(dout, idx, weight, m):
+    dout, pg = _f(dout)
+    idx, pi = _l(idx)
+    weight, pw = _f(weight)
+    B, C, n = dout.shape
+    d = np.zeros((B, C, m), dtype=np.float32)
+    lib().orc_three_interp_bwd(pg, pi, pw, B, C, m, n, d.ctypes.data_as(_F))
+    return d
+
+
+# ------------------------------------------------------------------ knn ----
+def knn_csr(x, y, k, ptr_x, ptr_y):
+    """returns (col [My,k] int64 with -1 padding, d2 [My,k])."""
+    x, px = _f(x)
+    y, py = _f(y)
+    ptr_x, ppx = _l(ptr_x)
+    ptr_y, ppy = _l(ptr_y)
+    C = ptr_x.shape[0] - 1
+    My = y.shape[0]
+    col = np.zeros((My, k), dtype=np.int64)
+    d2 = np.zeros((My, k), dtype=np.float32)
+    lib().orc_knn_csr(px, py, ppx, ppy, C, k, col.ctypes.data_as(_L), d2.ctypes.data_as(_F))
+    return col, d2
+
+
+def knn_edges(x, y, k, ptr_x, ptr_y):
+    """torch_cluster.knn layout: [2, E] with row = y index, col = x index."""
+    col, _ = knn_csr(x, y, k, ptr_x, ptr_y)
+    row = np.repeat(np.arange(col.shape[0], dtype=np.int64), k).reshape(col.shape)
+    keep = col >= 0
+    return np.stack([row[keep], col[keep]])
+
+
+# --------------------------------------------------------------- KPConv ----
+INFLUENCE = {"constant": 0, "linear": 1, "gaussian": 2}
+AGGREGATION = {"sum": 0, "closest": 1}
+
+
+def kpconv_fwd(q, s, nb, x, Kp, W, extent, influence="linear", aggregation="sum"):
+    q, pq = _f(q)
+    s, ps = _f(s)
+    nb, pn = _l(nb)
+    x, px = _f(x)
+    Kp, pk = _f(Kp)
+    W, pw = _f(W)
+    n, M = nb.shape
+    N0, Cin = x.shape
+    K, _, Cout = W.shape
+    out = np.zeros((n, Cout), dtype=np.float32)
+    lib().orc_kpconv_fwd(pq, ps, pn, px, pk, pw, ctypes.c_int64(n), ctypes.c_int64(N0), M, K, Cin, Cout,
+                         ctypes.c_float(extent), INFLUENCE[influence], AGGREGATION[aggregation],
+                         out.ctypes.data_as(_F))
+    return out
+
+
+def kpconv_bwd(q, s, nb, x, Kp, W, dout, extent, influence="linear", aggregation="sum"):
+    q, pq = _f(q)
+    s, ps = _f(s)
+    nb, pn = _l(nb)
+    x, px = _f(x)
+    Kp, pk = _f(Kp)
+    W, pw = _f(W)
+    dout, pg = _f(dout)
+    n, M = nb.shape
+    N0, Cin = x.shape
+    K, _, Cout = W.shape
+    dx = np.zeros((N0, Cin), dtype=np.float32)
+    dW = np.zeros((K, Cin, Cout), dtype=np.float32)
+    lib().orc_kpconv_bwd(pq, ps, pn, px, pk, pw, pg, ctypes.c_int64(n), ctypes.c_int64(N0), M, K, Cin, Cout,
+                         ctypes.c_float(extent), INFLUENCE[influence], AGGREGATION[aggregation],
+                         dx.ctypes.data_as(_F), dW.ctypes.data_as(_F))
+    return dx, dW
+
+
+def neighbor_max(x, nb):
+    x, px = _f(x)
+    nb, pn = _l(nb)
+    N0, C = x.shape
+    n, M = nb.shape
+    out = np.zeros((n, C), dtype=np.float32)
+    lib().orc_neighbor_max(px, pn, ctypes.c_int64(n), ctypes.c_int64(N0), M, C, out.ctypes.data_as(_F), None)
+    return out

@@ -1,0 +1,100 @@
+"""Generate golden vectors by running the REFERENCE's own code in this container.
+
+Only the KPConv aggregation is importable offline: it is
+loaded BY FILE PATH from /root/reference (nothing is copied), executed on CPU
+fp32 tensors, and inputs + outputs + autograd gradients are stored as small
+.npz fixtures next to this script.  /root/reference does not exist on the GPU
+box, so tests only ever read the committed .npz files.
+
+    python tests/golden/make_golden.py
+"""
+import importlib.util
+import os
+import struct
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _load_reference_kpconv_ops():
+    # convolution_ops.py imports torch_points3d.core.common_modules.gathering; provide
+    # exactly that module (also by file path) without importing the package __init__s.
+    def load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    for pkg in ["torch_points3d", "torch_points3d.core", "torch_points3d.core.common_modules"]:
+        sys.modules.setdefault(pkg, types.ModuleType(pkg))
+    load("torch_points3d.core.common_modules.gathering",
+         os.path.join(REF, "torch_points3d/core/common_modules/gathering.py"))
+    return load("ref_convolution_ops", os.path.join(REF, "torch_points3d/modules/KPConv/convolution_ops.py"))
+
+
+def read_kernel_ply(path):
+    """k_015_center.ply: ASCII header, then 15 x 3 little-endian float64."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    end = raw.index(b"end_header\n") + len(b"end_header\n")
+    body = raw[end:]
+    n = len(body) // 24
+    return np.array(struct.unpack("<%dd" % (3 * n), body[: 24 * n]), dtype=np.float64).reshape(n, 3)
+
+
+def make_case(ops, seed, n, N0, M, Cin, Cout, influence, aggregation, extent=0.05, shadow_frac=0.2, K=15):
+    g = torch.Generator().manual_seed(seed)
+    kp = read_kernel_ply(os.path.join(REF, "torch_points3d/modules/KPConv/kernels/dispositions/k_015_center.ply"))
+    K_points = torch.from_numpy((kp[:K] * 1.5 * extent).astype(np.float32))
+    support = torch.rand((N0, 3), generator=g) * 0.3
+    qsel = torch.randperm(N0, generator=g)[:n]
+    query = support[qsel] + 0.002 * torch.randn((n, 3), generator=g)
+    # neighbours: nearest ones (so that influences are non-trivial), then random shadows
+    d = torch.cdist(query, support)
+    nb = d.topk(M, largest=False).indices
+    mask = torch.rand((n, M), generator=g) < shadow_frac
+    nb = torch.where(mask, torch.full_like(nb, N0), nb)
+    nb[0, :] = N0  # one all-shadow row -> exactly 0 (linear / gaussian)
+    x = torch.randn((N0, Cin), generator=g)
+    W = torch.randn((K, Cin, Cout), generator=g) * 0.1
+    dout = torch.randn((n, Cout), generator=g)
+
+    x.requires_grad_(True)
+    W.requires_grad_(True)
+    out = ops.KPConv_ops(query, support, nb.clone(), x, K_points, W, extent, influence, aggregation)
+    out.backward(dout)
+    return dict(
+        query=query.numpy(), support=support.numpy(), neighbors=nb.numpy().astype(np.int64),
+        x=x.detach().numpy(), K_points=K_points.numpy(), W=W.detach().numpy(), dout=dout.numpy(),
+        extent=np.float32(extent), influence=influence, aggregation=aggregation,
+        out=out.detach().numpy(), dx=x.grad.numpy(), dW=W.grad.numpy(),
+    )
+
+
+def main():
+    ops = _load_reference_kpconv_ops()
+    cases = [
+        ("kpconv_linear_sum", dict(seed=11, n=96, N0=160, M=20, Cin=8, Cout=12, influence="linear", aggregation="sum")),
+        ("kpconv_gaussian_sum", dict(seed=12, n=64, N0=128, M=16, Cin=5, Cout=7, influence="gaussian", aggregation="sum")),
+        ("kpconv_constant_sum", dict(seed=13, n=64, N0=128, M=16, Cin=6, Cout=6, influence="constant", aggregation="sum")),
+        ("kpconv_linear_closest", dict(seed=14, n=64, N0=128, M=18, Cin=8, Cout=8, influence="linear", aggregation="closest")),
+        ("kpconv_linear_sum_c32", dict(seed=15, n=200, N0=300, M=34, Cin=32, Cout=32, influence="linear", aggregation="sum")),
+    ]
+    for name, kw in cases:
+        case = make_case(ops, **kw)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **case)
+        print(name, case["out"].shape, float(np.abs(case["out"]).mean()))
+    kp = read_kernel_ply(os.path.join(REF, "torch_points3d/modules/KPConv/kernels/dispositions/k_015_center.ply"))
+    # the 15 kernel-point disposition is DATA of the reference model (k_015_center.ply); kept as a fixture
+    np.save(os.path.join(HERE, "k_015_center.npy"), kp)
+    print("kernel points", kp.shape)
+
+
+if __name__ == "__main__":
+    main()
