@@ -1,0 +1,169 @@
+/*
+ * p3d_b200.h -- C ABI of libp3d_b200.so: hand-written sm_100a CUDA kernels for
+ * the per-layer sampling / grouping / neighbour-aggregation path of
+ * torch-points3d (leo-stan/torch-points3d).
+ *
+ * Contract
+ *   - plain pointers and sizes; every pointer is a DEVICE pointer unless named h_*;
+ *   - the caller owns all memory (inputs, outputs, workspaces); the library never
+ *     allocates, frees, synchronises the device or changes the current device;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - all tensors are contiguous, fp32 points/features, int64 indices unless stated;
+ *   - return value 0 = launched; <0 = error, text in p3d_last_error() (thread local);
+ *   - there is NO CPU fallback: without a CUDA device every entry point fails.
+ *
+ * Each entry point cites the reference interface it replaces.  The reference is
+ * pure Python; its FFI for this path is the pybind11 surface of two wheels
+ * (torch-points-kernels 0.7.0 `torch_points_kernels.points_cuda`, torch-cluster
+ * 1.5.9 `torch.ops.torch_cluster`) reached from the call sites cited below, plus
+ * the pure-torch KPConv_ops.  INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Floating-point rule: squared distances are fp32 ((dx*dx + dy*dy) + dz*dz),
+ * never contracted into FMAs -> indices are bit-exact
+ * against oracle/p3d_oracle.c.
+ */
+#ifndef P3D_B200_H
+#define P3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P3D_OK 0
+#define P3D_ERR_INVALID -1   /* bad argument (shape, null pointer, unsupported size) */
+#define P3D_ERR_CUDA -2      /* CUDA runtime reported an error at launch */
+#define P3D_ERR_WORKSPACE -3 /* workspace missing or too small */
+
+#define P3D_INFLUENCE_CONSTANT 0
+#define P3D_INFLUENCE_LINEAR 1
+#define P3D_INFLUENCE_GAUSSIAN 2
+#define P3D_AGGREGATION_SUM 0
+#define P3D_AGGREGATION_CLOSEST 1
+
+int p3d_version(void);
+const char *p3d_last_error(void);
+/* number of kernels this library has launched so far in this process (bench.py: gpu_launches) */
+uint64_t p3d_launch_count(void);
+/* compiled-for architecture string, e.g. "sm_100a" */
+const char *p3d_arch(void);
+
+/* ---------------------------------------------------------------- FPS ------
+ * Replaces tp.furthest_point_sample(xyz[B,N,3], npoint) -> idx[B,npoint]
+ *   reference call sites: torch_points3d/core/spatial_ops/sampling.py:100,
+ *                         torch_points3d/modules/VoteNet/proposal_module.py:57
+ * Start index 0, lowest-index tie-break.  idx_is_i64: 0 -> int32 out (what tpk's CUDA
+ * path returns), 1 -> int64 out (what core/base_conv/dense.py:75 casts to).
+ * N <= 131072 runs register-resident in one CTA / one thread-block cluster per cloud;
+ * larger N needs `ws` = B*N floats (min-distance scratch). */
+size_t p3d_fps_dense_ws_bytes(int B, int N);
+int p3d_fps_dense_f32(const float *xyz, int B, int N, int S, void *idx, int idx_is_i64, void *ws, size_t ws_bytes,
+                      void *stream);
+
+/* Replaces torch_geometric.nn.fps(x, batch, ratio, random_start=False) == torch_cluster.fps
+ *   reference call sites: core/spatial_ops/sampling.py:63,
+ *                         datasets/registration/utils.py:337, modules/VoteNet/dense_samplers.py:70,93
+ * CSR form: cloud c owns rows ptr[c]..ptr[c+1] and emits out_ptr[c+1]-out_ptr[c] GLOBAL
+ * indices at idx[out_ptr[c]..].  start (nullable): per-cloud LOCAL index of the first sample
+ * (random_start=True draws it on the host side; NULL = index 0, the pinned behaviour of
+ * test/test_fps.py:35-42).  max_n = host-known upper bound on the largest cloud (selects the
+ * register tiling); ws as above with total rows. */
+size_t p3d_fps_csr_ws_bytes(int64_t total_rows, int64_t max_n);
+int p3d_fps_csr_f32(const float *xyz, const int64_t *ptr, int num_clouds, const int64_t *out_ptr, int64_t *idx,
+                    const int64_t *start, int64_t max_n, void *ws, size_t ws_bytes, void *stream);
+
+/* --------------------------------------------------------- ball query ------
+ * Replaces tp.ball_query(radius, nsample, x[B,N,3], y[B,S,3], mode="dense") -> (idx, dist2)
+ *   reference call site: core/spatial_ops/neighbour_finder.py:164
+ * First `nsample` candidates in index order with d2 < r2 (strict != 0) or d2 <= r2;
+ * padding = first hit, empty ball = 0; dist2 (nullable) padded with -1. */
+int p3d_ball_query_dense_f32(const float *x, const float *y, int B, int N, int S, float radius, int nsample,
+                             int strict, int64_t *idx, float *dist2, void *stream);
+
+/* Replaces tp.ball_query(..., mode="partial_dense", batch_x, batch_y)
+ *   reference call site: core/spatial_ops/neighbour_finder.py:35-37
+ * batch_x[Nx], batch_y[Ny]: sorted cloud ids (int64).  GLOBAL indices into x, unfilled
+ * slots = shadow (the reference uses x.shape[0]), dist2 (nullable) = -1.  The cloud
+ * ranges are found on the device (no blocking D2H copy of batch_x[-1]). */
+int p3d_ball_query_batch_f32(const float *x, const float *y, const int64_t *batch_x, const int64_t *batch_y,
+                             int64_t Nx, int64_t Ny, float radius, int nsample, int strict, int64_t shadow,
+                             int64_t *idx, float *dist2, void *stream);
+
+/* ---------------------------------------------------------------- knn ------
+ * Replaces torch_geometric.nn.knn(x, y, k, batch_x, batch_y) == torch_cluster.knn
+ *   reference call sites: core/spatial_ops/neighbour_finder.py:47, interpolate.py:25,70
+ * col[Ny,k]: GLOBAL support indices, ascending d2, ties -> lower index, -1 where the cloud
+ * has fewer than k supports; d2 (nullable) likewise (-1).  batch_* nullable = one cloud.
+ * k <= 128. */
+int p3d_knn_batch_f32(const float *x, const float *y, const int64_t *batch_x, const int64_t *batch_y, int64_t Nx,
+                      int64_t Ny, int k, int64_t *col, float *d2, void *stream);
+
+/* Dense-layout knn: tp.knn(pos_support[B,N,3], pos[B,M,3], k) -> (idx[B,M,k], dist2[B,M,k])
+ *   reference call sites: core/data_transform/transforms.py:16 (dense_knn), datasets/registration/*
+ * indices are local to the cloud; k <= N required by the caller. */
+int p3d_knn_dense_f32(const float *x, const float *y, int B, int N, int M, int k, int64_t *idx, float *d2,
+                      void *stream);
+
+/* Replaces tp.three_nn(unknown[B,n,3], known[B,m,3]) -> (dist[B,n,3] = sqrt(d2), idx[B,n,3])
+ *   reference call site: core/base_conv/dense.py:136 */
+int p3d_three_nn_f32(const float *unknown, const float *known, int B, int n, int m, float *dist, int64_t *idx,
+                     void *stream);
+
+/* ----------------------------------------------------------- grouping ------
+ * Replaces tp.grouping_operation(features[B,C,N], idx[B,S,K]) -> [B,C,S,K]
+ *   reference call sites: modules/pointnet2/dense.py:38,45; modules/RSConv/dense.py:147,152,...
+ * out is addressed as out[b*out_batch_stride + (c_off + c)*S*K + s*K + k] so that the
+ * caller can write straight into a concatenated [B,3+C,S,K] tensor
+ * (out_batch_stride = C*S*K, c_off = 0 for the plain op). */
+int p3d_group_fwd_f32(const float *feat, const int64_t *idx, int B, int C, int N, int S, int K, float *out,
+                      int64_t out_batch_stride, int c_off, void *stream);
+/* backward (autograd of the gather): dfeat[b,c,i] += sum_{(s,k): idx=i} dout[...]; dfeat must be
+ * zero-initialised by the caller.  dout is addressed like `out` above. */
+int p3d_group_bwd_f32(const float *dout, const int64_t *idx, int B, int C, int N, int S, int K, float *dfeat,
+                      int64_t dout_batch_stride, int c_off, void *stream);
+/* Fused PointNetMSGDown._prepare_features xyz part (modules/pointnet2/dense.py:37-42):
+ * out[b, c, s, k] = (pos[b, idx[b,s,k], c] - new_pos[b, s, c]) / norm   for c in 0..2,
+ * norm = 1 unless normalize_xyz.  pos is the untransposed [B,N,3] tensor. */
+int p3d_group_xyz_f32(const float *pos, const float *new_pos, const int64_t *idx, int B, int N, int S, int K,
+                      float norm, float *out, int64_t out_batch_stride, void *stream);
+
+/* ---------------------------------------------------- three_interpolate ----
+ * Replaces tp.three_interpolate(features[B,C,m], idx[B,n,3], weight[B,n,3]) -> [B,C,n]
+ *   reference call site: core/base_conv/dense.py:140 */
+int p3d_three_interp_fwd_f32(const float *feat, const int64_t *idx, const float *weight, int B, int C, int m,
+                             int n, float *out, void *stream);
+/* backward w.r.t. features; dfeat zero-initialised by the caller */
+int p3d_three_interp_bwd_f32(const float *dout, const int64_t *idx, const float *weight, int B, int C, int m,
+                             int n, float *dfeat, void *stream);
+
+/* ------------------------------------------------------------- KPConv ------
+ * Replaces KPConv_ops(query, support, neighbors, features, K_points, K_values, KP_extent,
+ *                     KP_influence, aggregation_mode) -> [n, Cout]
+ *   reference: torch_points3d/modules/KPConv/convolution_ops.py:19-107
+ *   called from modules/KPConv/kernels.py:83-93
+ * neighbors[n,M] int64, entries >= N0 or < 0 are shadow neighbours (point at 1e6, zero
+ * feature).  K <= 16 kernel points.  One fused kernel: no [n,M,K] / [n,M,Cin] / [n,K,Cin]
+ * intermediate is written to HBM. */
+int p3d_kpconv_fwd_f32(const float *query, const float *support, const int64_t *neighbors, const float *feat,
+                       const float *k_points, const float *k_values, int64_t n, int64_t N0, int M, int K, int Cin,
+                       int Cout, float extent, int influence, int aggregation, float *out, void *stream);
+/* autograd backward: dfeat[N0,Cin] (zero-initialised by the caller, nullable) and
+ * dweights[K,Cin,Cout] (zero-initialised by the caller, nullable).  ws: p3d_kpconv_bwd_ws_bytes. */
+size_t p3d_kpconv_bwd_ws_bytes(int64_t n, int M, int K, int Cin, int Cout);
+int p3d_kpconv_bwd_f32(const float *query, const float *support, const int64_t *neighbors, const float *feat,
+                       const float *k_points, const float *k_values, const float *dout, int64_t n, int64_t N0,
+                       int M, int K, int Cin, int Cout, float extent, int influence, int aggregation,
+                       float *dfeat, float *dweights, void *ws, size_t ws_bytes, void *stream);
+
+/* Strided-shortcut neighbour max-pool (modules/KPConv/blocks.py:206-210):
+ * out[p,c] = max_m x'[neighbors[p,m], c], x' = cat(x, zeros); arg (nullable) = winning row
+ * (N0 for the shadow row) for the backward pass. */
+int p3d_neighbor_max_f32(const float *x, const int64_t *neighbors, int64_t n, int64_t N0, int M, int C,
+                         float *out, int64_t *arg, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P3D_B200_H */

@@ -76,14 +76,17 @@ def fps_counts(ptr, ratio):
     return np.ceil(np.float32(ratio) * n.astype(np.float32)).astype(np.int64)
 
 
-def fps_csr(xyz, ptr, counts):
+def fps_csr(xyz, ptr, counts, start=None):
     xyz, p = _f(xyz)
     ptr, pp = _l(ptr)
     C = ptr.shape[0] - 1
     out_ptr = np.zeros(C + 1, dtype=np.int64)
     np.cumsum(np.asarray(counts, dtype=np.int64), out=out_ptr[1:])
     idx = np.zeros(int(out_ptr[-1]), dtype=np.int64)
-    lib().orc_fps_csr(p, pp, C, out_ptr.ctypes.data_as(_L), idx.ctypes.data_as(_L))
+    ps = None
+    if start is not None:
+        start, ps = _l(start)
+    lib().orc_fps_csr(p, pp, C, out_ptr.ctypes.data_as(_L), idx.ctypes.data_as(_L), ps)
     return idx
 
 

@@ -1,0 +1,138 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports exactly what
+include/p3d_b200.h declares, and the host-side mirror keeps the reference's argument checking
+and error behaviour.  No compute calls (no GPU here)."""
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+import __graft_entry__ as entry
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def cabi():
+    entry.build()
+    from torch_points3d_b200 import _cabi
+    return _cabi
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "p3d_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(p3d_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_what_the_library_exports(cabi):
+    declared = _header_functions()
+    assert len(declared) >= 20
+    out = subprocess.run(["nm", "-D", "--defined-only", cabi.LIB_PATH], capture_output=True, text=True, check=True)
+    exported = sorted(set(re.findall(r" T (p3d_[a-z0-9_]+)", out.stdout)))
+    assert exported == declared
+    assert sorted(cabi.SIGNATURES) == declared  # ctypes binding covers every entry point
+
+
+def test_library_loads_and_reports_arch(cabi):
+    lib = cabi.lib()
+    assert lib.p3d_arch() == b"sm_100a"
+    assert lib.p3d_version() >= 100
+    assert lib.p3d_launch_count() >= 0
+    assert lib.p3d_fps_dense_ws_bytes(4, 1024) == 0
+    assert lib.p3d_fps_dense_ws_bytes(2, 200000) == 2 * 200000 * 4
+    assert lib.p3d_kpconv_bwd_ws_bytes(10, 34, 15, 32, 32) == 2 * 10 * 15 * 32 * 4
+
+
+def test_sass_is_sm100a_only(cabi):
+    out = subprocess.run(["cuobjdump", "-lelf", cabi.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}
+
+
+def test_argument_validation_is_reported_not_crashed(cabi):
+    lib = cabi.lib()
+    # S > N is rejected on the host side of the ABI before any CUDA call
+    assert lib.p3d_fps_dense_f32(None, 1, 4, 5, None, 1, None, 0, None) == -1
+    assert b"npoint" in lib.p3d_last_error()
+    assert lib.p3d_knn_batch_f32(None, None, None, None, 4, 4, 0, None, None, None) == -1
+    assert lib.p3d_three_nn_f32(None, None, 1, 4, 2, None, None, None) == -1
+    assert lib.p3d_kpconv_fwd_f32(None, None, None, None, None, None, 4, 4, 200, 15, 8, 8, 1.0, 1, 0, None, None) == -1
+    # empty problems are a successful no-op
+    assert lib.p3d_fps_dense_f32(None, 0, 4, 2, None, 1, None, 0, None) == 0
+    assert lib.p3d_ball_query_dense_f32(None, None, 0, 0, 0, 0.1, 4, 1, None, None, None) == 0
+
+
+def test_no_cpu_fallback():
+    from torch_points3d_b200 import ops
+    xyz = torch.rand(2, 16, 3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.furthest_point_sample(xyz, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.ball_query(0.2, 4, xyz, xyz[:, :4])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.grouping_operation(torch.rand(2, 3, 16), torch.zeros(2, 4, 4, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.KPConv_ops(xyz[0], xyz[0], torch.zeros(16, 4, dtype=torch.long), torch.rand(16, 8), torch.rand(15, 3),
+                       torch.rand(15, 8, 8), 0.1, "linear", "sum")
+
+
+def test_reference_error_behaviour():
+    """same exception types as torch_points_kernels / the reference wrappers"""
+    from torch_points3d_b200 import ops, spatial_ops as so
+    xyz = torch.rand(2, 16, 3)
+    with pytest.raises(ValueError):
+        ops.furthest_point_sample(xyz, 17)                      # tpk: npoint > N
+    with pytest.raises(Exception, match="batch_x and batch_y should be provided"):
+        ops.ball_query(0.1, 4, xyz[0], xyz[0], mode="partial_dense")
+    with pytest.raises(Exception, match="should not be provided"):
+        ops.ball_query(0.1, 4, xyz, xyz, mode="dense", batch_x=torch.zeros(16, dtype=torch.long))
+    with pytest.raises(NotImplementedError):
+        ops.ball_query(0.1, 4, xyz, xyz, sort=True)
+    with pytest.raises(ValueError):
+        ops.three_nn(xyz, xyz[:, :2])
+    with pytest.raises(ValueError):
+        ops.KPConv_ops(xyz[0], xyz[0], None, torch.rand(16, 8), torch.rand(15, 3), torch.rand(15, 8, 8), 0.1,
+                       "cubic", "sum")
+    with pytest.raises(ValueError):
+        so.DenseFPSSampler(num_to_sample=4).sample(xyz[0])     # sampling.py:97-98
+    with pytest.raises(ValueError):
+        so.FPSSampler(ratio=0.5).sample(xyz, None)             # sampling.py:60-61
+    with pytest.raises(ValueError):
+        so.BaseSampler.__init__(so.FPSSampler.__new__(so.FPSSampler), ratio=0.5, num_to_sample=3)
+    with pytest.raises(Exception):
+        so.DenseFPSSampler()
+    with pytest.raises(ValueError):
+        so.MultiscaleRadiusNeighbourFinder([0.1, 0.2], [4])
+    with pytest.raises(ValueError):
+        so.DenseRadiusNeighbourFinder([0.1], [4]).find_neighbours(xyz, xyz, scale_idx=1)
+
+
+def test_sampler_count_rules():
+    from torch_points3d_b200 import spatial_ops as so
+    s = so.FPSSampler(ratio=0.5)
+    assert s._get_num_to_sample(10) == 5 and s._get_ratio_to_sample(10) == 0.5   # test_sampler.py:16-23
+    s = so.FPSSampler(num_to_sample=5)
+    assert s._get_num_to_sample(10) == 5 and s._get_ratio_to_sample(10) == 0.5
+    f = so.MultiscaleRadiusNeighbourFinder([0.1, 0.2], 8)
+    assert f.num_scales == 2 and f._max_num_neighbors == [8, 8]
+    f = so.MultiscaleRadiusNeighbourFinder(0.3, [8, 16])
+    assert f._radius == [0.3, 0.3]
+    assert so.RadiusNeighbourFinder(0.1, 4, conv_type="PARTIAL_DENSE")._conv_type == "partial_dense"
+
+
+def test_kernel_points_fixture_matches_reference_disposition(golden_dir):
+    import numpy as np
+    from torch_points3d_b200 import kpconv
+    kp = kpconv.load_kernels(1.0, random_rotation=False)
+    ref = np.load(os.path.join(golden_dir, "k_015_center.npy"))
+    assert kp.shape == (15, 3) and np.allclose(kp, ref.astype(np.float32))
+    assert np.allclose(kp[0], 0)                       # 'center' disposition: first kernel point at the origin
+    rot = kpconv.load_kernels(0.06)                    # rotation + 1% jitter keeps the radii
+    assert abs(np.linalg.norm(rot, axis=1)[1:].mean() - 0.06 * np.linalg.norm(ref, axis=1)[1:].mean()) < 0.01
+    layer = kpconv.KPConvLayer(8, 16, point_influence=0.04, add_one=True)
+    assert layer.weight.shape == (15, 9, 16) and not layer.K_points.requires_grad
+    assert "K_points" in layer.state_dict()            # checkpoints carry the kernel points (kernels.py:66-68)

@@ -1,0 +1,319 @@
+// fps.cu -- furthest point sampling for sm_100a.
+//
+// Replaces tp.furthest_point_sample (core/spatial_ops/sampling.py:100) and
+// torch_geometric.nn.fps / torch_cluster.fps (sampling.py:63) -- semantics in SURVEY.md A.1:
+// start index 0, mind = 1e10, per round mind = min(mind, d2(p, last)), next = first argmax.
+//
+// Design (latency-bound: S-1 dependent argmax rounds per cloud):
+//   * one CTA -- or one thread-block CLUSTER of up to 16 CTAs -- per cloud;
+//   * every thread keeps its PPT points AND their running min-distances in registers for
+//     the whole kernel: HBM is touched once (12 B/point in, 4|8 B/sample out);
+//   * per round: register update -> warp argmax with two redux.sync (max of the fp32 bit
+//     pattern, then min index among the maxima == lowest-index tie-break) -> one 20-byte
+//     record per warp in shared memory -> ONE __syncthreads -> every warp reduces the <=32
+//     records redundantly, so the winner's coordinates are known everywhere without a
+//     second barrier (records are double-buffered by round parity);
+//   * clusters: each CTA's winner record is pushed into every peer's shared memory through
+//     DSMEM, then one barrier.cluster per round.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace p3d {
+
+struct __align__(8) FpsRec {
+    unsigned key;  // fp32 bit pattern of the candidate's min-distance (>= +0 -> order preserving)
+    unsigned idx;  // local index inside the cloud, 0xffffffff = none
+    float x, y, z;
+    unsigned pad;
+};
+
+__device__ __forceinline__ void warp_argmax(unsigned key, unsigned idx, unsigned &wkey, unsigned &widx) {
+    wkey = __reduce_max_sync(0xffffffffu, key);
+    const unsigned cand = (key == wkey) ? idx : 0xffffffffu;
+    widx = __reduce_min_sync(0xffffffffu, cand);
+}
+
+template <int T, int PPT, int CLUSTER, typename IdxT>
+__global__ void __launch_bounds__(T, 1)
+fps_reg_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr, int64_t n_dense,
+               const int64_t *__restrict__ out_ptr, int64_t s_dense, IdxT *__restrict__ out,
+               const int64_t *__restrict__ first) {
+    constexpr int NW = T / 32;
+    __shared__ FpsRec rec[2][32];
+    __shared__ FpsRec crec[2][CLUSTER];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int cloud = blockIdx.x / CLUSTER;
+    const int rank = blockIdx.x % CLUSTER;
+
+    int64_t start, n, s, obase, add;
+    if (ptr != nullptr) {
+        start = ptr[cloud];
+        n = ptr[cloud + 1] - start;
+        obase = out_ptr[cloud];
+        s = out_ptr[cloud + 1] - obase;
+        add = start;  // CSR form emits global indices
+    } else {
+        start = (int64_t)cloud * n_dense;
+        n = n_dense;
+        obase = (int64_t)cloud * s_dense;
+        s = s_dense;
+        add = 0;
+    }
+    if (s > n) s = n;  // host validates; keeps the kernel safe
+
+    const float *__restrict__ p = xyz + 3 * start;
+    float px[PPT], py[PPT], pz[PPT], md[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int64_t i = (int64_t)j * (CLUSTER * T) + rank * T + tid;
+        if (i < n) {
+            px[j] = p[3 * i];
+            py[j] = p[3 * i + 1];
+            pz[j] = p[3 * i + 2];
+            md[j] = 1e10f;
+        } else {
+            px[j] = py[j] = pz[j] = 0.f;
+            md[j] = -1.f;  // never selected: min(-1, d) stays -1 and -1 > best is false
+        }
+    }
+    float lx = 0.f, ly = 0.f, lz = 0.f;
+    int64_t f0 = 0;
+    if (n > 0) {
+        if (first != nullptr) {
+            f0 = first[cloud];
+            f0 = f0 < 0 ? 0 : (f0 >= n ? n - 1 : f0);
+        }
+        lx = p[3 * f0];
+        ly = p[3 * f0 + 1];
+        lz = p[3 * f0 + 2];
+    }
+    if (tid == 0 && rank == 0 && s > 0) out[obase] = (IdxT)(add + f0);
+
+    for (int64_t r = 1; r < s; ++r) {
+        const int buf = (int)(r & 1);
+        float best = -1.f, bx = 0.f, by = 0.f, bz = 0.f;
+        unsigned bi = 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const float d = sqdist3(px[j], py[j], pz[j], lx, ly, lz);
+            const float m = fminf(md[j], d);
+            md[j] = m;
+            if (m > best) {  // strict: the lowest index wins inside a thread (indices ascend with j)
+                best = m;
+                bi = (unsigned)(j * (CLUSTER * T) + rank * T + tid);
+                bx = px[j];
+                by = py[j];
+                bz = pz[j];
+            }
+        }
+        const unsigned key = best >= 0.f ? __float_as_uint(best) : 0u;
+        unsigned wkey, widx;
+        warp_argmax(key, bi, wkey, widx);
+        if (key == wkey && bi == widx) {
+            FpsRec rr;
+            rr.key = wkey; rr.idx = widx; rr.x = bx; rr.y = by; rr.z = bz; rr.pad = 0;
+            rec[buf][warp] = rr;
+        }
+        __syncthreads();
+
+        unsigned k2 = 0u, i2 = 0xffffffffu;
+        if (lane < NW) {
+            k2 = rec[buf][lane].key;
+            i2 = rec[buf][lane].idx;
+        }
+        unsigned ckey, cidx;
+        warp_argmax(k2, i2, ckey, cidx);
+        int src = __ffs(__ballot_sync(0xffffffffu, k2 == ckey && i2 == cidx)) - 1;
+
+        if constexpr (CLUSTER == 1) {
+            lx = rec[buf][src].x;
+            ly = rec[buf][src].y;
+            lz = rec[buf][src].z;
+            if (tid == 0) out[obase + r] = (IdxT)(add + (int64_t)cidx);
+        } else {
+            cg::cluster_group cluster = cg::this_cluster();
+            if (warp == 0 && lane < CLUSTER) {
+                FpsRec rr = rec[buf][src];
+                rr.key = ckey;
+                rr.idx = cidx;
+                FpsRec *dst = cluster.map_shared_rank(&crec[buf][rank], lane);
+                *dst = rr;
+            }
+            cluster.sync();
+            unsigned k3 = 0u, i3 = 0xffffffffu;
+            if (lane < CLUSTER) {
+                k3 = crec[buf][lane].key;
+                i3 = crec[buf][lane].idx;
+            }
+            unsigned gkey, gidx;
+            warp_argmax(k3, i3, gkey, gidx);
+            src = __ffs(__ballot_sync(0xffffffffu, k3 == gkey && i3 == gidx)) - 1;
+            lx = crec[buf][src].x;
+            ly = crec[buf][src].y;
+            lz = crec[buf][src].z;
+            if (tid == 0 && rank == 0) out[obase + r] = (IdxT)(add + (int64_t)gidx);
+        }
+    }
+    if constexpr (CLUSTER > 1) {
+        // no CTA may exit while a peer can still write into its shared memory
+        cg::this_cluster().sync();
+    }
+}
+
+// Fallback for clouds larger than 131072 points: one 1024-thread CTA per cloud, points read
+// from global/L2 every round, min-distances in a caller-provided workspace.
+template <typename IdxT>
+__global__ void __launch_bounds__(1024, 1)
+fps_big_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr, int64_t n_dense,
+               const int64_t *__restrict__ out_ptr, int64_t s_dense, IdxT *__restrict__ out,
+               float *__restrict__ mind, const int64_t *__restrict__ first) {
+    __shared__ FpsRec rec[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cloud = blockIdx.x;
+    int64_t start, n, s, obase, add;
+    if (ptr != nullptr) {
+        start = ptr[cloud]; n = ptr[cloud + 1] - start;
+        obase = out_ptr[cloud]; s = out_ptr[cloud + 1] - obase; add = start;
+    } else {
+        start = (int64_t)cloud * n_dense; n = n_dense;
+        obase = (int64_t)cloud * s_dense; s = s_dense; add = 0;
+    }
+    if (s > n) s = n;
+    const float *__restrict__ p = xyz + 3 * start;
+    float *__restrict__ md = mind + start;
+    for (int64_t i = tid; i < n; i += 1024) md[i] = 1e10f;
+    float lx = 0.f, ly = 0.f, lz = 0.f;
+    int64_t f0 = 0;
+    if (n > 0) {
+        if (first != nullptr) { f0 = first[cloud]; f0 = f0 < 0 ? 0 : (f0 >= n ? n - 1 : f0); }
+        lx = p[3 * f0]; ly = p[3 * f0 + 1]; lz = p[3 * f0 + 2];
+    }
+    if (tid == 0 && s > 0) out[obase] = (IdxT)(add + f0);
+    for (int64_t r = 1; r < s; ++r) {
+        const int buf = (int)(r & 1);
+        float best = -1.f, bx = 0.f, by = 0.f, bz = 0.f;
+        unsigned bi = 0xffffffffu;
+        for (int64_t i = tid; i < n; i += 1024) {
+            const float x = p[3 * i], y = p[3 * i + 1], z = p[3 * i + 2];
+            const float m = fminf(md[i], sqdist3(x, y, z, lx, ly, lz));
+            md[i] = m;
+            if (m > best) { best = m; bi = (unsigned)i; bx = x; by = y; bz = z; }
+        }
+        const unsigned key = best >= 0.f ? __float_as_uint(best) : 0u;
+        unsigned wkey, widx;
+        warp_argmax(key, bi, wkey, widx);
+        if (key == wkey && bi == widx) {
+            FpsRec rr;
+            rr.key = wkey; rr.idx = widx; rr.x = bx; rr.y = by; rr.z = bz; rr.pad = 0;
+            rec[buf][warp] = rr;
+        }
+        __syncthreads();
+        const unsigned k2 = rec[buf][lane].key, i2 = rec[buf][lane].idx;
+        unsigned ckey, cidx;
+        warp_argmax(k2, i2, ckey, cidx);
+        const int src = __ffs(__ballot_sync(0xffffffffu, k2 == ckey && i2 == cidx)) - 1;
+        lx = rec[buf][src].x; ly = rec[buf][src].y; lz = rec[buf][src].z;
+        if (tid == 0) out[obase + r] = (IdxT)(add + (int64_t)cidx);
+    }
+}
+
+template <int T, int PPT, int CLUSTER, typename IdxT>
+static int launch_reg(const float *xyz, const int64_t *ptr, int64_t n_dense, const int64_t *out_ptr,
+                      int64_t s_dense, IdxT *out, const int64_t *first, int clouds, cudaStream_t st) {
+    auto kern = fps_reg_kernel<T, PPT, CLUSTER, IdxT>;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(clouds * CLUSTER));
+    cfg.blockDim = dim3(T);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (CLUSTER > 8) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) {
+            set_error("fps: non-portable cluster size refused: %s", cudaGetErrorString(e));
+            return P3D_ERR_CUDA;
+        }
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, xyz, ptr, n_dense, out_ptr, s_dense, out, first);
+    if (e != cudaSuccess) {
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        set_error("fps launch (T=%d PPT=%d CLUSTER=%d): %s", T, PPT, CLUSTER, cudaGetErrorString(e));
+        return P3D_ERR_CUDA;
+    }
+    return finish_launch("fps");
+}
+
+template <typename IdxT>
+static int fps_dispatch(const float *xyz, const int64_t *ptr, int64_t n_dense, const int64_t *out_ptr,
+                        int64_t s_dense, IdxT *out, const int64_t *first, int clouds, int64_t max_n, float *ws,
+                        size_t ws_bytes, int64_t total_rows, cudaStream_t st) {
+    if (clouds == 0) return P3D_OK;
+#define P3D_FPS_CASE(LIM, T, PPT, CL) \
+    if (max_n <= (LIM)) return launch_reg<T, PPT, CL, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, clouds, st);
+    P3D_FPS_CASE(256, 64, 4, 1)
+    P3D_FPS_CASE(512, 128, 4, 1)
+    P3D_FPS_CASE(1024, 256, 4, 1)
+    P3D_FPS_CASE(2048, 512, 4, 1)
+    P3D_FPS_CASE(4096, 1024, 4, 1)
+    P3D_FPS_CASE(8192, 1024, 8, 1)
+    P3D_FPS_CASE(16384, 1024, 8, 2)
+    P3D_FPS_CASE(32768, 1024, 8, 4)
+    P3D_FPS_CASE(65536, 1024, 8, 8)
+    P3D_FPS_CASE(131072, 1024, 8, 16)
+#undef P3D_FPS_CASE
+    if (ws == nullptr || ws_bytes < (size_t)total_rows * sizeof(float)) {
+        set_error("fps: clouds of more than 131072 points need a workspace of %lld bytes",
+                  (long long)(total_rows * (int64_t)sizeof(float)));
+        return P3D_ERR_WORKSPACE;
+    }
+    fps_big_kernel<IdxT><<<clouds, 1024, 0, st>>>(xyz, ptr, n_dense, out_ptr, s_dense, out, ws, first);
+    return finish_launch("fps_big");
+}
+
+}  // namespace p3d
+
+using namespace p3d;
+
+P3D_EXPORT size_t p3d_fps_dense_ws_bytes(int B, int N) {
+    return N > 131072 ? (size_t)B * (size_t)N * sizeof(float) : 0;
+}
+
+P3D_EXPORT int p3d_fps_dense_f32(const float *xyz, int B, int N, int S, void *idx, int idx_is_i64, void *ws,
+                                 size_t ws_bytes, void *stream) {
+    P3D_REQUIRE(B >= 0 && N >= 0 && S >= 0, "fps_dense: negative dimension");
+    P3D_REQUIRE(S <= N, "fps_dense: npoint (%d) > N (%d)", S, N);
+    if (B == 0 || S == 0) return P3D_OK;
+    P3D_REQUIRE(xyz && idx, "fps_dense: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (idx_is_i64)
+        return fps_dispatch<int64_t>(xyz, nullptr, N, nullptr, S, (int64_t *)idx, nullptr, B, N, (float *)ws, ws_bytes,
+                                     (int64_t)B * N, st);
+    return fps_dispatch<int32_t>(xyz, nullptr, N, nullptr, S, (int32_t *)idx, nullptr, B, N, (float *)ws, ws_bytes,
+                                 (int64_t)B * N, st);
+}
+
+P3D_EXPORT size_t p3d_fps_csr_ws_bytes(int64_t total_rows, int64_t max_n) {
+    return max_n > 131072 ? (size_t)total_rows * sizeof(float) : 0;
+}
+
+P3D_EXPORT int p3d_fps_csr_f32(const float *xyz, const int64_t *ptr, int num_clouds, const int64_t *out_ptr,
+                               int64_t *idx, const int64_t *start, int64_t max_n, void *ws, size_t ws_bytes,
+                               void *stream) {
+    P3D_REQUIRE(num_clouds >= 0 && max_n >= 0, "fps_csr: negative dimension");
+    if (num_clouds == 0) return P3D_OK;
+    P3D_REQUIRE(xyz && ptr && out_ptr && idx, "fps_csr: null pointer");
+    return fps_dispatch<int64_t>(xyz, ptr, 0, out_ptr, 0, idx, start, num_clouds, max_n, (float *)ws, ws_bytes,
+                                 ws_bytes / sizeof(float), (cudaStream_t)stream);
+}

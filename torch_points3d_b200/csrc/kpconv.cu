@@ -1,0 +1,357 @@
+// kpconv.cu -- rigid KPConv neighbour aggregation (fp32 SIMT path) for sm_100a.
+//
+// Replaces KPConv_ops (torch_points3d/modules/KPConv/convolution_ops.py:19-107), called from
+// KPConvLayer.forward (modules/KPConv/kernels.py:83-93).
+//
+// Forward, one fused kernel: a warp owns T consecutive query points.  Per point it computes the
+// [M x 16] kernel-point influence table in shared memory (kpconv_common.cuh), gathers the
+// neighbour feature rows straight from L2 (lanes over channels -> one 128-byte line per row
+// and 32-channel slab) and accumulates wf[k][c] = sum_m w[k][m] * x[nb[m]][c] in 16
+// registers; the [16 x 32 x T] slab of weighted features stays in shared memory and is
+// contracted against the kernel weights W[k][c][:] with lanes over output channels.
+// None of the reference's intermediates ([n,M,K,3] differences, [n,M,K] weights,
+// [n,M,Cin] gathered features, [n,K,Cin] weighted features, [K,n,Cout] kernel outputs)
+// exists in HBM.  This path is exact fp32 (1e-5 parity against the oracle); the tcgen05
+// path for the kernel-point contraction lives in kpconv_tc.cu.
+//
+// Backward: wf and d(wf) go through a caller-provided workspace and two plain tiled
+// SGEMMs (dW = wf^T dout, dwf = dout W^T), then one scatter kernel recomputes the influence
+// weights and accumulates dfeat with fp32 reductions at L2.
+#include "kpconv_common.cuh"
+
+namespace p3d {
+
+constexpr int KPF_WARPS = 8;
+constexpr int KPF_T = 4;  // query points per warp per pass
+
+// wf[k] (16 accumulators per lane, lane = channel c0+lane) of one point
+__device__ __forceinline__ void kp_weighted_features(const float *__restrict__ x, int Cin, int c0, int M,
+                                                     const float *wsm, const int *jsm, int lane, float (&acc)[KP_K]) {
+#pragma unroll
+    for (int k = 0; k < KP_K; ++k) acc[k] = 0.f;
+    const int c = c0 + lane;
+    const bool cok = c < Cin;
+    for (int m = 0; m < M; ++m) {
+        const int j = jsm[m];
+        if (j < 0) continue;  // warp-uniform
+        const float xv = cok ? __ldg(x + (int64_t)j * Cin + c) : 0.f;
+        const float4 *w4 = reinterpret_cast<const float4 *>(wsm + m * KP_K);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const float4 w = w4[g];
+            acc[4 * g + 0] = fmaf(w.x, xv, acc[4 * g + 0]);
+            acc[4 * g + 1] = fmaf(w.y, xv, acc[4 * g + 1]);
+            acc[4 * g + 2] = fmaf(w.z, xv, acc[4 * g + 2]);
+            acc[4 * g + 3] = fmaf(w.w, xv, acc[4 * g + 3]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(KPF_WARPS * 32)
+kpconv_fwd_simt_kernel(const float *__restrict__ q, const float *__restrict__ s, const int64_t *__restrict__ nb,
+                       const float *__restrict__ x, const float *__restrict__ kp, const float *__restrict__ W,
+                       int64_t n, int64_t N0, int M, int Mpad, int K, int Cin, int Cout, KpGeom g,
+                       float *__restrict__ out) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per_warp = Mpad * KP_K + Mpad + KP_K * 32 * KPF_T;
+    float *wsm = smem + (size_t)warp * per_warp;
+    int *jsm = reinterpret_cast<int *>(wsm + Mpad * KP_K);
+    float *wfs = wsm + Mpad * KP_K + Mpad;  // [16][T][32]
+
+    const int kk = lane & 15;
+    const float kx = kk < K ? __ldg(kp + 3 * kk) : 0.f;
+    const float ky = kk < K ? __ldg(kp + 3 * kk + 1) : 0.f;
+    const float kz = kk < K ? __ldg(kp + 3 * kk + 2) : 0.f;
+
+    const int64_t tiles = (n + KPF_T - 1) / KPF_T;
+    for (int64_t tile = (int64_t)blockIdx.x * KPF_WARPS + warp; tile < tiles; tile += (int64_t)gridDim.x * KPF_WARPS) {
+        const int64_t p0 = tile * KPF_T;
+        for (int c0 = 0; c0 < Cin; c0 += 32) {
+            for (int t = 0; t < KPF_T; ++t) {
+                const int64_t p = p0 + t;
+                float acc[KP_K];
+                if (p < n) {
+                    kp_point_weights(q + 3 * p, s, nb + p * M, N0, M, K, g, kx, ky, kz, wsm, jsm, lane);
+                    kp_weighted_features(x, Cin, c0, M, wsm, jsm, lane, acc);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < KP_K; ++k) acc[k] = 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < KP_K; ++k) wfs[(k * KPF_T + t) * 32 + lane] = acc[k];
+                __syncwarp();
+            }
+            const int cw = (Cin - c0 < 32) ? (Cin - c0) : 32;
+            for (int o0 = 0; o0 < Cout; o0 += 32) {
+                const int o = o0 + lane;
+                const bool ook = o < Cout;
+                float a[KPF_T];
+#pragma unroll
+                for (int t = 0; t < KPF_T; ++t) a[t] = 0.f;
+                for (int k = 0; k < K; ++k) {
+                    const float *__restrict__ wrow = W + ((int64_t)k * Cin + c0) * Cout + o;
+                    const float *wk = wfs + k * KPF_T * 32;
+#pragma unroll 4
+                    for (int c = 0; c < cw; ++c) {
+                        const float wv = ook ? __ldg(wrow + (int64_t)c * Cout) : 0.f;
+#pragma unroll
+                        for (int t = 0; t < KPF_T; ++t) a[t] = fmaf(wk[t * 32 + c], wv, a[t]);
+                    }
+                }
+                if (ook) {
+#pragma unroll
+                    for (int t = 0; t < KPF_T; ++t) {
+                        const int64_t p = p0 + t;
+                        if (p < n) {
+                            float *dst = out + p * Cout + o;
+                            *dst = (c0 == 0) ? a[t] : (*dst + a[t]);  // rows are warp-private
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// wf[p][k][c] (K real kernel points) -> workspace, for the backward pass
+__global__ void __launch_bounds__(KPF_WARPS * 32)
+kpconv_wf_kernel(const float *__restrict__ q, const float *__restrict__ s, const int64_t *__restrict__ nb,
+                 const float *__restrict__ x, const float *__restrict__ kp, int64_t n, int64_t N0, int M, int Mpad,
+                 int K, int Cin, KpGeom g, float *__restrict__ wf) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *wsm = smem + (size_t)warp * (Mpad * KP_K + Mpad);
+    int *jsm = reinterpret_cast<int *>(wsm + Mpad * KP_K);
+    const int kk = lane & 15;
+    const float kx = kk < K ? __ldg(kp + 3 * kk) : 0.f;
+    const float ky = kk < K ? __ldg(kp + 3 * kk + 1) : 0.f;
+    const float kz = kk < K ? __ldg(kp + 3 * kk + 2) : 0.f;
+    for (int64_t p = (int64_t)blockIdx.x * KPF_WARPS + warp; p < n; p += (int64_t)gridDim.x * KPF_WARPS) {
+        kp_point_weights(q + 3 * p, s, nb + p * M, N0, M, K, g, kx, ky, kz, wsm, jsm, lane);
+        for (int c0 = 0; c0 < Cin; c0 += 32) {
+            float acc[KP_K];
+            kp_weighted_features(x, Cin, c0, M, wsm, jsm, lane, acc);
+            if (c0 + lane < Cin) {
+#pragma unroll
+                for (int k = 0; k < KP_K; ++k)
+                    if (k < K) wf[(p * K + k) * Cin + c0 + lane] = acc[k];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// dfeat[nb[p,m]][c] += sum_k w[p,k,m] * dwf[p][k][c]
+__global__ void __launch_bounds__(KPF_WARPS * 32)
+kpconv_scatter_kernel(const float *__restrict__ q, const float *__restrict__ s, const int64_t *__restrict__ nb,
+                      const float *__restrict__ kp, const float *__restrict__ dwf, int64_t n, int64_t N0, int M,
+                      int Mpad, int K, int Cin, KpGeom g, float *__restrict__ dfeat) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *wsm = smem + (size_t)warp * (Mpad * KP_K + Mpad);
+    int *jsm = reinterpret_cast<int *>(wsm + Mpad * KP_K);
+    const int kk = lane & 15;
+    const float kx = kk < K ? __ldg(kp + 3 * kk) : 0.f;
+    const float ky = kk < K ? __ldg(kp + 3 * kk + 1) : 0.f;
+    const float kz = kk < K ? __ldg(kp + 3 * kk + 2) : 0.f;
+    for (int64_t p = (int64_t)blockIdx.x * KPF_WARPS + warp; p < n; p += (int64_t)gridDim.x * KPF_WARPS) {
+        kp_point_weights(q + 3 * p, s, nb + p * M, N0, M, K, g, kx, ky, kz, wsm, jsm, lane);
+        for (int c0 = 0; c0 < Cin; c0 += 32) {
+            const int c = c0 + lane;
+            float d[KP_K];
+#pragma unroll
+            for (int k = 0; k < KP_K; ++k) d[k] = (k < K && c < Cin) ? __ldg(dwf + (p * K + k) * Cin + c) : 0.f;
+            for (int m = 0; m < M; ++m) {
+                const int j = jsm[m];
+                if (j < 0) continue;
+                const float4 *w4 = reinterpret_cast<const float4 *>(wsm + m * KP_K);
+                float v = 0.f;
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) {
+                    const float4 w = w4[gq];
+                    v = fmaf(w.x, d[4 * gq], v);
+                    v = fmaf(w.y, d[4 * gq + 1], v);
+                    v = fmaf(w.z, d[4 * gq + 2], v);
+                    v = fmaf(w.w, d[4 * gq + 3], v);
+                }
+                if (c < Cin) atomicAdd(dfeat + (int64_t)j * Cin + c, v);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// C[i][j] (+)= sum_k A(i,k) * B(k,j) with arbitrary element strides; 64x64x16 tiles, 4x4 per
+// thread; gridDim.z splits k (partial sums are reduced with fp32 atomics into a zeroed C).
+__global__ void __launch_bounds__(256)
+sgemm_strided_kernel(const float *__restrict__ A, int64_t sai, int64_t sak, const float *__restrict__ B, int64_t sbk,
+                     int64_t sbj, float *__restrict__ C, int64_t ldc, int64_t Mr, int64_t Nc, int64_t Kd,
+                     int64_t k_per_split, int atomic) {
+    __shared__ float As[16][64 + 4], Bs[16][64 + 4];
+    const int tid = threadIdx.x;
+    const int64_t i0 = (int64_t)blockIdx.y * 64, j0 = (int64_t)blockIdx.x * 64;
+    const int64_t kb = (int64_t)blockIdx.z * k_per_split;
+    const int64_t ke = (kb + k_per_split < Kd) ? kb + k_per_split : Kd;
+    const int ty = tid / 16, tx = tid % 16;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    for (int64_t k0 = kb; k0 < ke; k0 += 16) {
+        for (int e = tid; e < 16 * 64; e += 256) {
+            int kk_, ii;
+            if (sak == 1) { kk_ = e % 16; ii = e / 16; } else { ii = e % 64; kk_ = e / 64; }
+            const int64_t i = i0 + ii, k = k0 + kk_;
+            As[kk_][ii] = (i < Mr && k < ke) ? __ldg(A + i * sai + k * sak) : 0.f;
+            int kb_, jj;
+            if (sbk == 1) { kb_ = e % 16; jj = e / 16; } else { jj = e % 64; kb_ = e / 64; }
+            const int64_t j = j0 + jj, k2 = k0 + kb_;
+            Bs[kb_][jj] = (j < Nc && k2 < ke) ? __ldg(B + k2 * sbk + j * sbj) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { a[u] = As[k][ty * 4 + u]; b[u] = Bs[k][tx * 4 + u]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(a[u], b[v], acc[u][v]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int64_t i = i0 + ty * 4 + u, j = j0 + tx * 4 + v;
+            if (i < Mr && j < Nc) {
+                if (atomic) atomicAdd(C + i * ldc + j, acc[u][v]);
+                else C[i * ldc + j] = acc[u][v];
+            }
+        }
+}
+
+static KpGeom make_geom(float extent, int influence, int aggregation) {
+    KpGeom g;
+    g.extent = extent;
+    const float sig = extent * 0.3f;
+    g.gauss_den = 2.0f * sig * sig + 1e-9f;
+    g.influence = influence;
+    g.aggregation = aggregation;
+    return g;
+}
+
+static int check_common(const char *who, int64_t n, int64_t N0, int M, int K, int Cin, int Cout, int influence,
+                        int aggregation) {
+    P3D_REQUIRE(n >= 0 && N0 >= 0, "%s: negative point count", who);
+    P3D_REQUIRE(M >= 1 && M <= 128, "%s: neighbours per point must be in [1, 128], got %d", who, M);
+    P3D_REQUIRE(K >= 1 && K <= KP_K, "%s: kernel points must be in [1, 16], got %d", who, K);
+    P3D_REQUIRE(Cin >= 1 && Cout >= 1, "%s: channel counts must be positive", who);
+    P3D_REQUIRE(N0 < (int64_t)1 << 31, "%s: more than 2^31 support points", who);
+    P3D_REQUIRE(influence >= 0 && influence <= 2, "%s: unknown KP_influence %d", who, influence);
+    P3D_REQUIRE(aggregation >= 0 && aggregation <= 1, "%s: unknown aggregation_mode %d", who, aggregation);
+    return P3D_OK;
+}
+
+int kpconv_fwd_simt(const float *query, const float *support, const int64_t *neighbors, const float *feat,
+                    const float *k_points, const float *k_values, int64_t n, int64_t N0, int M, int K, int Cin,
+                    int Cout, float extent, int influence, int aggregation, float *out, cudaStream_t st) {
+    const int Mpad = (M + 31) / 32 * 32;
+    const size_t smem = (size_t)KPF_WARPS * (Mpad * KP_K + Mpad + KP_K * 32 * KPF_T) * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(kpconv_fwd_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_done = true;
+    }
+    const int64_t tiles = (n + KPF_T - 1) / KPF_T;
+    int64_t grid = (tiles + KPF_WARPS - 1) / KPF_WARPS;
+    if (grid > 8 * kNumSMs) grid = 8 * kNumSMs;
+    kpconv_fwd_simt_kernel<<<(unsigned)grid, KPF_WARPS * 32, smem, st>>>(
+        query, support, neighbors, feat, k_points, k_values, n, N0, M, Mpad, K, Cin, Cout,
+        make_geom(extent, influence, aggregation), out);
+    return finish_launch("kpconv_fwd_simt");
+}
+
+}  // namespace p3d
+
+using namespace p3d;
+
+namespace p3d {
+// kpconv_tc.cu: tcgen05 path for the kernel-point contraction; returns 1 when it does not
+// support the shape (the caller then uses the exact fp32 kernel above)
+int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neighbors, const float *feat,
+                  const float *k_points, const float *k_values, int64_t n, int64_t N0, int M, int K, int Cin,
+                  int Cout, float extent, int influence, int aggregation, float *out, cudaStream_t st);
+}  // namespace p3d
+
+P3D_EXPORT int p3d_kpconv_fwd_f32(const float *query, const float *support, const int64_t *neighbors,
+                                  const float *feat, const float *k_points, const float *k_values, int64_t n,
+                                  int64_t N0, int M, int K, int Cin, int Cout, float extent, int influence,
+                                  int aggregation, float *out, void *stream) {
+    if (int e = check_common("kpconv_fwd", n, N0, M, K, Cin, Cout, influence, aggregation)) return e;
+    if (n == 0) return P3D_OK;
+    P3D_REQUIRE(query && neighbors && k_points && k_values && out && (N0 == 0 || (support && feat)),
+                "kpconv_fwd: null pointer");
+    return kpconv_fwd_simt(query, support, neighbors, feat, k_points, k_values, n, N0, M, K, Cin, Cout, extent,
+                           influence, aggregation, out, (cudaStream_t)stream);
+}
+
+P3D_EXPORT size_t p3d_kpconv_bwd_ws_bytes(int64_t n, int M, int K, int Cin, int Cout) {
+    (void)M;
+    (void)Cout;
+    return (size_t)2 * (size_t)n * (size_t)K * (size_t)Cin * sizeof(float);
+}
+
+P3D_EXPORT int p3d_kpconv_bwd_f32(const float *query, const float *support, const int64_t *neighbors,
+                                  const float *feat, const float *k_points, const float *k_values, const float *dout,
+                                  int64_t n, int64_t N0, int M, int K, int Cin, int Cout, float extent,
+                                  int influence, int aggregation, float *dfeat, float *dweights, void *ws,
+                                  size_t ws_bytes, void *stream) {
+    if (int e = check_common("kpconv_bwd", n, N0, M, K, Cin, Cout, influence, aggregation)) return e;
+    if (n == 0 || (dfeat == nullptr && dweights == nullptr)) return P3D_OK;
+    P3D_REQUIRE(query && neighbors && k_points && k_values && dout && (N0 == 0 || (support && feat)),
+                "kpconv_bwd: null pointer");
+    if (ws == nullptr || ws_bytes < p3d_kpconv_bwd_ws_bytes(n, M, K, Cin, Cout)) {
+        set_error("kpconv_bwd: workspace of %zu bytes required", p3d_kpconv_bwd_ws_bytes(n, M, K, Cin, Cout));
+        return P3D_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const KpGeom g = make_geom(extent, influence, aggregation);
+    const int Mpad = (M + 31) / 32 * 32;
+    const size_t smem = (size_t)KPF_WARPS * (Mpad * KP_K + Mpad) * sizeof(float);
+    float *wf = (float *)ws;
+    float *dwf = wf + (size_t)n * K * Cin;
+    const int64_t KC = (int64_t)K * Cin;
+    int64_t grid = (n + KPF_WARPS - 1) / KPF_WARPS;
+    if (grid > 16 * kNumSMs) grid = 16 * kNumSMs;
+    if (dweights) {
+        kpconv_wf_kernel<<<(unsigned)grid, KPF_WARPS * 32, smem, st>>>(query, support, neighbors, feat, k_points, n,
+                                                                     N0, M, Mpad, K, Cin, g, wf);
+        if (int e = finish_launch("kpconv_wf")) return e;
+        // dW[kc][o] += sum_p wf[p][kc] * dout[p][o]
+        const int64_t tiles = ((KC + 63) / 64) * ((Cout + 63) / 64);
+        int64_t split = (2 * kNumSMs + tiles - 1) / tiles;
+        int64_t kps = (n + split - 1) / split;
+        kps = (kps + 15) / 16 * 16;
+        if (kps < 64) kps = 64;
+        split = (n + kps - 1) / kps;
+        dim3 gd((unsigned)((Cout + 63) / 64), (unsigned)((KC + 63) / 64), (unsigned)split);
+        sgemm_strided_kernel<<<gd, 256, 0, st>>>(wf, 1, KC, dout, Cout, 1, dweights, Cout, KC, Cout, n, kps, 1);
+        if (int e = finish_launch("kpconv_dW_gemm")) return e;
+    }
+    if (dfeat) {
+        // dwf[p][kc] = sum_o dout[p][o] * W[kc][o]
+        dim3 gd((unsigned)((KC + 63) / 64), (unsigned)((n + 63) / 64), 1);
+        sgemm_strided_kernel<<<gd, 256, 0, st>>>(dout, Cout, 1, k_values, 1, Cout, dwf, KC, n, KC, Cout, Cout, 0);
+        if (int e = finish_launch("kpconv_dwf_gemm")) return e;
+        kpconv_scatter_kernel<<<(unsigned)grid, KPF_WARPS * 32, smem, st>>>(query, support, neighbors, k_points, dwf,
+                                                                          n, N0, M, Mpad, K, Cin, g, dfeat);
+        if (int e = finish_launch("kpconv_scatter")) return e;
+    }
+    return P3D_OK;
+}

@@ -1,0 +1,391 @@
+// neighbors.cu -- ball query (dense + batch/CSR), knn and three_nn for sm_100a.
+//
+// Replaces tp.ball_query (core/spatial_ops/neighbour_finder.py:35-37,164), torch_cluster.knn via
+// torch_geometric.nn.knn (neighbour_finder.py:47, interpolate.py:25,70) and tp.three_nn
+// (core/base_conv/dense.py:136).  Semantics: SURVEY.md Appendix A.2/A.3/A.5/A.6.
+//
+// Design: candidates are swept in index order through a shared-memory tile (SoA x|y|z, one
+// coalesced pass over the cloud per CTA); a WARP owns a query and tests 32 candidates per
+// step (conflict-free LDS), `__ballot_sync` + popc gives every hit its output slot in
+// candidate order ("first K in index order" survives the parallel scan), hits are written
+// straight to their final slot and a warp stops as soon as its row is full.  A CTA carries
+// 8*QPW queries per sweep so a tile loaded once is reused 8*QPW times from shared memory.
+// Cloud ranges of the batch (partial-dense / CSR) form are found on the device with a 32-ary
+// warp search over the sorted batch vector: no host round trip.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace p3d {
+
+constexpr int NB_TILE = 2048;  // candidate points per shared-memory tile (24 KB)
+constexpr int NB_WARPS = 8;
+
+struct RangeCache {
+    int64_t c[2], x0[2], x1[2];
+};
+
+// candidate range [x0, x1) of the cloud that owns query q (executed by a whole warp)
+template <bool DENSE>
+__device__ __forceinline__ void query_range(int64_t q, const int64_t *__restrict__ batch_x,
+                                            const int64_t *__restrict__ batch_y, int64_t Nx, int64_t n_dense,
+                                            int64_t s_dense, const RangeCache &rc, int lane, int64_t &x0,
+                                            int64_t &x1) {
+    if (DENSE) {
+        const int64_t b = q / s_dense;
+        x0 = b * n_dense;
+        x1 = x0 + n_dense;
+    } else if (batch_x == nullptr || batch_y == nullptr) {
+        x0 = 0;
+        x1 = Nx;
+    } else {
+        const int64_t c = batch_y[q];
+        if (c == rc.c[0]) { x0 = rc.x0[0]; x1 = rc.x1[0]; }
+        else if (c == rc.c[1]) { x0 = rc.x0[1]; x1 = rc.x1[1]; }
+        else {
+            x0 = warp_lower_bound(batch_x, Nx, c, lane);
+            x1 = warp_lower_bound(batch_x, Nx, c + 1, lane);
+        }
+    }
+}
+
+template <bool DENSE>
+__device__ __forceinline__ void cta_ranges(int64_t q0, int64_t q1, const int64_t *__restrict__ batch_x,
+                                           const int64_t *__restrict__ batch_y, int64_t Nx, RangeCache &rc,
+                                           int warp, int lane) {
+    if (!DENSE && batch_x != nullptr && batch_y != nullptr) {
+        if (warp < 2) {
+            const int64_t c = batch_y[warp == 0 ? q0 : q1 - 1];
+            const int64_t a = warp_lower_bound(batch_x, Nx, c, lane);
+            const int64_t b = warp_lower_bound(batch_x, Nx, c + 1, lane);
+            if (lane == 0) { rc.c[warp] = c; rc.x0[warp] = a; rc.x1[warp] = b; }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void load_tile(const float *__restrict__ x, int64_t tb, int tn, float *sx, float *sy,
+                                          float *sz, int tid, int nthreads) {
+    const float *__restrict__ src = x + 3 * tb;
+    for (int f = tid; f < 3 * tn; f += nthreads) {
+        const float v = __ldg(src + f);
+        const int p = f / 3, c = f - 3 * p;
+        float *dst = c == 0 ? sx : (c == 1 ? sy : sz);
+        dst[p] = v;
+    }
+}
+
+// ------------------------------------------------------------------ ball query -----------
+template <bool DENSE, int QPW>
+__global__ void __launch_bounds__(NB_WARPS * 32)
+ball_query_kernel(const float *__restrict__ x, const float *__restrict__ y, const int64_t *__restrict__ batch_x,
+                  const int64_t *__restrict__ batch_y, int64_t Nx, int64_t Ny, int64_t n_dense, int64_t s_dense,
+                  float r2, int K, int strict, int64_t shadow, int64_t *__restrict__ idx,
+                  float *__restrict__ dist2) {
+    constexpr int QPC = NB_WARPS * QPW;
+    __shared__ float sx[NB_TILE], sy[NB_TILE], sz[NB_TILE];
+    __shared__ RangeCache rc;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q0 = (int64_t)blockIdx.x * QPC;
+    const int64_t q1 = (q0 + QPC < Ny) ? q0 + QPC : Ny;
+
+    cta_ranges<DENSE>(q0, q1, batch_x, batch_y, Nx, rc, warp, lane);
+
+    float qx[QPW], qy[QPW], qz[QPW];
+    int64_t x0[QPW], x1[QPW];
+    int cnt[QPW];
+    int64_t first[QPW];
+    int64_t X0 = INT64_MAX, X1 = 0;
+#pragma unroll
+    for (int u = 0; u < QPW; ++u) {
+        const int64_t q = q0 + warp * QPW + u;
+        cnt[u] = 0;
+        first[u] = 0;
+        if (q < q1) {
+            qx[u] = __ldg(y + 3 * q);
+            qy[u] = __ldg(y + 3 * q + 1);
+            qz[u] = __ldg(y + 3 * q + 2);
+            query_range<DENSE>(q, batch_x, batch_y, Nx, n_dense, s_dense, rc, lane, x0[u], x1[u]);
+        } else {
+            qx[u] = qy[u] = qz[u] = 0.f;
+            x0[u] = x1[u] = 0;
+            cnt[u] = K;  // nothing to do
+        }
+    }
+    // CTA sweep range = union of the ranges of its first and last query (clouds are contiguous)
+    {
+        int64_t a, b;
+        query_range<DENSE>(q0, batch_x, batch_y, Nx, n_dense, s_dense, rc, lane, a, b);
+        X0 = a;
+        query_range<DENSE>(q1 - 1, batch_x, batch_y, Nx, n_dense, s_dense, rc, lane, a, b);
+        X1 = b;
+    }
+
+    bool first_tile = true;
+    for (int64_t tb = X0; tb < X1; tb += NB_TILE) {
+        bool mydone = true;
+#pragma unroll
+        for (int u = 0; u < QPW; ++u) mydone = mydone && (cnt[u] >= K || tb >= x1[u]);
+        if (!first_tile) {
+            if (__syncthreads_and(mydone)) break;  // also: previous tile fully consumed
+        }
+        first_tile = false;
+        const int tn = (int)((X1 - tb < NB_TILE) ? (X1 - tb) : NB_TILE);
+        load_tile(x, tb, tn, sx, sy, sz, tid, NB_WARPS * 32);
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < QPW; ++u) {
+            if (cnt[u] >= K) continue;
+            const int64_t q = q0 + warp * QPW + u;
+            const int64_t off = DENSE ? x0[u] : 0;  // dense mode reports indices local to the cloud
+            int lo = (int)((x0[u] > tb ? x0[u] : tb) - tb);
+            int hi = (int)((x1[u] < tb + tn ? x1[u] : tb + tn) - tb);
+            int64_t *__restrict__ row = idx + q * K;
+            float *__restrict__ drow = dist2 ? dist2 + q * K : nullptr;
+            int c = cnt[u];
+            for (int i0 = lo; i0 < hi && c < K; i0 += 32) {
+                const int i = i0 + lane;
+                const bool ok = i < hi;
+                const int ii = ok ? i : lo;
+                const float d = sqdist3(sx[ii], sy[ii], sz[ii], qx[u], qy[u], qz[u]);
+                const bool hit = ok && (strict ? (d < r2) : (d <= r2));
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (m) {
+                    const int pos = c + __popc(m & lanemask_lt());
+                    if (hit && pos < K) {
+                        row[pos] = tb + i - off;
+                        if (drow) drow[pos] = d;
+                    }
+                    if (c == 0) first[u] = tb + i0 + (__ffs(m) - 1) - off;
+                    c += __popc(m);
+                }
+            }
+            cnt[u] = c;
+        }
+    }
+    // padding: dense -> first hit (or 0 for an empty ball); batch -> shadow index; dist2 -> -1
+#pragma unroll
+    for (int u = 0; u < QPW; ++u) {
+        const int64_t q = q0 + warp * QPW + u;
+        if (q >= q1) continue;
+        const int c = cnt[u] < K ? cnt[u] : K;
+        const int64_t padv = DENSE ? (c > 0 ? first[u] : 0) : shadow;
+        for (int e = c + lane; e < K; e += 32) {
+            idx[q * K + e] = padv;
+            if (dist2) dist2[q * K + e] = -1.f;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------- knn -----------
+// Sorted top-k list per query in shared memory (warp-private), ascending d2, ties keep the
+// lower index (strict '<' admission against the current k-th distance, insertion after all
+// entries <= the new distance; candidates arrive in index order).
+__device__ __forceinline__ void knn_insert(float *dl, int *il, int k, int &len, float &tau, float nd, int ni,
+                                           int lane) {
+    int pos = 0;
+    for (int c = 0; c < len; c += 32) {
+        const int e = c + lane;
+        const float v = e < len ? dl[e] : CUDART_INF_F;
+        pos += __popc(__ballot_sync(0xffffffffu, v <= nd));
+    }
+    const int newlen = len < k ? len + 1 : k;
+    for (int top = newlen - 1; top > pos; top -= 32) {  // elements [pos, newlen-1) move up by one
+        const int e = top - 1 - lane;
+        float v = 0.f;
+        int iv = 0;
+        if (e >= pos) { v = dl[e]; iv = il[e]; }
+        __syncwarp();
+        if (e >= pos) { dl[e + 1] = v; il[e + 1] = iv; }
+        __syncwarp();
+    }
+    if (lane == 0) { dl[pos] = nd; il[pos] = ni; }
+    __syncwarp();
+    len = newlen;
+    tau = len == k ? dl[k - 1] : CUDART_INF_F;
+}
+
+template <bool DENSE, int QPW>
+__global__ void __launch_bounds__(NB_WARPS * 32)
+knn_kernel(const float *__restrict__ x, const float *__restrict__ y, const int64_t *__restrict__ batch_x,
+           const int64_t *__restrict__ batch_y, int64_t Nx, int64_t Ny, int64_t n_dense, int64_t s_dense, int k,
+           int sqrt_out, int64_t *__restrict__ col, float *__restrict__ dout) {
+    constexpr int QPC = NB_WARPS * QPW;
+    __shared__ float sx[NB_TILE], sy[NB_TILE], sz[NB_TILE];
+    __shared__ RangeCache rc;
+    extern __shared__ __align__(16) unsigned char dyn[];
+    float *dl_all = reinterpret_cast<float *>(dyn);            // [QPC][k]
+    int *il_all = reinterpret_cast<int *>(dl_all + QPC * k);  // [QPC][k] index relative to X0
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q0 = (int64_t)blockIdx.x * QPC;
+    const int64_t q1 = (q0 + QPC < Ny) ? q0 + QPC : Ny;
+
+    cta_ranges<DENSE>(q0, q1, batch_x, batch_y, Nx, rc, warp, lane);
+
+    float qx[QPW], qy[QPW], qz[QPW], tau[QPW];
+    int64_t x0[QPW], x1[QPW];
+    int len[QPW];
+#pragma unroll
+    for (int u = 0; u < QPW; ++u) {
+        const int64_t q = q0 + warp * QPW + u;
+        len[u] = 0;
+        tau[u] = CUDART_INF_F;
+        if (q < q1) {
+            qx[u] = __ldg(y + 3 * q);
+            qy[u] = __ldg(y + 3 * q + 1);
+            qz[u] = __ldg(y + 3 * q + 2);
+            query_range<DENSE>(q, batch_x, batch_y, Nx, n_dense, s_dense, rc, lane, x0[u], x1[u]);
+        } else {
+            qx[u] = qy[u] = qz[u] = 0.f;
+            x0[u] = x1[u] = 0;
+        }
+    }
+    int64_t X0, X1;
+    {
+        int64_t a, b;
+        query_range<DENSE>(q0, batch_x, batch_y, Nx, n_dense, s_dense, rc, lane, a, b);
+        X0 = a;
+        query_range<DENSE>(q1 - 1, batch_x, batch_y, Nx, n_dense, s_dense, rc, lane, a, b);
+        X1 = b;
+    }
+
+    for (int64_t tb = X0; tb < X1; tb += NB_TILE) {
+        const int tn = (int)((X1 - tb < NB_TILE) ? (X1 - tb) : NB_TILE);
+        if (tb != X0) __syncthreads();
+        load_tile(x, tb, tn, sx, sy, sz, tid, NB_WARPS * 32);
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < QPW; ++u) {
+            float *dl = dl_all + (warp * QPW + u) * k;
+            int *il = il_all + (warp * QPW + u) * k;
+            int lo = (int)((x0[u] > tb ? x0[u] : tb) - tb);
+            int hi = (int)((x1[u] < tb + tn ? x1[u] : tb + tn) - tb);
+            int ln = len[u];
+            float t = tau[u];
+            for (int i0 = lo; i0 < hi; i0 += 32) {
+                const int i = i0 + lane;
+                const bool ok = i < hi;
+                const int ii = ok ? i : lo;
+                const float d = sqdist3(sx[ii], sy[ii], sz[ii], qx[u], qy[u], qz[u]);
+                unsigned m = __ballot_sync(0xffffffffu, ok && d < t);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float nd = __shfl_sync(0xffffffffu, d, src);
+                    if (nd < t) knn_insert(dl, il, k, ln, t, nd, (int)(tb - X0) + i0 + src, lane);
+                }
+            }
+            len[u] = ln;
+            tau[u] = t;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < QPW; ++u) {
+        const int64_t q = q0 + warp * QPW + u;
+        if (q >= q1) continue;
+        const float *dl = dl_all + (warp * QPW + u) * k;
+        const int *il = il_all + (warp * QPW + u) * k;
+        const int64_t off = DENSE ? x0[u] : 0;
+        for (int e = lane; e < k; e += 32) {
+            const bool have = e < len[u];
+            col[q * k + e] = have ? (X0 + il[e] - off) : -1;
+            if (dout) {
+                float v = have ? dl[e] : -1.f;
+                if (have && sqrt_out) v = sqrtf(v);
+                dout[q * k + e] = v;
+            }
+        }
+    }
+}
+
+template <bool DENSE>
+static int launch_ball_query(const float *x, const float *y, const int64_t *bx, const int64_t *by, int64_t Nx,
+                             int64_t Ny, int64_t n_dense, int64_t s_dense, float radius, int K, int strict,
+                             int64_t shadow, int64_t *idx, float *dist2, cudaStream_t st) {
+    if (Ny == 0 || K == 0) return P3D_OK;
+    const float r2 = radius * radius;
+    if (Ny >= (int64_t)NB_WARPS * 4 * 2 * kNumSMs) {
+        const int64_t grid = (Ny + NB_WARPS * 4 - 1) / (NB_WARPS * 4);
+        ball_query_kernel<DENSE, 4><<<(unsigned)grid, NB_WARPS * 32, 0, st>>>(
+            x, y, bx, by, Nx, Ny, n_dense, s_dense, r2, K, strict, shadow, idx, dist2);
+    } else {
+        const int64_t grid = (Ny + NB_WARPS - 1) / NB_WARPS;
+        ball_query_kernel<DENSE, 1><<<(unsigned)grid, NB_WARPS * 32, 0, st>>>(
+            x, y, bx, by, Nx, Ny, n_dense, s_dense, r2, K, strict, shadow, idx, dist2);
+    }
+    return finish_launch("ball_query");
+}
+
+template <bool DENSE>
+static int launch_knn(const float *x, const float *y, const int64_t *bx, const int64_t *by, int64_t Nx, int64_t Ny,
+                      int64_t n_dense, int64_t s_dense, int k, int sqrt_out, int64_t *col, float *d,
+                      cudaStream_t st) {
+    if (Ny == 0 || k == 0) return P3D_OK;
+    if (Ny >= (int64_t)NB_WARPS * 4 * 2 * kNumSMs && k <= 32) {
+        const int64_t grid = (Ny + NB_WARPS * 4 - 1) / (NB_WARPS * 4);
+        const size_t dyn = (size_t)NB_WARPS * 4 * k * 8;
+        knn_kernel<DENSE, 4><<<(unsigned)grid, NB_WARPS * 32, dyn, st>>>(x, y, bx, by, Nx, Ny, n_dense, s_dense, k,
+                                                                        sqrt_out, col, d);
+    } else {
+        const int64_t grid = (Ny + NB_WARPS - 1) / NB_WARPS;
+        const size_t dyn = (size_t)NB_WARPS * k * 8;
+        knn_kernel<DENSE, 1><<<(unsigned)grid, NB_WARPS * 32, dyn, st>>>(x, y, bx, by, Nx, Ny, n_dense, s_dense, k,
+                                                                        sqrt_out, col, d);
+    }
+    return finish_launch("knn");
+}
+
+}  // namespace p3d
+
+using namespace p3d;
+
+P3D_EXPORT int p3d_ball_query_dense_f32(const float *x, const float *y, int B, int N, int S, float radius,
+                                        int nsample, int strict, int64_t *idx, float *dist2, void *stream) {
+    P3D_REQUIRE(B >= 0 && N >= 0 && S >= 0 && nsample >= 0, "ball_query_dense: negative dimension");
+    if (B == 0 || S == 0 || nsample == 0) return P3D_OK;
+    P3D_REQUIRE(x && y && idx, "ball_query_dense: null pointer");
+    return launch_ball_query<true>(x, y, nullptr, nullptr, (int64_t)B * N, (int64_t)B * S, N, S, radius, nsample,
+                                   strict, 0, idx, dist2, (cudaStream_t)stream);
+}
+
+P3D_EXPORT int p3d_ball_query_batch_f32(const float *x, const float *y, const int64_t *batch_x,
+                                        const int64_t *batch_y, int64_t Nx, int64_t Ny, float radius, int nsample,
+                                        int strict, int64_t shadow, int64_t *idx, float *dist2, void *stream) {
+    P3D_REQUIRE(Nx >= 0 && Ny >= 0 && nsample >= 0, "ball_query_batch: negative dimension");
+    if (Ny == 0 || nsample == 0) return P3D_OK;
+    P3D_REQUIRE(y && idx && (x || Nx == 0), "ball_query_batch: null pointer");
+    P3D_REQUIRE((batch_x == nullptr) == (batch_y == nullptr), "ball_query_batch: give both batch vectors or none");
+    return launch_ball_query<false>(x, y, batch_x, batch_y, Nx, Ny, 0, 1, radius, nsample, strict, shadow, idx,
+                                    dist2, (cudaStream_t)stream);
+}
+
+P3D_EXPORT int p3d_knn_batch_f32(const float *x, const float *y, const int64_t *batch_x, const int64_t *batch_y,
+                                 int64_t Nx, int64_t Ny, int k, int64_t *col, float *d2, void *stream) {
+    P3D_REQUIRE(Nx >= 0 && Ny >= 0, "knn: negative dimension");
+    P3D_REQUIRE(k >= 1 && k <= 128, "knn: k must be in [1, 128], got %d", k);
+    if (Ny == 0) return P3D_OK;
+    P3D_REQUIRE(y && col && (x || Nx == 0), "knn: null pointer");
+    P3D_REQUIRE((batch_x == nullptr) == (batch_y == nullptr), "knn: give both batch vectors or none");
+    return launch_knn<false>(x, y, batch_x, batch_y, Nx, Ny, 0, 1, k, 0, col, d2, (cudaStream_t)stream);
+}
+
+P3D_EXPORT int p3d_knn_dense_f32(const float *x, const float *y, int B, int N, int M, int k, int64_t *idx, float *d2,
+                                 void *stream) {
+    P3D_REQUIRE(B >= 0 && N >= 0 && M >= 0, "knn_dense: negative dimension");
+    P3D_REQUIRE(k >= 1 && k <= 128, "knn_dense: k must be in [1, 128], got %d", k);
+    if (B == 0 || M == 0) return P3D_OK;
+    P3D_REQUIRE(y && idx && (x || N == 0), "knn_dense: null pointer");
+    return launch_knn<true>(x, y, nullptr, nullptr, (int64_t)B * N, (int64_t)B * M, N, M, k, 0, idx, d2,
+                            (cudaStream_t)stream);
+}
+
+P3D_EXPORT int p3d_three_nn_f32(const float *unknown, const float *known, int B, int n, int m, float *dist,
+                                int64_t *idx, void *stream) {
+    P3D_REQUIRE(B >= 0 && n >= 0, "three_nn: negative dimension");
+    P3D_REQUIRE(m >= 3, "three_nn: needs at least 3 known points, got %d", m);
+    if (B == 0 || n == 0) return P3D_OK;
+    P3D_REQUIRE(unknown && known && dist && idx, "three_nn: null pointer");
+    return launch_knn<true>(known, unknown, nullptr, nullptr, (int64_t)B * m, (int64_t)B * n, m, n, 3, 1, idx, dist,
+                            (cudaStream_t)stream);
+}

@@ -1,0 +1,483 @@
+"""Torch-facing operators over the C ABI (include/p3d_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the stream; every operator below is one
+(or a few) launches of hand-written sm_100a kernels in libp3d_b200.so on
+`torch.cuda.current_stream()`.  There is no CPU path and no PyTorch re-implementation to fall
+back to: CPU tensors raise `RuntimeError`.
+
+Signatures and error behaviour follow the reference's operator surface:
+  torch-points-kernels 0.7.0  (furthest_point_sample, ball_query, grouping_operation, three_nn,
+                               three_interpolate, knn)   -- see compat/tp.py
+  torch-cluster 1.5.9 via torch_geometric.nn (fps, knn, radius, knn_interpolate) -- compat/cluster.py
+  torch_points3d/modules/KPConv/convolution_ops.py:19-107 (KPConv_ops)
+"""
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi
+
+INFLUENCE = {"constant": 0, "linear": 1, "gaussian": 2}
+AGGREGATION = {"sum": 0, "closest": 1}
+
+
+# ------------------------------------------------------------------ plumbing ---------------
+def _require_cuda(name: str, *tensors) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                "%s: expected CUDA tensors (torch_points3d_b200 has no CPU fallback; the CPU restatement "
+                "lives in oracle/ and is test infrastructure only)" % name)
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError("%s: tensors are on different devices (%s vs %s)" % (name, dev, t.device))
+    if dev is None:
+        raise RuntimeError("%s: no tensor given" % name)
+    return dev
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.contiguous() if t.dtype == torch.float32 else t.to(torch.float32).contiguous()
+
+
+def _i64(t: torch.Tensor) -> torch.Tensor:
+    return t.contiguous() if t.dtype == torch.int64 else t.to(torch.int64).contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _call(dev: torch.device, name: str, *args) -> None:
+    with torch.cuda.device(dev):
+        _cabi.call(name, *args, _stream())
+
+
+def batch_to_ptr(batch: torch.Tensor, num_clouds: Optional[int] = None) -> torch.Tensor:
+    """sorted batch vector -> CSR ptr [C+1] (device, int64)."""
+    if num_clouds is None:
+        num_clouds = int(batch[-1].item()) + 1 if batch.numel() else 0
+    counts = torch.bincount(batch, minlength=num_clouds)
+    ptr = torch.zeros(num_clouds + 1, dtype=torch.int64, device=batch.device)
+    torch.cumsum(counts, 0, out=ptr[1:])
+    return ptr
+
+
+# ----------------------------------------------------------------------- FPS ---------------
+def furthest_point_sample(xyz: torch.Tensor, npoint: int) -> torch.Tensor:
+    """tp.furthest_point_sample(xyz[B,N,3], npoint) -> idx[B,npoint]
+    (reference call site core/spatial_ops/sampling.py:100).  Start index 0, lowest-index
+    tie-break.  Returns int64 (tpk's CUDA path returned int32 and every caller cast it with
+    `.long()`, core/base_conv/dense.py:75)."""
+    if xyz.dim() != 3 or xyz.shape[2] != 3:
+        raise ValueError("furthest_point_sample expects xyz of shape [B, N, 3]")
+    B, N, _ = xyz.shape
+    if npoint > N:
+        raise ValueError("caanot sample %i points from an input set of %i points" % (npoint, N))
+    dev = _require_cuda("furthest_point_sample", xyz)
+    xyz = _f32(xyz)
+    idx = torch.empty((B, npoint), dtype=torch.int64, device=dev)
+    ws_bytes = _cabi.lib().p3d_fps_dense_ws_bytes(B, N)
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
+    _call(dev, "p3d_fps_dense_f32", xyz.data_ptr(), B, N, npoint, idx.data_ptr(), 1, _ptr(ws), ws_bytes)
+    return idx
+
+
+def fps(x: torch.Tensor, batch: Optional[torch.Tensor] = None, ratio: float = 0.5,
+        random_start: bool = True) -> torch.Tensor:
+    """torch_geometric.nn.fps == torch_cluster.fps (reference call site sampling.py:63):
+    per cloud ceil(ratio * N_c) samples, GLOBAL int64 indices, concatenated in cloud order."""
+    if x.dim() != 2 or x.shape[1] != 3:
+        raise ValueError("fps expects x of shape [N, 3]")
+    dev = _require_cuda("fps", x, batch)
+    x = _f32(x)
+    n_total = x.shape[0]
+    if batch is None:
+        ptr = torch.tensor([0, n_total], dtype=torch.int64, device=dev)
+    else:
+        if batch.numel() != n_total:
+            raise ValueError("fps: batch must hold one entry per point")
+        ptr = batch_to_ptr(_i64(batch))
+    sizes = ptr[1:] - ptr[:-1]
+    counts = torch.ceil(sizes.to(torch.float32) * ratio).to(torch.int64)  # torch_cluster 1.5.x: ceil
+    counts = torch.minimum(counts, sizes)
+    out_ptr = torch.zeros_like(ptr)
+    torch.cumsum(counts, 0, out=out_ptr[1:])
+    # the output length and the largest cloud are shapes: one small D2H, like torch_cluster's own
+    host = torch.stack([out_ptr[-1], sizes.max() if sizes.numel() else out_ptr[-1]]).tolist()
+    total_out, max_n = int(host[0]), int(host[1])
+    idx = torch.empty(total_out, dtype=torch.int64, device=dev)
+    start = None
+    if random_start:
+        start = (torch.rand(sizes.shape[0], device=dev) * sizes.to(torch.float32)).to(torch.int64)
+        start = torch.minimum(start, torch.clamp(sizes - 1, min=0))
+    ws_bytes = _cabi.lib().p3d_fps_csr_ws_bytes(n_total, max_n)
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
+    _call(dev, "p3d_fps_csr_f32", x.data_ptr(), ptr.data_ptr(), ptr.shape[0] - 1, out_ptr.data_ptr(),
+          idx.data_ptr(), _ptr(start), max_n, _ptr(ws), ws_bytes)
+    return idx
+
+
+# ---------------------------------------------------------------- ball query ---------------
+def ball_query(radius: float, nsample: int, x: torch.Tensor, y: torch.Tensor, mode: str = "dense",
+               batch_x: Optional[torch.Tensor] = None, batch_y: Optional[torch.Tensor] = None,
+               sort: bool = False, return_dist: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """tp.ball_query (reference call sites neighbour_finder.py:35-37 and :164).
+
+    dense:          x[B,N,3], y[B,S,3] -> idx[B,S,nsample] (padded with the first hit, 0 when the
+                    ball is empty), dist2[B,S,nsample] (-1 padded); strict d2 < r2.
+    partial_dense:  x[N,3], y[n,3], batch_x, batch_y -> idx[n,nsample] padded with the shadow
+                    index x.shape[0], dist2 padded with -1; d2 <= r2.
+    `return_dist=False` skips the dist2 store (every reference call site discards it)."""
+    if mode is None:
+        raise Exception('The mode should be defined within ["partial_dense | dense"]')
+    mode = mode.lower()
+    if sort:
+        raise NotImplementedError("ball_query(sort=True) is only defined for the reference's CPU path")
+    if mode == "partial_dense":
+        if batch_x is None or batch_y is None:
+            raise Exception("batch_x and batch_y should be provided")
+        if x.dim() != 2 or y.dim() != 2:
+            raise AssertionError("partial_dense ball_query expects x[N,3] and y[n,3]")
+        dev = _require_cuda("ball_query", x, y, batch_x, batch_y)
+        x, y, batch_x, batch_y = _f32(x), _f32(y), _i64(batch_x), _i64(batch_y)
+        n = y.shape[0]
+        idx = torch.empty((n, nsample), dtype=torch.int64, device=dev)
+        dist2 = torch.empty((n, nsample), dtype=torch.float32, device=dev) if return_dist else None
+        _call(dev, "p3d_ball_query_batch_f32", x.data_ptr(), y.data_ptr(), batch_x.data_ptr(), batch_y.data_ptr(),
+              x.shape[0], n, float(radius), int(nsample), 0, x.shape[0], idx.data_ptr(), _ptr(dist2))
+        return idx, dist2
+    if mode == "dense":
+        if batch_x is not None or batch_y is not None:
+            raise Exception("batch_x and batch_y should not be provided")
+        if x.dim() != 3 or y.dim() != 3:
+            raise AssertionError("dense ball_query expects x[B,N,3] and y[B,S,3]")
+        dev = _require_cuda("ball_query", x, y)
+        x, y = _f32(x), _f32(y)
+        B, N, _ = x.shape
+        S = y.shape[1]
+        idx = torch.empty((B, S, nsample), dtype=torch.int64, device=dev)
+        dist2 = torch.empty((B, S, nsample), dtype=torch.float32, device=dev) if return_dist else None
+        _call(dev, "p3d_ball_query_dense_f32", x.data_ptr(), y.data_ptr(), B, N, S, float(radius), int(nsample), 1,
+              idx.data_ptr(), _ptr(dist2))
+        return idx, dist2
+    raise Exception("unrecognized mode {}".format(mode))
+
+
+def radius(x: torch.Tensor, y: torch.Tensor, r: float, batch_x: Optional[torch.Tensor] = None,
+           batch_y: Optional[torch.Tensor] = None, max_num_neighbors: int = 32, num_workers: int = 1) -> torch.Tensor:
+    """torch_geometric.nn.radius == torch_cluster.radius (reference call sites
+    neighbour_finder.py:33,141): edge list [2,E], row = index into y, col = index into x,
+    at most max_num_neighbors per query in candidate index order; strict d2 < r2."""
+    dev = _require_cuda("radius", x, y, batch_x, batch_y)
+    x, y = _f32(x.view(-1, 1) if x.dim() == 1 else x), _f32(y.view(-1, 1) if y.dim() == 1 else y)
+    if x.shape[1] != 3:
+        raise ValueError("radius: only 3-D points are supported")
+    if (batch_x is None) != (batch_y is None):
+        if batch_x is None:
+            batch_x = torch.zeros(x.shape[0], dtype=torch.int64, device=dev)
+        else:
+            batch_y = torch.zeros(y.shape[0], dtype=torch.int64, device=dev)
+    n = y.shape[0]
+    shadow = -1
+    idx = torch.empty((n, max_num_neighbors), dtype=torch.int64, device=dev)
+    _call(dev, "p3d_ball_query_batch_f32", x.data_ptr(), y.data_ptr(), _ptr(None if batch_x is None else _i64(batch_x)),
+          _ptr(None if batch_y is None else _i64(batch_y)), x.shape[0], n, float(r), int(max_num_neighbors), 1, shadow,
+          idx.data_ptr(), None)
+    keep = idx >= 0
+    row = torch.arange(n, device=dev).view(-1, 1).expand_as(idx)[keep]
+    return torch.stack([row, idx[keep]], dim=0)
+
+
+# ----------------------------------------------------------------------- knn ---------------
+def knn_table(x: torch.Tensor, y: torch.Tensor, k: int, batch_x: Optional[torch.Tensor] = None,
+              batch_y: Optional[torch.Tensor] = None, return_dist: bool = True):
+    """k nearest supports (rows of x) of every query (row of y) inside its cloud:
+    col[Ny,k] global indices ascending in d2 (ties -> lower index), -1 where the cloud has fewer
+    than k points; d2[Ny,k] likewise."""
+    dev = _require_cuda("knn", x, y, batch_x, batch_y)
+    x, y = _f32(x), _f32(y)
+    if x.dim() != 2 or y.dim() != 2 or x.shape[1] != 3 or y.shape[1] != 3:
+        raise ValueError("knn expects x[N,3] and y[M,3]")
+    if (batch_x is None) != (batch_y is None):
+        if batch_x is None:
+            batch_x = torch.zeros(x.shape[0], dtype=torch.int64, device=dev)
+        else:
+            batch_y = torch.zeros(y.shape[0], dtype=torch.int64, device=dev)
+    bx = None if batch_x is None else _i64(batch_x)
+    by = None if batch_y is None else _i64(batch_y)
+    col = torch.empty((y.shape[0], k), dtype=torch.int64, device=dev)
+    d2 = torch.empty((y.shape[0], k), dtype=torch.float32, device=dev) if return_dist else None
+    _call(dev, "p3d_knn_batch_f32", x.data_ptr(), y.data_ptr(), _ptr(bx), _ptr(by), x.shape[0], y.shape[0], int(k),
+          col.data_ptr(), _ptr(d2))
+    return col, d2
+
+
+def knn_edges(x: torch.Tensor, y: torch.Tensor, k: int, batch_x: Optional[torch.Tensor] = None,
+              batch_y: Optional[torch.Tensor] = None, cosine: bool = False, num_workers: int = 1) -> torch.Tensor:
+    """torch_geometric.nn.knn == torch_cluster.knn (reference call sites neighbour_finder.py:47,
+    interpolate.py:25): [2,E] int64, row = y index, col = x index, ascending distance per y."""
+    if cosine:
+        raise NotImplementedError("knn(cosine=True) is not on the reference's point-cloud path")
+    col, _ = knn_table(x, y, k, batch_x, batch_y, return_dist=False)
+    n = col.shape[0]
+    row = torch.arange(n, device=col.device).view(-1, 1).expand_as(col)
+    if batch_x is None and batch_y is None and x.shape[0] >= k:
+        return torch.stack([row.reshape(-1), col.reshape(-1)], dim=0)  # every row is full: no sync
+    keep = col >= 0
+    return torch.stack([row[keep], col[keep]], dim=0)
+
+
+def knn_dense(pos_support: torch.Tensor, pos: torch.Tensor, k: int):
+    """tp.knn(pos_support[B,N,3], pos[B,M,3], k) -> (idx[B,M,k], dist2[B,M,k]) (tpk: CPU only)."""
+    if pos_support.dim() != 3 or pos.dim() != 3:
+        raise AssertionError("knn expects pos_support[B,N,3] and pos[B,M,3]")
+    dev = _require_cuda("knn", pos_support, pos)
+    xs, ys = _f32(pos_support), _f32(pos)
+    B, N, _ = xs.shape
+    M = ys.shape[1]
+    if k > N:
+        raise ValueError("knn: k (%d) larger than the number of support points (%d)" % (k, N))
+    idx = torch.empty((B, M, k), dtype=torch.int64, device=dev)
+    d2 = torch.empty((B, M, k), dtype=torch.float32, device=dev)
+    _call(dev, "p3d_knn_dense_f32", xs.data_ptr(), ys.data_ptr(), B, N, M, int(k), idx.data_ptr(), d2.data_ptr())
+    return idx, d2
+
+
+def three_nn(unknown: torch.Tensor, known: torch.Tensor):
+    """tp.three_nn(unknown[B,n,3], known[B,m,3]) -> (dist[B,n,3] = sqrt(d2), idx[B,n,3])
+    (reference call site core/base_conv/dense.py:136)."""
+    if unknown.dim() != 3 or known.dim() != 3:
+        raise AssertionError("three_nn expects unknown[B,n,3] and known[B,m,3]")
+    if known.shape[1] < 3:
+        raise ValueError("Not enough points. It should be at least 3 but got %i" % known.shape[1])
+    dev = _require_cuda("three_nn", unknown, known)
+    unknown, known = _f32(unknown), _f32(known)
+    B, n, _ = unknown.shape
+    m = known.shape[1]
+    dist = torch.empty((B, n, 3), dtype=torch.float32, device=dev)
+    idx = torch.empty((B, n, 3), dtype=torch.int64, device=dev)
+    _call(dev, "p3d_three_nn_f32", unknown.data_ptr(), known.data_ptr(), B, n, m, dist.data_ptr(), idx.data_ptr())
+    return dist, idx
+
+
+# ------------------------------------------------------------------ grouping ---------------
+class _Grouping(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, features, idx):
+        dev = _require_cuda("grouping_operation", features, idx)
+        features, idx = _f32(features), _i64(idx)
+        B, C, N = features.shape
+        _, S, K = idx.shape
+        out = torch.empty((B, C, S, K), dtype=torch.float32, device=dev)
+        _call(dev, "p3d_group_fwd_f32", features.data_ptr(), idx.data_ptr(), B, C, N, S, K, out.data_ptr(),
+              C * S * K, 0)
+        ctx.save_for_backward(idx)
+        ctx.N = N
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        grad_out = _f32(grad_out)
+        B, C, S, K = grad_out.shape
+        dfeat = torch.zeros((B, C, ctx.N), dtype=torch.float32, device=grad_out.device)
+        _call(grad_out.device, "p3d_group_bwd_f32", grad_out.data_ptr(), idx.data_ptr(), B, C, ctx.N, S, K,
+              dfeat.data_ptr(), C * S * K, 0)
+        return dfeat, None
+
+
+def grouping_operation(features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """tp.grouping_operation(features[B,C,N], idx[B,S,K]) -> [B,C,S,K]
+    (reference call sites modules/pointnet2/dense.py:38,45; modules/RSConv/dense.py:147,...)."""
+    if features.dim() != 3 or idx.dim() != 3 or features.shape[0] != idx.shape[0]:
+        raise AssertionError("grouping_operation expects features[B,C,N] and idx[B,S,K]")
+    return _Grouping.apply(features, idx)
+
+
+class _GroupXyzFeat(torch.autograd.Function):
+    """PointNetMSGDown._prepare_features (modules/pointnet2/dense.py:36-54) in two launches that
+    write straight into the concatenated [B, 3+C, S, K] tensor: no transpose of pos, no
+    grouped_pos temporary, no torch.cat copy."""
+
+    @staticmethod
+    def forward(ctx, x, pos, new_pos, idx, norm, use_xyz):
+        dev = _require_cuda("group_features", pos, new_pos, idx, x)
+        pos, new_pos, idx = _f32(pos), _f32(new_pos), _i64(idx)
+        B, N, _ = pos.shape
+        _, S, K = idx.shape
+        C = 0 if x is None else x.shape[1]
+        c_xyz = 3 if use_xyz else 0
+        out = torch.empty((B, c_xyz + C, S, K), dtype=torch.float32, device=dev)
+        stride = (c_xyz + C) * S * K
+        if use_xyz:
+            _call(dev, "p3d_group_xyz_f32", pos.data_ptr(), new_pos.data_ptr(), idx.data_ptr(), B, N, S, K,
+                  float(norm), out.data_ptr(), stride)
+        if x is not None:
+            x = _f32(x)
+            _call(dev, "p3d_group_fwd_f32", x.data_ptr(), idx.data_ptr(), B, C, N, S, K, out.data_ptr(), stride,
+                  c_xyz)
+        ctx.save_for_backward(idx)
+        ctx.dims = (B, C, N, S, K, c_xyz)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        B, C, N, S, K, c_xyz = ctx.dims
+        dx = None
+        if C > 0 and ctx.needs_input_grad[0]:
+            grad_out = _f32(grad_out)
+            dx = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
+            _call(grad_out.device, "p3d_group_bwd_f32", grad_out.data_ptr(), idx.data_ptr(), B, C, N, S, K,
+                  dx.data_ptr(), (c_xyz + C) * S * K, c_xyz)
+        return dx, None, None, None, None, None
+
+
+def group_features(x, pos, new_pos, idx, normalize_by: Optional[float] = None, use_xyz: bool = True):
+    """fused `_prepare_features`: cat([(pos[idx] - new_pos) / r, x[idx]], dim=1) -> [B,3+C,S,K].
+    Positions carry no gradient (as in the reference, where pos never requires grad)."""
+    if x is None and not use_xyz:
+        raise AssertionError("Cannot have not features and not use xyz as a feature!")
+    norm = 1.0 if normalize_by is None else float(normalize_by)
+    return _GroupXyzFeat.apply(x, pos, new_pos, idx, norm, use_xyz)
+
+
+# --------------------------------------------------------- three_interpolate ---------------
+class _ThreeInterpolate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, features, idx, weight):
+        dev = _require_cuda("three_interpolate", features, idx, weight)
+        features, idx, weight = _f32(features), _i64(idx), _f32(weight)
+        B, C, m = features.shape
+        n = idx.shape[1]
+        out = torch.empty((B, C, n), dtype=torch.float32, device=dev)
+        _call(dev, "p3d_three_interp_fwd_f32", features.data_ptr(), idx.data_ptr(), weight.data_ptr(), B, C, m, n,
+              out.data_ptr())
+        ctx.save_for_backward(idx, weight)
+        ctx.m = m
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, weight = ctx.saved_tensors
+        grad_out = _f32(grad_out)
+        B, C, n = grad_out.shape
+        dfeat = torch.zeros((B, C, ctx.m), dtype=torch.float32, device=grad_out.device)
+        _call(grad_out.device, "p3d_three_interp_bwd_f32", grad_out.data_ptr(), idx.data_ptr(), weight.data_ptr(), B,
+              C, ctx.m, n, dfeat.data_ptr())
+        return dfeat, None, None
+
+
+def three_interpolate(features: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """tp.three_interpolate(features[B,C,m], idx[B,n,3], weight[B,n,3]) -> [B,C,n]
+    (reference call site core/base_conv/dense.py:140); differentiable w.r.t. features."""
+    if features.dim() != 3 or idx.dim() != 3 or weight.shape != idx.shape or idx.shape[2] != 3:
+        raise AssertionError("three_interpolate expects features[B,C,m], idx[B,n,3], weight[B,n,3]")
+    return _ThreeInterpolate.apply(features, idx, weight)
+
+
+def knn_interpolate(x, pos_x, pos_y, batch_x=None, batch_y=None, k: int = 3, num_workers: int = 1):
+    """torch_geometric.nn.knn_interpolate (reference call sites message_passing.py:173,
+    interpolate.py:70; formula restated by the reference at interpolate.py:25-30,55-57):
+    y = sum_k w x[col] / sum_k w with w = 1 / clamp(d2, 1e-16) over the k nearest pos_x."""
+    col, d2 = knn_table(pos_x, pos_y, k, batch_x, batch_y, return_dist=True)
+    valid = col >= 0
+    w = torch.where(valid, 1.0 / torch.clamp(d2, min=1e-16), torch.zeros_like(d2))
+    feats = x[col.clamp(min=0)]  # [Ny, k, C]
+    num = (feats * w.unsqueeze(-1)).sum(1)
+    return num / w.sum(1, keepdim=True)
+
+
+# -------------------------------------------------------------------- KPConv ---------------
+class _KPConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, query, support, neighbors, feat, k_points, k_values, extent, influence, aggregation):
+        dev = _require_cuda("KPConv_ops", query, support, neighbors, feat, k_points, k_values)
+        query, support, feat = _f32(query), _f32(support), _f32(feat)
+        k_points, k_values, neighbors = _f32(k_points), _f32(k_values), _i64(neighbors)
+        n, M = neighbors.shape
+        N0, Cin = feat.shape
+        K, _, Cout = k_values.shape
+        out = torch.empty((n, Cout), dtype=torch.float32, device=dev)
+        _call(dev, "p3d_kpconv_fwd_f32", query.data_ptr(), support.data_ptr(), neighbors.data_ptr(), feat.data_ptr(),
+              k_points.data_ptr(), k_values.data_ptr(), n, N0, M, K, Cin, Cout, float(extent), influence,
+              aggregation, out.data_ptr())
+        ctx.save_for_backward(query, support, neighbors, feat, k_points, k_values)
+        ctx.cfg = (float(extent), influence, aggregation)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        query, support, neighbors, feat, k_points, k_values = ctx.saved_tensors
+        extent, influence, aggregation = ctx.cfg
+        dev = grad_out.device
+        grad_out = _f32(grad_out)
+        n, M = neighbors.shape
+        N0, Cin = feat.shape
+        K, _, Cout = k_values.shape
+        need_x, need_w = ctx.needs_input_grad[3], ctx.needs_input_grad[5]
+        dfeat = torch.zeros_like(feat) if need_x else None
+        dW = torch.zeros_like(k_values) if need_w else None
+        if need_x or need_w:
+            ws_bytes = _cabi.lib().p3d_kpconv_bwd_ws_bytes(n, M, K, Cin, Cout)
+            ws = torch.empty(max(ws_bytes // 4, 1), dtype=torch.float32, device=dev)
+            _call(dev, "p3d_kpconv_bwd_f32", query.data_ptr(), support.data_ptr(), neighbors.data_ptr(),
+                  feat.data_ptr(), k_points.data_ptr(), k_values.data_ptr(), grad_out.data_ptr(), n, N0, M, K, Cin,
+                  Cout, extent, influence, aggregation, _ptr(dfeat), _ptr(dW), ws.data_ptr(), ws_bytes)
+        return None, None, None, dfeat, None, dW, None, None, None
+
+
+def KPConv_ops(query_points, support_points, neighbors_indices, features, K_points, K_values, KP_extent,
+               KP_influence, aggregation_mode):
+    """KPConv_ops (torch_points3d/modules/KPConv/convolution_ops.py:19-107), same positional
+    signature.  neighbors_indices[n,M] int64; entries == support_points.shape[0] (or -1, as
+    gathering.py:10 allows) are shadow neighbours.  Differentiable w.r.t. features and K_values
+    (K_points is a non-trainable Parameter in the reference, kernels.py:66-68)."""
+    if KP_influence not in INFLUENCE:
+        raise ValueError("Unknown influence function type (config.KP_influence)")
+    if aggregation_mode not in AGGREGATION:
+        raise ValueError("Unknown convolution mode. Should be 'closest' or 'sum'")
+    if K_values.dim() != 3 or K_values.shape[0] != K_points.shape[0] or K_values.shape[1] != features.shape[1]:
+        raise AssertionError("K_values must be [n_kernel_points, Cin, Cout]")
+    return _KPConv.apply(query_points, support_points, neighbors_indices, features, K_points, K_values,
+                         float(KP_extent), INFLUENCE[KP_influence], AGGREGATION[aggregation_mode])
+
+
+class _NeighborMax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, neighbors):
+        dev = _require_cuda("neighbor_max", x, neighbors)
+        x, neighbors = _f32(x), _i64(neighbors)
+        N0, C = x.shape
+        n, M = neighbors.shape
+        out = torch.empty((n, C), dtype=torch.float32, device=dev)
+        arg = torch.empty((n, C), dtype=torch.int64, device=dev)
+        _call(dev, "p3d_neighbor_max_f32", x.data_ptr(), neighbors.data_ptr(), n, N0, M, C, out.data_ptr(),
+              arg.data_ptr())
+        ctx.save_for_backward(arg)
+        ctx.N0 = N0
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (arg,) = ctx.saved_tensors
+        n, C = grad_out.shape
+        dx = torch.zeros((ctx.N0 + 1, C), dtype=grad_out.dtype, device=grad_out.device)
+        dx.scatter_add_(0, arg, grad_out.contiguous())
+        return dx[:-1], None
+
+
+def neighbor_max(x: torch.Tensor, neighbors: torch.Tensor) -> torch.Tensor:
+    """strided-shortcut max-pool of ResnetBBlock (modules/KPConv/blocks.py:206-210):
+    max over the neighbour rows of cat(x, zeros(1,C))."""
+    return _NeighborMax.apply(x, neighbors)

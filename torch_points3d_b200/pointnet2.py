@@ -1,0 +1,106 @@
+"""Host-side mirror of the dense PointNet++ layers that drive the operators:
+  BaseDenseConvolutionDown.forward   torch_points3d/core/base_conv/dense.py:60-87
+  PointNetMSGDown                    torch_points3d/modules/pointnet2/dense.py:11-75
+  DenseFPModule                      torch_points3d/core/base_conv/dense.py:126-147
+Same constructor arguments and tensor layouts (pos [B,N,3], x [B,C,N]); the MLPs are stock
+PyTorch (1x1 Conv2d + BatchNorm2d + LeakyReLU, common_modules/dense_modules.py:5-29), the
+sampling / grouping / interpolation steps run on libp3d_b200.so.
+"""
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .spatial_ops import DenseFPSSampler, DenseRadiusNeighbourFinder
+
+
+def MLP2D(channels, bias=False, bn=True, activation=None):
+    """dense_modules.py:25-29"""
+    layers = []
+    for i in range(len(channels) - 1):
+        layers.append(nn.Conv2d(channels[i], channels[i + 1], kernel_size=(1, 1), stride=(1, 1), bias=bias))
+        if bn:
+            layers.append(nn.BatchNorm2d(channels[i + 1]))
+        layers.append(activation if activation is not None else nn.LeakyReLU(negative_slope=0.01))
+    return nn.Sequential(*layers)
+
+
+class PointNetMSGDown(nn.Module):
+    """modules/pointnet2/dense.py:11-75 on top of core/base_conv/dense.py:60-87."""
+
+    def __init__(self, npoint=None, radii=None, nsample=None, down_conv_nn=None, bn=True,
+                 activation=None, use_xyz=True, normalize_xyz=False, fused_grouping=True, **kwargs):
+        super().__init__()
+        assert len(radii) == len(nsample) == len(down_conv_nn)
+        self.sampler = DenseFPSSampler(num_to_sample=npoint)
+        self.neighbour_finder = DenseRadiusNeighbourFinder(radii, nsample)
+        self.use_xyz = use_xyz
+        self.npoint = npoint
+        self.mlps = nn.ModuleList([MLP2D(nn_i, bn=bn, activation=activation, bias=False) for nn_i in down_conv_nn])
+        self.radii = radii
+        self.normalize_xyz = normalize_xyz
+        self.fused_grouping = fused_grouping
+
+    def _prepare_features(self, x, pos, new_pos, idx, scale_idx):
+        if self.fused_grouping:
+            return ops.group_features(x, pos, new_pos, idx,
+                                      normalize_by=self.radii[scale_idx] if self.normalize_xyz else None,
+                                      use_xyz=self.use_xyz or x is None)
+        # the reference's op-by-op formulation (dense.py:36-54)
+        new_pos_trans = pos.transpose(1, 2).contiguous()
+        grouped_pos = ops.grouping_operation(new_pos_trans, idx)
+        grouped_pos = grouped_pos - new_pos.transpose(1, 2).unsqueeze(-1)
+        if self.normalize_xyz:
+            grouped_pos = grouped_pos / self.radii[scale_idx]
+        if x is not None:
+            grouped_features = ops.grouping_operation(x, idx)
+            return torch.cat([grouped_pos, grouped_features], dim=1) if self.use_xyz else grouped_features
+        assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
+        return grouped_pos
+
+    def conv(self, x, pos, new_pos, radius_idx, scale_idx):
+        assert scale_idx < len(self.mlps)
+        new_features = self._prepare_features(x, pos, new_pos, radius_idx, scale_idx)
+        new_features = self.mlps[scale_idx](new_features)
+        new_features = F.max_pool2d(new_features, kernel_size=[1, new_features.size(3)])
+        return new_features.squeeze(-1)
+
+    def forward(self, data, sample_idx=None, **kwargs):
+        x, pos = data.x, data.pos
+        idx = sample_idx if sample_idx is not None else self.sampler(pos)
+        idx = idx.unsqueeze(-1).repeat(1, 1, pos.shape[-1]).long()
+        new_pos = pos.gather(1, idx)
+        ms_x = []
+        for scale_idx in range(self.neighbour_finder.num_scales):
+            radius_idx = self.neighbour_finder(pos, new_pos, scale_idx=scale_idx)
+            ms_x.append(self.conv(x, pos, new_pos, radius_idx, scale_idx))
+        return SimpleNamespace(pos=new_pos, x=torch.cat(ms_x, 1), sampling_id=idx[:, :, 0])
+
+
+class DenseFPModule(nn.Module):
+    """core/base_conv/dense.py:102-147: three_nn + inverse-distance weights + three_interpolate,
+    concatenate the skip features, MLP."""
+
+    def __init__(self, up_conv_nn, bn=True, bias=False, activation=None, **kwargs):
+        super().__init__()
+        self.nn = MLP2D(up_conv_nn, bn=bn, activation=activation, bias=False)
+
+    def conv(self, pos, pos_skip, x):
+        assert pos_skip.shape[2] == 3
+        if pos is not None:
+            dist, idx = ops.three_nn(pos_skip, pos)
+            dist_recip = 1.0 / (dist + 1e-8)
+            norm = torch.sum(dist_recip, dim=2, keepdim=True)
+            weight = dist_recip / norm
+            return ops.three_interpolate(x, idx, weight)
+        return x.expand(*(x.size()[0:2] + (pos_skip.size(1),)))
+
+    def forward(self, data, **kwargs):
+        data, data_skip = data
+        new_features = self.conv(data.pos, data_skip.pos, data.x)
+        if data_skip.x is not None:
+            new_features = torch.cat([new_features, data_skip.x], dim=1)
+        new_features = self.nn(new_features.unsqueeze(-1))
+        return SimpleNamespace(x=new_features.squeeze(-1), pos=data_skip.pos)
