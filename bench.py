@@ -1,0 +1,467 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the sampling / grouping / neighbour-aggregation path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (BASELINE.json configs[1], "C2"): the operator chain of one PointNet++ MSG part-seg
+forward+backward pass over a ShapeNet-shaped batch of 16 clouds x 2048 points -- FPS 2048->512
+and 512->128, five dense ball queries, the fused xyz+feature grouping of every scale, both
+three_nn / three_interpolate layers, and the backward kernels of every grouping / interpolation
+(shapes from conf/models/segmentation/pointnet2.yaml:95-130).  The MLPs between the operators
+are stock cuDNN/cuBLAS in the reference and are not part of the path.  One step = one pass of
+that chain over one batch; metric = clouds/s.  With N GPUs every rank runs its own batch
+(clouds shard, no data-path collective; weak scaling).
+
+The JSON line also carries the KPConv layer numbers (points/s, C3 layer 32->32, ~50k points,
+<=34 neighbours) under "kpconv", the roofline of the dominant kernel and the CPU baseline.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B_CLOUDS, N_PTS = 16, 2048
+METRIC = "PointNet++ MSG SA/FP operator chain fwd+bwd (FPS + ball_query + grouping + three_nn/interpolate)"
+UNIT = "clouds/s"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# --------------------------------------------------------------------------- inputs -----------
+def make_host_inputs(seed):
+    from torch_points3d_b200 import synthetic
+    rng = np.random.default_rng(seed)
+    pos = synthetic.surface_clouds(B_CLOUDS, N_PTS, seed)
+    nrm = pos / (np.linalg.norm(pos, axis=-1, keepdims=True) + 1e-12)
+    h = dict(pos=pos, x0=np.ascontiguousarray(nrm.transpose(0, 2, 1)).astype(np.float32))
+    h["x1"] = rng.standard_normal((B_CLOUDS, 320, 512)).astype(np.float32)    # SA1 output features
+    h["x2"] = rng.standard_normal((B_CLOUDS, 256, 128)).astype(np.float32)    # FP2 input (SA2 level)
+    h["x3"] = rng.standard_normal((B_CLOUDS, 128, 512)).astype(np.float32)    # FP3 input (SA1 level)
+    return h
+
+
+# ------------------------------------------------------------------- the b200 arm -------------
+class Chain:
+    """the C2 operator chain on one GPU through the public API (torch_points3d_b200.ops)"""
+
+    def __init__(self, dev, seed):
+        import torch
+        from torch_points3d_b200 import synthetic
+        self.torch, self.dev = torch, dev
+        self.sa = synthetic.C2_SA
+        self.host = {k: torch.from_numpy(v).pin_memory() for k, v in make_host_inputs(seed).items()}
+        self.d = {k: torch.empty_like(v, device=dev) for k, v in self.host.items()}
+        for k in ("x0", "x1", "x2", "x3"):
+            self.d[k].requires_grad_(True)
+        g = torch.Generator(device=dev).manual_seed(seed)
+        # upstream gradients of every grouped / interpolated tensor (what the MLP backward would deliver)
+        self.g_sa = [[torch.randn((B_CLOUDS, 3 + l["cin"], l["npoint"], k), device=dev, generator=g)
+                      for k in l["nsample"]] for l in self.sa]
+        self.g_fp = [torch.randn((B_CLOUDS, 256, 512), device=dev, generator=g),
+                     torch.randn((B_CLOUDS, 128, 2048), device=dev, generator=g)]
+        self.result_host = torch.empty(B_CLOUDS * (512 + 128) + 1, dtype=torch.float32).pin_memory()
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
+        self.d2h_bytes = self.result_host.numel() * 4
+
+    def upload(self):
+        for k, v in self.host.items():
+            self.d[k].data.copy_(v, non_blocking=True)
+
+    def step(self):
+        """returns a small result tensor: the sampled indices of both levels + a gradient checksum"""
+        torch = self.torch
+        from torch_points3d_b200 import ops
+        d = self.d
+        pos, feats = d["pos"], [d["x0"], d["x1"]]
+        check = torch.zeros((), device=self.dev)
+        samples = []
+        for li, l in enumerate(self.sa):
+            idx = ops.furthest_point_sample(pos, l["npoint"])
+            samples.append(idx)
+            new_pos = pos.gather(1, idx.unsqueeze(-1).expand(-1, -1, 3))
+            for si, (r, k) in enumerate(zip(l["radii"], l["nsample"])):
+                ridx = ops.ball_query(r, k, pos, new_pos, return_dist=False)[0]
+                grouped = ops.group_features(feats[li], pos, new_pos, ridx)
+                (gx,) = torch.autograd.grad(grouped, feats[li], self.g_sa[li][si])
+                check = check + gx[0, 0, 0]
+            d["pos%d" % (li + 1)] = new_pos
+            pos = new_pos
+        # FP2: 512 unknown (SA1 level) from 128 known (SA2 level); FP3: 2048 unknown from 512 known
+        for fi, (unknown, known, x) in enumerate([(d["pos1"], d["pos2"], d["x2"]), (d["pos"], d["pos1"], d["x3"])]):
+            dist, idx = ops.three_nn(unknown, known)
+            recip = 1.0 / (dist + 1e-8)                       # core/base_conv/dense.py:137-139
+            weight = recip / torch.sum(recip, dim=2, keepdim=True)
+            out = ops.three_interpolate(x, idx, weight)
+            (gx,) = torch.autograd.grad(out, x, self.g_fp[fi])
+            check = check + gx[0, 0, 0]
+        return torch.cat([samples[0].reshape(-1).float(), samples[1].reshape(-1).float(), check.reshape(1)])
+
+    def algorithmic_bytes_dominant(self):
+        """group_fwd of SA2 scale 2: 4*C*N + 8*S*K + 4*C*S*K per cloud"""
+        C, Np, S, K = 320, 512, 128, 128
+        return B_CLOUDS * (4 * C * Np + 8 * S * K + 4 * C * S * K)
+
+
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.samples.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.05)
+
+    def summary(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the b200 arm has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    from torch_points3d_b200 import _cabi, ops
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    chain = Chain(dev, seed=1002 + 97 * rank)
+    chain.upload()
+    torch.cuda.synchronize()
+
+    # ---- eager warm-up (also loads modules, sets kernel attributes), launch count per step ----
+    for _ in range(2):
+        chain.step()
+    torch.cuda.synchronize()
+    c0 = _cabi.launch_count()
+    chain.step()
+    torch.cuda.synchronize()
+    launches_per_step = _cabi.launch_count() - c0
+
+    # ---- capture one step in a CUDA graph (the chain is launch-bound from Python otherwise) ----
+    graph, graph_out, use_graph = None, None, not args.no_graph
+    if use_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                chain.step()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                graph_out = chain.step()
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            if rank == 0:
+                print("bench.py: CUDA graph capture failed (%s); timing eagerly" % e, file=sys.stderr)
+            graph, use_graph = None, False
+            torch.cuda.synchronize()
+
+    def one_step():
+        if graph is not None:
+            graph.replay()
+            return graph_out
+        return chain.step()
+
+    # ---- device-resident timed region ----
+    for _ in range(args.warmup):
+        one_step()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        one_step()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.summary() if sampler else None
+
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the result, every step ----
+    def e2e_step():
+        chain.upload()
+        out = one_step()
+        chain.result_host.copy_(out, non_blocking=True)
+
+    for _ in range(max(3, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms_total = float(ms2.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (group_fwd, SA2 scale 2: 335 MB of stores) ----
+    peaks, peaks_src = _peaks()
+    x1 = chain.d["x1"].detach()
+    ridx = ops.ball_query(0.8, 128, chain.d["pos1"], chain.d["pos2"], return_dist=False)[0]
+    outs = [torch.empty((B_CLOUDS, 320, 128, 128), device=dev) for _ in range(2)]  # 2 x 335 MB > 126 MB L2
+
+    def dominant(i):
+        _cabi.call("p3d_group_fwd_f32", x1.data_ptr(), ridx.data_ptr(), B_CLOUDS, 320, 512, 128, 128,
+                   outs[i & 1].data_ptr(), 320 * 128 * 128, 0, torch.cuda.current_stream().cuda_stream)
+
+    for i in range(5):
+        dominant(i)
+    reps = max(args.steps, 20)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(reps):
+        dominant(i)
+    e1.record()
+    torch.cuda.synchronize()
+    dom_ms = e0.elapsed_time(e1) / reps
+    dom_bytes = chain.algorithmic_bytes_dominant()
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "group_fwd_kernel (SA2 scale 2, [16,320,512] -> [16,320,128,128])",
+                "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": _ncu_traffic(),
+                "algorithmic_bytes": dom_bytes, "avg_launch_ms": round(dom_ms, 5), "peak_source": peaks_src}
+
+    kp = bench_kpconv(dev, args)
+    cpu = cpu_baseline(max_seconds=12.0)
+
+    clouds = B_CLOUDS * world * args.steps
+    line = {
+        "metric": METRIC, "value": round(clouds / (ms_total * 1e-3), 2), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: PointNet++ MSG part-seg op chain fwd+bwd, batch 16 x 2048 pts per GPU "
+                               "(SA1 512 pts r[.1,.2,.4] k[32,64,128] C=3; SA2 128 pts r[.4,.8] k[64,128] C=320; "
+                               "FP 128->512 C=256, 512->2048 C=128)",
+                   "clouds_per_gpu": B_CLOUDS, "points_per_cloud": N_PTS, "parallelism": "clouds sharded x%d" % world,
+                   "cuda_graph": bool(use_graph),
+                   "l2": "each step streams ~1.1 GB of grouped tensors (> 126 MB L2), no flush needed"},
+        "e2e": {"value": round(clouds / (e2e_ms_total * 1e-3), 2), "unit": UNIT,
+                "h2d_bytes_per_step": chain.h2d_bytes, "d2h_bytes_per_step": chain.d2h_bytes,
+                "ms_per_step": round(e2e_ms_total / args.steps, 4)},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "launches_per_step": int(launches_per_step),
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "kpconv": kp,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None"""
+    path = os.path.join(ROOT, "profiles", "dominant_traffic.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return json.load(f).get("dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            return None
+    return None
+
+
+def bench_kpconv(dev, args):
+    """KPConv layer points/s on the C3 layer-0b shape: ~50k points, M = 34, Cin = Cout = 32."""
+    import torch
+    from torch_points3d_b200 import kpconv, ops, synthetic
+    pos_h, batch_h = synthetic.indoor_spheres()
+    pos, batch = torch.from_numpy(pos_h).to(dev), torch.from_numpy(batch_h).to(dev)
+    n = pos.shape[0]
+    nb = ops.ball_query(0.1, 34, pos, pos, mode="partial_dense", batch_x=batch, batch_y=batch, return_dist=False)[0]
+    g = torch.Generator(device=dev).manual_seed(3)
+    x = torch.randn((n, 32), device=dev, generator=g, requires_grad=True)
+    W = (torch.randn((15, 32, 32), device=dev, generator=g) * 0.1).requires_grad_(True)
+    kp = torch.from_numpy(kpconv.load_kernels(0.06, random_rotation=False)).to(dev)
+    dout = torch.randn((n, 32), device=dev, generator=g)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(args.steps, 10)
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def fwd():
+        with torch.no_grad():
+            return ops.KPConv_ops(pos, pos, nb, x, kp, W, 0.04, "linear", "sum")
+
+    def fwd_bwd():
+        out = ops.KPConv_ops(pos, pos, nb, x, kp, W, 0.04, "linear", "sum")
+        torch.autograd.grad(out, (x, W), dout)
+
+    def query():
+        ops.ball_query(0.1, 34, pos, pos, mode="partial_dense", batch_x=batch, batch_y=batch, return_dist=False)
+
+    t_f, t_fb, t_q = timed(fwd), timed(fwd_bwd), timed(query)
+    flops = n * (2 * 15 * 34 * 32 + 2 * 15 * 32 * 32 + 12 * 15 * 34)
+    return {"workload": "C3 layer 0b: KPConv 32->32, %d points in 8 spheres, M=34, K=15, linear/sum" % n,
+            "fwd_points_per_s": round(n / (t_f * 1e-3), 1), "fwd_ms": round(t_f, 4),
+            "fwd_bwd_points_per_s": round(n / (t_fb * 1e-3), 1), "fwd_bwd_ms": round(t_fb, 4),
+            "fwd_tflops": round(flops / (t_f * 1e-3) / 1e12, 3),
+            "neighbour_search_ms": round(t_q, 4), "unit": "points/s"}
+
+
+# ------------------------------------------------------------ CPU arm (oracle port) -----------
+def cpu_chain_once(h, clouds):
+    """the same chain on host cores with the oracle (oracle/p3d_oracle.c, OpenMP over clouds/queries)"""
+    import oracle
+    from torch_points3d_b200 import synthetic
+    pos = h["pos"][:clouds]
+    feats = [h["x0"][:clouds], h["x1"][:clouds]]
+    levels = [pos]
+    for li, l in enumerate(synthetic.C2_SA):
+        idx = oracle.fps_dense(pos, l["npoint"])
+        new_pos = np.take_along_axis(pos, idx[..., None], 1)
+        pos_t = np.ascontiguousarray(pos.transpose(0, 2, 1))
+        for r, k in zip(l["radii"], l["nsample"]):
+            ridx, _ = oracle.ball_query_dense(r, k, pos, new_pos)
+            gp = oracle.group_fwd(pos_t, ridx)
+            gp -= new_pos.transpose(0, 2, 1)[..., None]
+            gf = oracle.group_fwd(feats[li], ridx)
+            oracle.group_bwd(gf, ridx, pos.shape[1])      # gradient of the gather (dout := gf, same bytes)
+        pos = new_pos
+        levels.append(pos)
+    for unknown, known, x in [(levels[1], levels[2], h["x2"][:clouds]), (levels[0], levels[1], h["x3"][:clouds])]:
+        dist, idx = oracle.three_nn(unknown, known)
+        recip = 1.0 / (dist + 1e-8)
+        w = (recip / recip.sum(2, keepdims=True)).astype(np.float32)
+        out = oracle.three_interpolate_fwd(x, idx, w)
+        oracle.three_interpolate_bwd(out, idx, w, known.shape[1])
+    return clouds
+
+
+def cpu_baseline(max_seconds=12.0, clouds=B_CLOUDS):
+    import oracle
+    h = make_host_inputs(1002)
+    cpu_chain_once(h, 1)  # warm (builds / loads the oracle)
+    t0 = time.perf_counter()
+    done = 0
+    while True:
+        done += cpu_chain_once(h, clouds)
+        dt = time.perf_counter() - t0
+        if dt > max_seconds or done >= 64:
+            break
+    return {"value": round(done / dt, 3), "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+            "sample": "%d clouds of the same C2 chain through oracle/p3d_oracle.c (OpenMP, %d threads, %.1f s)"
+                      % (done, oracle.num_threads(), dt)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  The
+    reference's own arithmetic lives in un-vendored wheels (torch-points-kernels, torch-cluster)
+    that cannot be installed offline, so this times the oracle port."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    import oracle
+    from oracle import build as oracle_build
+    oracle_build.build()
+    h = make_host_inputs(1002)
+    clouds = B_CLOUDS  # the whole 16-cloud batch per step; the number of steps is bounded below
+    for _ in range(max(1, min(args.warmup, 3))):
+        cpu_chain_once(h, clouds)
+    steps = min(args.steps, 50)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_chain_once(h, clouds)
+    dt = time.perf_counter() - t0
+    value = round(clouds * steps / dt, 3)
+    sample = "%d of the 16 clouds per step, %d steps, oracle/p3d_oracle.c with %d OpenMP threads" % (
+        clouds, steps, oracle.num_threads())
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": round(dt / steps * 1e3, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2: PointNet++ MSG part-seg op chain fwd+bwd, batch 16 x 2048 pts (CPU sample)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph replay")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
