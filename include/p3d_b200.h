@@ -119,13 +119,18 @@ int p3d_three_nn_f32(const float *unknown, const float *known, int B, int n, int
  * (out_batch_stride = C*S*K, c_off = 0 for the plain op). */
 int p3d_group_fwd_f32(const float *feat, const int64_t *idx, int B, int C, int N, int S, int K, float *out,
                       int64_t out_batch_stride, int c_off, void *stream);
-/* backward (autograd of the gather): dfeat[b,c,i] += sum_{(s,k): idx=i} dout[...]; dfeat must be
- * zero-initialised by the caller.  dout is addressed like `out` above. */
+/* backward (autograd of the gather): dfeat[b,c,i] = sum_{(s,k): idx=i} dout[...]; dfeat is
+ * overwritten.  dout is addressed like `out` above.  With a workspace of
+ * p3d_group_bwd_ws_bytes() the sum is atomic-free and deterministic (the index tensor is
+ * inverted by a stable counting sort, slots are summed in increasing (s,k) order); source tables
+ * of more than 4096 points per cloud report 0 workspace bytes and use fp32 reductions at L2. */
+size_t p3d_group_bwd_ws_bytes(int B, int N, int S, int K);
 int p3d_group_bwd_f32(const float *dout, const int64_t *idx, int B, int C, int N, int S, int K, float *dfeat,
-                      int64_t dout_batch_stride, int c_off, void *stream);
+                      int64_t dout_batch_stride, int c_off, void *ws, size_t ws_bytes, void *stream);
 /* Fused PointNetMSGDown._prepare_features xyz part (modules/pointnet2/dense.py:37-42):
- * out[b, c, s, k] = (pos[b, idx[b,s,k], c] - new_pos[b, s, c]) / norm   for c in 0..2,
- * norm = 1 unless normalize_xyz.  pos is the untransposed [B,N,3] tensor. */
+ * out[b, c, s, k] = (pos[b, idx[b,s,k], c] - new_pos[b, s, c]) * (1/norm)   for c in 0..2,
+ * norm = 1 unless normalize_xyz (ATen evaluates `tensor /= python_float` on CUDA as a multiply
+ * by the fp32 reciprocal; the kernel does the same).  pos is the untransposed [B,N,3] tensor. */
 int p3d_group_xyz_f32(const float *pos, const float *new_pos, const int64_t *idx, int B, int N, int S, int K,
                       float norm, float *out, int64_t out_batch_stride, void *stream);
 
@@ -134,9 +139,11 @@ int p3d_group_xyz_f32(const float *pos, const float *new_pos, const int64_t *idx
  *   reference call site: core/base_conv/dense.py:140 */
 int p3d_three_interp_fwd_f32(const float *feat, const int64_t *idx, const float *weight, int B, int C, int m,
                              int n, float *out, void *stream);
-/* backward w.r.t. features; dfeat zero-initialised by the caller */
+/* backward w.r.t. features; dfeat is overwritten; workspace and determinism as for
+ * p3d_group_bwd_f32 (m <= 4096 known points per cloud, else fp32 reductions at L2) */
+size_t p3d_three_interp_bwd_ws_bytes(int B, int m, int n);
 int p3d_three_interp_bwd_f32(const float *dout, const int64_t *idx, const float *weight, int B, int C, int m,
-                             int n, float *dfeat, void *stream);
+                             int n, float *dfeat, void *ws, size_t ws_bytes, void *stream);
 
 /* ------------------------------------------------------------- KPConv ------
  * Replaces KPConv_ops(query, support, neighbors, features, K_points, K_values, KP_extent,

@@ -305,7 +305,8 @@ def test_group_features_matches_reference_formulation():
         if normalize:
             gp = gp / normalize
         ref = torch.cat([gp, ops.grouping_operation(x2, ridx)], dim=1)
-        assert torch.equal(fused, ref)
+        assert torch.equal(fused[:, 3:], ref[:, 3:])
+        assert torch.equal(fused[:, :3], ref[:, :3]), normalize
         g = torch.randn_like(ref)
         fused.backward(g)
         ref.backward(g)

@@ -17,6 +17,8 @@
 //     DSMEM, then one barrier.cluster per round.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -260,6 +262,21 @@ static int fps_dispatch(const float *xyz, const int64_t *ptr, int64_t n_dense, c
                         int64_t s_dense, IdxT *out, const int64_t *first, int clouds, int64_t max_n, float *ws,
                         size_t ws_bytes, int64_t total_rows, cudaStream_t st) {
     if (clouds == 0) return P3D_OK;
+    // tuning hook (bench/tune_fps.py): P3D_FPS_FORCE="T,PPT" selects a single-CTA variant by hand
+    if (const char *force = getenv("P3D_FPS_FORCE")) {
+        int ft = 0, fp = 0;
+        if (sscanf(force, "%d,%d", &ft, &fp) == 2 && (int64_t)ft * fp >= max_n) {
+#define P3D_FPS_FORCED(T, PPT) \
+    if (ft == T && fp == PPT)  \
+        return launch_reg<T, PPT, 1, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, clouds, st);
+            P3D_FPS_FORCED(64, 8) P3D_FPS_FORCED(64, 16) P3D_FPS_FORCED(64, 32)
+            P3D_FPS_FORCED(128, 4) P3D_FPS_FORCED(128, 8) P3D_FPS_FORCED(128, 16)
+            P3D_FPS_FORCED(256, 4) P3D_FPS_FORCED(256, 8) P3D_FPS_FORCED(512, 4) P3D_FPS_FORCED(1024, 2)
+            P3D_FPS_FORCED(1024, 4) P3D_FPS_FORCED(512, 2) P3D_FPS_FORCED(256, 2) P3D_FPS_FORCED(32, 32)
+            P3D_FPS_FORCED(32, 16)
+#undef P3D_FPS_FORCED
+        }
+    }
 #define P3D_FPS_CASE(LIM, T, PPT, CL) \
     if (max_n <= (LIM)) return launch_reg<T, PPT, CL, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, clouds, st);
     P3D_FPS_CASE(256, 64, 4, 1)

@@ -324,6 +324,12 @@ P3D_EXPORT int p3d_kpconv_bwd_f32(const float *query, const float *support, cons
     const KpGeom g = make_geom(extent, influence, aggregation);
     const int Mpad = (M + 31) / 32 * 32;
     const size_t smem = (size_t)KPF_WARPS * (Mpad * KP_K + Mpad) * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(kpconv_wf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(kpconv_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        attr_done = true;
+    }
     float *wf = (float *)ws;
     float *dwf = wf + (size_t)n * K * Cin;
     const int64_t KC = (int64_t)K * Cin;

@@ -299,6 +299,54 @@ knn_kernel(const float *__restrict__ x, const float *__restrict__ y, const int64
     }
 }
 
+
+// -------------------------------------------------------------------- three_nn -----------
+// One THREAD per unknown point; the known points stream through a shared-memory tile of packed
+// float4 (one broadcast LDS.128 per candidate for the whole warp); the best three live in
+// registers with the strict '<' cascade of the reference kernel (ties keep the lower index).
+constexpr int TNN_THREADS = 128;
+constexpr int TNN_TILE = 1024;
+
+__global__ void __launch_bounds__(TNN_THREADS)
+three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ known, int n, int m,
+                float *__restrict__ dist, int64_t *__restrict__ idx) {
+    __shared__ float4 tile[TNN_TILE];
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * TNN_THREADS + threadIdx.x;
+    const bool live = q < n;
+    const float *__restrict__ u = unknown + ((int64_t)b * n + (live ? q : 0)) * 3;
+    const float qx = __ldg(u), qy = __ldg(u + 1), qz = __ldg(u + 2);
+    const float *__restrict__ kb = known + (int64_t)b * m * 3;
+    float b1 = CUDART_INF_F, b2 = CUDART_INF_F, b3 = CUDART_INF_F;
+    int i1 = 0, i2 = 0, i3 = 0;
+    for (int tb = 0; tb < m; tb += TNN_TILE) {
+        const int tn = (m - tb < TNN_TILE) ? (m - tb) : TNN_TILE;
+        __syncthreads();
+        for (int i = threadIdx.x; i < tn; i += TNN_THREADS) {
+            const float *__restrict__ c = kb + (int64_t)(tb + i) * 3;
+            tile[i] = make_float4(__ldg(c), __ldg(c + 1), __ldg(c + 2), 0.f);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int i = 0; i < tn; ++i) {
+            const float4 c = tile[i];
+            const float d = sqdist3(qx, qy, qz, c.x, c.y, c.z);
+            if (d < b3) {
+                const int k = tb + i;
+                if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k; }
+                else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = k; }
+                else { b3 = d; i3 = k; }
+            }
+        }
+    }
+    if (live) {
+        float *__restrict__ dd = dist + ((int64_t)b * n + q) * 3;
+        int64_t *__restrict__ ii = idx + ((int64_t)b * n + q) * 3;
+        dd[0] = __fsqrt_rn(b1); dd[1] = __fsqrt_rn(b2); dd[2] = __fsqrt_rn(b3);
+        ii[0] = i1; ii[1] = i2; ii[2] = i3;
+    }
+}
+
 template <bool DENSE>
 static int launch_ball_query(const float *x, const float *y, const int64_t *bx, const int64_t *by, int64_t Nx,
                              int64_t Ny, int64_t n_dense, int64_t s_dense, float radius, int K, int strict,
@@ -386,6 +434,8 @@ P3D_EXPORT int p3d_three_nn_f32(const float *unknown, const float *known, int B,
     P3D_REQUIRE(m >= 3, "three_nn: needs at least 3 known points, got %d", m);
     if (B == 0 || n == 0) return P3D_OK;
     P3D_REQUIRE(unknown && known && dist && idx, "three_nn: null pointer");
-    return launch_knn<true>(known, unknown, nullptr, nullptr, (int64_t)B * m, (int64_t)B * n, m, n, 3, 1, idx, dist,
-                            (cudaStream_t)stream);
+    P3D_REQUIRE(B <= 65535, "three_nn: batch size must be <= 65535");
+    dim3 grid((unsigned)((n + TNN_THREADS - 1) / TNN_THREADS), (unsigned)B);
+    three_nn_kernel<<<grid, TNN_THREADS, 0, (cudaStream_t)stream>>>(unknown, known, n, m, dist, idx);
+    return finish_launch("three_nn");
 }

@@ -271,6 +271,20 @@ def three_nn(unknown: torch.Tensor, known: torch.Tensor):
 
 
 # ------------------------------------------------------------------ grouping ---------------
+def _workspace(nbytes: int, dev: torch.device) -> Optional[torch.Tensor]:
+    return torch.empty(nbytes, dtype=torch.uint8, device=dev) if nbytes else None
+
+
+def _group_bwd(grad_out, idx, B, C, N, S, K, batch_stride, c_off):
+    dev = grad_out.device
+    dfeat = torch.empty((B, C, N), dtype=torch.float32, device=dev)
+    ws_bytes = _cabi.lib().p3d_group_bwd_ws_bytes(B, N, S, K)
+    ws = _workspace(ws_bytes, dev)
+    _call(dev, "p3d_group_bwd_f32", grad_out.data_ptr(), idx.data_ptr(), B, C, N, S, K, dfeat.data_ptr(),
+          batch_stride, c_off, _ptr(ws), ws_bytes)
+    return dfeat
+
+
 class _Grouping(torch.autograd.Function):
     @staticmethod
     def forward(ctx, features, idx):
@@ -290,9 +304,7 @@ class _Grouping(torch.autograd.Function):
         (idx,) = ctx.saved_tensors
         grad_out = _f32(grad_out)
         B, C, S, K = grad_out.shape
-        dfeat = torch.zeros((B, C, ctx.N), dtype=torch.float32, device=grad_out.device)
-        _call(grad_out.device, "p3d_group_bwd_f32", grad_out.data_ptr(), idx.data_ptr(), B, C, ctx.N, S, K,
-              dfeat.data_ptr(), C * S * K, 0)
+        dfeat = _group_bwd(grad_out, idx, B, C, ctx.N, S, K, C * S * K, 0)
         return dfeat, None
 
 
@@ -337,9 +349,7 @@ class _GroupXyzFeat(torch.autograd.Function):
         dx = None
         if C > 0 and ctx.needs_input_grad[0]:
             grad_out = _f32(grad_out)
-            dx = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
-            _call(grad_out.device, "p3d_group_bwd_f32", grad_out.data_ptr(), idx.data_ptr(), B, C, N, S, K,
-                  dx.data_ptr(), (c_xyz + C) * S * K, c_xyz)
+            dx = _group_bwd(grad_out, idx, B, C, N, S, K, (c_xyz + C) * S * K, c_xyz)
         return dx, None, None, None, None, None
 
 
@@ -372,9 +382,11 @@ class _ThreeInterpolate(torch.autograd.Function):
         idx, weight = ctx.saved_tensors
         grad_out = _f32(grad_out)
         B, C, n = grad_out.shape
-        dfeat = torch.zeros((B, C, ctx.m), dtype=torch.float32, device=grad_out.device)
+        dfeat = torch.empty((B, C, ctx.m), dtype=torch.float32, device=grad_out.device)
+        ws_bytes = _cabi.lib().p3d_three_interp_bwd_ws_bytes(B, ctx.m, n)
+        ws = _workspace(ws_bytes, grad_out.device)
         _call(grad_out.device, "p3d_three_interp_bwd_f32", grad_out.data_ptr(), idx.data_ptr(), weight.data_ptr(), B,
-              C, ctx.m, n, dfeat.data_ptr())
+              C, ctx.m, n, dfeat.data_ptr(), _ptr(ws), ws_bytes)
         return dfeat, None, None
 
 
