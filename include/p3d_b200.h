@@ -124,7 +124,7 @@ int p3d_group_fwd_f32(const float *feat, const int64_t *idx, int B, int C, int N
  * p3d_group_bwd_ws_bytes() the sum is atomic-free and deterministic (the index tensor is
  * inverted by a stable counting sort, slots are summed in increasing (s,k) order); source tables
  * of more than 4096 points per cloud report 0 workspace bytes and use fp32 reductions at L2. */
-size_t p3d_group_bwd_ws_bytes(int B, int N, int S, int K);
+size_t p3d_group_bwd_ws_bytes(int B, int C, int N, int S, int K);
 int p3d_group_bwd_f32(const float *dout, const int64_t *idx, int B, int C, int N, int S, int K, float *dfeat,
                       int64_t dout_batch_stride, int c_off, void *ws, size_t ws_bytes, void *stream);
 /* Fused PointNetMSGDown._prepare_features xyz part (modules/pointnet2/dense.py:37-42):
@@ -141,7 +141,7 @@ int p3d_three_interp_fwd_f32(const float *feat, const int64_t *idx, const float 
                              int n, float *out, void *stream);
 /* backward w.r.t. features; dfeat is overwritten; workspace and determinism as for
  * p3d_group_bwd_f32 (m <= 4096 known points per cloud, else fp32 reductions at L2) */
-size_t p3d_three_interp_bwd_ws_bytes(int B, int m, int n);
+size_t p3d_three_interp_bwd_ws_bytes(int B, int C, int m, int n);
 int p3d_three_interp_bwd_f32(const float *dout, const int64_t *idx, const float *weight, int B, int C, int m,
                              int n, float *dfeat, void *ws, size_t ws_bytes, void *stream);
 

@@ -12,6 +12,9 @@
 // [B,C,S*K] int64 index tensor is materialised (the upstream formulation's `.repeat`).
 #include <math_constants.h>
 
+#include <cstdlib>
+
+#include "async.cuh"
 #include "common.cuh"
 
 namespace p3d {
@@ -209,14 +212,19 @@ neighbor_max_kernel(const float *__restrict__ x, const int64_t *__restrict__ nb,
 // Both scatter-type gradients (grouping, three_interpolate) are sums over "all output slots e
 // that read source point j".  Instead of fp32 atomics at L2 (one RED per element: the bound of
 // the first version of these kernels) the index tensor is inverted once per call:
-//   invert_kernel   -- per cloud and per chunk of EC consecutive slots, a STABLE counting sort of
-//                      the slots by source point: order[b][chunk][EC] (uint16 slot offsets) and
-//                      seg[b][chunk][N+1].  Per-warp histograms make the placement deterministic.
-//   *_bwd_sorted    -- a CTA owns CC channel rows of one cloud, streams the gradient rows chunk by
-//                      chunk through shared memory (coalesced float4, register double buffering)
-//                      and every thread sums the lists of its own source points out of shared
-//                      memory in increasing slot order.  No atomics, deterministic, each
-//                      gradient element is read from HBM exactly once.
+//   invert_kernel   -- per cloud and per chunk of EC consecutive slots:
+//                      (1) run-length compression in slot order: a run of equal consecutive
+//                          indices (ball-query padding repeats the first hit up to K times) is
+//                          represented by its first slot, and recorded in runs[] as (start, len);
+//                      (2) a STABLE counting sort of the run heads by source point:
+//                          order[b][chunk][EC] (uint16 slot offsets), seg[b][chunk][N+1].
+//                      Per-warp histograms make the placement deterministic.
+//   bwd_sorted      -- a CTA owns SB_CC channel rows of one cloud and streams the gradient rows chunk
+//                      by chunk through a shared-memory ring filled by TMA bulk copies.  Per chunk,
+//                      warps first fold every run into its head slot (coalesced shared-memory reads,
+//                      fixed shuffle tree), then every thread sums the short lists of its own source
+//                      points in increasing slot order.  No atomics, deterministic, each gradient
+//                      element is read from HBM exactly once.
 constexpr int INV_WARPS = 8;
 constexpr int INV_MAX_N = 4096;   // per-warp histograms: N * 8 * 4 B of shared memory
 constexpr int SB_THREADS = 512;
@@ -224,14 +232,34 @@ constexpr int SB_KPT = 4;         // source points per thread (one z-block cover
 constexpr int SB_CC = 4;          // channel rows per CTA
 constexpr int SB_EC_GROUP = 2048; // slots per chunk (grouping)
 constexpr int SB_EC_INTERP = 3072;  // slots per chunk (three_interpolate: 1024 points x 3 taps)
+constexpr int SB_MAX_STAGES = 4;
+
+constexpr int INV_MAX_EC = 3072;  // SB_EC_INTERP
+constexpr int INV_STEPS = INV_MAX_EC / (INV_WARPS * 32);  // 32-slot steps per warp: 12
+
+// position of the first set bit at or after `pos` in a bit vector of `words` 32-bit words (or `limit`)
+__device__ __forceinline__ int next_set_bit(const unsigned *bits, int words, int pos, int limit) {
+    int w = pos >> 5;
+    if (w >= words) return limit;
+    unsigned m = bits[w] & (0xffffffffu << (pos & 31));
+    while (m == 0u) {
+        if (++w >= words) return limit;
+        m = bits[w];
+    }
+    const int r = (w << 5) + __ffs(m) - 1;
+    return r < limit ? r : limit;
+}
 
 __global__ void __launch_bounds__(INV_WARPS * 32)
-invert_kernel(const int64_t *__restrict__ keys, int64_t E, int N, int EC, int nchunks,
-              uint16_t *__restrict__ order, int *__restrict__ seg) {
+invert_kernel(const int64_t *__restrict__ keys, int64_t E, int N, int EC, int nchunks, int compress,
+              uint16_t *__restrict__ order, int *__restrict__ seg, uint32_t *__restrict__ runs,
+              int *__restrict__ nruns) {
     extern __shared__ int ism[];
     int *hist = ism;                  // [N][INV_WARPS]
     int *rowsum = ism + (size_t)N * INV_WARPS;  // [N]
     __shared__ int warp_tot[INV_WARPS];
+    __shared__ int warp_runs[INV_WARPS];
+    __shared__ unsigned headbits[INV_MAX_EC / 32];  // bit e = slot e is a run head
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int chunk = blockIdx.x, b = blockIdx.y;
     const int64_t e0 = (int64_t)chunk * EC;
@@ -239,17 +267,63 @@ invert_kernel(const int64_t *__restrict__ keys, int64_t E, int N, int EC, int nc
     const int64_t *__restrict__ kb = keys + (int64_t)b * E + e0;
     uint16_t *__restrict__ ob = order + ((int64_t)b * nchunks + chunk) * EC;
     int *__restrict__ sb = seg + ((int64_t)b * nchunks + chunk) * (N + 1);
+    uint32_t *__restrict__ rb = runs + ((int64_t)b * nchunks + chunk) * (EC / 2);
+    const int words = (EC + 31) / 32;
 
     for (int i = tid; i < N * INV_WARPS; i += INV_WARPS * 32) hist[i] = 0;
-    __syncthreads();
     const int sub = ((len + INV_WARPS * 32 - 1) / (INV_WARPS * 32)) * 32;  // slots per warp (multiple of 32)
     const int w0 = warp * sub;
     const int w1 = (w0 + sub < len) ? (w0 + sub) : len;
-    for (int e = w0 + lane; e < w1; e += 32) {
-        const int64_t j = __ldg(kb + e);
-        if (j >= 0 && j < N) atomicAdd(&hist[(int)j * INV_WARPS + warp], 1);
+    // all keys of this warp's slots in registers (one coalesced load per step, issued back to back)
+    int key[INV_STEPS];
+#pragma unroll
+    for (int s = 0; s < INV_STEPS; ++s) {
+        const int e = w0 + s * 32 + lane;
+        int64_t j = -1;
+        if (s * 32 < sub && e < w1) j = __ldg(kb + e);
+        key[s] = (j >= 0 && j < N) ? (int)j : -1;
     }
+    int64_t jprev = -2;  // key of the slot just before this warp's range (lane 0 of step 0 needs it)
+    if (compress && w0 > 0 && w0 < len) jprev = __ldg(kb + w0 - 1);
+    __syncthreads();  // hist zeroed
+    unsigned headm[INV_STEPS];
+    int carry = (int)((jprev >= 0 && jprev < N) ? jprev : -2);
+#pragma unroll
+    for (int s = 0; s < INV_STEPS; ++s) {
+        headm[s] = 0u;
+        if (s * 32 < sub) {
+            int prev = __shfl_up_sync(0xffffffffu, key[s], 1);
+            if (lane == 0) prev = carry;
+            const bool head = key[s] >= 0 && (!compress || key[s] != prev);
+            headm[s] = __ballot_sync(0xffffffffu, head);
+            // headbits marks every slot that BREAKS a run: heads and slots with an out-of-range index
+            const unsigned breakm = headm[s] | __ballot_sync(0xffffffffu, key[s] < 0);
+            if (head) atomicAdd(&hist[key[s] * INV_WARPS + warp], 1);
+            carry = __shfl_sync(0xffffffffu, key[s], 31);
+            if (lane == 0 && w0 + s * 32 < EC) headbits[(w0 >> 5) + s] = breakm;
+        }
+    }
+    // words past the chunk length are empty
+    for (int w = ((len + 31) >> 5) + tid; w < words; w += INV_WARPS * 32) headbits[w] = 0u;
     __syncthreads();
+    // a RUN START is a head whose next slot exists, holds the same key and therefore is not a head
+    int my_runs = 0;
+    unsigned runm[INV_STEPS];
+#pragma unroll
+    for (int s = 0; s < INV_STEPS; ++s) {
+        runm[s] = 0u;
+        if (s * 32 < sub && compress) {
+            const int e = w0 + s * 32 + lane;
+            bool rs = false;
+            if ((headm[s] >> lane) & 1u) {
+                const int nx = e + 1;
+                rs = nx < len && !((headbits[nx >> 5] >> (nx & 31)) & 1u);
+            }
+            runm[s] = __ballot_sync(0xffffffffu, rs);
+            my_runs += __popc(runm[s]);
+        }
+    }
+    if (lane == 0) warp_runs[warp] = my_runs;
     for (int j = tid; j < N; j += INV_WARPS * 32) {
         int t = 0;
 #pragma unroll
@@ -287,50 +361,71 @@ invert_kernel(const int64_t *__restrict__ keys, int64_t E, int N, int EC, int nc
             base = run;
         }
     }
-    if (tid == INV_WARPS * 32 - 1) sb[N] = base;  // last thread ends on the total count
+    if (tid == INV_WARPS * 32 - 1) sb[N] = base;  // the last thread ends on the total count
+    int run_base = 0;
+    for (int w = 0; w < warp; ++w) run_base += warp_runs[w];
+    if (tid == INV_WARPS * 32 - 1) nruns[(int64_t)b * nchunks + chunk] = run_base + my_runs;
     __syncthreads();
-    // stable placement: every warp walks its own slots in order
-    for (int eb = w0; eb < w1; eb += 32) {
-        const int e = eb + lane;
-        int64_t j = -1;
-        if (e < w1) j = __ldg(kb + e);
-        const bool valid = (j >= 0 && j < N);
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const unsigned peers = __match_any_sync(act, (int)j);
-            const int rank = __popc(peers & lanemask_lt());
-            const int leader = __ffs(peers) - 1;
-            int pos = 0;
-            if (lane == leader) {
-                pos = hist[(int)j * INV_WARPS + warp];
-                hist[(int)j * INV_WARPS + warp] = pos + __popc(peers);
+    // stable placement of the heads + run table: every warp walks its own slots in order
+#pragma unroll
+    for (int s = 0; s < INV_STEPS; ++s) {
+        if (s * 32 < sub) {
+            const int e = w0 + s * 32 + lane;
+            if ((runm[s] >> lane) & 1u) {
+                const int end = next_set_bit(headbits, words, e + 1, len);  // next head (or the chunk end)
+                rb[run_base + __popc(runm[s] & lanemask_lt())] = ((uint32_t)e << 16) | (uint32_t)(end - e - 1);
             }
-            pos = __shfl_sync(peers, pos, leader);
-            ob[pos + rank] = (uint16_t)e;
+            run_base += __popc(runm[s]);
+            const bool valid = (headm[s] >> lane) & 1u;
+            if (valid) {
+                const unsigned peers = __match_any_sync(headm[s], key[s]);
+                const int rank = __popc(peers & lanemask_lt());
+                const int leader = __ffs(peers) - 1;
+                int pos = 0;
+                if (lane == leader) {
+                    pos = hist[key[s] * INV_WARPS + warp];
+                    hist[key[s] * INV_WARPS + warp] = pos + __popc(peers);
+                }
+                pos = __shfl_sync(peers, pos, leader);
+                ob[pos + rank] = (uint16_t)e;
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 
 // INTERP = false: dfeat[b,c,j] = sum_{e: idx[b,e]=j} dout[b, c_off+c, e]
-// INTERP = true : dfeat[b,c,j] = sum_{e: idx[b,e]=j} dout[b, c, e/3] * weight[b, e]
+// INTERP = true : dfeat[b,c,j] = sum_{e: idx[b,e]=j} dout[b, c, e/3] * weight[b, e]   (no compression)
+// One pipeline stage in shared memory: [SB_CC][Wd] gradient values | (INTERP: [EC] weights) |
+// [EC] uint16 sorted head slots | (!INTERP: [EC/2] uint32 runs); the per-key list bounds (seg) are
+// prefetched one chunk ahead in registers, so the inner loops touch shared memory only.
+// gridDim.z = key blocks x splits: split s sums chunks [s*cps, (s+1)*cps) into its own partial
+// gradient (reduced in split order by reduce_partials_kernel), which gives small-C problems
+// (C = 3 at the first SA level) enough CTAs without atomics.
 template <bool INTERP>
-__global__ void __launch_bounds__(SB_THREADS)
+__global__ void __launch_bounds__(SB_THREADS, 2)
 bwd_sorted_kernel(const float *__restrict__ dout, const float *__restrict__ weight, const uint16_t *__restrict__ order,
-                  const int *__restrict__ seg, int C, int N, int64_t E, int EC, int nchunks,
-                  float *__restrict__ dfeat, int64_t dout_batch_stride, int c_off) {
-    extern __shared__ __align__(16) float stage[];  // [2][SB_CC * W + (INTERP ? EC : 0)]
+                  const int *__restrict__ seg, const uint32_t *__restrict__ runs, const int *__restrict__ nruns, int C,
+                  int N, int64_t E, int EC, int nchunks, int splits, int cps, float *__restrict__ dst_base,
+                  int64_t split_stride, int64_t dout_batch_stride, int c_off, int SB_STAGES, int use_tma) {
+    extern __shared__ __align__(128) float stage[];
+    __shared__ __align__(8) uint64_t full[SB_MAX_STAGES];
     const int Wd = INTERP ? EC / 3 : EC;             // gradient values per channel row and chunk
-    const int buf_floats = SB_CC * Wd + (INTERP ? EC : 0);
-    const int tid = threadIdx.x;
+    const int buf_floats = SB_CC * Wd + (INTERP ? EC : 0) + EC / 2 + (INTERP ? 0 : EC / 2);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
     const int c0 = blockIdx.x * SB_CC;
     const int cc = (C - c0 < SB_CC) ? (C - c0) : SB_CC;
-    const int jbase = blockIdx.z * (SB_KPT * SB_THREADS);
+    const int split = blockIdx.z % splits;
+    const int jbase = (blockIdx.z / splits) * (SB_KPT * SB_THREADS);
+    const int ch_lo = split * cps;
+    const int ch_hi = (ch_lo + cps < nchunks) ? (ch_lo + cps) : nchunks;
     const int64_t Ed = INTERP ? E / 3 : E;  // length of a gradient row
     const float *__restrict__ gb = dout + (int64_t)b * dout_batch_stride + (int64_t)(c_off + c0) * Ed;
     const float *__restrict__ wb = INTERP ? weight + (int64_t)b * E : nullptr;
-    const bool vec = ((Ed & 3) == 0) && ((((uintptr_t)gb) & 15) == 0) && ((Wd & 3) == 0);
+    // TMA bulk copies need 16-byte aligned rows and lengths
+    const bool tma = use_tma && ((Ed & 3) == 0) && ((((uintptr_t)gb) & 15) == 0) && ((Wd & 3) == 0) &&
+                     (!INTERP || (((E & 3) == 0) && ((((uintptr_t)wb) & 15) == 0)));
 
     float acc[SB_KPT][SB_CC];
 #pragma unroll
@@ -338,76 +433,198 @@ bwd_sorted_kernel(const float *__restrict__ dout, const float *__restrict__ weig
 #pragma unroll
         for (int c = 0; c < SB_CC; ++c) acc[k][c] = 0.f;
 
-    auto fill = [&](int chunk, float *dst) {
+    if (tid == 0) {
+        for (int s = 0; s < SB_STAGES; ++s) mbar_init(&full[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    // producer side (thread 0): all copies of one chunk land on one mbarrier
+    auto issue = [&](int chunk) {
+        float *dst = stage + (size_t)((chunk - ch_lo) % SB_STAGES) * buf_floats;
+        uint64_t *bar = &full[(chunk - ch_lo) % SB_STAGES];
         const int64_t d0 = (int64_t)chunk * Wd;
         const int dl = (int)((Ed - d0 < Wd) ? (Ed - d0) : Wd);
-        if (vec) {
-            const int q4 = Wd / 4;
-            for (int i = tid; i < cc * q4; i += SB_THREADS) {
-                const int ch = i / q4, p4 = i - ch * q4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p4 * 4 < dl) v = __ldcs(reinterpret_cast<const float4 *>(gb + (int64_t)ch * Ed + d0) + p4);
-                reinterpret_cast<float4 *>(dst + ch * Wd)[p4] = v;
-            }
-        } else {
-            for (int i = tid; i < cc * Wd; i += SB_THREADS) {
-                const int ch = i / Wd, p = i - ch * Wd;
-                dst[ch * Wd + p] = p < dl ? __ldcs(gb + (int64_t)ch * Ed + d0 + p) : 0.f;
-            }
+        const int64_t e0 = (int64_t)chunk * EC;
+        const int el = (int)((E - e0 < EC) ? (E - e0) : EC);
+        const uint32_t bytes = (uint32_t)(cc * dl * 4 + EC * 2 + (INTERP ? el * 4 : EC * 2));
+        fence_proxy_async();  // the run folding wrote this stage through the generic proxy
+        mbar_arrive_expect_tx(bar, bytes);
+        for (int ch = 0; ch < cc; ++ch) bulk_g2s(dst + ch * Wd, gb + (int64_t)ch * Ed + d0, (uint32_t)dl * 4, bar);
+        if (INTERP) bulk_g2s(dst + SB_CC * Wd, wb + e0, (uint32_t)el * 4, bar);
+        float *tail = dst + SB_CC * Wd + (INTERP ? EC : 0);
+        bulk_g2s(tail, order + ((int64_t)b * nchunks + chunk) * EC, (uint32_t)EC * 2, bar);
+        if (!INTERP) bulk_g2s(tail + EC / 2, runs + ((int64_t)b * nchunks + chunk) * (EC / 2), (uint32_t)EC * 2, bar);
+    };
+    // fallback for unaligned shapes: cooperative synchronous fill
+    auto fill = [&](int chunk) {
+        float *dst = stage + (size_t)((chunk - ch_lo) % SB_STAGES) * buf_floats;
+        const int64_t d0 = (int64_t)chunk * Wd;
+        const int dl = (int)((Ed - d0 < Wd) ? (Ed - d0) : Wd);
+        for (int i = tid; i < cc * Wd; i += SB_THREADS) {
+            const int ch = i / Wd, p = i - ch * Wd;
+            dst[ch * Wd + p] = p < dl ? __ldcs(gb + (int64_t)ch * Ed + d0 + p) : 0.f;
         }
         if (INTERP) {
             const int64_t e0 = (int64_t)chunk * EC;
             const int el = (int)((E - e0 < EC) ? (E - e0) : EC);
             for (int i = tid; i < EC; i += SB_THREADS) dst[SB_CC * Wd + i] = i < el ? __ldg(wb + e0 + i) : 0.f;
         }
+        const uint4 *__restrict__ osrc = reinterpret_cast<const uint4 *>(order + ((int64_t)b * nchunks + chunk) * EC);
+        uint4 *odst = reinterpret_cast<uint4 *>(dst + SB_CC * Wd + (INTERP ? EC : 0));
+        for (int i = tid; i < EC / 8; i += SB_THREADS) odst[i] = __ldg(osrc + i);
+        if (!INTERP) {
+            const uint4 *__restrict__ rsrc =
+                reinterpret_cast<const uint4 *>(runs + ((int64_t)b * nchunks + chunk) * (EC / 2));
+            for (int i = tid; i < EC / 8; i += SB_THREADS) odst[EC / 8 + i] = __ldg(rsrc + i);
+        }
     };
-
-    fill(0, stage);
-    __syncthreads();
-    for (int chunk = 0; chunk < nchunks; ++chunk) {
-        float *cur = stage + (size_t)(chunk & 1) * buf_floats;
-        if (chunk + 1 < nchunks) fill(chunk + 1, stage + (size_t)((chunk + 1) & 1) * buf_floats);
-        const uint16_t *__restrict__ ob = order + ((int64_t)b * nchunks + chunk) * EC;
+    int s0[SB_KPT], s1[SB_KPT], nr = 0;
+    // key slots of this thread that exist at all (N = 512 -> 1): the others cost no instructions
+    const int kpt = (N - jbase + SB_THREADS - 1) / SB_THREADS < SB_KPT ? (N - jbase + SB_THREADS - 1) / SB_THREADS : SB_KPT;
+#pragma unroll
+    for (int k = 0; k < SB_KPT; ++k) s0[k] = s1[k] = 0;
+    auto bounds = [&](int chunk) {
         const int *__restrict__ sb = seg + ((int64_t)b * nchunks + chunk) * (N + 1);
-        const float *wst = cur + SB_CC * Wd;
 #pragma unroll
         for (int k = 0; k < SB_KPT; ++k) {
+            if (k >= kpt) break;
             const int j = jbase + k * SB_THREADS + tid;
-            if (j < N) {
-                const int s0 = __ldg(sb + j), s1 = __ldg(sb + j + 1);
-                for (int t = s0; t < s1; ++t) {
-                    const int e = ob[t];
-                    if (INTERP) {
-                        const float w = wst[e];
-                        const int p = e / 3;
+            s0[k] = j < N ? __ldg(sb + j) : 0;
+            s1[k] = j < N ? __ldg(sb + j + 1) : 0;
+        }
+        if (!INTERP) nr = __ldg(nruns + (int64_t)b * nchunks + chunk);
+    };
+
+    if (tma) {
+        if (tid == 0)
+            for (int c = ch_lo; c < ch_hi && c < ch_lo + SB_STAGES - 1; ++c) issue(c);
+    } else if (ch_lo < ch_hi) {
+        fill(ch_lo);
+        __syncthreads();
+    }
+    if (ch_lo < ch_hi) bounds(ch_lo);
+    for (int chunk = ch_lo; chunk < ch_hi; ++chunk) {
+        const int it = chunk - ch_lo;
+        float *cur = stage + (size_t)(it % SB_STAGES) * buf_floats;
+        int a0[SB_KPT], a1[SB_KPT];
 #pragma unroll
-                        for (int c = 0; c < SB_CC; ++c) acc[k][c] = fmaf(cur[c * Wd + p], w, acc[k][c]);
-                    } else {
+        for (int k = 0; k < SB_KPT; ++k) { a0[k] = s0[k]; a1[k] = s1[k]; }
+        const int nr_cur = nr;
+        if (tma) {
+            if (tid == 0 && chunk + SB_STAGES - 1 < ch_hi) issue(chunk + SB_STAGES - 1);
+        } else if (chunk + 1 < ch_hi) {
+            fill(chunk + 1);
+        }
+        if (chunk + 1 < ch_hi) bounds(chunk + 1);
+        if (tma) mbar_wait(&full[it % SB_STAGES], (uint32_t)((it / SB_STAGES) & 1));
+        const float *wst = cur + SB_CC * Wd;
+        const uint16_t *ob = reinterpret_cast<const uint16_t *>(cur + SB_CC * Wd + (INTERP ? EC : 0));
+        if (!INTERP) {
+            // fold every run of repeated indices into its head slot: one warp per run, lanes stride
+            // the run, fixed xor tree -> deterministic
+            const uint32_t *rt = reinterpret_cast<const uint32_t *>(ob + EC);
+            for (int r = warp; r < nr_cur; r += SB_THREADS / 32) {
+                const uint32_t rr = rt[r];
+                const int st = (int)(rr >> 16), ln = (int)(rr & 0xffffu) + 1;
 #pragma unroll
-                        for (int c = 0; c < SB_CC; ++c) acc[k][c] += cur[c * Wd + e];
+                for (int c = 0; c < SB_CC; ++c) {
+                    float v = 0.f;
+                    for (int i = lane; i < ln; i += 32) v += cur[c * Wd + st + i];
+#pragma unroll
+                    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                    if (lane == 0) cur[c * Wd + st] = v;
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int k = 0; k < SB_KPT; ++k) {
+            if (k >= kpt) break;
+            int t = a0[k];
+            const int te = a1[k];
+            for (; t + 1 < te; t += 2) {  // two independent gathers in flight, summed in slot order
+                const int ea = ob[t], eb = ob[t + 1];
+                if (INTERP) {
+                    const float wa = wst[ea], wv = wst[eb];
+                    const int pa = ea / 3, pb = eb / 3;
+#pragma unroll
+                    for (int c = 0; c < SB_CC; ++c) {
+                        const float va = cur[c * Wd + pa], vb = cur[c * Wd + pb];
+                        acc[k][c] = fmaf(vb, wv, fmaf(va, wa, acc[k][c]));
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < SB_CC; ++c) {
+                        const float va = cur[c * Wd + ea], vb = cur[c * Wd + eb];
+                        acc[k][c] = (acc[k][c] + va) + vb;
                     }
                 }
             }
+            if (t < te) {
+                const int ea = ob[t];
+                if (INTERP) {
+                    const float wa = wst[ea];
+                    const int pa = ea / 3;
+#pragma unroll
+                    for (int c = 0; c < SB_CC; ++c) acc[k][c] = fmaf(cur[c * Wd + pa], wa, acc[k][c]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < SB_CC; ++c) acc[k][c] += cur[c * Wd + ea];
+                }
+            }
         }
-        __syncthreads();
+        __syncthreads();  // stage (it % SB_STAGES) may be refilled from the next iteration on
     }
+    float *__restrict__ dst = dst_base + (int64_t)split * split_stride;
 #pragma unroll
     for (int k = 0; k < SB_KPT; ++k) {
         const int j = jbase + k * SB_THREADS + tid;
         if (j < N) {
 #pragma unroll
             for (int c = 0; c < SB_CC; ++c)
-                if (c < cc) dfeat[((int64_t)b * C + c0 + c) * N + j] = acc[k][c];
+                if (c < cc) dst[((int64_t)b * C + c0 + c) * N + j] = acc[k][c];
         }
     }
 }
 
-static size_t inverse_ws_bytes(int B, int N, int64_t E, int EC) {
-    const int64_t nchunks = (E + EC - 1) / EC;
-    size_t order = (size_t)B * nchunks * EC * sizeof(uint16_t);
-    order = (order + 255) / 256 * 256;
-    const size_t seg = (size_t)B * nchunks * (N + 1) * sizeof(int);
-    return order + seg;
+// out[i] = ((p[0][i] + p[1][i]) + ...) in split order
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float *__restrict__ part, int splits, int64_t n, float *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        float s = part[i];
+        for (int k = 1; k < splits; ++k) s += part[(int64_t)k * n + i];
+        out[i] = s;
+    }
+}
+
+static int pick_splits(int B, int C, int N, int nchunks) {
+    const int64_t ctas = (int64_t)((C + SB_CC - 1) / SB_CC) * B * ((N + SB_KPT * SB_THREADS - 1) / (SB_KPT * SB_THREADS));
+    int splits = 1;
+    if (ctas < 2 * kNumSMs) splits = (int)((2 * kNumSMs + ctas - 1) / ctas);
+    if (splits > nchunks) splits = nchunks;
+    if (splits > 16) splits = 16;
+    return splits < 1 ? 1 : splits;
+}
+
+static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+struct InverseLayout {
+    size_t order, seg, runs, nruns, total;
+    int nchunks, splits;
+};
+
+static InverseLayout inverse_layout(int B, int C, int N, int64_t E, int EC) {
+    InverseLayout L;
+    L.nchunks = (int)((E + EC - 1) / EC);
+    L.order = 0;
+    L.seg = L.order + align256((size_t)B * L.nchunks * EC * sizeof(uint16_t));
+    L.runs = L.seg + align256((size_t)B * L.nchunks * (N + 1) * sizeof(int));
+    L.nruns = L.runs + align256((size_t)B * L.nchunks * (EC / 2) * sizeof(uint32_t));
+    const size_t part = L.nruns + align256((size_t)B * L.nchunks * sizeof(int));
+    L.splits = pick_splits(B, C, N, L.nchunks);
+    L.total = part + (L.splits > 1 ? (size_t)L.splits * B * C * N * sizeof(float) : 0);
+    return L;
 }
 
 template <bool INTERP>
@@ -415,29 +632,49 @@ static int launch_bwd_sorted(const float *dout, const float *weight, const int64
                              int64_t E, float *dfeat, int64_t dout_batch_stride, int c_off, void *ws,
                              cudaStream_t st) {
     const int EC = INTERP ? SB_EC_INTERP : SB_EC_GROUP;
-    const int nchunks = (int)((E + EC - 1) / EC);
-    size_t order_bytes = (size_t)B * nchunks * EC * sizeof(uint16_t);
-    order_bytes = (order_bytes + 255) / 256 * 256;
-    uint16_t *order = (uint16_t *)ws;
-    int *seg = (int *)((char *)ws + order_bytes);
+    const InverseLayout L = inverse_layout(B, C, N, E, EC);
+    const int nchunks = L.nchunks;
+    char *w8 = (char *)ws;
+    uint16_t *order = (uint16_t *)(w8 + L.order);
+    int *seg = (int *)(w8 + L.seg);
+    uint32_t *runs = (uint32_t *)(w8 + L.runs);
+    int *nruns = (int *)(w8 + L.nruns);
+    float *part = (float *)(w8 + L.nruns + align256((size_t)B * nchunks * sizeof(int)));
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(bwd_sorted_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        cudaFuncSetAttribute(bwd_sorted_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(bwd_sorted_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(bwd_sorted_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_done = true;
     }
     const size_t inv_smem = ((size_t)N * INV_WARPS + N) * sizeof(int);
-    invert_kernel<<<dim3((unsigned)nchunks, (unsigned)B), INV_WARPS * 32, inv_smem, st>>>(keys, E, N, EC, nchunks,
-                                                                                       order, seg);
+    invert_kernel<<<dim3((unsigned)nchunks, (unsigned)B), INV_WARPS * 32, inv_smem, st>>>(
+        keys, E, N, EC, nchunks, INTERP ? 0 : 1, order, seg, runs, nruns);
     if (int e = finish_launch("invert")) return e;
     const int Wd = INTERP ? EC / 3 : EC;
-    const size_t smem = (size_t)2 * (SB_CC * Wd + (INTERP ? EC : 0)) * sizeof(float);
-    dim3 grid((unsigned)((C + SB_CC - 1) / SB_CC), (unsigned)B,
-              (unsigned)((N + SB_KPT * SB_THREADS - 1) / (SB_KPT * SB_THREADS)));
-    bwd_sorted_kernel<INTERP><<<grid, SB_THREADS, smem, st>>>(dout, weight, order, seg, C, N, E, EC, nchunks, dfeat,
-                                                             dout_batch_stride, c_off);
-    return finish_launch(INTERP ? "three_interp_bwd_sorted" : "group_bwd_sorted");
+    int SB_STAGES = 2, use_tma = 1;
+    if (const char *e = getenv("P3D_BWD_STAGES")) SB_STAGES = atoi(e);   // tuning hooks
+    if (const char *e = getenv("P3D_BWD_TMA")) use_tma = atoi(e);
+    if (SB_STAGES < 2) SB_STAGES = 2;
+    if (SB_STAGES > SB_MAX_STAGES) SB_STAGES = SB_MAX_STAGES;
+    const size_t smem =
+        (size_t)SB_STAGES * (SB_CC * Wd + (INTERP ? EC : 0) + EC / 2 + (INTERP ? 0 : EC / 2)) * sizeof(float);
+    const int splits = L.splits;
+    const int cps = (nchunks + splits - 1) / splits;
+    const int zblocks = (N + SB_KPT * SB_THREADS - 1) / (SB_KPT * SB_THREADS);
+    dim3 grid((unsigned)((C + SB_CC - 1) / SB_CC), (unsigned)B, (unsigned)(zblocks * splits));
+    const int64_t total = (int64_t)B * C * N;
+    bwd_sorted_kernel<INTERP><<<grid, SB_THREADS, smem, st>>>(dout, weight, order, seg, runs, nruns, C, N, E, EC,
+                                                             nchunks, splits, cps, splits > 1 ? part : dfeat, total,
+                                                             dout_batch_stride, c_off, SB_STAGES, use_tma);
+    if (int e = finish_launch(INTERP ? "three_interp_bwd_sorted" : "group_bwd_sorted")) return e;
+    if (splits > 1) {
+        int64_t gr = (total + 255) / 256;
+        if (gr > 4 * kNumSMs) gr = 4 * kNumSMs;
+        reduce_partials_kernel<<<(unsigned)gr, 256, 0, st>>>(part, splits, total, dfeat);
+        return finish_launch("reduce_partials");
+    }
+    return P3D_OK;
 }
 
 static int pick_cc(int C, int N, bool &staged) {
@@ -487,9 +724,9 @@ P3D_EXPORT int p3d_group_fwd_f32(const float *feat, const int64_t *idx, int B, i
     return finish_launch("group_fwd");
 }
 
-P3D_EXPORT size_t p3d_group_bwd_ws_bytes(int B, int N, int S, int K) {
+P3D_EXPORT size_t p3d_group_bwd_ws_bytes(int B, int C, int N, int S, int K) {
     if (N > INV_MAX_N || B > 65535) return 0;  // atomic path needs no workspace
-    return inverse_ws_bytes(B, N, (int64_t)S * K, SB_EC_GROUP);
+    return inverse_layout(B, C, N, (int64_t)S * K, SB_EC_GROUP).total;
 }
 
 P3D_EXPORT int p3d_group_bwd_f32(const float *dout, const int64_t *idx, int B, int C, int N, int S, int K,
@@ -505,7 +742,7 @@ P3D_EXPORT int p3d_group_bwd_f32(const float *dout, const int64_t *idx, int B, i
         return P3D_OK;
     }
     P3D_REQUIRE(dout && idx, "group_bwd: null pointer");
-    const size_t need = p3d_group_bwd_ws_bytes(B, N, S, K);
+    const size_t need = p3d_group_bwd_ws_bytes(B, C, N, S, K);
     if (need > 0 && ws != nullptr && ws_bytes >= need)
         return launch_bwd_sorted<false>(dout, nullptr, idx, B, C, N, E, dfeat, dout_batch_stride, c_off, ws, st);
     if (need > 0) {
@@ -568,9 +805,9 @@ P3D_EXPORT int p3d_three_interp_fwd_f32(const float *feat, const int64_t *idx, c
     return finish_launch("three_interp_fwd");
 }
 
-P3D_EXPORT size_t p3d_three_interp_bwd_ws_bytes(int B, int m, int n) {
+P3D_EXPORT size_t p3d_three_interp_bwd_ws_bytes(int B, int C, int m, int n) {
     if (m > INV_MAX_N || B > 65535) return 0;
-    return inverse_ws_bytes(B, m, (int64_t)n * 3, SB_EC_INTERP);
+    return inverse_layout(B, C, m, (int64_t)n * 3, SB_EC_INTERP).total;
 }
 
 P3D_EXPORT int p3d_three_interp_bwd_f32(const float *dout, const int64_t *idx, const float *weight, int B, int C,
@@ -584,7 +821,7 @@ P3D_EXPORT int p3d_three_interp_bwd_f32(const float *dout, const int64_t *idx, c
         return P3D_OK;
     }
     P3D_REQUIRE(dout && idx && weight, "three_interpolate_bwd: null pointer");
-    const size_t need = p3d_three_interp_bwd_ws_bytes(B, m, n);
+    const size_t need = p3d_three_interp_bwd_ws_bytes(B, C, m, n);
     if (need > 0 && ws != nullptr && ws_bytes >= need)
         return launch_bwd_sorted<true>(dout, weight, idx, B, C, m, (int64_t)n * 3, dfeat, (int64_t)C * n, 0, ws, st);
     if (need > 0) {

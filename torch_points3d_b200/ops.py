@@ -278,7 +278,7 @@ def _workspace(nbytes: int, dev: torch.device) -> Optional[torch.Tensor]:
 def _group_bwd(grad_out, idx, B, C, N, S, K, batch_stride, c_off):
     dev = grad_out.device
     dfeat = torch.empty((B, C, N), dtype=torch.float32, device=dev)
-    ws_bytes = _cabi.lib().p3d_group_bwd_ws_bytes(B, N, S, K)
+    ws_bytes = _cabi.lib().p3d_group_bwd_ws_bytes(B, C, N, S, K)
     ws = _workspace(ws_bytes, dev)
     _call(dev, "p3d_group_bwd_f32", grad_out.data_ptr(), idx.data_ptr(), B, C, N, S, K, dfeat.data_ptr(),
           batch_stride, c_off, _ptr(ws), ws_bytes)
@@ -383,7 +383,7 @@ class _ThreeInterpolate(torch.autograd.Function):
         grad_out = _f32(grad_out)
         B, C, n = grad_out.shape
         dfeat = torch.empty((B, C, ctx.m), dtype=torch.float32, device=grad_out.device)
-        ws_bytes = _cabi.lib().p3d_three_interp_bwd_ws_bytes(B, ctx.m, n)
+        ws_bytes = _cabi.lib().p3d_three_interp_bwd_ws_bytes(B, C, ctx.m, n)
         ws = _workspace(ws_bytes, grad_out.device)
         _call(grad_out.device, "p3d_three_interp_bwd_f32", grad_out.data_ptr(), idx.data_ptr(), weight.data_ptr(), B,
               C, ctx.m, n, dfeat.data_ptr(), _ptr(ws), ws_bytes)
