@@ -119,10 +119,16 @@ def main():
             x = torch.randn((n, cin), device=DEV, generator=g, requires_grad=True)
             W = (torch.randn((15, cin, cout), device=DEV, generator=g) * 0.1).requires_grad_(True)
             flops = n * (2 * 15 * 34 * cin + 2 * 15 * cin * cout)
-            def fwd():
-                with torch.no_grad():
-                    return ops.KPConv_ops(pos, pos, nb, x, kp, W, 0.04, "linear", "sum")
-            timed("C3 kpconv fwd %d->%d n=%d (%.1f GFLOP)" % (cin, cout, n, flops / 1e9), fwd)
+            for prec in ("fp32", "tensor"):
+                def fwd():
+                    with torch.no_grad():
+                        return ops.KPConv_ops(pos, pos, nb, x, kp, W, 0.04, "linear", "sum", precision=prec)
+                timed("C3 kpconv fwd %s %d->%d n=%d (%.1f GFLOP)" % (prec, cin, cout, n, flops / 1e9), fwd)
+            with torch.no_grad():
+                a = ops.KPConv_ops(pos, pos, nb, x, kp, W, 0.04, "linear", "sum", precision="fp32")
+                b = ops.KPConv_ops(pos, pos, nb, x, kp, W, 0.04, "linear", "sum", precision="tensor")
+            print("      tensor vs fp32: max|diff|/max|out| = %.3e  (identical bits: %s)" % (
+                float((a - b).abs().max() / a.abs().max()), bool(torch.equal(a, b))))
             out = ops.KPConv_ops(pos, pos, nb, x, kp, W, 0.04, "linear", "sum")
             gout = torch.randn_like(out)
             timed("C3 kpconv bwd %d->%d" % (cin, cout),

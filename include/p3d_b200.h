@@ -42,6 +42,8 @@ extern "C" {
 #define P3D_INFLUENCE_GAUSSIAN 2
 #define P3D_AGGREGATION_SUM 0
 #define P3D_AGGREGATION_CLOSEST 1
+#define P3D_PRECISION_FP32 0   /* exact fp32 SIMT arithmetic (1e-5 relative against the oracle) */
+#define P3D_PRECISION_TENSOR 1 /* kernel-point contraction on tcgen05, bf16 hi+lo split operands, fp32 accumulate */
 
 int p3d_version(void);
 const char *p3d_last_error(void);
@@ -152,10 +154,17 @@ int p3d_three_interp_bwd_f32(const float *dout, const int64_t *idx, const float 
  *   called from modules/KPConv/kernels.py:83-93
  * neighbors[n,M] int64, entries >= N0 or < 0 are shadow neighbours (point at 1e6, zero
  * feature).  K <= 16 kernel points.  One fused kernel: no [n,M,K] / [n,M,Cin] / [n,K,Cin]
- * intermediate is written to HBM. */
+ * intermediate is written to HBM.
+ * precision = P3D_PRECISION_TENSOR runs the (kernel point x Cin) -> Cout contraction on tcgen05
+ * tensor cores (TMA-fed pre-split weights, fp32 accumulation in TMEM; operands are bf16 hi+lo pairs,
+ * three MMAs per product: relative error ~1e-5 of max|out|, stated and tested at 2e-5) when
+ * Cin % 32 == 0, Cout % 32 == 0, Cout <= 512, M <= 40 and a workspace of
+ * p3d_kpconv_fwd_ws_bytes() is given; other shapes and P3D_PRECISION_FP32 use exact fp32 SIMT. */
+size_t p3d_kpconv_fwd_ws_bytes(int K, int Cin, int Cout);
 int p3d_kpconv_fwd_f32(const float *query, const float *support, const int64_t *neighbors, const float *feat,
                        const float *k_points, const float *k_values, int64_t n, int64_t N0, int M, int K, int Cin,
-                       int Cout, float extent, int influence, int aggregation, float *out, void *stream);
+                       int Cout, float extent, int influence, int aggregation, int precision, float *out,
+                       void *ws, size_t ws_bytes, void *stream);
 /* autograd backward: dfeat[N0,Cin] (zero-initialised by the caller, nullable) and
  * dweights[K,Cin,Cout] (zero-initialised by the caller, nullable).  ws: p3d_kpconv_bwd_ws_bytes. */
 size_t p3d_kpconv_bwd_ws_bytes(int64_t n, int M, int K, int Cin, int Cout);

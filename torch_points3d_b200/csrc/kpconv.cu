@@ -286,17 +286,29 @@ namespace p3d {
 // support the shape (the caller then uses the exact fp32 kernel above)
 int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neighbors, const float *feat,
                   const float *k_points, const float *k_values, int64_t n, int64_t N0, int M, int K, int Cin,
-                  int Cout, float extent, int influence, int aggregation, float *out, cudaStream_t st);
+                  int Cout, float extent, int influence, int aggregation, float *out, void *ws, size_t ws_bytes,
+                  cudaStream_t st);
+size_t kpconv_tc_ws_bytes(int K, int Cin, int Cout);
 }  // namespace p3d
+
+P3D_EXPORT size_t p3d_kpconv_fwd_ws_bytes(int K, int Cin, int Cout) { return kpconv_tc_ws_bytes(K, Cin, Cout); }
 
 P3D_EXPORT int p3d_kpconv_fwd_f32(const float *query, const float *support, const int64_t *neighbors,
                                   const float *feat, const float *k_points, const float *k_values, int64_t n,
                                   int64_t N0, int M, int K, int Cin, int Cout, float extent, int influence,
-                                  int aggregation, float *out, void *stream) {
+                                  int aggregation, int precision, float *out, void *ws, size_t ws_bytes,
+                                  void *stream) {
     if (int e = check_common("kpconv_fwd", n, N0, M, K, Cin, Cout, influence, aggregation)) return e;
     if (n == 0) return P3D_OK;
     P3D_REQUIRE(query && neighbors && k_points && k_values && out && (N0 == 0 || (support && feat)),
                 "kpconv_fwd: null pointer");
+    P3D_REQUIRE(precision == P3D_PRECISION_FP32 || precision == P3D_PRECISION_TENSOR,
+                "kpconv_fwd: unknown precision %d", precision);
+    if (precision == P3D_PRECISION_TENSOR) {
+        const int r = kpconv_fwd_tc(query, support, neighbors, feat, k_points, k_values, n, N0, M, K, Cin, Cout,
+                                    extent, influence, aggregation, out, ws, ws_bytes, (cudaStream_t)stream);
+        if (r <= 0) return r;  // launched (0) or failed (<0); 1 = shape not covered by the tensor path
+    }
     return kpconv_fwd_simt(query, support, neighbors, feat, k_points, k_values, n, N0, M, K, Cin, Cout, extent,
                            influence, aggregation, out, (cudaStream_t)stream);
 }

@@ -1,0 +1,424 @@
+// kpconv_tc.cu -- rigid KPConv forward with the kernel-point contraction on tcgen05 tensor cores.
+//
+// Replaces KPConv_ops (torch_points3d/modules/KPConv/convolution_ops.py:19-107).
+//
+//   out[p, :] = sum_k wf[p, k, :] @ W[k]          wf[p, k, c] = sum_m w[p, k, m] * x[nb[p, m], c]
+//
+// A CTA owns a tile of 128 query points (the M dimension of the MMA).  The contraction over
+// (kernel point, input channel) is cut into PASSES of 8 kernel points x 32 channels = 256 K-elements:
+//
+//   producers (8 warps, SIMT)  -- per point: influence weights of the 8 kernel points of this pass
+//       (lanes = neighbours, warp ballots give one bit mask of influencing neighbours per kernel
+//       point: the linear influence is ~6% dense, so only ~1 kernel point per neighbour does any
+//       work), the influencing neighbour rows are staged once in shared memory (back-to-back LDGs)
+//       and wf[8][32] is accumulated from shared memory; the result is split into bf16 hi + lo and
+//       written with two 16-byte stores per lane into the A operand tile [128 x 256] (K-major,
+//       128-byte swizzle -- the canonical UMMA layout).
+//   MMA warp (one elected thread) -- W tiles (pre-split bf16 hi/lo, pre-swizzled by
+//       kpconv_prep_w_kernel) arrive by TMA bulk copy; D[128 x 32] += A_hi*B_hi + A_lo*B_hi +
+//       A_hi*B_lo (bf16x2 split: ~2^-17 relative, fp32 accumulation in TMEM), one N = 32 column
+//       chunk of Cout at a time; tcgen05.commit hands the A tile back to the producers.
+//   epilogue (warps 0-3) -- tcgen05.ld of the [128 x Cout] accumulator, 128-byte row stores.
+//
+// No [n,M,K], [n,M,Cin], [n,K,Cin] or [K,n,Cout] intermediate exists in HBM.
+#include <cuda_bf16.h>
+
+#include "async.cuh"
+#include "kpconv_common.cuh"
+
+namespace p3d {
+
+constexpr int TC_TILE = 128;          // query points per tile (UMMA M)
+constexpr int TC_PWARPS = 8;          // producer warps
+constexpr int TC_THREADS = (TC_PWARPS + 1) * 32;
+constexpr int TC_MCAP = 40;           // neighbours per point supported by this path
+constexpr int TC_KH = 8;              // kernel points per pass
+constexpr int TC_NCH = 32;            // output channels per MMA (UMMA N)
+constexpr int TC_A_BYTES = 2 * 4 * TC_TILE * 128;  // hi|lo x 4 chunks x 128 rows x 128 B = 128 KB
+constexpr int TC_W_BYTES = 2 * 4 * TC_NCH * 128;   // hi|lo x 4 chunks x 32 rows x 128 B  =  32 KB
+constexpr int TC_SCRATCH_FLOATS = TC_KH * TC_MCAP + TC_MCAP * 32;  // per producer warp: weights + staged rows
+
+// ---- tcgen05 / TMEM wrappers -------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
+// start address >> 4 | LBO (unused for swizzled K-major) | SBO = 1024 B between 8-row groups |
+// version 1 | layout SWIZZLE_128B (2)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// cute::UMMA::InstrDescriptor: D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint32_t tc_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);  // .x = a (low 16 bits), .y = b
+    return *reinterpret_cast<const uint32_t *>(&v);
+}
+
+// ---- W image: bf16 hi/lo, K-major, 128-byte swizzled tiles ---------------------------------
+// tile(s, h, nc) = [hi|lo][4 chunks of 64 K][32 rows = outputs 32nc..][128 B]; K index inside a pass
+// = c * 8 + kk  (c = channel inside the 32-channel slab s, kk = kernel point inside half h).
+__global__ void __launch_bounds__(256)
+kpconv_prep_w_kernel(const float *__restrict__ W, int K, int Cin, int Cout, uint8_t *__restrict__ img) {
+    const int tile = blockIdx.x;  // ((s * 2 + h) * ncs + nc)
+    const int ncs = Cout / TC_NCH;
+    const int nc = tile % ncs, h = (tile / ncs) & 1, s = tile / (2 * ncs);
+    uint8_t *base = img + (size_t)tile * TC_W_BYTES;
+    for (int i = threadIdx.x; i < 4 * TC_NCH * 64; i += 256) {
+        const int e = i & 63, r = (i >> 6) & 31, kc = i >> 11;
+        const int kidx = kc * 64 + e;
+        const int c = kidx >> 3, kk = kidx & 7;
+        const int kp = h * TC_KH + kk;
+        const float v = kp < K ? __ldg(W + ((int64_t)kp * Cin + s * 32 + c) * Cout + nc * TC_NCH + r) : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        const int off = (kc * TC_NCH + r) * 128 + (((e >> 3) ^ (r & 7)) << 4) + ((e & 7) << 1);
+        *reinterpret_cast<__nv_bfloat16 *>(base + off) = hi;
+        *reinterpret_cast<__nv_bfloat16 *>(base + 4 * TC_NCH * 128 + off) = lo;
+    }
+}
+
+// ---- producer: wf[8 kernel points][32 channels] of one query point ----------------------
+struct TcPoint {
+    int j0, j1;           // feature row of neighbour lane / 32+lane (-1 = shadow or absent)
+    float x0, y0, z0;     // centred neighbour lane
+    float x1, y1, z1;     // centred neighbour 32+lane
+};
+
+__device__ __forceinline__ void tc_load_point(const float *__restrict__ q, const float *__restrict__ s,
+                                              const int64_t *__restrict__ nbp, int64_t N0, int M, int lane,
+                                              TcPoint &P) {
+    const float qx = __ldg(q), qy = __ldg(q + 1), qz = __ldg(q + 2);
+    int64_t a = lane < M ? __ldg(nbp + lane) : -1;
+    int64_t b = 32 + lane < M ? __ldg(nbp + 32 + lane) : -1;
+    if (a >= N0) a = -1;
+    if (b >= N0) b = -1;
+    P.j0 = (int)a;
+    P.j1 = (int)b;
+    float ax = 1e6f, ay = 1e6f, az = 1e6f, bx = 1e6f, by = 1e6f, bz = 1e6f;
+    if (a >= 0) { ax = __ldg(s + 3 * a); ay = __ldg(s + 3 * a + 1); az = __ldg(s + 3 * a + 2); }
+    if (b >= 0) { bx = __ldg(s + 3 * b); by = __ldg(s + 3 * b + 1); bz = __ldg(s + 3 * b + 2); }
+    P.x0 = __fsub_rn(ax, qx); P.y0 = __fsub_rn(ay, qy); P.z0 = __fsub_rn(az, qz);
+    P.x1 = __fsub_rn(bx, qx); P.y1 = __fsub_rn(by, qy); P.z1 = __fsub_rn(bz, qz);
+}
+
+// influence weights of kernel points 8h .. 8h+7 on every neighbour: wsm[kk][m] and one bit mask of
+// influencing neighbours per kernel point (mask0: neighbours 0-31, mask1: neighbours 32-39)
+__device__ __forceinline__ void tc_weights(const TcPoint &P, const float4 *kps, int K, int M, int h, const KpGeom &g,
+                                           float *wsm, unsigned (&mask0)[TC_KH], unsigned (&mask1)[TC_KH], int lane) {
+    // closest mode: the winning kernel point of every neighbour over ALL K kernel points (first minimum)
+    int best0 = -1, best1 = -1;
+    if (g.aggregation == P3D_AGGREGATION_CLOSEST) {
+        float bd0 = CUDART_INF_F, bd1 = CUDART_INF_F;
+        for (int k = 0; k < K; ++k) {
+            const float4 kp = kps[k];
+            const float d0 = sqdist3(P.x0, P.y0, P.z0, kp.x, kp.y, kp.z);
+            const float d1 = sqdist3(P.x1, P.y1, P.z1, kp.x, kp.y, kp.z);
+            if (d0 < bd0) { bd0 = d0; best0 = k; }
+            if (d1 < bd1) { bd1 = d1; best1 = k; }
+        }
+    }
+#pragma unroll
+    for (int kk = 0; kk < TC_KH; ++kk) {
+        const int k = h * TC_KH + kk;
+        const float4 kp = kps[k];
+        float w = kp_influence(sqdist3(P.x0, P.y0, P.z0, kp.x, kp.y, kp.z), g);
+        if (g.aggregation == P3D_AGGREGATION_CLOSEST && best0 != k) w = 0.f;
+        const bool nz = P.j0 >= 0 && k < K && w > 0.f;
+        mask0[kk] = __ballot_sync(0xffffffffu, nz);
+        wsm[kk * TC_MCAP + lane] = w;
+        mask1[kk] = 0u;
+    }
+    if (M > 32) {
+        // neighbours 32..39: lane = (mm = lane % 8, kq = lane / 8), two steps cover the 8 kernel points
+        const int mm = lane & 7, kq = lane >> 3;
+        const float cx = __shfl_sync(0xffffffffu, P.x1, mm), cy = __shfl_sync(0xffffffffu, P.y1, mm);
+        const float cz = __shfl_sync(0xffffffffu, P.z1, mm);
+        const int jj = __shfl_sync(0xffffffffu, P.j1, mm);
+        const int bb = __shfl_sync(0xffffffffu, best1, mm);
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int kk = kq + 4 * it;
+            const int k = h * TC_KH + kk;
+            const float4 kp = kps[k];
+            float w = kp_influence(sqdist3(cx, cy, cz, kp.x, kp.y, kp.z), g);
+            if (g.aggregation == P3D_AGGREGATION_CLOSEST && bb != k) w = 0.f;
+            const bool nz = jj >= 0 && k < K && w > 0.f;
+            const unsigned bal = __ballot_sync(0xffffffffu, nz);
+            wsm[kk * TC_MCAP + 32 + mm] = w;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) mask1[qq + 4 * it] = (bal >> (8 * qq)) & 0xffu;
+        }
+    }
+    __syncwarp();
+}
+
+// stage the neighbour rows named by `rows` (bit m -> neighbour base+m) into xs[m][lane]
+__device__ __forceinline__ void tc_stage_rows(unsigned rows, int jreg, int base, const float *__restrict__ xcol,
+                                              int Cin, float *xs, int lane) {
+    while (rows) {
+        int mm[4];
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            mm[u] = rows ? __ffs(rows) - 1 : -1;
+            rows &= rows - 1;  // 0 stays 0
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v[u] = 0.f;
+            if (mm[u] >= 0) {
+                const int j = __shfl_sync(0xffffffffu, jreg, mm[u]);
+                v[u] = __ldg(xcol + (int64_t)j * Cin);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (mm[u] >= 0) xs[(base + mm[u]) * 32 + lane] = v[u];
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, const int64_t *__restrict__ nb,
+                     const float *__restrict__ x, const float *__restrict__ kp, const uint8_t *__restrict__ wimg,
+                     int64_t n, int64_t N0, int M, int K, int Cin, int Cout, KpGeom g, uint32_t tmem_cols,
+                     float *__restrict__ out) {
+    extern __shared__ uint8_t smem_raw[];
+    // the UMMA 128-byte swizzle atoms need 1024-byte aligned tiles (the launch adds 1 KB of slack)
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *a_tile = smem;                       // [hi|lo][4][128][128 B]
+    uint8_t *w_tile = smem + TC_A_BYTES;          // [hi|lo][4][32][128 B]
+    float *scratch = reinterpret_cast<float *>(smem + TC_A_BYTES + TC_W_BYTES);
+    __shared__ float4 kps[KP_K];
+    __shared__ __align__(8) uint64_t bar_a_empty, bar_w_full, bar_w_empty, bar_d_full;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slabs = Cin / 32, ncs = Cout / TC_NCH;
+    const int64_t ntiles = (n + TC_TILE - 1) / TC_TILE;
+
+    if (tid < KP_K) kps[tid] = tid < K ? make_float4(__ldg(kp + 3 * tid), __ldg(kp + 3 * tid + 1), __ldg(kp + 3 * tid + 2), 0.f)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) {
+        mbar_init(&bar_a_empty, 1);
+        mbar_init(&bar_w_full, 1);
+        mbar_init(&bar_w_empty, 1);
+        mbar_init(&bar_d_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == TC_PWARPS) tmem_alloc(&tmem_base_s, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    uint32_t pass = 0;       // global pass counter (phase of bar_a_empty)
+    uint32_t wloads = 0;     // W tiles loaded so far (phases of bar_w_full / bar_w_empty; MMA thread only)
+    uint32_t tile_iter = 0;  // phase of bar_d_full
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
+        const int64_t p_base = tile * TC_TILE;
+        for (int sl = 0; sl < slabs; ++sl) {
+            for (int h = 0; h < 2; ++h, ++pass) {
+                if (warp < TC_PWARPS) {
+                    // ------------------------------------------------ producers ------------------
+                    float *wsm = scratch + (size_t)warp * TC_SCRATCH_FLOATS;
+                    float *xs = wsm + TC_KH * TC_MCAP;
+                    if (pass > 0) mbar_wait(&bar_a_empty, (pass - 1) & 1);  // previous pass' MMAs have read the A tile
+                    for (int pi = 0; pi < TC_TILE / TC_PWARPS; ++pi) {
+                        const int row = warp * (TC_TILE / TC_PWARPS) + pi;
+                        const int64_t p = p_base + row;
+                        float acc[TC_KH];
+#pragma unroll
+                        for (int kk = 0; kk < TC_KH; ++kk) acc[kk] = 0.f;
+                        if (p < n) {
+                            TcPoint P;
+                            tc_load_point(q + 3 * p, s, nb + p * M, N0, M, lane, P);
+                            unsigned mask0[TC_KH], mask1[TC_KH];
+                            tc_weights(P, kps, K, M, h, g, wsm, mask0, mask1, lane);
+                            unsigned rows0 = 0u, rows1 = 0u;
+#pragma unroll
+                            for (int kk = 0; kk < TC_KH; ++kk) { rows0 |= mask0[kk]; rows1 |= mask1[kk]; }
+                            const float *xcol = x + sl * 32 + lane;
+                            tc_stage_rows(rows0, P.j0, 0, xcol, Cin, xs, lane);
+                            tc_stage_rows(rows1, P.j1, 32, xcol, Cin, xs, lane);
+#pragma unroll
+                            for (int kk = 0; kk < TC_KH; ++kk) {
+                                unsigned mk = mask0[kk];
+                                float a = 0.f;
+                                while (mk) {
+                                    const int m = __ffs(mk) - 1;
+                                    mk &= mk - 1;
+                                    a = fmaf(wsm[kk * TC_MCAP + m], xs[m * 32 + lane], a);
+                                }
+                                mk = mask1[kk];
+                                while (mk) {
+                                    const int m = 32 + __ffs(mk) - 1;
+                                    mk &= mk - 1;
+                                    a = fmaf(wsm[kk * TC_MCAP + m], xs[m * 32 + lane], a);
+                                }
+                                acc[kk] = a;
+                            }
+                            __syncwarp();  // wsm / xs are rewritten for the next point
+                        }
+                        // bf16 hi/lo split, K index = lane * 8 + kk: 16 contiguous bytes per lane
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float a0 = acc[2 * u], a1 = acc[2 * u + 1];
+                            const float h0 = __bfloat162float(__float2bfloat16_rn(a0));
+                            const float h1 = __bfloat162float(__float2bfloat16_rn(a1));
+                            hi[u] = pack_bf16(h0, h1);
+                            lo[u] = pack_bf16(a0 - h0, a1 - h1);
+                        }
+                        const int off = ((lane >> 3) * TC_TILE + row) * 128 + (((lane & 7) ^ (row & 7)) << 4);
+                        *reinterpret_cast<uint4 *>(a_tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4 *>(a_tile + TC_A_BYTES / 2 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                    fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+                }
+                __syncthreads();  // A tile of this pass complete (the MMA warp waits here too)
+                if (warp == TC_PWARPS) {
+                    // ------------------------------------------------ MMA issuer -----------------
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t idesc = tc_idesc(TC_TILE, TC_NCH);
+                        const uint32_t a_addr = smem_u32(a_tile), w_addr = smem_u32(w_tile);
+                        for (int nc = 0; nc < ncs; ++nc, ++wloads) {
+                            if (wloads > 0) mbar_wait(&bar_w_empty, (wloads - 1) & 1);  // W tile buffer is free
+                            mbar_arrive_expect_tx(&bar_w_full, TC_W_BYTES);
+                            bulk_g2s(w_tile, wimg + ((size_t)(sl * 2 + h) * ncs + nc) * TC_W_BYTES, TC_W_BYTES,
+                                     &bar_w_full);
+                            mbar_wait(&bar_w_full, wloads & 1);
+                            tc_fence_after();
+                            const uint32_t d = tmem_base + (uint32_t)(nc * TC_NCH);
+#pragma unroll 1
+                            for (int kc = 0; kc < 4; ++kc) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    const uint32_t ko = (uint32_t)(ks * 32);
+                                    const uint64_t a_hi = tc_smem_desc(a_addr + kc * (TC_TILE * 128) + ko);
+                                    const uint64_t a_lo = tc_smem_desc(a_addr + TC_A_BYTES / 2 + kc * (TC_TILE * 128) + ko);
+                                    const uint64_t b_hi = tc_smem_desc(w_addr + kc * (TC_NCH * 128) + ko);
+                                    const uint64_t b_lo = tc_smem_desc(w_addr + TC_W_BYTES / 2 + kc * (TC_NCH * 128) + ko);
+                                    const uint32_t first = (sl == 0 && h == 0 && kc == 0 && ks == 0) ? 0u : 1u;
+                                    tc_mma_bf16(d, a_hi, b_hi, idesc, first);
+                                    tc_mma_bf16(d, a_lo, b_hi, idesc, 1u);
+                                    tc_mma_bf16(d, a_hi, b_lo, idesc, 1u);
+                                }
+                            }
+                            tc_commit(&bar_w_empty);
+                        }
+                        tc_commit(&bar_a_empty);
+                        if (sl == slabs - 1 && h == 1) tc_commit(&bar_d_full);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        // ---------------------------------------------------------- epilogue --------------------
+        if (warp < 4) {
+            mbar_wait(&bar_d_full, tile_iter & 1);
+            tc_fence_after();
+            const int64_t p = p_base + warp * 32 + lane;
+            for (int nc = 0; nc < ncs; ++nc) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(nc * TC_NCH), v);
+                if (p < n) {
+                    float4 *dst = reinterpret_cast<float4 *>(out + p * Cout + nc * TC_NCH);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) dst[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                }
+            }
+            tc_fence_before();  // the next tile's first MMA overwrites D after the next __syncthreads
+        }
+    }
+    __syncthreads();
+    if (warp == TC_PWARPS) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+size_t kpconv_tc_ws_bytes(int K, int Cin, int Cout) {
+    if (K > KP_K || Cin % 32 != 0 || Cout % TC_NCH != 0 || Cout > 512) return 0;
+    return (size_t)(Cin / 32) * 2 * (Cout / TC_NCH) * TC_W_BYTES;
+}
+
+// returns 1 when the shape is not supported by this path (the caller then runs the fp32 SIMT kernel)
+int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neighbors, const float *feat,
+                  const float *k_points, const float *k_values, int64_t n, int64_t N0, int M, int K, int Cin,
+                  int Cout, float extent, int influence, int aggregation, float *out, void *ws, size_t ws_bytes,
+                  cudaStream_t st) {
+    const size_t need = kpconv_tc_ws_bytes(K, Cin, Cout);
+    if (need == 0 || M > TC_MCAP || ws == nullptr || ws_bytes < need) return 1;
+    if ((((uintptr_t)out) & 15) != 0 || (((uintptr_t)ws) & 15) != 0) return 1;
+    KpGeom g;
+    g.extent = extent;
+    const float sig = extent * 0.3f;
+    g.gauss_den = 2.0f * sig * sig + 1e-9f;
+    g.influence = influence;
+    g.aggregation = aggregation;
+    const int tiles_w = (Cin / 32) * 2 * (Cout / TC_NCH);
+    kpconv_prep_w_kernel<<<tiles_w, 256, 0, st>>>(k_values, K, Cin, Cout, (uint8_t *)ws);
+    if (int e = finish_launch("kpconv_prep_w")) return e;
+    const size_t smem = TC_A_BYTES + TC_W_BYTES + (size_t)TC_PWARPS * TC_SCRATCH_FLOATS * sizeof(float) + 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(kpconv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
+        attr_done = true;
+    }
+    uint32_t cols = 32;
+    while ((int)cols < Cout) cols <<= 1;
+    const int64_t ntiles = (n + TC_TILE - 1) / TC_TILE;
+    const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+    kpconv_fwd_tc_kernel<<<grid, TC_THREADS, smem, st>>>(query, support, neighbors, feat, k_points,
+                                                         (const uint8_t *)ws, n, N0, M, K, Cin, Cout, g, cols, out);
+    return finish_launch("kpconv_fwd_tc");
+}
+
+}  // namespace p3d

@@ -20,6 +20,11 @@ from . import _cabi
 
 INFLUENCE = {"constant": 0, "linear": 1, "gaussian": 2}
 AGGREGATION = {"sum": 0, "closest": 1}
+PRECISION = {"fp32": 0, "tensor": 1}
+# KPConv forward arithmetic: "tensor" = kernel-point contraction on tcgen05 (bf16 hi+lo split operands,
+# fp32 accumulate; <= 2e-5 of max|out| against the fp32 oracle) where the shape allows it,
+# "fp32" = exact fp32 SIMT kernel everywhere (<= 1e-5).
+KPCONV_PRECISION = "tensor"
 
 
 # ------------------------------------------------------------------ plumbing ---------------
@@ -413,7 +418,8 @@ def knn_interpolate(x, pos_x, pos_y, batch_x=None, batch_y=None, k: int = 3, num
 # -------------------------------------------------------------------- KPConv ---------------
 class _KPConv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, query, support, neighbors, feat, k_points, k_values, extent, influence, aggregation):
+    def forward(ctx, query, support, neighbors, feat, k_points, k_values, extent, influence, aggregation,
+                precision):
         dev = _require_cuda("KPConv_ops", query, support, neighbors, feat, k_points, k_values)
         query, support, feat = _f32(query), _f32(support), _f32(feat)
         k_points, k_values, neighbors = _f32(k_points), _f32(k_values), _i64(neighbors)
@@ -421,9 +427,11 @@ class _KPConv(torch.autograd.Function):
         N0, Cin = feat.shape
         K, _, Cout = k_values.shape
         out = torch.empty((n, Cout), dtype=torch.float32, device=dev)
+        ws_bytes = _cabi.lib().p3d_kpconv_fwd_ws_bytes(K, Cin, Cout) if precision else 0
+        ws = _workspace(ws_bytes, dev)
         _call(dev, "p3d_kpconv_fwd_f32", query.data_ptr(), support.data_ptr(), neighbors.data_ptr(), feat.data_ptr(),
               k_points.data_ptr(), k_values.data_ptr(), n, N0, M, K, Cin, Cout, float(extent), influence,
-              aggregation, out.data_ptr())
+              aggregation, precision, out.data_ptr(), _ptr(ws), ws_bytes)
         ctx.save_for_backward(query, support, neighbors, feat, k_points, k_values)
         ctx.cfg = (float(extent), influence, aggregation)
         return out
@@ -446,11 +454,11 @@ class _KPConv(torch.autograd.Function):
             _call(dev, "p3d_kpconv_bwd_f32", query.data_ptr(), support.data_ptr(), neighbors.data_ptr(),
                   feat.data_ptr(), k_points.data_ptr(), k_values.data_ptr(), grad_out.data_ptr(), n, N0, M, K, Cin,
                   Cout, extent, influence, aggregation, _ptr(dfeat), _ptr(dW), ws.data_ptr(), ws_bytes)
-        return None, None, None, dfeat, None, dW, None, None, None
+        return None, None, None, dfeat, None, dW, None, None, None, None
 
 
 def KPConv_ops(query_points, support_points, neighbors_indices, features, K_points, K_values, KP_extent,
-               KP_influence, aggregation_mode):
+               KP_influence, aggregation_mode, precision=None):
     """KPConv_ops (torch_points3d/modules/KPConv/convolution_ops.py:19-107), same positional
     signature.  neighbors_indices[n,M] int64; entries == support_points.shape[0] (or -1, as
     gathering.py:10 allows) are shadow neighbours.  Differentiable w.r.t. features and K_values
@@ -462,7 +470,8 @@ def KPConv_ops(query_points, support_points, neighbors_indices, features, K_poin
     if K_values.dim() != 3 or K_values.shape[0] != K_points.shape[0] or K_values.shape[1] != features.shape[1]:
         raise AssertionError("K_values must be [n_kernel_points, Cin, Cout]")
     return _KPConv.apply(query_points, support_points, neighbors_indices, features, K_points, K_values,
-                         float(KP_extent), INFLUENCE[KP_influence], AGGREGATION[aggregation_mode])
+                         float(KP_extent), INFLUENCE[KP_influence], AGGREGATION[aggregation_mode],
+                         PRECISION[precision or KPCONV_PRECISION])
 
 
 class _NeighborMax(torch.autograd.Function):
