@@ -28,15 +28,16 @@
 
 namespace p3d {
 
-constexpr int TC_TILE = 128;          // query points per tile (UMMA M)
+constexpr int TC_TILE = 64;           // query points per tile (rows 0-63 of the M = 128 MMA; rows 64-127 are junk)
+constexpr int TC_MMA_M = 128;
 constexpr int TC_PWARPS = 8;          // producer warps
 constexpr int TC_THREADS = (TC_PWARPS + 1) * 32;
 constexpr int TC_MCAP = 40;           // neighbours per point supported by this path
-constexpr int TC_KH = 8;              // kernel points per pass
 constexpr int TC_NCH = 32;            // output channels per MMA (UMMA N)
-constexpr int TC_A_BYTES = 2 * 4 * TC_TILE * 128;  // hi|lo x 4 chunks x 128 rows x 128 B = 128 KB
-constexpr int TC_W_BYTES = 2 * 4 * TC_NCH * 128;   // hi|lo x 4 chunks x 32 rows x 128 B  =  32 KB
-constexpr int TC_SCRATCH_FLOATS = TC_KH * TC_MCAP + TC_MCAP * 32;  // per producer warp: weights + staged rows
+constexpr int TC_A_CHUNK = TC_TILE * 128;            // one 64-K chunk of the A tile: 64 rows x 128 B = 8 KB
+constexpr int TC_A_BYTES = 2 * 8 * TC_A_CHUNK;       // hi|lo x 8 chunks = 128 KB
+constexpr int TC_W_PIECE = 2 * 4 * TC_NCH * 128;     // hi|lo x 4 chunks x 32 rows x 128 B = 32 KB (half a slab of K)
+constexpr int TC_SCRATCH_FLOATS = KP_K * TC_MCAP + TC_MCAP * 32;  // per producer warp: weights + staged rows
 
 // ---- tcgen05 / TMEM wrappers -------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols) {
@@ -100,20 +101,20 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 // ---- W image: bf16 hi/lo, K-major, 128-byte swizzled tiles ---------------------------------
-// tile(s, h, nc) = [hi|lo][4 chunks of 64 K][32 rows = outputs 32nc..][128 B]; K index inside a pass
-// = c * 8 + kk  (c = channel inside the 32-channel slab s, kk = kernel point inside half h).
+// piece(s, nc, q) = [hi|lo][4 chunks of 64 K][32 rows = outputs 32nc..][128 B], q = K half of the slab;
+// K index inside a slab = c * 16 + k  (c = channel inside the 32-channel slab s, k = kernel point,
+// kernel points >= K are zero rows).
 __global__ void __launch_bounds__(256)
 kpconv_prep_w_kernel(const float *__restrict__ W, int K, int Cin, int Cout, uint8_t *__restrict__ img) {
-    const int tile = blockIdx.x;  // ((s * 2 + h) * ncs + nc)
+    const int piece = blockIdx.x;  // ((s * ncs + nc) * 2 + q)
     const int ncs = Cout / TC_NCH;
-    const int nc = tile % ncs, h = (tile / ncs) & 1, s = tile / (2 * ncs);
-    uint8_t *base = img + (size_t)tile * TC_W_BYTES;
+    const int qh = piece & 1, nc = (piece >> 1) % ncs, s = (piece >> 1) / ncs;
+    uint8_t *base = img + (size_t)piece * TC_W_PIECE;
     for (int i = threadIdx.x; i < 4 * TC_NCH * 64; i += 256) {
         const int e = i & 63, r = (i >> 6) & 31, kc = i >> 11;
-        const int kidx = kc * 64 + e;
-        const int c = kidx >> 3, kk = kidx & 7;
-        const int kp = h * TC_KH + kk;
-        const float v = kp < K ? __ldg(W + ((int64_t)kp * Cin + s * 32 + c) * Cout + nc * TC_NCH + r) : 0.f;
+        const int kidx = (qh * 4 + kc) * 64 + e;
+        const int c = kidx >> 4, k = kidx & 15;
+        const float v = k < K ? __ldg(W + ((int64_t)k * Cin + s * 32 + c) * Cout + nc * TC_NCH + r) : 0.f;
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
         const int off = (kc * TC_NCH + r) * 128 + (((e >> 3) ^ (r & 7)) << 4) + ((e & 7) << 1);
@@ -122,7 +123,7 @@ kpconv_prep_w_kernel(const float *__restrict__ W, int K, int Cin, int Cout, uint
     }
 }
 
-// ---- producer: wf[8 kernel points][32 channels] of one query point ----------------------
+// ---- producer: wf[16 kernel points][32 channels] of one query point -----------------------
 struct TcPoint {
     int j0, j1;           // feature row of neighbour lane / 32+lane (-1 = shadow or absent)
     float x0, y0, z0;     // centred neighbour lane
@@ -146,80 +147,72 @@ __device__ __forceinline__ void tc_load_point(const float *__restrict__ q, const
     P.x1 = __fsub_rn(bx, qx); P.y1 = __fsub_rn(by, qy); P.z1 = __fsub_rn(bz, qz);
 }
 
-// influence weights of kernel points 8h .. 8h+7 on every neighbour: wsm[kk][m] and one bit mask of
+// influence of one kernel point, throughput version for the tensor path: sqrt.approx + multiply by
+// 1/extent instead of the correctly rounded sqrt and division of the fp32 path (difference <= 3 ulp of
+// the weight, far inside the bf16x2 operand error)
+__device__ __forceinline__ float tc_influence(float cx, float cy, float cz, const float4 kp, const KpGeom &g,
+                                              float inv_extent, float &d2) {
+    const float dx = cx - kp.x, dy = cy - kp.y, dz = cz - kp.z;
+    d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    if (g.influence == P3D_INFLUENCE_LINEAR) {
+        float r;
+        asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(d2));
+        return fmaxf(fmaf(-r, inv_extent, 1.0f), 0.f);
+    }
+    if (g.influence == P3D_INFLUENCE_CONSTANT) return 1.0f;
+    return __expf(-d2 / g.gauss_den);
+}
+
+// influence weights of all 16 kernel points on every neighbour: wsm[k][m] and one bit mask of
 // influencing neighbours per kernel point (mask0: neighbours 0-31, mask1: neighbours 32-39)
-__device__ __forceinline__ void tc_weights(const TcPoint &P, const float4 *kps, int K, int M, int h, const KpGeom &g,
-                                           float *wsm, unsigned (&mask0)[TC_KH], unsigned (&mask1)[TC_KH], int lane) {
+__device__ __forceinline__ void tc_weights(const TcPoint &P, const float4 *kps, int K, int M, const KpGeom &g,
+                                           float inv_extent, float *wsm, unsigned (&mask0)[KP_K],
+                                           unsigned (&mask1)[KP_K], int lane) {
+    const bool closest = g.aggregation == P3D_AGGREGATION_CLOSEST;
     // closest mode: the winning kernel point of every neighbour over ALL K kernel points (first minimum)
     int best0 = -1, best1 = -1;
-    if (g.aggregation == P3D_AGGREGATION_CLOSEST) {
+    if (closest) {
         float bd0 = CUDART_INF_F, bd1 = CUDART_INF_F;
         for (int k = 0; k < K; ++k) {
             const float4 kp = kps[k];
-            const float d0 = sqdist3(P.x0, P.y0, P.z0, kp.x, kp.y, kp.z);
-            const float d1 = sqdist3(P.x1, P.y1, P.z1, kp.x, kp.y, kp.z);
+            float d0, d1;
+            tc_influence(P.x0, P.y0, P.z0, kp, g, inv_extent, d0);
+            tc_influence(P.x1, P.y1, P.z1, kp, g, inv_extent, d1);
             if (d0 < bd0) { bd0 = d0; best0 = k; }
             if (d1 < bd1) { bd1 = d1; best1 = k; }
         }
     }
 #pragma unroll
-    for (int kk = 0; kk < TC_KH; ++kk) {
-        const int k = h * TC_KH + kk;
-        const float4 kp = kps[k];
-        float w = kp_influence(sqdist3(P.x0, P.y0, P.z0, kp.x, kp.y, kp.z), g);
-        if (g.aggregation == P3D_AGGREGATION_CLOSEST && best0 != k) w = 0.f;
+    for (int k = 0; k < KP_K; ++k) {
+        float d2;
+        float w = tc_influence(P.x0, P.y0, P.z0, kps[k], g, inv_extent, d2);
+        if (closest && best0 != k) w = 0.f;
         const bool nz = P.j0 >= 0 && k < K && w > 0.f;
-        mask0[kk] = __ballot_sync(0xffffffffu, nz);
-        wsm[kk * TC_MCAP + lane] = w;
-        mask1[kk] = 0u;
+        mask0[k] = __ballot_sync(0xffffffffu, nz);
+        wsm[k * TC_MCAP + lane] = w;
+        mask1[k] = 0u;
     }
     if (M > 32) {
-        // neighbours 32..39: lane = (mm = lane % 8, kq = lane / 8), two steps cover the 8 kernel points
+        // neighbours 32..39: lane = (mm = lane % 8, kq = lane / 8), four steps cover the 16 kernel points
         const int mm = lane & 7, kq = lane >> 3;
         const float cx = __shfl_sync(0xffffffffu, P.x1, mm), cy = __shfl_sync(0xffffffffu, P.y1, mm);
         const float cz = __shfl_sync(0xffffffffu, P.z1, mm);
         const int jj = __shfl_sync(0xffffffffu, P.j1, mm);
         const int bb = __shfl_sync(0xffffffffu, best1, mm);
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
-            const int kk = kq + 4 * it;
-            const int k = h * TC_KH + kk;
-            const float4 kp = kps[k];
-            float w = kp_influence(sqdist3(cx, cy, cz, kp.x, kp.y, kp.z), g);
-            if (g.aggregation == P3D_AGGREGATION_CLOSEST && bb != k) w = 0.f;
+        for (int it = 0; it < 4; ++it) {
+            const int k = kq + 4 * it;
+            float d2;
+            float w = tc_influence(cx, cy, cz, kps[k], g, inv_extent, d2);
+            if (closest && bb != k) w = 0.f;
             const bool nz = jj >= 0 && k < K && w > 0.f;
             const unsigned bal = __ballot_sync(0xffffffffu, nz);
-            wsm[kk * TC_MCAP + 32 + mm] = w;
+            wsm[k * TC_MCAP + 32 + mm] = w;
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) mask1[qq + 4 * it] = (bal >> (8 * qq)) & 0xffu;
         }
     }
     __syncwarp();
-}
-
-// stage the neighbour rows named by `rows` (bit m -> neighbour base+m) into xs[m][lane]
-__device__ __forceinline__ void tc_stage_rows(unsigned rows, int jreg, int base, const float *__restrict__ xcol,
-                                              int Cin, float *xs, int lane) {
-    while (rows) {
-        int mm[4];
-        float v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            mm[u] = rows ? __ffs(rows) - 1 : -1;
-            rows &= rows - 1;  // 0 stays 0
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            v[u] = 0.f;
-            if (mm[u] >= 0) {
-                const int j = __shfl_sync(0xffffffffu, jreg, mm[u]);
-                v[u] = __ldg(xcol + (int64_t)j * Cin);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (mm[u] >= 0) xs[(base + mm[u]) * 32 + lane] = v[u];
-    }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -230,9 +223,9 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
     extern __shared__ uint8_t smem_raw[];
     // the UMMA 128-byte swizzle atoms need 1024-byte aligned tiles (the launch adds 1 KB of slack)
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t *a_tile = smem;                       // [hi|lo][4][128][128 B]
-    uint8_t *w_tile = smem + TC_A_BYTES;          // [hi|lo][4][32][128 B]
-    float *scratch = reinterpret_cast<float *>(smem + TC_A_BYTES + TC_W_BYTES);
+    uint8_t *a_tile = smem;                       // [hi|lo][8 chunks][64 rows][128 B]
+    uint8_t *w_tile = smem + TC_A_BYTES;          // [hi|lo][4 chunks][32 rows][128 B]
+    float *scratch = reinterpret_cast<float *>(smem + TC_A_BYTES + TC_W_PIECE);
     __shared__ float4 kps[KP_K];
     __shared__ __align__(8) uint64_t bar_a_empty, bar_w_full, bar_w_empty, bar_d_full;
     __shared__ uint32_t tmem_base_s;
@@ -240,6 +233,7 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slabs = Cin / 32, ncs = Cout / TC_NCH;
     const int64_t ntiles = (n + TC_TILE - 1) / TC_TILE;
+    const float inv_extent = 1.0f / g.extent;
 
     if (tid < KP_K) kps[tid] = tid < K ? make_float4(__ldg(kp + 3 * tid), __ldg(kp + 3 * tid + 1), __ldg(kp + 3 * tid + 2), 0.f)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -257,95 +251,111 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
     const uint32_t tmem_base = tmem_base_s;
 
     uint32_t pass = 0;       // global pass counter (phase of bar_a_empty)
-    uint32_t wloads = 0;     // W tiles loaded so far (phases of bar_w_full / bar_w_empty; MMA thread only)
+    uint32_t wloads = 0;     // W pieces loaded so far (phases of bar_w_full / bar_w_empty; MMA thread only)
     uint32_t tile_iter = 0;  // phase of bar_d_full
+    constexpr int PPW = TC_TILE / TC_PWARPS;  // points per producer warp and pass
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
         const int64_t p_base = tile * TC_TILE;
-        for (int sl = 0; sl < slabs; ++sl) {
-            for (int h = 0; h < 2; ++h, ++pass) {
-                if (warp < TC_PWARPS) {
-                    // ------------------------------------------------ producers ------------------
-                    float *wsm = scratch + (size_t)warp * TC_SCRATCH_FLOATS;
-                    float *xs = wsm + TC_KH * TC_MCAP;
-                    if (pass > 0) mbar_wait(&bar_a_empty, (pass - 1) & 1);  // previous pass' MMAs have read the A tile
-                    for (int pi = 0; pi < TC_TILE / TC_PWARPS; ++pi) {
-                        const int row = warp * (TC_TILE / TC_PWARPS) + pi;
-                        const int64_t p = p_base + row;
-                        float acc[TC_KH];
-#pragma unroll
-                        for (int kk = 0; kk < TC_KH; ++kk) acc[kk] = 0.f;
-                        if (p < n) {
-                            TcPoint P;
-                            tc_load_point(q + 3 * p, s, nb + p * M, N0, M, lane, P);
-                            unsigned mask0[TC_KH], mask1[TC_KH];
-                            tc_weights(P, kps, K, M, h, g, wsm, mask0, mask1, lane);
-                            unsigned rows0 = 0u, rows1 = 0u;
-#pragma unroll
-                            for (int kk = 0; kk < TC_KH; ++kk) { rows0 |= mask0[kk]; rows1 |= mask1[kk]; }
-                            const float *xcol = x + sl * 32 + lane;
-                            tc_stage_rows(rows0, P.j0, 0, xcol, Cin, xs, lane);
-                            tc_stage_rows(rows1, P.j1, 32, xcol, Cin, xs, lane);
-#pragma unroll
-                            for (int kk = 0; kk < TC_KH; ++kk) {
-                                unsigned mk = mask0[kk];
-                                float a = 0.f;
-                                while (mk) {
-                                    const int m = __ffs(mk) - 1;
-                                    mk &= mk - 1;
-                                    a = fmaf(wsm[kk * TC_MCAP + m], xs[m * 32 + lane], a);
-                                }
-                                mk = mask1[kk];
-                                while (mk) {
-                                    const int m = 32 + __ffs(mk) - 1;
-                                    mk &= mk - 1;
-                                    a = fmaf(wsm[kk * TC_MCAP + m], xs[m * 32 + lane], a);
-                                }
-                                acc[kk] = a;
-                            }
-                            __syncwarp();  // wsm / xs are rewritten for the next point
-                        }
-                        // bf16 hi/lo split, K index = lane * 8 + kk: 16 contiguous bytes per lane
-                        uint32_t hi[4], lo[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float a0 = acc[2 * u], a1 = acc[2 * u + 1];
-                            const float h0 = __bfloat162float(__float2bfloat16_rn(a0));
-                            const float h1 = __bfloat162float(__float2bfloat16_rn(a1));
-                            hi[u] = pack_bf16(h0, h1);
-                            lo[u] = pack_bf16(a0 - h0, a1 - h1);
-                        }
-                        const int off = ((lane >> 3) * TC_TILE + row) * 128 + (((lane & 7) ^ (row & 7)) << 4);
-                        *reinterpret_cast<uint4 *>(a_tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4 *>(a_tile + TC_A_BYTES / 2 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    }
-                    fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+        for (int sl = 0; sl < slabs; ++sl, ++pass) {
+            if (warp < TC_PWARPS) {
+                // ---------------------------------------------------- producers ------------------
+                float *wsm = scratch + (size_t)warp * TC_SCRATCH_FLOATS;
+                float *xs = wsm + KP_K * TC_MCAP;
+                const float *xcol = x + sl * 32 + lane;
+                TcPoint P, Pn;
+                {
+                    const int64_t p = p_base + warp * PPW;
+                    if (p < n) tc_load_point(q + 3 * p, s, nb + p * M, N0, M, lane, P);
                 }
-                __syncthreads();  // A tile of this pass complete (the MMA warp waits here too)
-                if (warp == TC_PWARPS) {
-                    // ------------------------------------------------ MMA issuer -----------------
-                    tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t idesc = tc_idesc(TC_TILE, TC_NCH);
-                        const uint32_t a_addr = smem_u32(a_tile), w_addr = smem_u32(w_tile);
-                        for (int nc = 0; nc < ncs; ++nc, ++wloads) {
-                            if (wloads > 0) mbar_wait(&bar_w_empty, (wloads - 1) & 1);  // W tile buffer is free
-                            mbar_arrive_expect_tx(&bar_w_full, TC_W_BYTES);
-                            bulk_g2s(w_tile, wimg + ((size_t)(sl * 2 + h) * ncs + nc) * TC_W_BYTES, TC_W_BYTES,
+                if (pass > 0) mbar_wait(&bar_a_empty, (pass - 1) & 1);  // the previous pass' MMAs have read the A tile
+                for (int pi = 0; pi < PPW; ++pi) {
+                    const int row = warp * PPW + pi;
+                    const int64_t p = p_base + row;
+                    float acc[KP_K];
+#pragma unroll
+                    for (int k = 0; k < KP_K; ++k) acc[k] = 0.f;
+                    if (p < n) {
+                        // all neighbour rows of this point in flight at once (their latency hides behind the
+                        // influence weights), and the geometry of the NEXT point right behind them
+                        float v[TC_MCAP];
+#pragma unroll
+                        for (int m = 0; m < TC_MCAP; ++m) {
+                            const int j = __shfl_sync(0xffffffffu, m < 32 ? P.j0 : P.j1, m & 31);
+                            v[m] = (m < M && j >= 0) ? __ldg(xcol + (int64_t)j * Cin) : 0.f;
+                        }
+                        if (pi + 1 < PPW && p + 1 < n) tc_load_point(q + 3 * (p + 1), s, nb + (p + 1) * M, N0, M, lane, Pn);
+                        unsigned mask0[KP_K], mask1[KP_K];
+                        tc_weights(P, kps, K, M, g, inv_extent, wsm, mask0, mask1, lane);
+#pragma unroll
+                        for (int m = 0; m < TC_MCAP; ++m) xs[m * 32 + lane] = v[m];
+#pragma unroll
+                        for (int k = 0; k < KP_K - 1; ++k) {  // kernel point 15 is padding
+                            unsigned mk = mask0[k];
+                            float a = 0.f;
+                            while (mk) {
+                                const int m = __ffs(mk) - 1;
+                                mk &= mk - 1;
+                                a = fmaf(wsm[k * TC_MCAP + m], xs[m * 32 + lane], a);
+                            }
+                            mk = mask1[k];
+                            while (mk) {
+                                const int m = 32 + __ffs(mk) - 1;
+                                mk &= mk - 1;
+                                a = fmaf(wsm[k * TC_MCAP + m], xs[m * 32 + lane], a);
+                            }
+                            acc[k] = a;
+                        }
+                        __syncwarp();  // wsm is rewritten for the next point
+                        P = Pn;
+                    }
+                    // bf16 hi/lo split; K index = lane * 16 + k: 32 contiguous bytes per lane and operand
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float a0 = acc[2 * u], a1 = acc[2 * u + 1];
+                        const float h0 = __bfloat162float(__float2bfloat16_rn(a0));
+                        const float h1 = __bfloat162float(__float2bfloat16_rn(a1));
+                        hi[u] = pack_bf16(h0, h1);
+                        lo[u] = pack_bf16(a0 - h0, a1 - h1);
+                    }
+                    uint8_t *rowp = a_tile + (lane >> 2) * TC_A_CHUNK + row * 128;
+                    const int g0 = (lane & 3) * 2, sw = row & 7;
+                    *reinterpret_cast<uint4 *>(rowp + ((g0 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4 *>(rowp + (((g0 + 1) ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    rowp += TC_A_BYTES / 2;
+                    *reinterpret_cast<uint4 *>(rowp + ((g0 ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4 *>(rowp + (((g0 + 1) ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                }
+                fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+            }
+            __syncthreads();  // A tile of this pass complete (the MMA warp waits here too)
+            if (warp == TC_PWARPS) {
+                // ---------------------------------------------------- MMA issuer -----------------
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t idesc = tc_idesc(TC_MMA_M, TC_NCH);
+                    const uint32_t a_addr = smem_u32(a_tile), w_addr = smem_u32(w_tile);
+                    for (int nc = 0; nc < ncs; ++nc) {
+                        const uint32_t d = tmem_base + (uint32_t)(nc * TC_NCH);
+                        for (int qh = 0; qh < 2; ++qh, ++wloads) {
+                            if (wloads > 0) mbar_wait(&bar_w_empty, (wloads - 1) & 1);  // W buffer is free
+                            mbar_arrive_expect_tx(&bar_w_full, TC_W_PIECE);
+                            bulk_g2s(w_tile, wimg + ((size_t)(sl * ncs + nc) * 2 + qh) * TC_W_PIECE, TC_W_PIECE,
                                      &bar_w_full);
                             mbar_wait(&bar_w_full, wloads & 1);
                             tc_fence_after();
-                            const uint32_t d = tmem_base + (uint32_t)(nc * TC_NCH);
 #pragma unroll 1
                             for (int kc = 0; kc < 4; ++kc) {
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks) {
                                     const uint32_t ko = (uint32_t)(ks * 32);
-                                    const uint64_t a_hi = tc_smem_desc(a_addr + kc * (TC_TILE * 128) + ko);
-                                    const uint64_t a_lo = tc_smem_desc(a_addr + TC_A_BYTES / 2 + kc * (TC_TILE * 128) + ko);
+                                    const uint32_t ac = a_addr + (uint32_t)((qh * 4 + kc) * TC_A_CHUNK) + ko;
+                                    const uint64_t a_hi = tc_smem_desc(ac);
+                                    const uint64_t a_lo = tc_smem_desc(ac + TC_A_BYTES / 2);
                                     const uint64_t b_hi = tc_smem_desc(w_addr + kc * (TC_NCH * 128) + ko);
-                                    const uint64_t b_lo = tc_smem_desc(w_addr + TC_W_BYTES / 2 + kc * (TC_NCH * 128) + ko);
-                                    const uint32_t first = (sl == 0 && h == 0 && kc == 0 && ks == 0) ? 0u : 1u;
+                                    const uint64_t b_lo = tc_smem_desc(w_addr + TC_W_PIECE / 2 + kc * (TC_NCH * 128) + ko);
+                                    const uint32_t first = (sl == 0 && qh == 0 && kc == 0 && ks == 0) ? 0u : 1u;
                                     tc_mma_bf16(d, a_hi, b_hi, idesc, first);
                                     tc_mma_bf16(d, a_lo, b_hi, idesc, 1u);
                                     tc_mma_bf16(d, a_hi, b_lo, idesc, 1u);
@@ -353,15 +363,15 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                             }
                             tc_commit(&bar_w_empty);
                         }
-                        tc_commit(&bar_a_empty);
-                        if (sl == slabs - 1 && h == 1) tc_commit(&bar_d_full);
                     }
-                    __syncwarp();
+                    tc_commit(&bar_a_empty);
+                    if (sl == slabs - 1) tc_commit(&bar_d_full);
                 }
+                __syncwarp();
             }
         }
-        // ---------------------------------------------------------- epilogue --------------------
-        if (warp < 4) {
+        // -------------------------------------------------------------- epilogue ----------------
+        if (warp < TC_TILE / 32) {
             mbar_wait(&bar_d_full, tile_iter & 1);
             tc_fence_after();
             const int64_t p = p_base + warp * 32 + lane;
@@ -386,7 +396,7 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
 
 size_t kpconv_tc_ws_bytes(int K, int Cin, int Cout) {
     if (K > KP_K || Cin % 32 != 0 || Cout % TC_NCH != 0 || Cout > 512) return 0;
-    return (size_t)(Cin / 32) * 2 * (Cout / TC_NCH) * TC_W_BYTES;
+    return (size_t)(Cin / 32) * (Cout / TC_NCH) * 2 * TC_W_PIECE;
 }
 
 // returns 1 when the shape is not supported by this path (the caller then runs the fp32 SIMT kernel)
@@ -403,10 +413,10 @@ int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neigh
     g.gauss_den = 2.0f * sig * sig + 1e-9f;
     g.influence = influence;
     g.aggregation = aggregation;
-    const int tiles_w = (Cin / 32) * 2 * (Cout / TC_NCH);
+    const int tiles_w = (Cin / 32) * (Cout / TC_NCH) * 2;
     kpconv_prep_w_kernel<<<tiles_w, 256, 0, st>>>(k_values, K, Cin, Cout, (uint8_t *)ws);
     if (int e = finish_launch("kpconv_prep_w")) return e;
-    const size_t smem = TC_A_BYTES + TC_W_BYTES + (size_t)TC_PWARPS * TC_SCRATCH_FLOATS * sizeof(float) + 1024;
+    const size_t smem = TC_A_BYTES + TC_W_PIECE + (size_t)TC_PWARPS * TC_SCRATCH_FLOATS * sizeof(float) + 1024;
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(kpconv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
