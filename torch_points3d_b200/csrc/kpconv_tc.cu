@@ -150,25 +150,27 @@ __device__ __forceinline__ void tc_load_point(const float *__restrict__ q, const
 // influence of one kernel point, throughput version for the tensor path: sqrt.approx + multiply by
 // 1/extent instead of the correctly rounded sqrt and division of the fp32 path (difference <= 3 ulp of
 // the weight, far inside the bf16x2 operand error)
+template <int INFL>
 __device__ __forceinline__ float tc_influence(float cx, float cy, float cz, const float4 kp, const KpGeom &g,
                                               float inv_extent, float &d2) {
     const float dx = cx - kp.x, dy = cy - kp.y, dz = cz - kp.z;
     d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    if (g.influence == P3D_INFLUENCE_LINEAR) {
+    if (INFL == P3D_INFLUENCE_LINEAR) {
         float r;
         asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(d2));
         return fmaxf(fmaf(-r, inv_extent, 1.0f), 0.f);
     }
-    if (g.influence == P3D_INFLUENCE_CONSTANT) return 1.0f;
+    if (INFL == P3D_INFLUENCE_CONSTANT) return 1.0f;
     return __expf(-d2 / g.gauss_den);
 }
 
 // influence weights of all 16 kernel points on every neighbour: wsm[k][m] and one bit mask of
 // influencing neighbours per kernel point (mask0: neighbours 0-31, mask1: neighbours 32-39)
+template <int INFL, bool CLOSEST>
 __device__ __forceinline__ void tc_weights(const TcPoint &P, const float4 *kps, int K, int M, const KpGeom &g,
                                            float inv_extent, float *wsm, unsigned (&mask0)[KP_K],
                                            unsigned (&mask1)[KP_K], int lane) {
-    const bool closest = g.aggregation == P3D_AGGREGATION_CLOSEST;
+    constexpr bool closest = CLOSEST;
     // closest mode: the winning kernel point of every neighbour over ALL K kernel points (first minimum)
     int best0 = -1, best1 = -1;
     if (closest) {
@@ -176,8 +178,8 @@ __device__ __forceinline__ void tc_weights(const TcPoint &P, const float4 *kps, 
         for (int k = 0; k < K; ++k) {
             const float4 kp = kps[k];
             float d0, d1;
-            tc_influence(P.x0, P.y0, P.z0, kp, g, inv_extent, d0);
-            tc_influence(P.x1, P.y1, P.z1, kp, g, inv_extent, d1);
+            tc_influence<INFL>(P.x0, P.y0, P.z0, kp, g, inv_extent, d0);
+            tc_influence<INFL>(P.x1, P.y1, P.z1, kp, g, inv_extent, d1);
             if (d0 < bd0) { bd0 = d0; best0 = k; }
             if (d1 < bd1) { bd1 = d1; best1 = k; }
         }
@@ -185,7 +187,7 @@ __device__ __forceinline__ void tc_weights(const TcPoint &P, const float4 *kps, 
 #pragma unroll
     for (int k = 0; k < KP_K; ++k) {
         float d2;
-        float w = tc_influence(P.x0, P.y0, P.z0, kps[k], g, inv_extent, d2);
+        float w = tc_influence<INFL>(P.x0, P.y0, P.z0, kps[k], g, inv_extent, d2);
         if (closest && best0 != k) w = 0.f;
         const bool nz = P.j0 >= 0 && k < K && w > 0.f;
         mask0[k] = __ballot_sync(0xffffffffu, nz);
@@ -203,7 +205,7 @@ __device__ __forceinline__ void tc_weights(const TcPoint &P, const float4 *kps, 
         for (int it = 0; it < 4; ++it) {
             const int k = kq + 4 * it;
             float d2;
-            float w = tc_influence(cx, cy, cz, kps[k], g, inv_extent, d2);
+            float w = tc_influence<INFL>(cx, cy, cz, kps[k], g, inv_extent, d2);
             if (closest && bb != k) w = 0.f;
             const bool nz = jj >= 0 && k < K && w > 0.f;
             const unsigned bal = __ballot_sync(0xffffffffu, nz);
@@ -215,6 +217,7 @@ __device__ __forceinline__ void tc_weights(const TcPoint &P, const float4 *kps, 
     __syncwarp();
 }
 
+template <int INFL, bool CLOSEST>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, const int64_t *__restrict__ nb,
                      const float *__restrict__ x, const float *__restrict__ kp, const uint8_t *__restrict__ wimg,
@@ -286,21 +289,15 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                         }
                         if (pi + 1 < PPW && p + 1 < n) tc_load_point(q + 3 * (p + 1), s, nb + (p + 1) * M, N0, M, lane, Pn);
                         unsigned mask0[KP_K], mask1[KP_K];
-                        tc_weights(P, kps, K, M, g, inv_extent, wsm, mask0, mask1, lane);
+                        tc_weights<INFL, CLOSEST>(P, kps, K, M, g, inv_extent, wsm, mask0, mask1, lane);
 #pragma unroll
                         for (int m = 0; m < TC_MCAP; ++m) xs[m * 32 + lane] = v[m];
 #pragma unroll
                         for (int k = 0; k < KP_K - 1; ++k) {  // kernel point 15 is padding
-                            unsigned mk = mask0[k];
+                            unsigned long long mk = ((unsigned long long)mask1[k] << 32) | mask0[k];
                             float a = 0.f;
                             while (mk) {
-                                const int m = __ffs(mk) - 1;
-                                mk &= mk - 1;
-                                a = fmaf(wsm[k * TC_MCAP + m], xs[m * 32 + lane], a);
-                            }
-                            mk = mask1[k];
-                            while (mk) {
-                                const int m = 32 + __ffs(mk) - 1;
+                                const int m = __ffsll((long long)mk) - 1;
                                 mk &= mk - 1;
                                 a = fmaf(wsm[k * TC_MCAP + m], xs[m * 32 + lane], a);
                             }
@@ -417,17 +414,26 @@ int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neigh
     kpconv_prep_w_kernel<<<tiles_w, 256, 0, st>>>(k_values, K, Cin, Cout, (uint8_t *)ws);
     if (int e = finish_launch("kpconv_prep_w")) return e;
     const size_t smem = TC_A_BYTES + TC_W_PIECE + (size_t)TC_PWARPS * TC_SCRATCH_FLOATS * sizeof(float) + 1024;
+    using Kern = void (*)(const float *, const float *, const int64_t *, const float *, const float *, const uint8_t *,
+                          int64_t, int64_t, int, int, int, int, KpGeom, uint32_t, float *);
+    static const Kern kerns[3][2] = {
+        {kpconv_fwd_tc_kernel<P3D_INFLUENCE_CONSTANT, false>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_CONSTANT, true>},
+        {kpconv_fwd_tc_kernel<P3D_INFLUENCE_LINEAR, false>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_LINEAR, true>},
+        {kpconv_fwd_tc_kernel<P3D_INFLUENCE_GAUSSIAN, false>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_GAUSSIAN, true>}};
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(kpconv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 2; ++b)
+                cudaFuncSetAttribute(kerns[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
         attr_done = true;
     }
     uint32_t cols = 32;
     while ((int)cols < Cout) cols <<= 1;
     const int64_t ntiles = (n + TC_TILE - 1) / TC_TILE;
     const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
-    kpconv_fwd_tc_kernel<<<grid, TC_THREADS, smem, st>>>(query, support, neighbors, feat, k_points,
-                                                         (const uint8_t *)ws, n, N0, M, K, Cin, Cout, g, cols, out);
+    kerns[influence][aggregation]<<<grid, TC_THREADS, smem, st>>>(query, support, neighbors, feat, k_points,
+                                                                  (const uint8_t *)ws, n, N0, M, K, Cin, Cout, g, cols,
+                                                                  out);
     return finish_launch("kpconv_fwd_tc");
 }
 
