@@ -285,6 +285,7 @@ def run_b200(args):
                 "algorithmic_bytes": dom_bytes, "avg_launch_ms": round(dom_ms, 5), "peak_source": peaks_src}
 
     kp = bench_kpconv(dev, args) if not args.skip_extras else None
+    c4 = bench_c4(dev) if not args.skip_extras else None
     cpu = cpu_baseline(max_seconds=12.0) if not args.skip_extras else None
 
     clouds = B_CLOUDS * world * args.steps
@@ -303,7 +304,7 @@ def run_b200(args):
                 "ms_per_step": round(e2e_ms_total / args.steps, 4)},
         "gpu_launches": int(launches_per_step * args.steps),
         "launches_per_step": int(launches_per_step),
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "kpconv": kp,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "kpconv": kp, "c4": c4,
     }
     print(json.dumps(line))
     if world > 1:
@@ -351,7 +352,11 @@ def bench_kpconv(dev, args):
 
     def fwd():
         with torch.no_grad():
-            return ops.KPConv_ops(pos, pos, nb, x, kp, W, 0.04, "linear", "sum")
+            return ops.KPConv_ops(pos, pos, nb, x, kp, W, 0.04, "linear", "sum", precision="tensor")
+
+    def fwd_fp32():
+        with torch.no_grad():
+            return ops.KPConv_ops(pos, pos, nb, x, kp, W, 0.04, "linear", "sum", precision="fp32")
 
     def fwd_bwd():
         out = ops.KPConv_ops(pos, pos, nb, x, kp, W, 0.04, "linear", "sum")
@@ -360,13 +365,61 @@ def bench_kpconv(dev, args):
     def query():
         ops.ball_query(0.1, 34, pos, pos, mode="partial_dense", batch_x=batch, batch_y=batch, return_dist=False)
 
-    t_f, t_fb, t_q = timed(fwd), timed(fwd_bwd), timed(query)
+    t_f, t_f32, t_fb, t_q = timed(fwd), timed(fwd_fp32), timed(fwd_bwd), timed(query)
+    with torch.no_grad():
+        err = float((fwd() - fwd_fp32()).abs().max() / fwd_fp32().abs().max())
     flops = n * (2 * 15 * 34 * 32 + 2 * 15 * 32 * 32 + 12 * 15 * 34)
-    return {"workload": "C3 layer 0b: KPConv 32->32, %d points in 8 spheres, M=34, K=15, linear/sum" % n,
-            "fwd_points_per_s": round(n / (t_f * 1e-3), 1), "fwd_ms": round(t_f, 4),
-            "fwd_bwd_points_per_s": round(n / (t_fb * 1e-3), 1), "fwd_bwd_ms": round(t_fb, 4),
-            "fwd_tflops": round(flops / (t_f * 1e-3) / 1e12, 3),
-            "neighbour_search_ms": round(t_q, 4), "unit": "points/s"}
+    peaks, _ = _peaks()
+    res = {"workload": "C3 layer 0b: KPConv 32->32, %d points in 8 spheres, M=34, K=15, linear/sum" % n,
+           "fwd_points_per_s": round(n / (t_f * 1e-3), 1), "fwd_ms": round(t_f, 4),
+           "fwd_path": "tcgen05 (bf16 hi+lo operands, fp32 accumulate in TMEM)",
+           "fwd_fp32_simt_points_per_s": round(n / (t_f32 * 1e-3), 1), "fwd_fp32_simt_ms": round(t_f32, 4),
+           "tensor_vs_fp32_max_rel_diff": float("%.3e" % err),
+           "fwd_bwd_points_per_s": round(n / (t_fb * 1e-3), 1), "fwd_bwd_ms": round(t_fb, 4),
+           "fwd_tflops": round(flops / (t_f * 1e-3) / 1e12, 3),
+           "neighbour_search_ms": round(t_q, 4), "unit": "points/s"}
+    prof = os.path.join(ROOT, "profiles", "kpconv_tensor_pipe.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as f:
+                res["tensor_pipe"] = json.load(f)
+        except Exception:  # noqa: BLE001
+            pass
+    return res
+
+
+def bench_c4(dev):
+    """C4 (BASELINE.json configs[3]): SemanticKITTI-shaped FPS 4096 of 120k + knn k=16, this rank's clouds"""
+    import torch
+    from torch_points3d_b200 import ops, synthetic
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    from torch_points3d_b200.sharding import cloud_range
+    lo, hi = cloud_range(8, world, rank)
+    if hi <= lo:
+        return None
+    scans = torch.from_numpy(synthetic.lidar_scans(B=8)[lo:hi]).to(dev)
+    b = hi - lo
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    x = scans.reshape(-1, 3)
+    bx = torch.arange(b, device=dev).repeat_interleave(120000)
+    by = torch.arange(b, device=dev).repeat_interleave(4096)
+
+    def step():
+        qi = ops.furthest_point_sample(scans, 4096)
+        q = scans.gather(1, qi.unsqueeze(-1).expand(-1, -1, 3)).reshape(-1, 3)
+        return ops.knn_table(x, q, 16, bx, by, return_dist=False)[0]
+
+    step()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(2):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 2
+    return {"workload": "C4: FPS 4096 of 120000 + knn k=16, %d of 8 scans on this rank" % b,
+            "ms_per_batch": round(ms, 3), "clouds_per_s": round(b / (ms * 1e-3), 2)}
 
 
 # ------------------------------------------------------------ CPU arm (oracle port) -----------

@@ -264,8 +264,21 @@ static int fps_dispatch(const float *xyz, const int64_t *ptr, int64_t n_dense, c
     if (clouds == 0) return P3D_OK;
     // tuning hook (bench/tune_fps.py): P3D_FPS_FORCE="T,PPT" selects a single-CTA variant by hand
     if (const char *force = getenv("P3D_FPS_FORCE")) {
-        int ft = 0, fp = 0;
-        if (sscanf(force, "%d,%d", &ft, &fp) == 2 && (int64_t)ft * fp >= max_n) {
+        int ft = 0, fp = 0, fc = 1;
+        const int nf = sscanf(force, "%d,%d,%d", &ft, &fp, &fc);
+        if (nf == 3 && fc > 1 && (int64_t)ft * fp * fc >= max_n) {
+#define P3D_FPS_FORCED_CL(T, PPT, CL) \
+    if (ft == T && fp == PPT && fc == CL) \
+        return launch_reg<T, PPT, CL, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, clouds, st);
+            P3D_FPS_FORCED_CL(1024, 8, 16) P3D_FPS_FORCED_CL(512, 16, 16) P3D_FPS_FORCED_CL(256, 32, 16)
+            P3D_FPS_FORCED_CL(1024, 8, 8) P3D_FPS_FORCED_CL(512, 16, 8) P3D_FPS_FORCED_CL(512, 8, 8)
+            P3D_FPS_FORCED_CL(512, 8, 16) P3D_FPS_FORCED_CL(256, 16, 16) P3D_FPS_FORCED_CL(512, 32, 8)
+            P3D_FPS_FORCED_CL(1024, 16, 8) P3D_FPS_FORCED_CL(256, 8, 8) P3D_FPS_FORCED_CL(256, 8, 4)
+            P3D_FPS_FORCED_CL(128, 16, 8) P3D_FPS_FORCED_CL(256, 4, 2) P3D_FPS_FORCED_CL(128, 8, 2)
+            P3D_FPS_FORCED_CL(256, 4, 4) P3D_FPS_FORCED_CL(128, 4, 4) P3D_FPS_FORCED_CL(128, 8, 4)
+#undef P3D_FPS_FORCED_CL
+        }
+        if (nf == 2 && (int64_t)ft * fp >= max_n) {
 #define P3D_FPS_FORCED(T, PPT) \
     if (ft == T && fp == PPT)  \
         return launch_reg<T, PPT, 1, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, clouds, st);
@@ -288,7 +301,10 @@ static int fps_dispatch(const float *xyz, const int64_t *ptr, int64_t n_dense, c
     P3D_FPS_CASE(16384, 1024, 8, 2)
     P3D_FPS_CASE(32768, 1024, 8, 4)
     P3D_FPS_CASE(65536, 1024, 8, 8)
-    P3D_FPS_CASE(131072, 1024, 8, 16)
+    // 65537..131072 points (measured on B200, profiles/r1_fps_tuning.md): a 16-CTA cluster needs a whole GPC, so
+    // only ~4 run at once; with more clouds than that, 8-CTA clusters of fatter threads finish the batch sooner
+    if (max_n <= 131072 && clouds > 4) return launch_reg<512, 32, 8, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, clouds, st);
+    P3D_FPS_CASE(131072, 256, 32, 16)
 #undef P3D_FPS_CASE
     if (ws == nullptr || ws_bytes < (size_t)total_rows * sizeof(float)) {
         set_error("fps: clouds of more than 131072 points need a workspace of %lld bytes",

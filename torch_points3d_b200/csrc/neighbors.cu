@@ -347,6 +347,101 @@ three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ kno
     }
 }
 
+
+// ------------------------------------------------ knn, k <= 32: warp per query, list in lanes ----
+// Same candidate sweep as the ball query (SoA shared-memory tile, 32 candidates per warp step).  The
+// sorted best-k list of a query lives in REGISTERS ACROSS THE LANES of its warp (lane e = rank e), so an
+// insertion is one ballot + one shfl_up + a select: ~10 warp instructions instead of a shared-memory
+// shift loop, and it never serialises other queries.  Candidates are admitted in index order with a
+// strict '<' against the current k-th distance and placed after all entries <= their distance, so equal
+// distances keep the lower index first (the oracle's insertion rule).
+template <bool DENSE, int QPW>
+__global__ void __launch_bounds__(NB_WARPS * 32)
+knn_lane_kernel(const float *__restrict__ x, const float *__restrict__ y, const int64_t *__restrict__ batch_x,
+                const int64_t *__restrict__ batch_y, int64_t Nx, int64_t Ny, int64_t n_dense, int64_t s_dense, int k,
+                int64_t *__restrict__ col, float *__restrict__ dout) {
+    constexpr int QPC = NB_WARPS * QPW;
+    __shared__ float sx[NB_TILE], sy[NB_TILE], sz[NB_TILE];
+    __shared__ RangeCache rc;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q0 = (int64_t)blockIdx.x * QPC;
+    const int64_t q1 = (q0 + QPC < Ny) ? q0 + QPC : Ny;
+    cta_ranges<DENSE>(q0, q1, batch_x, batch_y, Nx, rc, warp, lane);
+
+    float qx[QPW], qy[QPW], qz[QPW], tau[QPW], bd[QPW];
+    int bi[QPW];
+    int64_t x0[QPW], x1[QPW];
+#pragma unroll
+    for (int u = 0; u < QPW; ++u) {
+        const int64_t q = q0 + warp * QPW + u;
+        tau[u] = CUDART_INF_F;
+        bd[u] = CUDART_INF_F;  // lanes >= k never matter: the admission test uses lane k-1
+        bi[u] = -1;
+        if (q < q1) {
+            qx[u] = __ldg(y + 3 * q); qy[u] = __ldg(y + 3 * q + 1); qz[u] = __ldg(y + 3 * q + 2);
+            query_range<DENSE>(q, batch_x, batch_y, Nx, n_dense, s_dense, rc, lane, x0[u], x1[u]);
+        } else {
+            qx[u] = qy[u] = qz[u] = 0.f;
+            x0[u] = x1[u] = 0;
+        }
+    }
+    int64_t X0, X1;
+    {
+        int64_t a, b;
+        query_range<DENSE>(q0, batch_x, batch_y, Nx, n_dense, s_dense, rc, lane, a, b);
+        X0 = a;
+        query_range<DENSE>(q1 - 1, batch_x, batch_y, Nx, n_dense, s_dense, rc, lane, a, b);
+        X1 = b;
+    }
+    for (int64_t tb = X0; tb < X1; tb += NB_TILE) {
+        const int tn = (int)((X1 - tb < NB_TILE) ? (X1 - tb) : NB_TILE);
+        if (tb != X0) __syncthreads();
+        load_tile(x, tb, tn, sx, sy, sz, tid, NB_WARPS * 32);
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < QPW; ++u) {
+            const int lo = (int)((x0[u] > tb ? x0[u] : tb) - tb);
+            const int hi = (int)((x1[u] < tb + tn ? x1[u] : tb + tn) - tb);
+            float t = tau[u], d_l = bd[u];
+            int i_l = bi[u];
+            for (int i0 = lo; i0 < hi; i0 += 32) {
+                const int i = i0 + lane;
+                const bool ok = i < hi;
+                const int ii = ok ? i : lo;
+                const float d = sqdist3(sx[ii], sy[ii], sz[ii], qx[u], qy[u], qz[u]);
+                unsigned m = __ballot_sync(0xffffffffu, ok && d < t);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float nd = __shfl_sync(0xffffffffu, d, src);
+                    if (nd < t) {  // warp-uniform
+                        const unsigned gt = __ballot_sync(0xffffffffu, d_l > nd);  // ranks that move up by one
+                        const float up_d = __shfl_up_sync(0xffffffffu, d_l, 1);
+                        const int up_i = __shfl_up_sync(0xffffffffu, i_l, 1);
+                        const int first = __ffs(gt) - 1;  // gt != 0: lane k-1 holds tau > nd
+                        if (lane == first) { d_l = nd; i_l = (int)(tb - X0) + i0 + src; }
+                        else if (lane > first) { d_l = up_d; i_l = up_i; }
+                        t = __shfl_sync(0xffffffffu, d_l, k - 1);
+                        m &= __ballot_sync(0xffffffffu, d < t);  // drop candidates the tighter bound now rejects
+                    }
+                }
+            }
+            tau[u] = t; bd[u] = d_l; bi[u] = i_l;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < QPW; ++u) {
+        const int64_t q = q0 + warp * QPW + u;
+        if (q >= q1) continue;
+        const int64_t off = DENSE ? x0[u] : 0;
+        if (lane < k) {
+            const bool have = bi[u] >= 0;
+            col[q * k + lane] = have ? (X0 + bi[u] - off) : -1;
+            if (dout) dout[q * k + lane] = have ? bd[u] : -1.f;
+        }
+    }
+}
+
 template <bool DENSE>
 static int launch_ball_query(const float *x, const float *y, const int64_t *bx, const int64_t *by, int64_t Nx,
                              int64_t Ny, int64_t n_dense, int64_t s_dense, float radius, int K, int strict,
@@ -370,6 +465,16 @@ static int launch_knn(const float *x, const float *y, const int64_t *bx, const i
                       int64_t n_dense, int64_t s_dense, int k, int sqrt_out, int64_t *col, float *d,
                       cudaStream_t st) {
     if (Ny == 0 || k == 0) return P3D_OK;
+    if (k <= 32 && !sqrt_out) {
+        if (Ny >= (int64_t)NB_WARPS * 4 * 2 * kNumSMs) {
+            const unsigned grid = (unsigned)((Ny + NB_WARPS * 4 - 1) / (NB_WARPS * 4));
+            knn_lane_kernel<DENSE, 4><<<grid, NB_WARPS * 32, 0, st>>>(x, y, bx, by, Nx, Ny, n_dense, s_dense, k, col, d);
+        } else {
+            const unsigned grid = (unsigned)((Ny + NB_WARPS - 1) / NB_WARPS);
+            knn_lane_kernel<DENSE, 1><<<grid, NB_WARPS * 32, 0, st>>>(x, y, bx, by, Nx, Ny, n_dense, s_dense, k, col, d);
+        }
+        return finish_launch("knn_lane");
+    }
     if (Ny >= (int64_t)NB_WARPS * 4 * 2 * kNumSMs && k <= 32) {
         const int64_t grid = (Ny + NB_WARPS * 4 - 1) / (NB_WARPS * 4);
         const size_t dyn = (size_t)NB_WARPS * 4 * k * 8;
