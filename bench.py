@@ -82,6 +82,31 @@ class Chain:
         for k, v in self.host.items():
             self.d[k].data.copy_(v, non_blocking=True)
 
+    def make_staging(self):
+        """two device staging sets: the H2D copy of step i+1 runs on a copy stream while step i computes"""
+        torch = self.torch
+        self.stage = [{k: torch.empty_like(v, device=self.dev) for k, v in self.host.items()} for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.staged = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.results = [self.torch.empty_like(self.result_host).pin_memory() for _ in range(2)]
+
+    def h2d_async(self, slot):
+        torch = self.torch
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[slot])  # the compute stream has read this staging set
+            for k, v in self.host.items():
+                self.stage[slot][k].copy_(v, non_blocking=True)
+            self.staged[slot].record(self.copy_stream)
+
+    def stage_to_inputs(self, slot):
+        torch = self.torch
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.staged[slot])
+        for k in self.host:
+            self.d[k].data.copy_(self.stage[slot][k], non_blocking=True)  # D2D into the graph's input buffers
+        self.consumed[slot].record(cur)
+
     def step(self):
         """returns a small result tensor: the sampled indices of both levels + a gradient checksum"""
         torch = self.torch
@@ -118,29 +143,31 @@ class Chain:
 
 
 class ClockSampler(threading.Thread):
+    """`nvidia-smi -lms 100` running beside the timed regions (the recipe's clocks line)"""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        self.index, self.samples, self.proc = index, [], None
 
     def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                if out.returncode == 0 and out.stdout.strip():
-                    self.samples.append([c.strip() for c in out.stdout.strip().split(",")])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.05)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if line.strip():
+                    self.samples.append([c.strip() for c in line.strip().split(",")])
+        except Exception:  # noqa: BLE001
+            pass
 
     def summary(self):
-        self._stop_evt.set()
-        self.join(timeout=6)
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=5)
         sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
@@ -220,6 +247,7 @@ def run_b200(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+        time.sleep(0.3)  # let the sampler come up before the timed regions
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -231,26 +259,34 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    clocks = sampler.summary() if sampler else None
 
-    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the result, every step ----
-    def e2e_step():
-        chain.upload()
-        out = one_step()
-        chain.result_host.copy_(out, non_blocking=True)
+    # ---- end to end: every step copies ITS inputs from pinned host memory (copy stream, one step ahead of
+    # the compute stream), runs the chain and reads its result back to pinned host memory ----
+    chain.make_staging()
+    for slot in range(2):
+        chain.consumed[slot].record(torch.cuda.current_stream())
 
-    for _ in range(max(3, args.warmup // 2)):
-        e2e_step()
+    def e2e_run(nsteps):
+        chain.h2d_async(0)
+        for i in range(nsteps):
+            slot = i & 1
+            if i + 1 < nsteps:
+                chain.h2d_async(slot ^ 1)
+            chain.stage_to_inputs(slot)
+            out = one_step()
+            chain.results[slot].copy_(out, non_blocking=True)
+
+    e2e_run(max(3, args.warmup // 2))
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     e1.record()
     barrier()
     ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_ms_total = float(ms2.item())
+    clocks = sampler.summary() if sampler else None
 
     if rank != 0:
         if world > 1:
