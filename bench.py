@@ -116,9 +116,8 @@ class Chain:
         check = torch.zeros((), device=self.dev)
         samples = []
         for li, l in enumerate(self.sa):
-            idx = ops.furthest_point_sample(pos, l["npoint"])
+            idx, new_pos = ops.furthest_point_sample(pos, l["npoint"], return_xyz=True)
             samples.append(idx)
-            new_pos = pos.gather(1, idx.unsqueeze(-1).expand(-1, -1, 3))
             for si, (r, k) in enumerate(zip(l["radii"], l["nsample"])):
                 ridx = ops.ball_query(r, k, pos, new_pos, return_dist=False)[0]
                 grouped = ops.group_features(feats[li], pos, new_pos, ridx)
@@ -128,9 +127,7 @@ class Chain:
             pos = new_pos
         # FP2: 512 unknown (SA1 level) from 128 known (SA2 level); FP3: 2048 unknown from 512 known
         for fi, (unknown, known, x) in enumerate([(d["pos1"], d["pos2"], d["x2"]), (d["pos"], d["pos1"], d["x3"])]):
-            dist, idx = ops.three_nn(unknown, known)
-            recip = 1.0 / (dist + 1e-8)                       # core/base_conv/dense.py:137-139
-            weight = recip / torch.sum(recip, dim=2, keepdim=True)
+            _, idx, weight = ops.three_nn(unknown, known, return_weight=True)  # weights of dense.py:137-139 fused
             out = ops.three_interpolate(x, idx, weight)
             (gx,) = torch.autograd.grad(out, x, self.g_fp[fi])
             check = check + gx[0, 0, 0]

@@ -59,10 +59,12 @@ const char *p3d_arch(void);
  * Start index 0, lowest-index tie-break.  idx_is_i64: 0 -> int32 out (what tpk's CUDA
  * path returns), 1 -> int64 out (what core/base_conv/dense.py:75 casts to).
  * N <= 131072 runs register-resident in one CTA / one thread-block cluster per cloud;
- * larger N needs `ws` = B*N floats (min-distance scratch). */
+ * larger N needs `ws` = B*N floats (min-distance scratch).
+ * new_xyz (nullable) [B,S,3]: the sampled coordinates, i.e. the `pos.gather(1, idx)` of
+ * core/base_conv/dense.py:75-76 for free (every round already knows its winner's coordinates). */
 size_t p3d_fps_dense_ws_bytes(int B, int N);
-int p3d_fps_dense_f32(const float *xyz, int B, int N, int S, void *idx, int idx_is_i64, void *ws, size_t ws_bytes,
-                      void *stream);
+int p3d_fps_dense_f32(const float *xyz, int B, int N, int S, void *idx, int idx_is_i64, float *new_xyz, void *ws,
+                      size_t ws_bytes, void *stream);
 
 /* Replaces torch_geometric.nn.fps(x, batch, ratio, random_start=False) == torch_cluster.fps
  *   reference call sites: core/spatial_ops/sampling.py:63,
@@ -109,9 +111,11 @@ int p3d_knn_dense_f32(const float *x, const float *y, int B, int N, int M, int k
                       void *stream);
 
 /* Replaces tp.three_nn(unknown[B,n,3], known[B,m,3]) -> (dist[B,n,3] = sqrt(d2), idx[B,n,3])
- *   reference call site: core/base_conv/dense.py:136 */
+ *   reference call site: core/base_conv/dense.py:136
+ * weight (nullable) [B,n,3]: the inverse-distance weights of core/base_conv/dense.py:137-139,
+ * (1/(d+1e-8)) / sum_t (1/(d_t+1e-8)), fused into the same kernel. */
 int p3d_three_nn_f32(const float *unknown, const float *known, int B, int n, int m, float *dist, int64_t *idx,
-                     void *stream);
+                     float *weight, void *stream);
 
 /* ----------------------------------------------------------- grouping ------
  * Replaces tp.grouping_operation(features[B,C,N], idx[B,S,K]) -> [B,C,S,K]

@@ -56,15 +56,15 @@ def test_sass_is_sm100a_only(cabi):
 def test_argument_validation_is_reported_not_crashed(cabi):
     lib = cabi.lib()
     # S > N is rejected on the host side of the ABI before any CUDA call
-    assert lib.p3d_fps_dense_f32(None, 1, 4, 5, None, 1, None, 0, None) == -1
+    assert lib.p3d_fps_dense_f32(None, 1, 4, 5, None, 1, None, None, 0, None) == -1
     assert b"npoint" in lib.p3d_last_error()
     assert lib.p3d_knn_batch_f32(None, None, None, None, 4, 4, 0, None, None, None) == -1
-    assert lib.p3d_three_nn_f32(None, None, 1, 4, 2, None, None, None) == -1
+    assert lib.p3d_three_nn_f32(None, None, 1, 4, 2, None, None, None, None) == -1
     assert lib.p3d_kpconv_fwd_f32(None, None, None, None, None, None, 4, 4, 200, 15, 8, 8, 1.0, 1, 0, 1, None, None,
                                   0, None) == -1
     assert lib.p3d_kpconv_fwd_ws_bytes(15, 32, 64) == 1 * 2 * 2 * 32768 and lib.p3d_kpconv_fwd_ws_bytes(15, 5, 64) == 0
     # empty problems are a successful no-op
-    assert lib.p3d_fps_dense_f32(None, 0, 4, 2, None, 1, None, 0, None) == 0
+    assert lib.p3d_fps_dense_f32(None, 0, 4, 2, None, 1, None, None, 0, None) == 0
     assert lib.p3d_ball_query_dense_f32(None, None, 0, 0, 0, 0.1, 4, 1, None, None, None) == 0
 
 

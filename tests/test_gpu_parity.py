@@ -63,6 +63,17 @@ def test_fps_dense_bit_exact(B, n, S):
     assert np.array_equal(got, oracle.fps_dense(xyz, S))
 
 
+def test_fps_fused_coordinates():
+    xyz = synthetic.surface_clouds(4, 3000, seed=9)
+    for S in (1, 257):
+        idx, new_xyz = ops.furthest_point_sample(T(xyz), S, return_xyz=True)
+        assert np.array_equal(N(idx), oracle.fps_dense(xyz, S))
+        assert np.array_equal(N(new_xyz), np.take_along_axis(xyz, N(idx)[..., None], 1))
+    big = synthetic.surface_clouds(1, 70000, seed=10)      # cluster path
+    idx, new_xyz = ops.furthest_point_sample(T(big), 40, return_xyz=True)
+    assert np.array_equal(N(new_xyz), np.take_along_axis(big, N(idx)[..., None], 1))
+
+
 def test_fps_ties_and_duplicates():
     dup = np.zeros((1, 6, 3), dtype=np.float32)
     dup[0, 2:4] = [1, 0, 0]
@@ -266,6 +277,9 @@ def test_knn_dense_and_three_nn():
         odist, oidx = oracle.three_nn(unknown, known)
         assert np.array_equal(N(idx), oidx)
         assert np.array_equal(N(dist), odist)  # correctly rounded sqrt on both sides
+    dist, idx, w = ops.three_nn(T(unknown), T(known), return_weight=True)
+    recip = 1.0 / (dist + 1e-8)                      # core/base_conv/dense.py:137-139
+    assert torch.allclose(w, recip / recip.sum(2, keepdim=True), rtol=1e-6, atol=0)
     known[:, 1] = known[:, 0]  # duplicated known point: tie -> lower index first
     dist, idx = ops.three_nn(T(unknown), T(known))
     assert np.array_equal(N(idx), oracle.three_nn(unknown, known)[1])

@@ -21,7 +21,7 @@ SIGNATURES = {
     "p3d_launch_count": (ctypes.c_uint64, []),
     "p3d_arch": (ctypes.c_char_p, []),
     "p3d_fps_dense_ws_bytes": (c_sz, [c_int, c_int]),
-    "p3d_fps_dense_f32": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_sz, c_vp]),
+    "p3d_fps_dense_f32": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_sz, c_vp]),
     "p3d_fps_csr_ws_bytes": (c_sz, [c_i64, c_i64]),
     "p3d_fps_csr_f32": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
     "p3d_ball_query_dense_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_f32, c_int, c_int, c_vp, c_vp, c_vp]),
@@ -29,7 +29,7 @@ SIGNATURES = {
                                          c_vp, c_vp]),
     "p3d_knn_batch_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp]),
     "p3d_knn_dense_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
-    "p3d_three_nn_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "p3d_three_nn_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "p3d_group_fwd_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64, c_int, c_vp]),
     "p3d_group_bwd_ws_bytes": (c_sz, [c_int, c_int, c_int, c_int, c_int]),
     "p3d_group_bwd_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64, c_int, c_vp, c_sz,

@@ -42,7 +42,7 @@ template <int T, int PPT, int CLUSTER, typename IdxT>
 __global__ void __launch_bounds__(T, 1)
 fps_reg_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr, int64_t n_dense,
                const int64_t *__restrict__ out_ptr, int64_t s_dense, IdxT *__restrict__ out,
-               const int64_t *__restrict__ first) {
+               const int64_t *__restrict__ first, float *__restrict__ new_xyz) {
     constexpr int NW = T / 32;
     __shared__ FpsRec rec[2][32];
     __shared__ FpsRec crec[2][CLUSTER];
@@ -95,7 +95,10 @@ fps_reg_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr, i
         ly = p[3 * f0 + 1];
         lz = p[3 * f0 + 2];
     }
-    if (tid == 0 && rank == 0 && s > 0) out[obase] = (IdxT)(add + f0);
+    if (tid == 0 && rank == 0 && s > 0) {
+        out[obase] = (IdxT)(add + f0);
+        if (new_xyz) { new_xyz[3 * obase] = lx; new_xyz[3 * obase + 1] = ly; new_xyz[3 * obase + 2] = lz; }
+    }
 
     for (int64_t r = 1; r < s; ++r) {
         const int buf = (int)(r & 1);
@@ -137,7 +140,10 @@ fps_reg_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr, i
             lx = rec[buf][src].x;
             ly = rec[buf][src].y;
             lz = rec[buf][src].z;
-            if (tid == 0) out[obase + r] = (IdxT)(add + (int64_t)cidx);
+            if (tid == 0) {
+                out[obase + r] = (IdxT)(add + (int64_t)cidx);
+                if (new_xyz) { float *o = new_xyz + 3 * (obase + r); o[0] = lx; o[1] = ly; o[2] = lz; }
+            }
         } else {
             cg::cluster_group cluster = cg::this_cluster();
             if (warp == 0 && lane < CLUSTER) {
@@ -159,7 +165,10 @@ fps_reg_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr, i
             lx = crec[buf][src].x;
             ly = crec[buf][src].y;
             lz = crec[buf][src].z;
-            if (tid == 0 && rank == 0) out[obase + r] = (IdxT)(add + (int64_t)gidx);
+            if (tid == 0 && rank == 0) {
+                out[obase + r] = (IdxT)(add + (int64_t)gidx);
+                if (new_xyz) { float *o = new_xyz + 3 * (obase + r); o[0] = lx; o[1] = ly; o[2] = lz; }
+            }
         }
     }
     if constexpr (CLUSTER > 1) {
@@ -174,7 +183,7 @@ template <typename IdxT>
 __global__ void __launch_bounds__(1024, 1)
 fps_big_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr, int64_t n_dense,
                const int64_t *__restrict__ out_ptr, int64_t s_dense, IdxT *__restrict__ out,
-               float *__restrict__ mind, const int64_t *__restrict__ first) {
+               float *__restrict__ mind, const int64_t *__restrict__ first, float *__restrict__ new_xyz) {
     __shared__ FpsRec rec[2][32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cloud = blockIdx.x;
@@ -196,7 +205,10 @@ fps_big_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr, i
         if (first != nullptr) { f0 = first[cloud]; f0 = f0 < 0 ? 0 : (f0 >= n ? n - 1 : f0); }
         lx = p[3 * f0]; ly = p[3 * f0 + 1]; lz = p[3 * f0 + 2];
     }
-    if (tid == 0 && s > 0) out[obase] = (IdxT)(add + f0);
+    if (tid == 0 && s > 0) {
+        out[obase] = (IdxT)(add + f0);
+        if (new_xyz) { new_xyz[3 * obase] = lx; new_xyz[3 * obase + 1] = ly; new_xyz[3 * obase + 2] = lz; }
+    }
     for (int64_t r = 1; r < s; ++r) {
         const int buf = (int)(r & 1);
         float best = -1.f, bx = 0.f, by = 0.f, bz = 0.f;
@@ -221,13 +233,16 @@ fps_big_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr, i
         warp_argmax(k2, i2, ckey, cidx);
         const int src = __ffs(__ballot_sync(0xffffffffu, k2 == ckey && i2 == cidx)) - 1;
         lx = rec[buf][src].x; ly = rec[buf][src].y; lz = rec[buf][src].z;
-        if (tid == 0) out[obase + r] = (IdxT)(add + (int64_t)cidx);
+        if (tid == 0) {
+            out[obase + r] = (IdxT)(add + (int64_t)cidx);
+            if (new_xyz) { float *o = new_xyz + 3 * (obase + r); o[0] = lx; o[1] = ly; o[2] = lz; }
+        }
     }
 }
 
 template <int T, int PPT, int CLUSTER, typename IdxT>
 static int launch_reg(const float *xyz, const int64_t *ptr, int64_t n_dense, const int64_t *out_ptr,
-                      int64_t s_dense, IdxT *out, const int64_t *first, int clouds, cudaStream_t st) {
+                      int64_t s_dense, IdxT *out, const int64_t *first, float *new_xyz, int clouds, cudaStream_t st) {
     auto kern = fps_reg_kernel<T, PPT, CLUSTER, IdxT>;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(clouds * CLUSTER));
@@ -248,7 +263,7 @@ static int launch_reg(const float *xyz, const int64_t *ptr, int64_t n_dense, con
             return P3D_ERR_CUDA;
         }
     }
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, xyz, ptr, n_dense, out_ptr, s_dense, out, first);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz);
     if (e != cudaSuccess) {
         g_launches.fetch_add(1, std::memory_order_relaxed);
         set_error("fps launch (T=%d PPT=%d CLUSTER=%d): %s", T, PPT, CLUSTER, cudaGetErrorString(e));
@@ -259,8 +274,8 @@ static int launch_reg(const float *xyz, const int64_t *ptr, int64_t n_dense, con
 
 template <typename IdxT>
 static int fps_dispatch(const float *xyz, const int64_t *ptr, int64_t n_dense, const int64_t *out_ptr,
-                        int64_t s_dense, IdxT *out, const int64_t *first, int clouds, int64_t max_n, float *ws,
-                        size_t ws_bytes, int64_t total_rows, cudaStream_t st) {
+                        int64_t s_dense, IdxT *out, const int64_t *first, float *new_xyz, int clouds, int64_t max_n,
+                        float *ws, size_t ws_bytes, int64_t total_rows, cudaStream_t st) {
     if (clouds == 0) return P3D_OK;
     // tuning hook (bench/tune_fps.py): P3D_FPS_FORCE="T,PPT" selects a single-CTA variant by hand
     if (const char *force = getenv("P3D_FPS_FORCE")) {
@@ -269,7 +284,7 @@ static int fps_dispatch(const float *xyz, const int64_t *ptr, int64_t n_dense, c
         if (nf == 3 && fc > 1 && (int64_t)ft * fp * fc >= max_n) {
 #define P3D_FPS_FORCED_CL(T, PPT, CL) \
     if (ft == T && fp == PPT && fc == CL) \
-        return launch_reg<T, PPT, CL, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, clouds, st);
+        return launch_reg<T, PPT, CL, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
             P3D_FPS_FORCED_CL(1024, 8, 16) P3D_FPS_FORCED_CL(512, 16, 16) P3D_FPS_FORCED_CL(256, 32, 16)
             P3D_FPS_FORCED_CL(1024, 8, 8) P3D_FPS_FORCED_CL(512, 16, 8) P3D_FPS_FORCED_CL(512, 8, 8)
             P3D_FPS_FORCED_CL(512, 8, 16) P3D_FPS_FORCED_CL(256, 16, 16) P3D_FPS_FORCED_CL(512, 32, 8)
@@ -281,7 +296,7 @@ static int fps_dispatch(const float *xyz, const int64_t *ptr, int64_t n_dense, c
         if (nf == 2 && (int64_t)ft * fp >= max_n) {
 #define P3D_FPS_FORCED(T, PPT) \
     if (ft == T && fp == PPT)  \
-        return launch_reg<T, PPT, 1, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, clouds, st);
+        return launch_reg<T, PPT, 1, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
             P3D_FPS_FORCED(64, 8) P3D_FPS_FORCED(64, 16) P3D_FPS_FORCED(64, 32)
             P3D_FPS_FORCED(128, 4) P3D_FPS_FORCED(128, 8) P3D_FPS_FORCED(128, 16)
             P3D_FPS_FORCED(256, 4) P3D_FPS_FORCED(256, 8) P3D_FPS_FORCED(512, 4) P3D_FPS_FORCED(1024, 2)
@@ -291,7 +306,7 @@ static int fps_dispatch(const float *xyz, const int64_t *ptr, int64_t n_dense, c
         }
     }
 #define P3D_FPS_CASE(LIM, T, PPT, CL) \
-    if (max_n <= (LIM)) return launch_reg<T, PPT, CL, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, clouds, st);
+    if (max_n <= (LIM)) return launch_reg<T, PPT, CL, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
     P3D_FPS_CASE(256, 64, 4, 1)
     P3D_FPS_CASE(512, 128, 4, 1)
     P3D_FPS_CASE(1024, 256, 4, 1)
@@ -303,7 +318,7 @@ static int fps_dispatch(const float *xyz, const int64_t *ptr, int64_t n_dense, c
     P3D_FPS_CASE(65536, 1024, 8, 8)
     // 65537..131072 points (measured on B200, profiles/r1_fps_tuning.md): a 16-CTA cluster needs a whole GPC, so
     // only ~4 run at once; with more clouds than that, 8-CTA clusters of fatter threads finish the batch sooner
-    if (max_n <= 131072 && clouds > 4) return launch_reg<512, 32, 8, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, clouds, st);
+    if (max_n <= 131072 && clouds > 4) return launch_reg<512, 32, 8, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
     P3D_FPS_CASE(131072, 256, 32, 16)
 #undef P3D_FPS_CASE
     if (ws == nullptr || ws_bytes < (size_t)total_rows * sizeof(float)) {
@@ -311,7 +326,7 @@ static int fps_dispatch(const float *xyz, const int64_t *ptr, int64_t n_dense, c
                   (long long)(total_rows * (int64_t)sizeof(float)));
         return P3D_ERR_WORKSPACE;
     }
-    fps_big_kernel<IdxT><<<clouds, 1024, 0, st>>>(xyz, ptr, n_dense, out_ptr, s_dense, out, ws, first);
+    fps_big_kernel<IdxT><<<clouds, 1024, 0, st>>>(xyz, ptr, n_dense, out_ptr, s_dense, out, ws, first, new_xyz);
     return finish_launch("fps_big");
 }
 
@@ -323,17 +338,17 @@ P3D_EXPORT size_t p3d_fps_dense_ws_bytes(int B, int N) {
     return N > 131072 ? (size_t)B * (size_t)N * sizeof(float) : 0;
 }
 
-P3D_EXPORT int p3d_fps_dense_f32(const float *xyz, int B, int N, int S, void *idx, int idx_is_i64, void *ws,
-                                 size_t ws_bytes, void *stream) {
+P3D_EXPORT int p3d_fps_dense_f32(const float *xyz, int B, int N, int S, void *idx, int idx_is_i64, float *new_xyz,
+                                 void *ws, size_t ws_bytes, void *stream) {
     P3D_REQUIRE(B >= 0 && N >= 0 && S >= 0, "fps_dense: negative dimension");
     P3D_REQUIRE(S <= N, "fps_dense: npoint (%d) > N (%d)", S, N);
     if (B == 0 || S == 0) return P3D_OK;
     P3D_REQUIRE(xyz && idx, "fps_dense: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     if (idx_is_i64)
-        return fps_dispatch<int64_t>(xyz, nullptr, N, nullptr, S, (int64_t *)idx, nullptr, B, N, (float *)ws, ws_bytes,
+        return fps_dispatch<int64_t>(xyz, nullptr, N, nullptr, S, (int64_t *)idx, nullptr, new_xyz, B, N, (float *)ws, ws_bytes,
                                      (int64_t)B * N, st);
-    return fps_dispatch<int32_t>(xyz, nullptr, N, nullptr, S, (int32_t *)idx, nullptr, B, N, (float *)ws, ws_bytes,
+    return fps_dispatch<int32_t>(xyz, nullptr, N, nullptr, S, (int32_t *)idx, nullptr, new_xyz, B, N, (float *)ws, ws_bytes,
                                  (int64_t)B * N, st);
 }
 
@@ -347,6 +362,6 @@ P3D_EXPORT int p3d_fps_csr_f32(const float *xyz, const int64_t *ptr, int num_clo
     P3D_REQUIRE(num_clouds >= 0 && max_n >= 0, "fps_csr: negative dimension");
     if (num_clouds == 0) return P3D_OK;
     P3D_REQUIRE(xyz && ptr && out_ptr && idx, "fps_csr: null pointer");
-    return fps_dispatch<int64_t>(xyz, ptr, 0, out_ptr, 0, idx, start, num_clouds, max_n, (float *)ws, ws_bytes,
+    return fps_dispatch<int64_t>(xyz, ptr, 0, out_ptr, 0, idx, start, nullptr, num_clouds, max_n, (float *)ws, ws_bytes,
                                  ws_bytes / sizeof(float), (cudaStream_t)stream);
 }

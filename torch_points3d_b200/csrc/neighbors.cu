@@ -309,7 +309,7 @@ constexpr int TNN_TILE = 1024;
 
 __global__ void __launch_bounds__(TNN_THREADS)
 three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ known, int n, int m,
-                float *__restrict__ dist, int64_t *__restrict__ idx) {
+                float *__restrict__ dist, int64_t *__restrict__ idx, float *__restrict__ weight) {
     __shared__ float4 tile[TNN_TILE];
     const int b = blockIdx.y;
     const int q = blockIdx.x * TNN_THREADS + threadIdx.x;
@@ -342,8 +342,16 @@ three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ kno
     if (live) {
         float *__restrict__ dd = dist + ((int64_t)b * n + q) * 3;
         int64_t *__restrict__ ii = idx + ((int64_t)b * n + q) * 3;
-        dd[0] = __fsqrt_rn(b1); dd[1] = __fsqrt_rn(b2); dd[2] = __fsqrt_rn(b3);
+        const float d1 = __fsqrt_rn(b1), d2 = __fsqrt_rn(b2), d3 = __fsqrt_rn(b3);
+        dd[0] = d1; dd[1] = d2; dd[2] = d3;
         ii[0] = i1; ii[1] = i2; ii[2] = i3;
+        if (weight) {  // DenseFPModule.conv, core/base_conv/dense.py:137-139
+            const float r1 = __fdiv_rn(1.0f, __fadd_rn(d1, 1e-8f)), r2 = __fdiv_rn(1.0f, __fadd_rn(d2, 1e-8f));
+            const float r3 = __fdiv_rn(1.0f, __fadd_rn(d3, 1e-8f));
+            const float norm = __fadd_rn(__fadd_rn(r1, r2), r3);
+            float *__restrict__ ww = weight + ((int64_t)b * n + q) * 3;
+            ww[0] = __fdiv_rn(r1, norm); ww[1] = __fdiv_rn(r2, norm); ww[2] = __fdiv_rn(r3, norm);
+        }
     }
 }
 
@@ -534,13 +542,13 @@ P3D_EXPORT int p3d_knn_dense_f32(const float *x, const float *y, int B, int N, i
 }
 
 P3D_EXPORT int p3d_three_nn_f32(const float *unknown, const float *known, int B, int n, int m, float *dist,
-                                int64_t *idx, void *stream) {
+                                int64_t *idx, float *weight, void *stream) {
     P3D_REQUIRE(B >= 0 && n >= 0, "three_nn: negative dimension");
     P3D_REQUIRE(m >= 3, "three_nn: needs at least 3 known points, got %d", m);
     if (B == 0 || n == 0) return P3D_OK;
     P3D_REQUIRE(unknown && known && dist && idx, "three_nn: null pointer");
     P3D_REQUIRE(B <= 65535, "three_nn: batch size must be <= 65535");
     dim3 grid((unsigned)((n + TNN_THREADS - 1) / TNN_THREADS), (unsigned)B);
-    three_nn_kernel<<<grid, TNN_THREADS, 0, (cudaStream_t)stream>>>(unknown, known, n, m, dist, idx);
+    three_nn_kernel<<<grid, TNN_THREADS, 0, (cudaStream_t)stream>>>(unknown, known, n, m, dist, idx, weight);
     return finish_launch("three_nn");
 }

@@ -78,11 +78,12 @@ def batch_to_ptr(batch: torch.Tensor, num_clouds: Optional[int] = None) -> torch
 
 
 # ----------------------------------------------------------------------- FPS ---------------
-def furthest_point_sample(xyz: torch.Tensor, npoint: int) -> torch.Tensor:
+def furthest_point_sample(xyz: torch.Tensor, npoint: int, return_xyz: bool = False):
     """tp.furthest_point_sample(xyz[B,N,3], npoint) -> idx[B,npoint]
     (reference call site core/spatial_ops/sampling.py:100).  Start index 0, lowest-index
     tie-break.  Returns int64 (tpk's CUDA path returned int32 and every caller cast it with
-    `.long()`, core/base_conv/dense.py:75)."""
+    `.long()`, core/base_conv/dense.py:75).  `return_xyz=True` also returns the sampled
+    coordinates [B,npoint,3] written by the same kernel (the `pos.gather(1, idx)` of dense.py:75-76)."""
     if xyz.dim() != 3 or xyz.shape[2] != 3:
         raise ValueError("furthest_point_sample expects xyz of shape [B, N, 3]")
     B, N, _ = xyz.shape
@@ -91,10 +92,12 @@ def furthest_point_sample(xyz: torch.Tensor, npoint: int) -> torch.Tensor:
     dev = _require_cuda("furthest_point_sample", xyz)
     xyz = _f32(xyz)
     idx = torch.empty((B, npoint), dtype=torch.int64, device=dev)
+    new_xyz = torch.empty((B, npoint, 3), dtype=torch.float32, device=dev) if return_xyz else None
     ws_bytes = _cabi.lib().p3d_fps_dense_ws_bytes(B, N)
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
-    _call(dev, "p3d_fps_dense_f32", xyz.data_ptr(), B, N, npoint, idx.data_ptr(), 1, _ptr(ws), ws_bytes)
-    return idx
+    _call(dev, "p3d_fps_dense_f32", xyz.data_ptr(), B, N, npoint, idx.data_ptr(), 1, _ptr(new_xyz), _ptr(ws),
+          ws_bytes)
+    return (idx, new_xyz) if return_xyz else idx
 
 
 def fps(x: torch.Tensor, batch: Optional[torch.Tensor] = None, ratio: float = 0.5,
@@ -258,9 +261,10 @@ def knn_dense(pos_support: torch.Tensor, pos: torch.Tensor, k: int):
     return idx, d2
 
 
-def three_nn(unknown: torch.Tensor, known: torch.Tensor):
+def three_nn(unknown: torch.Tensor, known: torch.Tensor, return_weight: bool = False):
     """tp.three_nn(unknown[B,n,3], known[B,m,3]) -> (dist[B,n,3] = sqrt(d2), idx[B,n,3])
-    (reference call site core/base_conv/dense.py:136)."""
+    (reference call site core/base_conv/dense.py:136).  `return_weight=True` appends the normalised
+    inverse-distance weights of dense.py:137-139, computed by the same kernel."""
     if unknown.dim() != 3 or known.dim() != 3:
         raise AssertionError("three_nn expects unknown[B,n,3] and known[B,m,3]")
     if known.shape[1] < 3:
@@ -271,8 +275,10 @@ def three_nn(unknown: torch.Tensor, known: torch.Tensor):
     m = known.shape[1]
     dist = torch.empty((B, n, 3), dtype=torch.float32, device=dev)
     idx = torch.empty((B, n, 3), dtype=torch.int64, device=dev)
-    _call(dev, "p3d_three_nn_f32", unknown.data_ptr(), known.data_ptr(), B, n, m, dist.data_ptr(), idx.data_ptr())
-    return dist, idx
+    weight = torch.empty((B, n, 3), dtype=torch.float32, device=dev) if return_weight else None
+    _call(dev, "p3d_three_nn_f32", unknown.data_ptr(), known.data_ptr(), B, n, m, dist.data_ptr(), idx.data_ptr(),
+          _ptr(weight))
+    return (dist, idx, weight) if return_weight else (dist, idx)
 
 
 # ------------------------------------------------------------------ grouping ---------------

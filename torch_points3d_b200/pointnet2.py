@@ -69,9 +69,14 @@ class PointNetMSGDown(nn.Module):
 
     def forward(self, data, sample_idx=None, **kwargs):
         x, pos = data.x, data.pos
-        idx = sample_idx if sample_idx is not None else self.sampler(pos)
-        idx = idx.unsqueeze(-1).repeat(1, 1, pos.shape[-1]).long()
-        new_pos = pos.gather(1, idx)
+        if sample_idx is None and self.fused_grouping and hasattr(self.sampler, "_num_to_sample"):
+            # FPS writes the sampled coordinates itself (== pos.gather(1, idx) of dense.py:75-76)
+            idx1, new_pos = ops.furthest_point_sample(pos, self.sampler._num_to_sample, return_xyz=True)
+            idx = idx1.unsqueeze(-1)
+        else:
+            idx = sample_idx if sample_idx is not None else self.sampler(pos)
+            idx = idx.unsqueeze(-1).repeat(1, 1, pos.shape[-1]).long()
+            new_pos = pos.gather(1, idx)
         ms_x = []
         for scale_idx in range(self.neighbour_finder.num_scales):
             radius_idx = self.neighbour_finder(pos, new_pos, scale_idx=scale_idx)
@@ -90,10 +95,8 @@ class DenseFPModule(nn.Module):
     def conv(self, pos, pos_skip, x):
         assert pos_skip.shape[2] == 3
         if pos is not None:
-            dist, idx = ops.three_nn(pos_skip, pos)
-            dist_recip = 1.0 / (dist + 1e-8)
-            norm = torch.sum(dist_recip, dim=2, keepdim=True)
-            weight = dist_recip / norm
+            # three_nn also emits the weights 1/(d+1e-8) / sum(1/(d+1e-8)) of dense.py:137-139
+            _, idx, weight = ops.three_nn(pos_skip, pos, return_weight=True)
             return ops.three_interpolate(x, idx, weight)
         return x.expand(*(x.size()[0:2] + (pos_skip.size(1),)))
 
