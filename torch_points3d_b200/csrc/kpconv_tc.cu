@@ -30,14 +30,15 @@ namespace p3d {
 
 constexpr int TC_TILE = 64;           // query points per tile (rows 0-63 of the M = 128 MMA; rows 64-127 are junk)
 constexpr int TC_MMA_M = 128;
-constexpr int TC_PWARPS = 8;          // producer warps
+constexpr int TC_PWARPS = 16;         // producer warps
 constexpr int TC_THREADS = (TC_PWARPS + 1) * 32;
 constexpr int TC_MCAP = 40;           // neighbours per point supported by this path
 constexpr int TC_NCH = 32;            // output channels per MMA (UMMA N)
 constexpr int TC_A_CHUNK = TC_TILE * 128;            // one 64-K chunk of the A tile: 64 rows x 128 B = 8 KB
 constexpr int TC_A_BYTES = 2 * 8 * TC_A_CHUNK;       // hi|lo x 8 chunks = 128 KB
-constexpr int TC_W_PIECE = 2 * 4 * TC_NCH * 128;     // hi|lo x 4 chunks x 32 rows x 128 B = 32 KB (half a slab of K)
-constexpr int TC_SCRATCH_FLOATS = KP_K * TC_MCAP + TC_MCAP * 32;  // per producer warp: weights + staged rows
+constexpr int TC_WCH = 2;                            // 64-K chunks per weight piece
+constexpr int TC_W_PIECE = 2 * TC_WCH * TC_NCH * 128;  // hi|lo x 2 chunks x 32 rows x 128 B = 16 KB (a quarter slab of K)
+constexpr int TC_SCRATCH_FLOATS = TC_MCAP * 32;      // per producer warp: staged neighbour rows
 
 // ---- tcgen05 / TMEM wrappers -------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols) {
@@ -106,20 +107,20 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // kernel points >= K are zero rows).
 __global__ void __launch_bounds__(256)
 kpconv_prep_w_kernel(const float *__restrict__ W, int K, int Cin, int Cout, uint8_t *__restrict__ img) {
-    const int piece = blockIdx.x;  // ((s * ncs + nc) * 2 + q)
+    const int piece = blockIdx.x;  // ((s * ncs + nc) * 4 + q)
     const int ncs = Cout / TC_NCH;
-    const int qh = piece & 1, nc = (piece >> 1) % ncs, s = (piece >> 1) / ncs;
+    const int qq = piece & 3, nc = (piece >> 2) % ncs, s = (piece >> 2) / ncs;
     uint8_t *base = img + (size_t)piece * TC_W_PIECE;
-    for (int i = threadIdx.x; i < 4 * TC_NCH * 64; i += 256) {
+    for (int i = threadIdx.x; i < TC_WCH * TC_NCH * 64; i += 256) {
         const int e = i & 63, r = (i >> 6) & 31, kc = i >> 11;
-        const int kidx = (qh * 4 + kc) * 64 + e;
+        const int kidx = (qq * TC_WCH + kc) * 64 + e;
         const int c = kidx >> 4, k = kidx & 15;
         const float v = k < K ? __ldg(W + ((int64_t)k * Cin + s * 32 + c) * Cout + nc * TC_NCH + r) : 0.f;
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
         const int off = (kc * TC_NCH + r) * 128 + (((e >> 3) ^ (r & 7)) << 4) + ((e & 7) << 1);
         *reinterpret_cast<__nv_bfloat16 *>(base + off) = hi;
-        *reinterpret_cast<__nv_bfloat16 *>(base + 4 * TC_NCH * 128 + off) = lo;
+        *reinterpret_cast<__nv_bfloat16 *>(base + TC_WCH * TC_NCH * 128 + off) = lo;
     }
 }
 
@@ -164,12 +165,14 @@ __device__ __forceinline__ float tc_influence(float cx, float cy, float cz, cons
     return __expf(-d2 / g.gauss_den);
 }
 
-// influence weights of all 16 kernel points on every neighbour: wsm[k][m] and one bit mask of
-// influencing neighbours per kernel point (mask0: neighbours 0-31, mask1: neighbours 32-39)
+// influence weights of all 16 kernel points on every neighbour, kept in REGISTERS: w0[k] = weight of kernel
+// point k on neighbour `lane`; w1[it] = weight of kernel point (lane/8 + 4*it) on neighbour 32 + lane%8; plus
+// one bit mask of influencing neighbours per kernel point (mask0: neighbours 0-31, mask1: 4 x 8 bits, kernel
+// point k in byte k%4 of mask1[k/4], neighbours 32-39)
 template <int INFL, bool CLOSEST>
 __device__ __forceinline__ void tc_weights(const TcPoint &P, const float4 *kps, int K, int M, const KpGeom &g,
-                                           float inv_extent, float *wsm, unsigned (&mask0)[KP_K],
-                                           unsigned (&mask1)[KP_K], int lane) {
+                                           float inv_extent, float (&w0)[KP_K], float (&w1)[4],
+                                           unsigned (&mask0)[KP_K], unsigned (&mask1)[4], int lane) {
     constexpr bool closest = CLOSEST;
     // closest mode: the winning kernel point of every neighbour over ALL K kernel points (first minimum)
     int best0 = -1, best1 = -1;
@@ -191,9 +194,10 @@ __device__ __forceinline__ void tc_weights(const TcPoint &P, const float4 *kps, 
         if (closest && best0 != k) w = 0.f;
         const bool nz = P.j0 >= 0 && k < K && w > 0.f;
         mask0[k] = __ballot_sync(0xffffffffu, nz);
-        wsm[k * TC_MCAP + lane] = w;
-        mask1[k] = 0u;
+        w0[k] = w;
     }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) { mask1[it] = 0u; w1[it] = 0.f; }
     if (M > 32) {
         // neighbours 32..39: lane = (mm = lane % 8, kq = lane / 8), four steps cover the 16 kernel points
         const int mm = lane & 7, kq = lane >> 3;
@@ -208,13 +212,10 @@ __device__ __forceinline__ void tc_weights(const TcPoint &P, const float4 *kps, 
             float w = tc_influence<INFL>(cx, cy, cz, kps[k], g, inv_extent, d2);
             if (closest && bb != k) w = 0.f;
             const bool nz = jj >= 0 && k < K && w > 0.f;
-            const unsigned bal = __ballot_sync(0xffffffffu, nz);
-            wsm[k * TC_MCAP + 32 + mm] = w;
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) mask1[qq + 4 * it] = (bal >> (8 * qq)) & 0xffu;
+            mask1[it] = __ballot_sync(0xffffffffu, nz);  // byte q = neighbours 32..39 of kernel point q + 4*it
+            w1[it] = w;
         }
     }
-    __syncwarp();
 }
 
 template <int INFL, bool CLOSEST>
@@ -227,7 +228,7 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
     // the UMMA 128-byte swizzle atoms need 1024-byte aligned tiles (the launch adds 1 KB of slack)
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *a_tile = smem;                       // [hi|lo][8 chunks][64 rows][128 B]
-    uint8_t *w_tile = smem + TC_A_BYTES;          // [hi|lo][4 chunks][32 rows][128 B]
+    uint8_t *w_tile = smem + TC_A_BYTES;          // [hi|lo][2 chunks][32 rows][128 B]
     float *scratch = reinterpret_cast<float *>(smem + TC_A_BYTES + TC_W_PIECE);
     __shared__ float4 kps[KP_K];
     __shared__ __align__(8) uint64_t bar_a_empty, bar_w_full, bar_w_empty, bar_d_full;
@@ -247,6 +248,7 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
         mbar_init(&bar_d_full, 1);
         fence_barrier_init();
     }
+    for (int i = tid; i < TC_PWARPS * TC_SCRATCH_FLOATS; i += TC_THREADS) scratch[i] = 0.f;  // staged rows: never NaN
     if (warp == TC_PWARPS) tmem_alloc(&tmem_base_s, tmem_cols);
     tc_fence_before();
     __syncthreads();
@@ -263,8 +265,8 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
         for (int sl = 0; sl < slabs; ++sl, ++pass) {
             if (warp < TC_PWARPS) {
                 // ---------------------------------------------------- producers ------------------
-                float *wsm = scratch + (size_t)warp * TC_SCRATCH_FLOATS;
-                float *xs = wsm + KP_K * TC_MCAP;
+                float *xs = scratch + (size_t)warp * TC_SCRATCH_FLOATS;
+                const uint32_t xs_addr = smem_u32(xs) + (uint32_t)lane * 4u;
                 const float *xcol = x + sl * 32 + lane;
                 TcPoint P, Pn;
                 {
@@ -279,31 +281,58 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
 #pragma unroll
                     for (int k = 0; k < KP_K; ++k) acc[k] = 0.f;
                     if (p < n) {
-                        // all neighbour rows of this point in flight at once (their latency hides behind the
-                        // influence weights), and the geometry of the NEXT point right behind them
-                        float v[TC_MCAP];
+                        // all neighbour rows of this point go straight to shared memory with cp.async (no
+                        // registers held, their latency hides behind the influence weights), and the geometry
+                        // of the NEXT point is fetched right behind them
 #pragma unroll
                         for (int m = 0; m < TC_MCAP; ++m) {
                             const int j = __shfl_sync(0xffffffffu, m < 32 ? P.j0 : P.j1, m & 31);
-                            v[m] = (m < M && j >= 0) ? __ldg(xcol + (int64_t)j * Cin) : 0.f;
+                            if (m < M && j >= 0)
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(xs_addr + m * 128u),
+                                             "l"(xcol + (int64_t)j * Cin)
+                                             : "memory");
                         }
+                        asm volatile("cp.async.commit_group;" ::: "memory");
                         if (pi + 1 < PPW && p + 1 < n) tc_load_point(q + 3 * (p + 1), s, nb + (p + 1) * M, N0, M, lane, Pn);
-                        unsigned mask0[KP_K], mask1[KP_K];
-                        tc_weights<INFL, CLOSEST>(P, kps, K, M, g, inv_extent, wsm, mask0, mask1, lane);
-#pragma unroll
-                        for (int m = 0; m < TC_MCAP; ++m) xs[m * 32 + lane] = v[m];
+                        float w0[KP_K], w1[4];
+                        unsigned mask0[KP_K], mask1[4];
+                        tc_weights<INFL, CLOSEST>(P, kps, K, M, g, inv_extent, w0, w1, mask0, mask1, lane);
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");  // each lane reads only what it copied
 #pragma unroll
                         for (int k = 0; k < KP_K - 1; ++k) {  // kernel point 15 is padding
-                            unsigned long long mk = ((unsigned long long)mask1[k] << 32) | mask0[k];
-                            float a = 0.f;
+                            // ~2.3 influencing neighbours per kernel point: the first three are taken without a
+                            // branch (an absent one reads row 0 with weight 0; rows never hold NaNs, see the
+                            // zero fill at kernel start), so the loads of a point are independent and pipeline;
+                            // weights come from the owning lane's register by shuffle
+                            unsigned mk = mask0[k];
+                            const int m1 = mk ? __ffs(mk) - 1 : 0;
+                            const bool h1 = mk != 0u;
+                            mk &= mk - 1;
+                            const int m2 = mk ? __ffs(mk) - 1 : 0;
+                            const bool h2 = mk != 0u;
+                            mk &= mk - 1;
+                            const int m3 = mk ? __ffs(mk) - 1 : 0;
+                            const bool h3 = mk != 0u;
+                            mk &= mk - 1;
+                            const float w1s = __shfl_sync(0xffffffffu, w0[k], m1);
+                            const float w2s = __shfl_sync(0xffffffffu, w0[k], m2);
+                            const float w3s = __shfl_sync(0xffffffffu, w0[k], m3);
+                            float a = (h1 ? w1s : 0.f) * xs[m1 * 32 + lane];
+                            a = fmaf(h2 ? w2s : 0.f, xs[m2 * 32 + lane], a);
+                            a = fmaf(h3 ? w3s : 0.f, xs[m3 * 32 + lane], a);
                             while (mk) {
-                                const int m = __ffsll((long long)mk) - 1;
+                                const int m = __ffs(mk) - 1;
                                 mk &= mk - 1;
-                                a = fmaf(wsm[k * TC_MCAP + m], xs[m * 32 + lane], a);
+                                a = fmaf(__shfl_sync(0xffffffffu, w0[k], m), xs[m * 32 + lane], a);
+                            }
+                            mk = (mask1[k >> 2] >> (8 * (k & 3))) & 0xffu;
+                            while (mk) {
+                                const int mm = __ffs(mk) - 1;
+                                mk &= mk - 1;
+                                a = fmaf(__shfl_sync(0xffffffffu, w1[k >> 2], mm + 8 * (k & 3)), xs[(32 + mm) * 32 + lane], a);
                             }
                             acc[k] = a;
                         }
-                        __syncwarp();  // wsm is rewritten for the next point
                         P = Pn;
                     }
                     // bf16 hi/lo split; K index = lane * 16 + k: 32 contiguous bytes per lane and operand
@@ -335,24 +364,24 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                     const uint32_t a_addr = smem_u32(a_tile), w_addr = smem_u32(w_tile);
                     for (int nc = 0; nc < ncs; ++nc) {
                         const uint32_t d = tmem_base + (uint32_t)(nc * TC_NCH);
-                        for (int qh = 0; qh < 2; ++qh, ++wloads) {
+                        for (int qq = 0; qq < 4; ++qq, ++wloads) {
                             if (wloads > 0) mbar_wait(&bar_w_empty, (wloads - 1) & 1);  // W buffer is free
                             mbar_arrive_expect_tx(&bar_w_full, TC_W_PIECE);
-                            bulk_g2s(w_tile, wimg + ((size_t)(sl * ncs + nc) * 2 + qh) * TC_W_PIECE, TC_W_PIECE,
+                            bulk_g2s(w_tile, wimg + ((size_t)(sl * ncs + nc) * 4 + qq) * TC_W_PIECE, TC_W_PIECE,
                                      &bar_w_full);
                             mbar_wait(&bar_w_full, wloads & 1);
                             tc_fence_after();
-#pragma unroll 1
-                            for (int kc = 0; kc < 4; ++kc) {
+#pragma unroll
+                            for (int kc = 0; kc < TC_WCH; ++kc) {
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks) {
                                     const uint32_t ko = (uint32_t)(ks * 32);
-                                    const uint32_t ac = a_addr + (uint32_t)((qh * 4 + kc) * TC_A_CHUNK) + ko;
+                                    const uint32_t ac = a_addr + (uint32_t)((qq * TC_WCH + kc) * TC_A_CHUNK) + ko;
                                     const uint64_t a_hi = tc_smem_desc(ac);
                                     const uint64_t a_lo = tc_smem_desc(ac + TC_A_BYTES / 2);
                                     const uint64_t b_hi = tc_smem_desc(w_addr + kc * (TC_NCH * 128) + ko);
                                     const uint64_t b_lo = tc_smem_desc(w_addr + TC_W_PIECE / 2 + kc * (TC_NCH * 128) + ko);
-                                    const uint32_t first = (sl == 0 && qh == 0 && kc == 0 && ks == 0) ? 0u : 1u;
+                                    const uint32_t first = (sl == 0 && qq == 0 && kc == 0 && ks == 0) ? 0u : 1u;
                                     tc_mma_bf16(d, a_hi, b_hi, idesc, first);
                                     tc_mma_bf16(d, a_lo, b_hi, idesc, 1u);
                                     tc_mma_bf16(d, a_hi, b_lo, idesc, 1u);
@@ -393,7 +422,7 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
 
 size_t kpconv_tc_ws_bytes(int K, int Cin, int Cout) {
     if (K > KP_K || Cin % 32 != 0 || Cout % TC_NCH != 0 || Cout > 512) return 0;
-    return (size_t)(Cin / 32) * (Cout / TC_NCH) * 2 * TC_W_PIECE;
+    return (size_t)(Cin / 32) * (Cout / TC_NCH) * 4 * TC_W_PIECE;
 }
 
 // returns 1 when the shape is not supported by this path (the caller then runs the fp32 SIMT kernel)
@@ -410,7 +439,7 @@ int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neigh
     g.gauss_den = 2.0f * sig * sig + 1e-9f;
     g.influence = influence;
     g.aggregation = aggregation;
-    const int tiles_w = (Cin / 32) * (Cout / TC_NCH) * 2;
+    const int tiles_w = (Cin / 32) * (Cout / TC_NCH) * 4;
     kpconv_prep_w_kernel<<<tiles_w, 256, 0, st>>>(k_values, K, Cin, Cout, (uint8_t *)ws);
     if (int e = finish_launch("kpconv_prep_w")) return e;
     const size_t smem = TC_A_BYTES + TC_W_PIECE + (size_t)TC_PWARPS * TC_SCRATCH_FLOATS * sizeof(float) + 1024;
