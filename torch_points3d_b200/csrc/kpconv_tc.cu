@@ -432,7 +432,7 @@ int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neigh
                   cudaStream_t st) {
     const size_t need = kpconv_tc_ws_bytes(K, Cin, Cout);
     if (need == 0 || M > TC_MCAP || ws == nullptr || ws_bytes < need) return 1;
-    if ((((uintptr_t)out) & 15) != 0 || (((uintptr_t)ws) & 15) != 0) return 1;
+    if ((((uintptr_t)out) & 15) != 0 || (((uintptr_t)ws) & 15) != 0) return 1;  // float4 row stores, TMA source
     KpGeom g;
     g.extent = extent;
     const float sig = extent * 0.3f;
