@@ -285,6 +285,12 @@ def run_b200(args):
     e2e_ms_total = float(ms2.item())
     clocks = sampler.summary() if sampler else None
 
+    stack = None
+    if not args.skip_extras:
+        try:
+            stack = bench_kpconv_stack(dev, world, rank)
+        except Exception as e:  # noqa: BLE001  (never lose the headline line to the secondary section)
+            stack = {"error": str(e)[:200]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -337,7 +343,7 @@ def run_b200(args):
                 "ms_per_step": round(e2e_ms_total / args.steps, 4)},
         "gpu_launches": int(launches_per_step * args.steps),
         "launches_per_step": int(launches_per_step),
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "kpconv": kp, "c4": c4,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "kpconv": kp, "kpconv_stack": stack, "c4": c4,
     }
     print(json.dumps(line))
     if world > 1:
@@ -419,6 +425,69 @@ def bench_kpconv(dev, args):
         except Exception:  # noqa: BLE001
             pass
     return res
+
+
+def bench_kpconv_stack(dev, world, rank):
+    """C3 / C5: the KPConvPaper encoder stack (conf/models/segmentation/kpconv.yaml:14-57, S3DIS-shaped spheres,
+    ~50k points per rank, max_num_neighbors clipped to 34), forward + backward + SGD step; with more than one
+    rank the model is wrapped in DistributedDataParallel (one NCCL gradient all-reduce per step, C5)."""
+    import torch
+    import torch.distributed as dist
+    from torch_points3d_b200 import kpconv, synthetic
+    pos_h, batch_h = synthetic.indoor_spheres(seed=1003 + 97 * rank)
+    pos, batch = torch.from_numpy(pos_h).to(dev), torch.from_numpy(batch_h).to(dev)
+    n = pos.shape[0]
+    torch.manual_seed(5)
+    enc = kpconv.KPConvEncoder(5, max_nn_cap=34).to(dev)
+    head = torch.nn.Linear(enc.out_channels, 13).to(dev)
+    model = torch.nn.Sequential()
+    model.add_module("enc", enc)
+    model.add_module("head", head)
+    params = list(model.parameters())
+    nparams = sum(p.numel() for p in params if p.requires_grad)
+    ddp = None
+    if world > 1:
+        class Wrapper(torch.nn.Module):
+            def __init__(self, enc, head):
+                super().__init__()
+                self.enc, self.head = enc, head
+
+            def forward(self, pos, x, batch):
+                return self.head(self.enc(pos, x, batch).x)
+        ddp = torch.nn.parallel.DistributedDataParallel(Wrapper(enc, head), device_ids=[dev.index])
+    opt = torch.optim.SGD([p for p in params if p.requires_grad], lr=0.01, momentum=0.98)
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    feats = torch.cat([torch.ones(n, 1, device=dev), torch.randn(n, 4, device=dev, generator=g)], 1)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        logits = ddp(pos, feats, batch) if ddp is not None else head(enc(pos, feats, batch).x)
+        labels = (torch.arange(logits.shape[0], device=dev) % 13)
+        loss = torch.nn.functional.cross_entropy(logits, labels)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    return {"workload": "C3/C5: KPConvPaper encoder stack (10 KPConv blocks, %.1f M params), ~%d points/rank in 8 spheres, "
+                        "fwd+bwd+SGD%s" % (nparams / 1e6, n, ", DDP over NCCL" if world > 1 else ""),
+            "ms_per_step": round(ms, 3), "points_per_s": round(world * n / (ms * 1e-3), 1),
+            "loss": round(float(loss.item()), 4), "unit": "points/s"}
 
 
 def bench_c4(dev):
@@ -537,7 +606,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph replay")

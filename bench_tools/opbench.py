@@ -129,10 +129,18 @@ def main():
                 b = ops.KPConv_ops(pos, pos, nb, x, kp, W, 0.04, "linear", "sum", precision="tensor")
             print("      tensor vs fp32: max|diff|/max|out| = %.3e  (identical bits: %s)" % (
                 float((a - b).abs().max() / a.abs().max()), bool(torch.equal(a, b))))
-            out = ops.KPConv_ops(pos, pos, nb, x, kp, W, 0.04, "linear", "sum")
-            gout = torch.randn_like(out)
-            timed("C3 kpconv bwd %d->%d" % (cin, cout),
-                  lambda: torch.autograd.grad(out, (x, W), gout, retain_graph=True), reps=5)
+            gout = torch.randn((n, cout), device=DEV, generator=g)
+            xd, Wd = x.detach(), W.detach()
+
+            def kbwd():
+                dfeat, dW = torch.zeros_like(xd), torch.zeros_like(Wd)
+                nbytes = _cabi.lib().p3d_kpconv_bwd_ws_bytes(n, 34, 15, cin, cout)
+                ws = torch.empty(nbytes // 4, dtype=torch.float32, device=DEV)
+                ops._call(torch.device(DEV), "p3d_kpconv_bwd_f32", pos.data_ptr(), pos.data_ptr(), nb.data_ptr(),
+                          xd.data_ptr(), kp.data_ptr(), Wd.data_ptr(), gout.data_ptr(), n, n, 34, 15, cin, cout, 0.04,
+                          1, 0, dfeat.data_ptr(), dW.data_ptr(), ws.data_ptr(), nbytes)
+                return dfeat, dW
+            timed("C3 kpconv bwd %d->%d" % (cin, cout), kbwd, reps=5)
 
 
 if __name__ == "__main__":

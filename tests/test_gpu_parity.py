@@ -470,6 +470,50 @@ def test_kpconv_layer_module_and_linearity():
     assert relerr(N(ya)[sub], ref) <= RTOL_TENSOR
 
 
+def test_resnet_block_against_reference_composition():
+    """ResnetBBlock (modules/KPConv/blocks.py:100-214), strided + bottleneck, eval-mode BN: our block ==
+    unary_1 -> KPConv_ops (CPU oracle) -> BN -> LeakyReLU -> unary_2 + shortcut_op(max over neighbour rows)"""
+    torch.manual_seed(3)
+    pos_h, batch_h = synthetic.indoor_spheres(num_spheres=2, raw_points=5000, radius=0.4, seed=91)
+    pos, batch = T(pos_h), T(batch_h)
+    block = kpconv.ResnetBBlock([64, 128], grid_size=0.08, prev_grid_size=0.04, max_num_neighbors=30,
+                                random_rotation=False).to(DEV).eval()
+    x = torch.randn(pos.shape[0], 64, device=DEV)
+    with torch.no_grad():
+        out = block(kpconv.Cloud(pos, x, batch))
+        q_pos, q_batch = kpconv.grid_subsample(pos, batch, 0.08)
+        assert torch.equal(out.pos, q_pos) and torch.equal(out.batch, q_batch)
+        assert 0 < q_pos.shape[0] < pos.shape[0]
+        nb = N(out.idx_neighboors)
+        ptr_x, ptr_y = oracle.batch_to_ptr(batch_h), oracle.batch_to_ptr(N(q_batch))
+        assert np.array_equal(nb, oracle.ball_query_csr(0.1, 30, pos_h, N(q_pos), ptr_x, ptr_y)[0])
+        h = block.unary_1(x)
+        layer = block.kp_conv.kp_conv
+        conv = oracle.kpconv_fwd(N(q_pos), pos_h, nb, N(h), N(layer.K_points), N(layer.weight), 0.04)
+        h2 = block.kp_conv.activation(block.kp_conv.bn(T(conv)))
+        main = block.unary_2(h2)
+        xs = torch.cat([x, torch.zeros_like(x[:1])])
+        want = main + block.shortcut_op(xs[out.idx_neighboors].max(1)[0])
+    assert relerr(N(out.x), N(want)) <= 5e-5
+
+
+def test_kpconv_encoder_stack_forward_backward():
+    """the KPConvPaper down-conv stack (conf/models/segmentation/kpconv.yaml:14-57) end to end on the device:
+    grid subsampling, partial-dense neighbour search, KPConv (tcgen05 where the shape allows), BN, shortcuts"""
+    torch.manual_seed(4)
+    pos_h, batch_h = synthetic.indoor_spheres(num_spheres=2, raw_points=24000, radius=0.62, seed=92)
+    pos, batch = T(pos_h), T(batch_h)
+    enc = kpconv.KPConvEncoder(5, max_nn_cap=34).to(DEV)
+    feats = torch.cat([torch.ones(pos.shape[0], 1, device=DEV), torch.randn(pos.shape[0], 4, device=DEV)], 1)
+    out = enc(pos, feats, batch)
+    assert out.x.shape[1] == enc.out_channels == 2048 and out.x.shape[0] == out.pos.shape[0] < pos.shape[0] // 50
+    assert torch.isfinite(out.x).all()
+    out.x.square().mean().backward()
+    grads = [p.grad for n_, p in enc.named_parameters() if p.requires_grad]
+    assert all(g is not None and torch.isfinite(g).all() for g in grads)
+    assert sum(float(g.abs().sum()) > 0 for g in grads) >= len(grads) - 2
+
+
 def test_neighbor_max():
     rng = np.random.default_rng(81)
     x = rng.standard_normal((500, 70)).astype(np.float32)

@@ -83,15 +83,56 @@ class KPConvLayer(torch.nn.Module):
             self.add_one)
 
 
+class Cloud:
+    """minimal stand-in for the torch_geometric `Data` objects the reference blocks pass around"""
+
+    def __init__(self, pos, x, batch, idx_neighboors=None):
+        self.pos, self.x, self.batch, self.idx_neighboors = pos, x, batch, idx_neighboors
+
+    def clone(self):
+        return Cloud(self.pos, self.x, self.batch, self.idx_neighboors)
+
+
+def grid_subsample(pos, batch, size):
+    """GridSampling3D(size, mode="mean") on the device (core/data_transform/grid_transform.py:84-141: voxel id per
+    point, consecutive cluster ids, per-voxel mean position; the batch id is constant inside a voxel).  Plain torch
+    ops: this is the strided blocks' query-set construction, a 'next' row of SURVEY.md section 8f, not a hot kernel.
+    Returns (q_pos [n,3], q_batch [n]) sorted by (batch, voxel)."""
+    vox = torch.floor(pos / size).to(torch.int64)
+    vox = vox - vox.min(0, keepdim=True).values
+    dims = vox.max(0).values + 1
+    key = ((batch.to(torch.int64) * dims[0] + vox[:, 0]) * dims[1] + vox[:, 1]) * dims[2] + vox[:, 2]
+    uniq, inv, cnt = torch.unique(key, return_inverse=True, return_counts=True)
+    # deterministic per-voxel mean: stable sort by voxel, fp64 running sum, differences at the voxel ends
+    order = torch.argsort(inv, stable=True)
+    csum = torch.cumsum(pos[order].to(torch.float64), 0)
+    ends = torch.cumsum(cnt, 0) - 1
+    seg = csum[ends]
+    seg[1:] = seg[1:] - csum[ends[:-1]]
+    q_pos = (seg / cnt.unsqueeze(1).to(torch.float64)).to(pos.dtype)
+    q_batch = (uniq // (dims[0] * dims[1] * dims[2])).to(batch.dtype)  # the batch id is the top digit of the key
+    return q_pos, q_batch
+
+
+class GridSampler:
+    def __init__(self, size):
+        self._size = size
+
+    def __call__(self, pos, batch):
+        return grid_subsample(pos, batch, self._size)
+
+    def __repr__(self):
+        return "GridSampler(%g)" % self._size
+
+
 class SimpleBlock(torch.nn.Module):
-    """blocks.py:15-97 (rigid): neighbour search (partial-dense ball query) -> KPConv -> BN ->
-    LeakyReLU(0.1).  `sampler(pos, batch) -> (q_pos, q_batch)` supplies the strided query set
-    (GridSampling3D in the reference, a 'next' row of SURVEY.md section 8f)."""
+    """blocks.py:15-97 (rigid): [grid subsampling of the queries when strided] -> neighbour search
+    (partial-dense ball query, radius 2.5 * sigma * prev_grid_size) -> KPConv -> BN -> LeakyReLU(0.1)."""
 
     RIGID_DENSITY = 2.5
 
     def __init__(self, down_conv_nn=None, grid_size=None, prev_grid_size=None, sigma=1.0, max_num_neighbors=16,
-                 activation=None, bn_momentum=0.02, bn=True, add_one=False, sampler=None, **kwargs):
+                 activation=None, bn_momentum=0.02, bn=True, add_one=False, **kwargs):
         super().__init__()
         assert len(down_conv_nn) == 2
         num_inputs, num_outputs = down_conv_nn
@@ -101,15 +142,107 @@ class SimpleBlock(torch.nn.Module):
         self.neighbour_finder = RadiusNeighbourFinder(search_radius, max_num_neighbors, conv_type=PARTIAL_DENSE)
         self.bn = torch.nn.BatchNorm1d(num_outputs, momentum=bn_momentum) if bn else None
         self.activation = activation if activation is not None else torch.nn.LeakyReLU(negative_slope=0.1)
-        self.sampler = sampler if prev_grid_size != grid_size else None
+        self.sampler = GridSampler(grid_size) if prev_grid_size != grid_size else None
+
+    def forward(self, data, **kwargs):
+        if self.sampler is not None:
+            q_pos, q_batch = self.sampler(data.pos, data.batch)
+        else:
+            q_pos, q_batch = data.pos, data.batch
+        idx_neighboors = self.neighbour_finder(data.pos, q_pos, batch_x=data.batch, batch_y=q_batch)
+        x = self.kp_conv(q_pos, data.pos, idx_neighboors, data.x)
+        if self.bn is not None:
+            x = self.bn(x)
+        return Cloud(q_pos, self.activation(x), q_batch, idx_neighboors)
+
+
+class ResnetBBlock(torch.nn.Module):
+    """blocks.py:100-214: unary_1 -> SimpleBlock(KPConv d_2 -> d_2) -> unary_2, plus the shortcut
+    (max over the neighbour rows when strided, a Linear+BN when the width changes)."""
+
+    def __init__(self, down_conv_nn=None, grid_size=None, prev_grid_size=None, sigma=1, max_num_neighbors=16,
+                 activation=None, has_bottleneck=True, bn_momentum=0.02, bn=True, add_one=False, **kwargs):
+        super().__init__()
+        assert len(down_conv_nn) == 2 or len(down_conv_nn) == 3, "down_conv_nn should be of size 2 or 3"
+        if len(down_conv_nn) == 2:
+            num_inputs, num_outputs = down_conv_nn
+            d_2 = num_outputs // 4
+        else:
+            num_inputs, d_2, num_outputs = down_conv_nn
+        act = activation if activation is not None else torch.nn.LeakyReLU(negative_slope=0.1)
+        self.is_strided = prev_grid_size != grid_size
+        self.has_bottleneck = has_bottleneck
+        kp_size = [d_2, d_2] if has_bottleneck else [num_inputs, num_outputs]
+        self.kp_conv = SimpleBlock(down_conv_nn=kp_size, grid_size=grid_size, prev_grid_size=prev_grid_size,
+                                   sigma=sigma, max_num_neighbors=max_num_neighbors, activation=act,
+                                   bn_momentum=bn_momentum, bn=bn, add_one=add_one, **kwargs)
+        Lin, BN = torch.nn.Linear, torch.nn.BatchNorm1d
+        if has_bottleneck:
+            if bn:
+                self.unary_1 = torch.nn.Sequential(Lin(num_inputs, d_2, bias=False), BN(d_2, momentum=bn_momentum), act)
+                self.unary_2 = torch.nn.Sequential(Lin(d_2, num_outputs, bias=False),
+                                                   BN(num_outputs, momentum=bn_momentum), act)
+            else:
+                self.unary_1 = torch.nn.Sequential(Lin(num_inputs, d_2, bias=False), act)
+                self.unary_2 = torch.nn.Sequential(Lin(d_2, num_outputs, bias=False), act)
+        if num_inputs != num_outputs:
+            self.shortcut_op = (torch.nn.Sequential(Lin(num_inputs, num_outputs, bias=False),
+                                                    BN(num_outputs, momentum=bn_momentum))
+                                if bn else Lin(num_inputs, num_outputs, bias=False))
+        else:
+            self.shortcut_op = torch.nn.Identity()
+        self.activation = act
+
+    def forward(self, data, **kwargs):
+        shortcut_x = data.x
+        inner = data.clone()
+        if self.has_bottleneck:
+            inner.x = self.unary_1(inner.x)
+        output = self.kp_conv(inner)
+        if self.has_bottleneck:
+            output.x = self.unary_2(output.x)
+        if self.is_strided:  # max over the neighbour rows of cat(x, zeros): one gather+max kernel
+            shortcut_x = ops.neighbor_max(shortcut_x, output.idx_neighboors)
+        output.x = output.x + self.shortcut_op(shortcut_x)
+        return output
+
+    @property
+    def sampler(self):
+        return self.kp_conv.sampler
+
+    @property
+    def neighbour_finder(self):
+        return self.kp_conv.neighbour_finder
+
+
+class KPConvEncoder(torch.nn.Module):
+    """The down-conv stack of KPConvPaper (conf/models/segmentation/kpconv.yaml:14-57): five KPDualBlocks,
+    [SimpleBlock, ResnetBBlock] then four [strided ResnetBBlock, ResnetBBlock], widths in_feat * 2^level,
+    grids first_subsampling * 2^level, max_num_neighbors from the YAML (clipped to `max_nn_cap`)."""
+
+    MAX_NN = [[25, 25], [25, 30], [30, 38], [38, 38], [38, 38]]
+
+    def __init__(self, feat_dim, in_feat=64, first_subsampling=0.04, levels=5, max_nn_cap=None, **kwargs):
+        super().__init__()
+        g, f = first_subsampling, in_feat
+        self.blocks = torch.nn.ModuleList()
+        for lv in range(levels):
+            nn_ = [min(v, max_nn_cap) if max_nn_cap else v for v in self.MAX_NN[lv]]
+            if lv == 0:
+                self.blocks.append(SimpleBlock([feat_dim, f], grid_size=g, prev_grid_size=g, max_num_neighbors=nn_[0],
+                                               **kwargs))
+                self.blocks.append(ResnetBBlock([f, 2 * f], grid_size=g, prev_grid_size=g, max_num_neighbors=nn_[1],
+                                                **kwargs))
+            else:
+                w = f * 2 ** lv
+                self.blocks.append(ResnetBBlock([w, w], grid_size=g * 2 ** lv, prev_grid_size=g * 2 ** (lv - 1),
+                                                max_num_neighbors=nn_[0], **kwargs))
+                self.blocks.append(ResnetBBlock([w, 2 * w], grid_size=g * 2 ** lv, prev_grid_size=g * 2 ** lv,
+                                                max_num_neighbors=nn_[1], **kwargs))
+        self.out_channels = in_feat * 2 ** levels
 
     def forward(self, pos, x, batch):
-        if self.sampler is not None:
-            q_pos, q_batch = self.sampler(pos, batch)
-        else:
-            q_pos, q_batch = pos, batch
-        idx_neighboors = self.neighbour_finder(pos, q_pos, batch_x=batch, batch_y=q_batch)
-        out = self.kp_conv(q_pos, pos, idx_neighboors, x)
-        if self.bn is not None:
-            out = self.bn(out)
-        return q_pos, self.activation(out), q_batch, idx_neighboors
+        data = Cloud(pos, x, batch)
+        for block in self.blocks:
+            data = block(data)
+        return data
