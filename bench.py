@@ -285,12 +285,16 @@ def run_b200(args):
     e2e_ms_total = float(ms2.item())
     clocks = sampler.summary() if sampler else None
 
-    stack = None
+    stack, c4 = None, None
     if not args.skip_extras:
         try:
             stack = bench_kpconv_stack(dev, world, rank)
         except Exception as e:  # noqa: BLE001  (never lose the headline line to the secondary section)
             stack = {"error": str(e)[:200]}
+        try:
+            c4 = bench_c4(dev) if world <= 8 else None
+        except Exception as e:  # noqa: BLE001
+            c4 = {"error": str(e)[:200]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -324,7 +328,6 @@ def run_b200(args):
                 "algorithmic_bytes": dom_bytes, "avg_launch_ms": round(dom_ms, 5), "peak_source": peaks_src}
 
     kp = bench_kpconv(dev, args) if not args.skip_extras else None
-    c4 = bench_c4(dev) if not args.skip_extras else None
     cpu = cpu_baseline(max_seconds=12.0) if not args.skip_extras else None
 
     clouds = B_CLOUDS * world * args.steps
@@ -498,8 +501,6 @@ def bench_c4(dev):
     rank = int(os.environ.get("RANK", "0"))
     from torch_points3d_b200.sharding import cloud_range
     lo, hi = cloud_range(8, world, rank)
-    if hi <= lo:
-        return None
     scans = torch.from_numpy(synthetic.lidar_scans(B=8)[lo:hi]).to(dev)
     b = hi - lo
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -519,9 +520,13 @@ def bench_c4(dev):
         step()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 2
-    return {"workload": "C4: FPS 4096 of 120000 + knn k=16, %d of 8 scans on this rank" % b,
-            "ms_per_batch": round(ms, 3), "clouds_per_s": round(b / (ms * 1e-3), 2)}
+    ms = torch.tensor([e0.elapsed_time(e1) / 2], device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    return {"workload": "C4: FPS 4096 of 120000 + knn k=16, batch of 8 scans sharded over %d GPU(s)" % world,
+            "ms_per_batch": round(ms, 3), "clouds_per_s": round(8 / (ms * 1e-3), 2)}
 
 
 # ------------------------------------------------------------ CPU arm (oracle port) -----------
@@ -555,6 +560,7 @@ def cpu_chain_once(h, clouds):
 
 def cpu_baseline(max_seconds=12.0, clouds=B_CLOUDS):
     import oracle
+    oracle.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use all host cores anyway
     h = make_host_inputs(1002)
     cpu_chain_once(h, 1)  # warm (builds / loads the oracle)
     t0 = time.perf_counter()
@@ -580,6 +586,7 @@ def run_reference(args):
     import oracle
     from oracle import build as oracle_build
     oracle_build.build()
+    oracle.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: use all host cores anyway
     h = make_host_inputs(1002)
     clouds = B_CLOUDS  # the whole 16-cloud batch per step; the number of steps is bounded below
     for _ in range(max(1, min(args.warmup, 3))):
