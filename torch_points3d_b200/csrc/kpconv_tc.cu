@@ -222,7 +222,7 @@ template <int INFL, bool CLOSEST>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, const int64_t *__restrict__ nb,
                      const float *__restrict__ x, const float *__restrict__ kp, const uint8_t *__restrict__ wimg,
-                     int64_t n, int64_t N0, int M, int K, int Cin, int Cout, KpGeom g, uint32_t tmem_cols,
+                     int64_t n, int64_t N0, int M, int K, int Cin, int Cout, KpGeom g, uint32_t tmem_cols, int ncpc,
                      float *__restrict__ out) {
     extern __shared__ uint8_t smem_raw[];
     // the UMMA 128-byte swizzle atoms need 1024-byte aligned tiles (the launch adds 1 KB of slack)
@@ -236,6 +236,10 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slabs = Cin / 32, ncs = Cout / TC_NCH;
+    // blockIdx.y owns the output-channel chunks [nc0, nc0 + ncl): small point sets (deep layers) are spread over
+    // the SMs by output channels, every CTA recomputing the (cheap) producer side of its tile
+    const int nc0 = blockIdx.y * ncpc;
+    const int ncl = (ncs - nc0 < ncpc) ? (ncs - nc0) : ncpc;
     const int64_t ntiles = (n + TC_TILE - 1) / TC_TILE;
     const float inv_extent = 1.0f / g.extent;
 
@@ -362,8 +366,9 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                 if (lane == 0) {
                     const uint32_t idesc = tc_idesc(TC_MMA_M, TC_NCH);
                     const uint32_t a_addr = smem_u32(a_tile), w_addr = smem_u32(w_tile);
-                    for (int nc = 0; nc < ncs; ++nc) {
-                        const uint32_t d = tmem_base + (uint32_t)(nc * TC_NCH);
+                    for (int ncq = 0; ncq < ncl; ++ncq) {
+                        const int nc = nc0 + ncq;
+                        const uint32_t d = tmem_base + (uint32_t)(ncq * TC_NCH);
                         for (int qq = 0; qq < 4; ++qq, ++wloads) {
                             if (wloads > 0) mbar_wait(&bar_w_empty, (wloads - 1) & 1);  // W buffer is free
                             mbar_arrive_expect_tx(&bar_w_full, TC_W_PIECE);
@@ -401,11 +406,11 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
             mbar_wait(&bar_d_full, tile_iter & 1);
             tc_fence_after();
             const int64_t p = p_base + warp * 32 + lane;
-            for (int nc = 0; nc < ncs; ++nc) {
+            for (int ncq = 0; ncq < ncl; ++ncq) {
                 float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(nc * TC_NCH), v);
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ncq * TC_NCH), v);
                 if (p < n) {
-                    float4 *dst = reinterpret_cast<float4 *>(out + p * Cout + nc * TC_NCH);
+                    float4 *dst = reinterpret_cast<float4 *>(out + p * Cout + (nc0 + ncq) * TC_NCH);
 #pragma unroll
                     for (int u = 0; u < 8; ++u) dst[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
                 }
@@ -444,7 +449,7 @@ int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neigh
     if (int e = finish_launch("kpconv_prep_w")) return e;
     const size_t smem = TC_A_BYTES + TC_W_PIECE + (size_t)TC_PWARPS * TC_SCRATCH_FLOATS * sizeof(float) + 1024;
     using Kern = void (*)(const float *, const float *, const int64_t *, const float *, const float *, const uint8_t *,
-                          int64_t, int64_t, int, int, int, int, KpGeom, uint32_t, float *);
+                          int64_t, int64_t, int, int, int, int, KpGeom, uint32_t, int, float *);
     static const Kern kerns[3][2] = {
         {kpconv_fwd_tc_kernel<P3D_INFLUENCE_CONSTANT, false>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_CONSTANT, true>},
         {kpconv_fwd_tc_kernel<P3D_INFLUENCE_LINEAR, false>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_LINEAR, true>},
@@ -456,13 +461,21 @@ int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neigh
                 cudaFuncSetAttribute(kerns[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
         attr_done = true;
     }
-    uint32_t cols = 32;
-    while ((int)cols < Cout) cols <<= 1;
     const int64_t ntiles = (n + TC_TILE - 1) / TC_TILE;
-    const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
+    const int ncs = Cout / TC_NCH;
+    int ygroups = 1;
+    if (ntiles < kNumSMs) {
+        ygroups = (int)((kNumSMs + ntiles - 1) / ntiles);
+        if (ygroups > ncs) ygroups = ncs;
+    }
+    const int ncpc = (ncs + ygroups - 1) / ygroups;
+    ygroups = (ncs + ncpc - 1) / ncpc;
+    uint32_t cols = 32;
+    while ((int)cols < ncpc * TC_NCH) cols <<= 1;
+    const dim3 grid((unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs), (unsigned)ygroups);
     kerns[influence][aggregation]<<<grid, TC_THREADS, smem, st>>>(query, support, neighbors, feat, k_points,
                                                                   (const uint8_t *)ws, n, N0, M, K, Cin, Cout, g, cols,
-                                                                  out);
+                                                                  ncpc, out);
     return finish_launch("kpconv_fwd_tc");
 }
 

@@ -105,11 +105,11 @@ def grid_subsample(pos, batch, size):
     uniq, inv, cnt = torch.unique(key, return_inverse=True, return_counts=True)
     # deterministic per-voxel mean: stable sort by voxel, fp64 running sum, differences at the voxel ends
     order = torch.argsort(inv, stable=True)
-    csum = torch.cumsum(pos[order].to(torch.float64), 0)
+    csum = torch.cumsum(pos[order].t().contiguous().to(torch.float64), 1)  # [3, N]: scan along the fast dimension
     ends = torch.cumsum(cnt, 0) - 1
-    seg = csum[ends]
-    seg[1:] = seg[1:] - csum[ends[:-1]]
-    q_pos = (seg / cnt.unsqueeze(1).to(torch.float64)).to(pos.dtype)
+    seg = csum[:, ends]
+    seg[:, 1:] = seg[:, 1:] - csum[:, ends[:-1]]
+    q_pos = (seg / cnt.unsqueeze(0).to(torch.float64)).t().contiguous().to(pos.dtype)
     q_batch = (uniq // (dims[0] * dims[1] * dims[2])).to(batch.dtype)  # the batch id is the top digit of the key
     return q_pos, q_batch
 
