@@ -14,6 +14,8 @@
 // warp search over the sorted batch vector: no host round trip.
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace p3d {
@@ -64,14 +66,53 @@ __device__ __forceinline__ void cta_ranges(int64_t q0, int64_t q1, const int64_t
     __syncthreads();
 }
 
+// AoS xyz -> SoA shared-memory tile.  All global loads of a thread are issued before the first shared
+// store (one memory round trip per tile instead of one per element); 16-byte loads when the tile starts
+// on a 16-byte boundary.
 __device__ __forceinline__ void load_tile(const float *__restrict__ x, int64_t tb, int tn, float *sx, float *sy,
                                           float *sz, int tid, int nthreads) {
     const float *__restrict__ src = x + 3 * tb;
-    for (int f = tid; f < 3 * tn; f += nthreads) {
-        const float v = __ldg(src + f);
+    const int nf = 3 * tn;
+    auto put = [&](int f, float v) {
         const int p = f / 3, c = f - 3 * p;
         float *dst = c == 0 ? sx : (c == 1 ? sy : sz);
         dst[p] = v;
+    };
+    if ((((uintptr_t)src) & 15) == 0) {
+        const float4 *__restrict__ s4 = reinterpret_cast<const float4 *>(src);
+        const int n4 = nf >> 2;
+        constexpr int U = 6;  // 6 x 256 threads x 4 floats = one full 2048-point tile
+        for (int g0 = tid; g0 < n4; g0 += U * nthreads) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int g = g0 + u * nthreads;
+                v[u] = g < n4 ? __ldg(s4 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int g = g0 + u * nthreads;
+                if (g < n4) {
+                    put(4 * g, v[u].x); put(4 * g + 1, v[u].y); put(4 * g + 2, v[u].z); put(4 * g + 3, v[u].w);
+                }
+            }
+        }
+        for (int f = (n4 << 2) + tid; f < nf; f += nthreads) put(f, __ldg(src + f));
+    } else {
+        constexpr int U = 8;
+        for (int f0 = tid; f0 < nf; f0 += U * nthreads) {
+            float v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int f = f0 + u * nthreads;
+                v[u] = f < nf ? __ldg(src + f) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int f = f0 + u * nthreads;
+                if (f < nf) put(f, v[u]);
+            }
+        }
     }
 }
 
@@ -143,21 +184,32 @@ ball_query_kernel(const float *__restrict__ x, const float *__restrict__ y, cons
             int64_t *__restrict__ row = idx + q * K;
             float *__restrict__ drow = dist2 ? dist2 + q * K : nullptr;
             int c = cnt[u];
-            for (int i0 = lo; i0 < hi && c < K; i0 += 32) {
-                const int i = i0 + lane;
-                const bool ok = i < hi;
-                const int ii = ok ? i : lo;
-                const float d = sqdist3(sx[ii], sy[ii], sz[ii], qx[u], qy[u], qz[u]);
-                const bool hit = ok && (strict ? (d < r2) : (d <= r2));
-                const unsigned m = __ballot_sync(0xffffffffu, hit);
-                if (m) {
-                    const int pos = c + __popc(m & lanemask_lt());
-                    if (hit && pos < K) {
-                        row[pos] = tb + i - off;
-                        if (drow) drow[pos] = d;
+            // 4 x 32 candidates per trip: the four distance chains and ballots are independent, only the
+            // slot assignment is sequential (scanning a few candidates past the K-th hit is harmless)
+            for (int i0 = lo; i0 < hi && c < K; i0 += 128) {
+                float d[4];
+                bool hit[4];
+                unsigned m[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int i = i0 + 32 * v + lane;
+                    const bool ok = i < hi;
+                    const int ii = ok ? i : lo;
+                    d[v] = sqdist3(sx[ii], sy[ii], sz[ii], qx[u], qy[u], qz[u]);
+                    hit[v] = ok && (strict ? (d[v] < r2) : (d[v] <= r2));
+                    m[v] = __ballot_sync(0xffffffffu, hit[v]);
+                }
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    if (m[v]) {
+                        const int pos = c + __popc(m[v] & lanemask_lt());
+                        if (hit[v] && pos < K) {
+                            row[pos] = tb + i0 + 32 * v + lane - off;
+                            if (drow) drow[pos] = d[v];
+                        }
+                        if (c == 0) first[u] = tb + i0 + 32 * v + (__ffs(m[v]) - 1) - off;
+                        c += __popc(m[v]);
                     }
-                    if (c == 0) first[u] = tb + i0 + (__ffs(m) - 1) - off;
-                    c += __popc(m);
                 }
             }
             cnt[u] = c;
@@ -456,9 +508,15 @@ static int launch_ball_query(const float *x, const float *y, const int64_t *bx, 
                              int64_t shadow, int64_t *idx, float *dist2, cudaStream_t st) {
     if (Ny == 0 || K == 0) return P3D_OK;
     const float r2 = radius * radius;
-    if (Ny >= (int64_t)NB_WARPS * 4 * 2 * kNumSMs) {
+    int qpw = Ny >= (int64_t)NB_WARPS * 4 * 2 * kNumSMs ? 4 : 1;
+    if (const char *e = getenv("P3D_BQ_QPW")) qpw = atoi(e);  // tuning hook
+    if (qpw == 4) {
         const int64_t grid = (Ny + NB_WARPS * 4 - 1) / (NB_WARPS * 4);
         ball_query_kernel<DENSE, 4><<<(unsigned)grid, NB_WARPS * 32, 0, st>>>(
+            x, y, bx, by, Nx, Ny, n_dense, s_dense, r2, K, strict, shadow, idx, dist2);
+    } else if (qpw == 2) {
+        const int64_t grid = (Ny + NB_WARPS * 2 - 1) / (NB_WARPS * 2);
+        ball_query_kernel<DENSE, 2><<<(unsigned)grid, NB_WARPS * 32, 0, st>>>(
             x, y, bx, by, Nx, Ny, n_dense, s_dense, r2, K, strict, shadow, idx, dist2);
     } else {
         const int64_t grid = (Ny + NB_WARPS - 1) / NB_WARPS;
