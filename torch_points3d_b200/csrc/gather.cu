@@ -186,27 +186,42 @@ three_interp_bwd_kernel(const float *__restrict__ dout, const int64_t *__restric
     }
 }
 
-// out[p,c] = max_m x'[nb[p,m], c];  one warp per query row chunk, lanes over channels
+// out[p,c] = max_m x'[nb[p,m], c];  one warp per query point, lanes over channels.  The M neighbour indices are
+// read once per point (one coalesced load, broadcast by shuffle) and the row gathers are issued four at a time.
 __global__ void __launch_bounds__(GR_THREADS)
 neighbor_max_kernel(const float *__restrict__ x, const int64_t *__restrict__ nb, int64_t n, int64_t N0, int M,
                     int C, float *__restrict__ out, int64_t *__restrict__ arg) {
     const int lane = threadIdx.x & 31;
     const int64_t p = (int64_t)blockIdx.x * (GR_THREADS / 32) + (threadIdx.x >> 5);
     if (p >= n) return;
-    for (int c = lane; c < C; c += 32) {
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        const int c = c0 + lane;
+        const bool cok = c < C;
         float best = -CUDART_INF_F;
         int64_t bi = N0;
-        for (int m = 0; m < M; ++m) {
-            int64_t j = __ldg(nb + p * M + m);
-            const bool shadow = (j < 0 || j >= N0);
-            const float v = shadow ? 0.f : __ldg(x + j * C + c);
-            if (v > best) { best = v; bi = shadow ? N0 : j; }
+        for (int m0 = 0; m0 < M; m0 += 32) {
+            int64_t jl = (m0 + lane < M) ? __ldg(nb + p * M + m0 + lane) : -1;
+            if (jl < 0 || jl >= N0) jl = -1;  // shadow row (zeros)
+            const int cnt = (M - m0 < 32) ? (M - m0) : 32;
+            for (int mm = 0; mm < cnt; mm += 4) {
+                int64_t j[4];
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    j[u] = __shfl_sync(0xffffffffu, jl, (mm + u) & 31);
+                    v[u] = (mm + u < cnt && j[u] >= 0 && cok) ? __ldg(x + j[u] * C + c) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (mm + u < cnt && v[u] > best) { best = v[u]; bi = j[u] < 0 ? N0 : j[u]; }
+            }
         }
-        out[p * C + c] = best;
-        if (arg) arg[p * C + c] = bi;
+        if (cok) {
+            out[p * C + c] = best;
+            if (arg) arg[p * C + c] = bi;
+        }
     }
 }
-
 
 // ------------------------------------------------- atomic-free backward (inverse index) ----
 // Both scatter-type gradients (grouping, three_interpolate) are sums over "all output slots e

@@ -66,53 +66,15 @@ __device__ __forceinline__ void cta_ranges(int64_t q0, int64_t q1, const int64_t
     __syncthreads();
 }
 
-// AoS xyz -> SoA shared-memory tile.  All global loads of a thread are issued before the first shared
-// store (one memory round trip per tile instead of one per element); 16-byte loads when the tile starts
-// on a 16-byte boundary.
 __device__ __forceinline__ void load_tile(const float *__restrict__ x, int64_t tb, int tn, float *sx, float *sy,
                                           float *sz, int tid, int nthreads) {
     const float *__restrict__ src = x + 3 * tb;
-    const int nf = 3 * tn;
-    auto put = [&](int f, float v) {
+#pragma unroll 4
+    for (int f = tid; f < 3 * tn; f += nthreads) {
+        const float v = __ldg(src + f);
         const int p = f / 3, c = f - 3 * p;
         float *dst = c == 0 ? sx : (c == 1 ? sy : sz);
         dst[p] = v;
-    };
-    if ((((uintptr_t)src) & 15) == 0) {
-        const float4 *__restrict__ s4 = reinterpret_cast<const float4 *>(src);
-        const int n4 = nf >> 2;
-        constexpr int U = 6;  // 6 x 256 threads x 4 floats = one full 2048-point tile
-        for (int g0 = tid; g0 < n4; g0 += U * nthreads) {
-            float4 v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int g = g0 + u * nthreads;
-                v[u] = g < n4 ? __ldg(s4 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int g = g0 + u * nthreads;
-                if (g < n4) {
-                    put(4 * g, v[u].x); put(4 * g + 1, v[u].y); put(4 * g + 2, v[u].z); put(4 * g + 3, v[u].w);
-                }
-            }
-        }
-        for (int f = (n4 << 2) + tid; f < nf; f += nthreads) put(f, __ldg(src + f));
-    } else {
-        constexpr int U = 8;
-        for (int f0 = tid; f0 < nf; f0 += U * nthreads) {
-            float v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int f = f0 + u * nthreads;
-                v[u] = f < nf ? __ldg(src + f) : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int f = f0 + u * nthreads;
-                if (f < nf) put(f, v[u]);
-            }
-        }
     }
 }
 

@@ -86,11 +86,12 @@ class KPConvLayer(torch.nn.Module):
 class Cloud:
     """minimal stand-in for the torch_geometric `Data` objects the reference blocks pass around"""
 
-    def __init__(self, pos, x, batch, idx_neighboors=None):
+    def __init__(self, pos, x, batch, idx_neighboors=None, nb_key=None):
         self.pos, self.x, self.batch, self.idx_neighboors = pos, x, batch, idx_neighboors
+        self.nb_key = nb_key  # (radius, max_num_neighbors) of a self-neighbour table of `pos`, if one is attached
 
     def clone(self):
-        return Cloud(self.pos, self.x, self.batch, self.idx_neighboors)
+        return Cloud(self.pos, self.x, self.batch, self.idx_neighboors, self.nb_key)
 
 
 def grid_subsample(pos, batch, size):
@@ -149,11 +150,16 @@ class SimpleBlock(torch.nn.Module):
             q_pos, q_batch = self.sampler(data.pos, data.batch)
         else:
             q_pos, q_batch = data.pos, data.batch
-        idx_neighboors = self.neighbour_finder(data.pos, q_pos, batch_x=data.batch, batch_y=q_batch)
+        key = (self.neighbour_finder._radius, self.neighbour_finder._max_num_neighbors)
+        if self.sampler is None and data.idx_neighboors is not None and data.nb_key == key:
+            idx_neighboors = data.idx_neighboors  # same points, radius and width as the previous block: same table
+        else:
+            idx_neighboors = self.neighbour_finder(data.pos, q_pos, batch_x=data.batch, batch_y=q_batch)
         x = self.kp_conv(q_pos, data.pos, idx_neighboors, data.x)
         if self.bn is not None:
             x = self.bn(x)
-        return Cloud(q_pos, self.activation(x), q_batch, idx_neighboors)
+        # the table describes self-neighbourhoods of q_pos only when this block was not strided
+        return Cloud(q_pos, self.activation(x), q_batch, idx_neighboors, key if self.sampler is None else None)
 
 
 class ResnetBBlock(torch.nn.Module):
