@@ -74,9 +74,9 @@ class Chain:
                       for k in l["nsample"]] for l in self.sa]
         self.g_fp = [torch.randn((B_CLOUDS, 256, 512), device=dev, generator=g),
                      torch.randn((B_CLOUDS, 128, 2048), device=dev, generator=g)]
-        self.result_host = torch.empty(B_CLOUDS * (512 + 128) + 1, dtype=torch.float32).pin_memory()
+        self.result_host = torch.empty(B_CLOUDS * (512 + 128) + 1, dtype=torch.int64).pin_memory()
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
-        self.d2h_bytes = self.result_host.numel() * 4
+        self.d2h_bytes = self.result_host.numel() * 8
 
     def upload(self):
         for k, v in self.host.items():
@@ -108,30 +108,30 @@ class Chain:
         self.consumed[slot].record(cur)
 
     def step(self):
-        """returns a small result tensor: the sampled indices of both levels + a gradient checksum"""
+        """one forward pass of the chain over the batch, then the backward pass in reverse layer order (the
+        order a training step runs them in).  Returns a small result tensor: the sampled indices of both
+        levels + one element of the last gradient."""
         torch = self.torch
         from torch_points3d_b200 import ops
         d = self.d
         pos, feats = d["pos"], [d["x0"], d["x1"]]
-        check = torch.zeros((), device=self.dev)
-        samples = []
+        samples, tape = [], []
         for li, l in enumerate(self.sa):
             idx, new_pos = ops.furthest_point_sample(pos, l["npoint"], return_xyz=True)
             samples.append(idx)
             for si, (r, k) in enumerate(zip(l["radii"], l["nsample"])):
                 ridx = ops.ball_query(r, k, pos, new_pos, return_dist=False)[0]
-                grouped = ops.group_features(feats[li], pos, new_pos, ridx)
-                (gx,) = torch.autograd.grad(grouped, feats[li], self.g_sa[li][si])
-                check = check + gx[0, 0, 0]
+                tape.append((ops.group_features(feats[li], pos, new_pos, ridx), feats[li], self.g_sa[li][si]))
             d["pos%d" % (li + 1)] = new_pos
             pos = new_pos
         # FP2: 512 unknown (SA1 level) from 128 known (SA2 level); FP3: 2048 unknown from 512 known
         for fi, (unknown, known, x) in enumerate([(d["pos1"], d["pos2"], d["x2"]), (d["pos"], d["pos1"], d["x3"])]):
             _, idx, weight = ops.three_nn(unknown, known, return_weight=True)  # weights of dense.py:137-139 fused
-            out = ops.three_interpolate(x, idx, weight)
-            (gx,) = torch.autograd.grad(out, x, self.g_fp[fi])
-            check = check + gx[0, 0, 0]
-        return torch.cat([samples[0].reshape(-1).float(), samples[1].reshape(-1).float(), check.reshape(1)])
+            tape.append((ops.three_interpolate(x, idx, weight), x, self.g_fp[fi]))
+        gx = None
+        for out, leaf, g in reversed(tape):
+            (gx,) = torch.autograd.grad(out, leaf, g)
+        return torch.cat([samples[0].reshape(-1), samples[1].reshape(-1), gx.reshape(-1)[:1].to(torch.int64)])
 
     def algorithmic_bytes_dominant(self):
         """group_fwd of SA2 scale 2: 4*C*N + 8*S*K + 4*C*S*K per cloud"""

@@ -89,7 +89,7 @@ def main():
             nb = _cabi.lib().p3d_three_interp_bwd_ws_bytes(B, C, kn.shape[1], unk.shape[1])
             ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
             ops._call(torch.device(DEV), "p3d_three_interp_bwd_f32", gout.data_ptr(), idx.data_ptr(), w.data_ptr(), B, C,
-                      kn.shape[1], unk.shape[1], d.data_ptr(), ws.data_ptr(), nb)
+                      kn.shape[1], unk.shape[1], d.data_ptr(), ws.data_ptr(), nb, 0)
             return d
         timed("three_interpolate bwd " + tag, ibwd, bytes_=B * 4 * C * (kn.shape[1] + unk.shape[1]))
 

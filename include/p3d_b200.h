@@ -131,8 +131,12 @@ int p3d_group_fwd_f32(const float *feat, const int64_t *idx, int B, int C, int N
  * inverted by a stable counting sort, slots are summed in increasing (s,k) order); source tables
  * of more than 4096 points per cloud report 0 workspace bytes and use fp32 reductions at L2. */
 size_t p3d_group_bwd_ws_bytes(int B, int C, int N, int S, int K);
+/* Optional: build the inverse index into `ws` ahead of time (it depends on idx only, so the forward pass
+ * can run it on a side stream); pass the same ws with prepared = 1 to p3d_group_bwd_f32 afterwards. */
+int p3d_group_bwd_prepare(const int64_t *idx, int B, int C, int N, int S, int K, void *ws, size_t ws_bytes,
+                          void *stream);
 int p3d_group_bwd_f32(const float *dout, const int64_t *idx, int B, int C, int N, int S, int K, float *dfeat,
-                      int64_t dout_batch_stride, int c_off, void *ws, size_t ws_bytes, void *stream);
+                      int64_t dout_batch_stride, int c_off, void *ws, size_t ws_bytes, int prepared, void *stream);
 /* Fused PointNetMSGDown._prepare_features xyz part (modules/pointnet2/dense.py:37-42):
  * out[b, c, s, k] = (pos[b, idx[b,s,k], c] - new_pos[b, s, c]) * (1/norm)   for c in 0..2,
  * norm = 1 unless normalize_xyz (ATen evaluates `tensor /= python_float` on CUDA as a multiply
@@ -148,8 +152,10 @@ int p3d_three_interp_fwd_f32(const float *feat, const int64_t *idx, const float 
 /* backward w.r.t. features; dfeat is overwritten; workspace and determinism as for
  * p3d_group_bwd_f32 (m <= 4096 known points per cloud, else fp32 reductions at L2) */
 size_t p3d_three_interp_bwd_ws_bytes(int B, int C, int m, int n);
+int p3d_three_interp_bwd_prepare(const int64_t *idx, int B, int C, int m, int n, void *ws, size_t ws_bytes,
+                                 void *stream);
 int p3d_three_interp_bwd_f32(const float *dout, const int64_t *idx, const float *weight, int B, int C, int m,
-                             int n, float *dfeat, void *ws, size_t ws_bytes, void *stream);
+                             int n, float *dfeat, void *ws, size_t ws_bytes, int prepared, void *stream);
 
 /* ------------------------------------------------------------- KPConv ------
  * Replaces KPConv_ops(query, support, neighbors, features, K_points, K_values, KP_extent,

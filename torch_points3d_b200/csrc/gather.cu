@@ -642,10 +642,12 @@ static InverseLayout inverse_layout(int B, int C, int N, int64_t E, int EC) {
     return L;
 }
 
+enum { BWD_ALL = 0, BWD_PREPARE = 1, BWD_PREPARED = 2 };
+
 template <bool INTERP>
 static int launch_bwd_sorted(const float *dout, const float *weight, const int64_t *keys, int B, int C, int N,
                              int64_t E, float *dfeat, int64_t dout_batch_stride, int c_off, void *ws,
-                             cudaStream_t st) {
+                             cudaStream_t st, int mode = BWD_ALL) {
     const int EC = INTERP ? SB_EC_INTERP : SB_EC_GROUP;
     const InverseLayout L = inverse_layout(B, C, N, E, EC);
     const int nchunks = L.nchunks;
@@ -662,10 +664,13 @@ static int launch_bwd_sorted(const float *dout, const float *weight, const int64
         cudaFuncSetAttribute(bwd_sorted_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_done = true;
     }
-    const size_t inv_smem = ((size_t)N * INV_WARPS + N) * sizeof(int);
-    invert_kernel<<<dim3((unsigned)nchunks, (unsigned)B), INV_WARPS * 32, inv_smem, st>>>(
-        keys, E, N, EC, nchunks, INTERP ? 0 : 1, order, seg, runs, nruns);
-    if (int e = finish_launch("invert")) return e;
+    if (mode != BWD_PREPARED) {
+        const size_t inv_smem = ((size_t)N * INV_WARPS + N) * sizeof(int);
+        invert_kernel<<<dim3((unsigned)nchunks, (unsigned)B), INV_WARPS * 32, inv_smem, st>>>(
+            keys, E, N, EC, nchunks, INTERP ? 0 : 1, order, seg, runs, nruns);
+        if (int e = finish_launch("invert")) return e;
+        if (mode == BWD_PREPARE) return P3D_OK;
+    }
     const int Wd = INTERP ? EC / 3 : EC;
     int SB_STAGES = 2, use_tma = 1;
     if (const char *e = getenv("P3D_BWD_STAGES")) SB_STAGES = atoi(e);   // tuning hooks
@@ -744,9 +749,23 @@ P3D_EXPORT size_t p3d_group_bwd_ws_bytes(int B, int C, int N, int S, int K) {
     return inverse_layout(B, C, N, (int64_t)S * K, SB_EC_GROUP).total;
 }
 
+P3D_EXPORT int p3d_group_bwd_prepare(const int64_t *idx, int B, int C, int N, int S, int K, void *ws, size_t ws_bytes,
+                                     void *stream) {
+    P3D_REQUIRE(B >= 0 && C >= 0 && N >= 0 && S >= 0 && K >= 0, "group_bwd_prepare: negative dimension");
+    const size_t need = p3d_group_bwd_ws_bytes(B, C, N, S, K);
+    if (need == 0 || B == 0 || C == 0 || N == 0 || (int64_t)S * K == 0) return P3D_OK;  // nothing to prepare
+    P3D_REQUIRE(idx, "group_bwd_prepare: null pointer");
+    if (ws == nullptr || ws_bytes < need) {
+        set_error("group_bwd_prepare: workspace of %zu bytes required (p3d_group_bwd_ws_bytes)", need);
+        return P3D_ERR_WORKSPACE;
+    }
+    return launch_bwd_sorted<false>(nullptr, nullptr, idx, B, C, N, (int64_t)S * K, nullptr, 0, 0, ws,
+                                    (cudaStream_t)stream, BWD_PREPARE);
+}
+
 P3D_EXPORT int p3d_group_bwd_f32(const float *dout, const int64_t *idx, int B, int C, int N, int S, int K,
                                  float *dfeat, int64_t dout_batch_stride, int c_off, void *ws, size_t ws_bytes,
-                                 void *stream) {
+                                 int prepared, void *stream) {
     P3D_REQUIRE(B >= 0 && C >= 0 && N >= 0 && S >= 0 && K >= 0, "group_bwd: negative dimension");
     const int64_t E = (int64_t)S * K;
     if (B == 0 || C == 0 || N == 0) return P3D_OK;
@@ -759,7 +778,8 @@ P3D_EXPORT int p3d_group_bwd_f32(const float *dout, const int64_t *idx, int B, i
     P3D_REQUIRE(dout && idx, "group_bwd: null pointer");
     const size_t need = p3d_group_bwd_ws_bytes(B, C, N, S, K);
     if (need > 0 && ws != nullptr && ws_bytes >= need)
-        return launch_bwd_sorted<false>(dout, nullptr, idx, B, C, N, E, dfeat, dout_batch_stride, c_off, ws, st);
+        return launch_bwd_sorted<false>(dout, nullptr, idx, B, C, N, E, dfeat, dout_batch_stride, c_off, ws, st,
+                                        prepared ? BWD_PREPARED : BWD_ALL);
     if (need > 0) {
         set_error("group_bwd: workspace of %zu bytes required (p3d_group_bwd_ws_bytes)", need);
         return P3D_ERR_WORKSPACE;
@@ -825,8 +845,23 @@ P3D_EXPORT size_t p3d_three_interp_bwd_ws_bytes(int B, int C, int m, int n) {
     return inverse_layout(B, C, m, (int64_t)n * 3, SB_EC_INTERP).total;
 }
 
+P3D_EXPORT int p3d_three_interp_bwd_prepare(const int64_t *idx, int B, int C, int m, int n, void *ws, size_t ws_bytes,
+                                            void *stream) {
+    P3D_REQUIRE(B >= 0 && C >= 0 && m >= 0 && n >= 0, "three_interpolate_bwd_prepare: negative dimension");
+    const size_t need = p3d_three_interp_bwd_ws_bytes(B, C, m, n);
+    if (need == 0 || B == 0 || C == 0 || m == 0 || n == 0) return P3D_OK;
+    P3D_REQUIRE(idx, "three_interpolate_bwd_prepare: null pointer");
+    if (ws == nullptr || ws_bytes < need) {
+        set_error("three_interpolate_bwd_prepare: workspace of %zu bytes required", need);
+        return P3D_ERR_WORKSPACE;
+    }
+    return launch_bwd_sorted<true>(nullptr, nullptr, idx, B, C, m, (int64_t)n * 3, nullptr, 0, 0, ws,
+                                   (cudaStream_t)stream, BWD_PREPARE);
+}
+
 P3D_EXPORT int p3d_three_interp_bwd_f32(const float *dout, const int64_t *idx, const float *weight, int B, int C,
-                                        int m, int n, float *dfeat, void *ws, size_t ws_bytes, void *stream) {
+                                        int m, int n, float *dfeat, void *ws, size_t ws_bytes, int prepared,
+                                        void *stream) {
     P3D_REQUIRE(B >= 0 && C >= 0 && m >= 0 && n >= 0, "three_interpolate_bwd: negative dimension");
     if (B == 0 || C == 0 || m == 0) return P3D_OK;
     P3D_REQUIRE(dfeat, "three_interpolate_bwd: null pointer");
@@ -838,7 +873,8 @@ P3D_EXPORT int p3d_three_interp_bwd_f32(const float *dout, const int64_t *idx, c
     P3D_REQUIRE(dout && idx && weight, "three_interpolate_bwd: null pointer");
     const size_t need = p3d_three_interp_bwd_ws_bytes(B, C, m, n);
     if (need > 0 && ws != nullptr && ws_bytes >= need)
-        return launch_bwd_sorted<true>(dout, weight, idx, B, C, m, (int64_t)n * 3, dfeat, (int64_t)C * n, 0, ws, st);
+        return launch_bwd_sorted<true>(dout, weight, idx, B, C, m, (int64_t)n * 3, dfeat, (int64_t)C * n, 0, ws, st,
+                                       prepared ? BWD_PREPARED : BWD_ALL);
     if (need > 0) {
         set_error("three_interpolate_bwd: workspace of %zu bytes required (p3d_three_interp_bwd_ws_bytes)", need);
         return P3D_ERR_WORKSPACE;

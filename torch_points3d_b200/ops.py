@@ -286,13 +286,62 @@ def _workspace(nbytes: int, dev: torch.device) -> Optional[torch.Tensor]:
     return torch.empty(nbytes, dtype=torch.uint8, device=dev) if nbytes else None
 
 
-def _group_bwd(grad_out, idx, B, C, N, S, K, batch_stride, c_off):
+# The backward of grouping / three_interpolate needs the inverse of the index tensor, which depends on the
+# indices only.  With PREPARE_INVERSE_IN_FORWARD the forward pass builds it on a side stream (it overlaps the
+# bandwidth-bound gather and whatever the caller runs next) and the backward only waits on an event.
+PREPARE_INVERSE_IN_FORWARD = True
+_side_streams = {}
+
+
+def _side_stream(dev: torch.device) -> torch.cuda.Stream:
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    st = _side_streams.get(key)
+    if st is None:
+        st = _side_streams[key] = torch.cuda.Stream(device=dev)
+    return st
+
+
+class _Prepared:
+    """inverse index being built on a side stream: workspace + the event the backward waits on"""
+
+    def __init__(self, name, dev, ws_bytes, *args):
+        self.ws_bytes = ws_bytes
+        self.ws = _workspace(ws_bytes, dev)
+        cur = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        side.wait_stream(cur)  # the indices (and the fresh workspace) are produced on the current stream
+        with torch.cuda.stream(side):
+            with torch.cuda.device(dev):
+                _cabi.call(name, *args, self.ws.data_ptr(), ws_bytes, side.cuda_stream)
+            self.event = torch.cuda.Event()
+            self.event.record(side)
+        if not torch.cuda.is_current_stream_capturing():
+            self.ws.record_stream(side)  # if no backward ever joins, the allocator still waits for the side stream
+
+    def join(self, dev):
+        torch.cuda.current_stream(dev).wait_event(self.event)
+
+
+def _prepare_group(idx, B, C, N, S, K):
+    if not PREPARE_INVERSE_IN_FORWARD:
+        return None
+    ws_bytes = _cabi.lib().p3d_group_bwd_ws_bytes(B, C, N, S, K)
+    if not ws_bytes:
+        return None
+    return _Prepared("p3d_group_bwd_prepare", idx.device, ws_bytes, idx.data_ptr(), B, C, N, S, K)
+
+
+def _group_bwd(grad_out, idx, B, C, N, S, K, batch_stride, c_off, prepared=None):
     dev = grad_out.device
     dfeat = torch.empty((B, C, N), dtype=torch.float32, device=dev)
-    ws_bytes = _cabi.lib().p3d_group_bwd_ws_bytes(B, C, N, S, K)
-    ws = _workspace(ws_bytes, dev)
+    if prepared is not None:
+        prepared.join(dev)
+        ws, ws_bytes, flag = prepared.ws, prepared.ws_bytes, 1
+    else:
+        ws_bytes = _cabi.lib().p3d_group_bwd_ws_bytes(B, C, N, S, K)
+        ws, flag = _workspace(ws_bytes, dev), 0
     _call(dev, "p3d_group_bwd_f32", grad_out.data_ptr(), idx.data_ptr(), B, C, N, S, K, dfeat.data_ptr(),
-          batch_stride, c_off, _ptr(ws), ws_bytes)
+          batch_stride, c_off, _ptr(ws), ws_bytes, flag)
     return dfeat
 
 
@@ -308,6 +357,7 @@ class _Grouping(torch.autograd.Function):
               C * S * K, 0)
         ctx.save_for_backward(idx)
         ctx.N = N
+        ctx.prepared = _prepare_group(idx, B, C, N, S, K) if ctx.needs_input_grad[0] else None
         return out
 
     @staticmethod
@@ -315,7 +365,7 @@ class _Grouping(torch.autograd.Function):
         (idx,) = ctx.saved_tensors
         grad_out = _f32(grad_out)
         B, C, S, K = grad_out.shape
-        dfeat = _group_bwd(grad_out, idx, B, C, ctx.N, S, K, C * S * K, 0)
+        dfeat = _group_bwd(grad_out, idx, B, C, ctx.N, S, K, C * S * K, 0, ctx.prepared)
         return dfeat, None
 
 
@@ -351,6 +401,7 @@ class _GroupXyzFeat(torch.autograd.Function):
                   c_xyz)
         ctx.save_for_backward(idx)
         ctx.dims = (B, C, N, S, K, c_xyz)
+        ctx.prepared = _prepare_group(idx, B, C, N, S, K) if (C > 0 and ctx.needs_input_grad[0]) else None
         return out
 
     @staticmethod
@@ -360,7 +411,7 @@ class _GroupXyzFeat(torch.autograd.Function):
         dx = None
         if C > 0 and ctx.needs_input_grad[0]:
             grad_out = _f32(grad_out)
-            dx = _group_bwd(grad_out, idx, B, C, N, S, K, (c_xyz + C) * S * K, c_xyz)
+            dx = _group_bwd(grad_out, idx, B, C, N, S, K, (c_xyz + C) * S * K, c_xyz, ctx.prepared)
         return dx, None, None, None, None, None
 
 
@@ -386,6 +437,11 @@ class _ThreeInterpolate(torch.autograd.Function):
               out.data_ptr())
         ctx.save_for_backward(idx, weight)
         ctx.m = m
+        ctx.prepared = None
+        if PREPARE_INVERSE_IN_FORWARD and ctx.needs_input_grad[0]:
+            ws_bytes = _cabi.lib().p3d_three_interp_bwd_ws_bytes(B, C, m, n)
+            if ws_bytes:
+                ctx.prepared = _Prepared("p3d_three_interp_bwd_prepare", dev, ws_bytes, idx.data_ptr(), B, C, m, n)
         return out
 
     @staticmethod
@@ -394,10 +450,14 @@ class _ThreeInterpolate(torch.autograd.Function):
         grad_out = _f32(grad_out)
         B, C, n = grad_out.shape
         dfeat = torch.empty((B, C, ctx.m), dtype=torch.float32, device=grad_out.device)
-        ws_bytes = _cabi.lib().p3d_three_interp_bwd_ws_bytes(B, C, ctx.m, n)
-        ws = _workspace(ws_bytes, grad_out.device)
+        if ctx.prepared is not None:
+            ctx.prepared.join(grad_out.device)
+            ws, ws_bytes, flag = ctx.prepared.ws, ctx.prepared.ws_bytes, 1
+        else:
+            ws_bytes = _cabi.lib().p3d_three_interp_bwd_ws_bytes(B, C, ctx.m, n)
+            ws, flag = _workspace(ws_bytes, grad_out.device), 0
         _call(grad_out.device, "p3d_three_interp_bwd_f32", grad_out.data_ptr(), idx.data_ptr(), weight.data_ptr(), B,
-              C, ctx.m, n, dfeat.data_ptr(), _ptr(ws), ws_bytes)
+              C, ctx.m, n, dfeat.data_ptr(), _ptr(ws), ws_bytes, flag)
         return dfeat, None, None
 
 
