@@ -371,19 +371,49 @@ three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ kno
 
 
 // ------------------------------------------------ knn, k <= 32: warp per query, list in lanes ----
-// Same candidate sweep as the ball query (SoA shared-memory tile, 32 candidates per warp step).  The
-// sorted best-k list of a query lives in REGISTERS ACROSS THE LANES of its warp (lane e = rank e), so an
-// insertion is one ballot + one shfl_up + a select: ~10 warp instructions instead of a shared-memory
-// shift loop, and it never serialises other queries.  Candidates are admitted in index order with a
-// strict '<' against the current k-th distance and placed after all entries <= their distance, so equal
-// distances keep the lower index first (the oracle's insertion rule).
+// Candidate sweep through a shared-memory tile, 32 candidates per warp step.  The sorted best-k list of
+// a query lives in REGISTERS ACROSS THE LANES of its warp (lane e = rank e), so an insertion is one
+// ballot + one shfl_up + a select (~10 warp instructions) and never serialises other queries.
+// The tile is stored TRANSPOSED (candidate j at [j % 64][j / 64], rows padded to 33 floats): step t
+// tests candidates t, 64+t, 128+t, ... instead of 32 consecutive ones.  Real clouds are spatially ordered
+// (LiDAR rings, voxel order), so consecutive candidates approach a query monotonically and EVERY one of
+// them would improve the running k-th distance; the strided order sees them like a random permutation
+// (k ln(N/k) insertions instead of O(N)).  Entries are ordered by (distance, index), so the result is
+// still "ascending distance, ties to the lower index" regardless of the visiting order.
+constexpr int KN_ROWS = 64, KN_PITCH = 33, KN_TILE = KN_ROWS * 32;
+
+// one warp step: every lane offers candidate (d, base + lane * KN_ROWS + s) if `ok`; admitted ones are merged
+// into the lane-resident list (d_l, i_l), kept sorted by (distance, index); (t, ti) = entry at rank k-1
+__device__ __forceinline__ void knn_lane_step(float d, bool ok, int base, int s, int k, int lane, float &d_l,
+                                              int &i_l, float &t, int &ti) {
+    unsigned m = __ballot_sync(0xffffffffu, ok && d <= t);
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const float nd = __shfl_sync(0xffffffffu, d, src);
+        const int ni = base + src * KN_ROWS + s;
+        if (nd < t || (nd == t && ni < ti)) {  // warp-uniform: lands before rank k-1
+            // ranks that move up by one: entries that sort after (nd, ni)
+            const unsigned gt = __ballot_sync(0xffffffffu, d_l > nd || (d_l == nd && i_l > ni));
+            const float up_d = __shfl_up_sync(0xffffffffu, d_l, 1);
+            const int up_i = __shfl_up_sync(0xffffffffu, i_l, 1);
+            const int first = __ffs(gt) - 1;
+            if (lane == first) { d_l = nd; i_l = ni; }
+            else if (lane > first) { d_l = up_d; i_l = up_i; }
+            t = __shfl_sync(0xffffffffu, d_l, k - 1);
+            ti = __shfl_sync(0xffffffffu, i_l, k - 1);
+            m &= __ballot_sync(0xffffffffu, d <= t);  // drop candidates the tighter bound rejects
+        }
+    }
+}
+
 template <bool DENSE, int QPW>
 __global__ void __launch_bounds__(NB_WARPS * 32)
 knn_lane_kernel(const float *__restrict__ x, const float *__restrict__ y, const int64_t *__restrict__ batch_x,
                 const int64_t *__restrict__ batch_y, int64_t Nx, int64_t Ny, int64_t n_dense, int64_t s_dense, int k,
                 int64_t *__restrict__ col, float *__restrict__ dout) {
     constexpr int QPC = NB_WARPS * QPW;
-    __shared__ float sx[NB_TILE], sy[NB_TILE], sz[NB_TILE];
+    __shared__ float sx[KN_ROWS * KN_PITCH], sy[KN_ROWS * KN_PITCH], sz[KN_ROWS * KN_PITCH];
     __shared__ RangeCache rc;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t q0 = (int64_t)blockIdx.x * QPC;
@@ -391,14 +421,15 @@ knn_lane_kernel(const float *__restrict__ x, const float *__restrict__ y, const 
     cta_ranges<DENSE>(q0, q1, batch_x, batch_y, Nx, rc, warp, lane);
 
     float qx[QPW], qy[QPW], qz[QPW], tau[QPW], bd[QPW];
-    int bi[QPW];
+    int bi[QPW], taui[QPW];
     int64_t x0[QPW], x1[QPW];
 #pragma unroll
     for (int u = 0; u < QPW; ++u) {
         const int64_t q = q0 + warp * QPW + u;
         tau[u] = CUDART_INF_F;
-        bd[u] = CUDART_INF_F;  // lanes >= k never matter: the admission test uses lane k-1
-        bi[u] = -1;
+        taui[u] = 0x7fffffff;
+        bd[u] = CUDART_INF_F;  // lanes >= k never matter: the admission test uses rank k-1
+        bi[u] = 0x7fffffff;    // empty slot (sorts after every real entry)
         if (q < q1) {
             qx[u] = __ldg(y + 3 * q); qy[u] = __ldg(y + 3 * q + 1); qz[u] = __ldg(y + 3 * q + 2);
             query_range<DENSE>(q, batch_x, batch_y, Nx, n_dense, s_dense, rc, lane, x0[u], x1[u]);
@@ -415,40 +446,53 @@ knn_lane_kernel(const float *__restrict__ x, const float *__restrict__ y, const 
         query_range<DENSE>(q1 - 1, batch_x, batch_y, Nx, n_dense, s_dense, rc, lane, a, b);
         X1 = b;
     }
-    for (int64_t tb = X0; tb < X1; tb += NB_TILE) {
-        const int tn = (int)((X1 - tb < NB_TILE) ? (X1 - tb) : NB_TILE);
+    // pass 0: step 0 of EVERY tile (candidates tb + 64 * lane, a 1/64 subsample of the cloud) straight from
+    // global memory.  It costs 1/64 of the sweep and leaves a k-th distance bound that only ~64 k candidates
+    // of the whole cloud can beat, so the main sweep (steps 1..63 of every tile) rarely inserts.
+#pragma unroll
+    for (int u = 0; u < QPW; ++u) {
+        float t = tau[u], d_l = bd[u];
+        int ti = taui[u], i_l = bi[u];
+        for (int64_t tb = X0; tb < X1; tb += KN_TILE) {
+            const int64_t cand = tb + (int64_t)lane * KN_ROWS;
+            const bool ok = cand >= x0[u] && cand < x1[u];
+            float d = 0.f;
+            if (ok) d = sqdist3(__ldg(x + 3 * cand), __ldg(x + 3 * cand + 1), __ldg(x + 3 * cand + 2), qx[u], qy[u], qz[u]);
+            knn_lane_step(d, ok, (int)(tb - X0), 0, k, lane, d_l, i_l, t, ti);
+        }
+        tau[u] = t; taui[u] = ti; bd[u] = d_l; bi[u] = i_l;
+    }
+    for (int64_t tb = X0; tb < X1; tb += KN_TILE) {
+        const int tn = (int)((X1 - tb < KN_TILE) ? (X1 - tb) : KN_TILE);
         if (tb != X0) __syncthreads();
-        load_tile(x, tb, tn, sx, sy, sz, tid, NB_WARPS * 32);
+        {
+            const float *__restrict__ src = x + 3 * tb;
+#pragma unroll 4
+            for (int f = tid; f < 3 * tn; f += NB_WARPS * 32) {
+                const float v = __ldg(src + f);
+                const int p = f / 3, c = f - 3 * p;
+                float *dst = c == 0 ? sx : (c == 1 ? sy : sz);
+                dst[(p & (KN_ROWS - 1)) * KN_PITCH + (p >> 6)] = v;
+            }
+        }
         __syncthreads();
 #pragma unroll
         for (int u = 0; u < QPW; ++u) {
             const int lo = (int)((x0[u] > tb ? x0[u] : tb) - tb);
             const int hi = (int)((x1[u] < tb + tn ? x1[u] : tb + tn) - tb);
+            if (lo >= hi) continue;  // warp-uniform
             float t = tau[u], d_l = bd[u];
-            int i_l = bi[u];
-            for (int i0 = lo; i0 < hi; i0 += 32) {
-                const int i = i0 + lane;
-                const bool ok = i < hi;
-                const int ii = ok ? i : lo;
-                const float d = sqdist3(sx[ii], sy[ii], sz[ii], qx[u], qy[u], qz[u]);
-                unsigned m = __ballot_sync(0xffffffffu, ok && d < t);
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const float nd = __shfl_sync(0xffffffffu, d, src);
-                    if (nd < t) {  // warp-uniform
-                        const unsigned gt = __ballot_sync(0xffffffffu, d_l > nd);  // ranks that move up by one
-                        const float up_d = __shfl_up_sync(0xffffffffu, d_l, 1);
-                        const int up_i = __shfl_up_sync(0xffffffffu, i_l, 1);
-                        const int first = __ffs(gt) - 1;  // gt != 0: lane k-1 holds tau > nd
-                        if (lane == first) { d_l = nd; i_l = (int)(tb - X0) + i0 + src; }
-                        else if (lane > first) { d_l = up_d; i_l = up_i; }
-                        t = __shfl_sync(0xffffffffu, d_l, k - 1);
-                        m &= __ballot_sync(0xffffffffu, d < t);  // drop candidates the tighter bound now rejects
-                    }
-                }
+            int ti = taui[u], i_l = bi[u];
+            const int base = (int)(tb - X0);
+#pragma unroll 2
+            for (int s = 1; s < KN_ROWS; ++s) {  // step 0 was pass 0
+                const int j = lane * KN_ROWS + s;  // candidate of this lane at this step
+                const bool ok = j >= lo && j < hi;
+                const int at = s * KN_PITCH + lane;
+                const float d = sqdist3(sx[at], sy[at], sz[at], qx[u], qy[u], qz[u]);
+                knn_lane_step(d, ok, base, s, k, lane, d_l, i_l, t, ti);
             }
-            tau[u] = t; bd[u] = d_l; bi[u] = i_l;
+            tau[u] = t; taui[u] = ti; bd[u] = d_l; bi[u] = i_l;
         }
     }
 #pragma unroll
@@ -457,7 +501,7 @@ knn_lane_kernel(const float *__restrict__ x, const float *__restrict__ y, const 
         if (q >= q1) continue;
         const int64_t off = DENSE ? x0[u] : 0;
         if (lane < k) {
-            const bool have = bi[u] >= 0;
+            const bool have = bi[u] != 0x7fffffff;
             col[q * k + lane] = have ? (X0 + bi[u] - off) : -1;
             if (dout) dout[q * k + lane] = have ? bd[u] : -1.f;
         }
