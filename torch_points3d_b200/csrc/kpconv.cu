@@ -289,6 +289,14 @@ int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neigh
                   int Cout, float extent, int influence, int aggregation, float *out, void *ws, size_t ws_bytes,
                   cudaStream_t st);
 size_t kpconv_tc_ws_bytes(int K, int Cin, int Cout);
+// sparse-influence backward helpers (kpconv_tc.cu)
+bool kpconv_sparse_supported(int M, int K, int Cin);
+int kpconv_wf_sparse(const float *query, const float *support, const int64_t *neighbors, const float *feat,
+                     const float *k_points, int64_t n, int64_t N0, int M, int K, int Cin, float extent, int influence,
+                     int aggregation, float *wf, cudaStream_t st);
+int kpconv_scatter_sparse(const float *query, const float *support, const int64_t *neighbors, const float *k_points,
+                          const float *dwf, int64_t n, int64_t N0, int M, int K, int Cin, float extent, int influence,
+                          int aggregation, float *dfeat, cudaStream_t st);
 }  // namespace p3d
 
 P3D_EXPORT size_t p3d_kpconv_fwd_ws_bytes(int K, int Cin, int Cout) { return kpconv_tc_ws_bytes(K, Cin, Cout); }
@@ -347,10 +355,17 @@ P3D_EXPORT int p3d_kpconv_bwd_f32(const float *query, const float *support, cons
     const int64_t KC = (int64_t)K * Cin;
     int64_t grid = (n + KPF_WARPS - 1) / KPF_WARPS;
     if (grid > 16 * kNumSMs) grid = 16 * kNumSMs;
+    const bool sparse = kpconv_sparse_supported(M, K, Cin);
     if (dweights) {
-        kpconv_wf_kernel<<<(unsigned)grid, KPF_WARPS * 32, smem, st>>>(query, support, neighbors, feat, k_points, n,
-                                                                     N0, M, Mpad, K, Cin, g, wf);
-        if (int e = finish_launch("kpconv_wf")) return e;
+        if (sparse) {
+            if (int e = kpconv_wf_sparse(query, support, neighbors, feat, k_points, n, N0, M, K, Cin, extent, influence,
+                                         aggregation, wf, st))
+                return e;
+        } else {
+            kpconv_wf_kernel<<<(unsigned)grid, KPF_WARPS * 32, smem, st>>>(query, support, neighbors, feat, k_points,
+                                                                         n, N0, M, Mpad, K, Cin, g, wf);
+            if (int e = finish_launch("kpconv_wf")) return e;
+        }
         // dW[kc][o] += sum_p wf[p][kc] * dout[p][o]
         const int64_t tiles = ((KC + 63) / 64) * ((Cout + 63) / 64);
         int64_t split = (2 * kNumSMs + tiles - 1) / tiles;
@@ -367,9 +382,15 @@ P3D_EXPORT int p3d_kpconv_bwd_f32(const float *query, const float *support, cons
         dim3 gd((unsigned)((KC + 63) / 64), (unsigned)((n + 63) / 64), 1);
         sgemm_strided_kernel<<<gd, 256, 0, st>>>(dout, Cout, 1, k_values, 1, Cout, dwf, KC, n, KC, Cout, Cout, 0);
         if (int e = finish_launch("kpconv_dwf_gemm")) return e;
-        kpconv_scatter_kernel<<<(unsigned)grid, KPF_WARPS * 32, smem, st>>>(query, support, neighbors, k_points, dwf,
-                                                                          n, N0, M, Mpad, K, Cin, g, dfeat);
-        if (int e = finish_launch("kpconv_scatter")) return e;
+        if (sparse) {
+            if (int e = kpconv_scatter_sparse(query, support, neighbors, k_points, dwf, n, N0, M, K, Cin, extent,
+                                              influence, aggregation, dfeat, st))
+                return e;
+        } else {
+            kpconv_scatter_kernel<<<(unsigned)grid, KPF_WARPS * 32, smem, st>>>(query, support, neighbors, k_points,
+                                                                              dwf, n, N0, M, Mpad, K, Cin, g, dfeat);
+            if (int e = finish_launch("kpconv_scatter")) return e;
+        }
     }
     return P3D_OK;
 }

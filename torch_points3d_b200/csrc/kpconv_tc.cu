@@ -425,6 +425,154 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
     }
 }
 
+// ---- backward helpers on the same sparse producers --------------------------------------------------
+// wf[p][k][c] = sum_m w[p,k,m] x[nb[p,m], c]  -> workspace (for dW = wf^T dout); one warp per point, the influence
+// table is computed once per point and reused for every 32-channel slab
+template <int INFL, bool CLOSEST>
+__global__ void __launch_bounds__(256)
+kpconv_wf_sparse_kernel(const float *__restrict__ q, const float *__restrict__ s, const int64_t *__restrict__ nb,
+                        const float *__restrict__ x, const float *__restrict__ kp, int64_t n, int64_t N0, int M, int K,
+                        int Cin, KpGeom g, float *__restrict__ wf) {
+    __shared__ float xs_all[8 * TC_MCAP * 32];
+    __shared__ float4 kps[KP_K];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < KP_K) kps[tid] = tid < K ? make_float4(__ldg(kp + 3 * tid), __ldg(kp + 3 * tid + 1), __ldg(kp + 3 * tid + 2), 0.f)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    float *xs = xs_all + warp * TC_MCAP * 32;
+    for (int i = lane; i < TC_MCAP * 32; i += 32) xs[i] = 0.f;
+    __syncthreads();
+    const uint32_t xs_addr = smem_u32(xs) + (uint32_t)lane * 4u;
+    const float inv_extent = 1.0f / g.extent;
+    for (int64_t p = (int64_t)blockIdx.x * 8 + warp; p < n; p += (int64_t)gridDim.x * 8) {
+        TcPoint P;
+        tc_load_point(q + 3 * p, s, nb + p * M, N0, M, lane, P);
+        float w0[KP_K], w1[4];
+        unsigned mask0[KP_K], mask1[4];
+        tc_weights<INFL, CLOSEST>(P, kps, K, M, g, inv_extent, w0, w1, mask0, mask1, lane);
+        for (int sl = 0; sl < Cin / 32; ++sl) {
+            const float *xcol = x + sl * 32 + lane;
+#pragma unroll
+            for (int m = 0; m < TC_MCAP; ++m) {
+                const int j = __shfl_sync(0xffffffffu, m < 32 ? P.j0 : P.j1, m & 31);
+                if (m < M && j >= 0)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(xs_addr + m * 128u),
+                                 "l"(xcol + (int64_t)j * Cin)
+                                 : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < KP_K - 1; ++k) {
+                unsigned mk = mask0[k];
+                float a = 0.f;
+                while (mk) {
+                    const int m = __ffs(mk) - 1;
+                    mk &= mk - 1;
+                    a = fmaf(__shfl_sync(0xffffffffu, w0[k], m), xs[m * 32 + lane], a);
+                }
+                mk = (mask1[k >> 2] >> (8 * (k & 3))) & 0xffu;
+                while (mk) {
+                    const int mm = __ffs(mk) - 1;
+                    mk &= mk - 1;
+                    a = fmaf(__shfl_sync(0xffffffffu, w1[k >> 2], mm + 8 * (k & 3)), xs[(32 + mm) * 32 + lane], a);
+                }
+                if (k < K) wf[(p * K + k) * Cin + sl * 32 + lane] = a;
+            }
+        }
+    }
+}
+
+// dfeat[nb[p,m]][c] += sum_k w[p,k,m] * dwf[p][k][c] over the influencing (k, m) pairs only
+template <int INFL, bool CLOSEST>
+__global__ void __launch_bounds__(256)
+kpconv_scatter_sparse_kernel(const float *__restrict__ q, const float *__restrict__ s, const int64_t *__restrict__ nb,
+                             const float *__restrict__ kp, const float *__restrict__ dwf, int64_t n, int64_t N0, int M,
+                             int K, int Cin, KpGeom g, float *__restrict__ dfeat) {
+    __shared__ float4 kps[KP_K];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < KP_K) kps[tid] = tid < K ? make_float4(__ldg(kp + 3 * tid), __ldg(kp + 3 * tid + 1), __ldg(kp + 3 * tid + 2), 0.f)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    const float inv_extent = 1.0f / g.extent;
+    for (int64_t p = (int64_t)blockIdx.x * 8 + warp; p < n; p += (int64_t)gridDim.x * 8) {
+        TcPoint P;
+        tc_load_point(q + 3 * p, s, nb + p * M, N0, M, lane, P);
+        float w0[KP_K], w1[4];
+        unsigned mask0[KP_K], mask1[4];
+        tc_weights<INFL, CLOSEST>(P, kps, K, M, g, inv_extent, w0, w1, mask0, mask1, lane);
+        for (int sl = 0; sl < Cin / 32; ++sl) {
+            const int c = sl * 32 + lane;
+            float d[KP_K];
+#pragma unroll
+            for (int k = 0; k < KP_K; ++k) d[k] = k < K ? __ldg(dwf + (p * K + k) * Cin + c) : 0.f;
+#pragma unroll
+            for (int k = 0; k < KP_K - 1; ++k) {
+                unsigned mk = mask0[k];
+                while (mk) {
+                    const int m = __ffs(mk) - 1;
+                    mk &= mk - 1;
+                    const int j = __shfl_sync(0xffffffffu, P.j0, m);
+                    atomicAdd(dfeat + (int64_t)j * Cin + c, __shfl_sync(0xffffffffu, w0[k], m) * d[k]);
+                }
+                mk = (mask1[k >> 2] >> (8 * (k & 3))) & 0xffu;
+                while (mk) {
+                    const int mm = __ffs(mk) - 1;
+                    mk &= mk - 1;
+                    const int j = __shfl_sync(0xffffffffu, P.j1, mm);
+                    atomicAdd(dfeat + (int64_t)j * Cin + c, __shfl_sync(0xffffffffu, w1[k >> 2], mm + 8 * (k & 3)) * d[k]);
+                }
+            }
+        }
+    }
+}
+
+static KpGeom tc_geom(float extent, int influence, int aggregation) {
+    KpGeom g;
+    g.extent = extent;
+    const float sig = extent * 0.3f;
+    g.gauss_den = 2.0f * sig * sig + 1e-9f;
+    g.influence = influence;
+    g.aggregation = aggregation;
+    return g;
+}
+
+bool kpconv_sparse_supported(int M, int K, int Cin) { return M <= TC_MCAP && K <= KP_K && Cin % 32 == 0; }
+
+#define P3D_KP_DISPATCH(KERNEL, ...)                                                          \
+    do {                                                                                      \
+        if (aggregation == P3D_AGGREGATION_CLOSEST) {                                         \
+            if (influence == P3D_INFLUENCE_CONSTANT) KERNEL<P3D_INFLUENCE_CONSTANT, true> __VA_ARGS__; \
+            else if (influence == P3D_INFLUENCE_LINEAR) KERNEL<P3D_INFLUENCE_LINEAR, true> __VA_ARGS__; \
+            else KERNEL<P3D_INFLUENCE_GAUSSIAN, true> __VA_ARGS__;                            \
+        } else {                                                                              \
+            if (influence == P3D_INFLUENCE_CONSTANT) KERNEL<P3D_INFLUENCE_CONSTANT, false> __VA_ARGS__; \
+            else if (influence == P3D_INFLUENCE_LINEAR) KERNEL<P3D_INFLUENCE_LINEAR, false> __VA_ARGS__; \
+            else KERNEL<P3D_INFLUENCE_GAUSSIAN, false> __VA_ARGS__;                           \
+        }                                                                                     \
+    } while (0)
+
+int kpconv_wf_sparse(const float *query, const float *support, const int64_t *neighbors, const float *feat,
+                     const float *k_points, int64_t n, int64_t N0, int M, int K, int Cin, float extent, int influence,
+                     int aggregation, float *wf, cudaStream_t st) {
+    const KpGeom g = tc_geom(extent, influence, aggregation);
+    int64_t grid = (n + 7) / 8;
+    if (grid > 16 * kNumSMs) grid = 16 * kNumSMs;
+    P3D_KP_DISPATCH(kpconv_wf_sparse_kernel, <<<(unsigned)grid, 256, 0, st>>>(query, support, neighbors, feat, k_points,
+                                                                             n, N0, M, K, Cin, g, wf));
+    return finish_launch("kpconv_wf_sparse");
+}
+
+int kpconv_scatter_sparse(const float *query, const float *support, const int64_t *neighbors, const float *k_points,
+                          const float *dwf, int64_t n, int64_t N0, int M, int K, int Cin, float extent, int influence,
+                          int aggregation, float *dfeat, cudaStream_t st) {
+    const KpGeom g = tc_geom(extent, influence, aggregation);
+    int64_t grid = (n + 7) / 8;
+    if (grid > 16 * kNumSMs) grid = 16 * kNumSMs;
+    P3D_KP_DISPATCH(kpconv_scatter_sparse_kernel, <<<(unsigned)grid, 256, 0, st>>>(query, support, neighbors, k_points,
+                                                                                  dwf, n, N0, M, K, Cin, g, dfeat));
+    return finish_launch("kpconv_scatter_sparse");
+}
+
 size_t kpconv_tc_ws_bytes(int K, int Cin, int Cout) {
     if (K > KP_K || Cin % 32 != 0 || Cout % TC_NCH != 0 || Cout > 512) return 0;
     return (size_t)(Cin / 32) * (Cout / TC_NCH) * 4 * TC_W_PIECE;
