@@ -42,7 +42,9 @@ def test_library_loads_and_reports_arch(cabi):
     assert lib.p3d_launch_count() >= 0
     assert lib.p3d_fps_dense_ws_bytes(4, 1024) == 0
     assert lib.p3d_fps_dense_ws_bytes(2, 200000) == 2 * 200000 * 4
-    assert lib.p3d_kpconv_bwd_ws_bytes(10, 34, 15, 32, 32) == 2 * 10 * 15 * 32 * 4
+    # wf + dwf buffers, plus the bf16 hi/lo image of W^T for the tensor-core dwf GEMM (15 x 32 outputs / 32 per chunk x 4 pieces x 16 KB)
+    assert lib.p3d_kpconv_bwd_ws_bytes(10, 34, 15, 32, 32) == 2 * 10 * 15 * 32 * 4 + 15 * 4 * 16384
+    assert lib.p3d_kpconv_bwd_ws_bytes(10, 34, 15, 5, 64) == 2 * 10 * 15 * 5 * 4
 
 
 def test_sass_is_sm100a_only(cabi):

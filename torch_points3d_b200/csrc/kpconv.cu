@@ -289,6 +289,11 @@ int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neigh
                   int Cout, float extent, int influence, int aggregation, float *out, void *ws, size_t ws_bytes,
                   cudaStream_t st);
 size_t kpconv_tc_ws_bytes(int K, int Cin, int Cout);
+// tensor-core / register-tiled GEMMs of the backward (kpconv_tc.cu)
+size_t gemm_tc_ws_bytes(int Kd, int N);
+int gemm_tc(const float *A, int64_t lda, const float *Bp, int64_t sbk, int64_t sbj, int64_t R, int Kd, int N, float *C,
+            int64_t ldc, void *ws, size_t ws_bytes, cudaStream_t st);
+int dw_accumulate(const float *A, const float *B, int64_t n, int R, int Cn, float *dW, cudaStream_t st);
 // sparse-influence backward helpers (kpconv_tc.cu)
 bool kpconv_sparse_supported(int M, int K, int Cin);
 int kpconv_wf_sparse(const float *query, const float *support, const int64_t *neighbors, const float *feat,
@@ -323,8 +328,8 @@ P3D_EXPORT int p3d_kpconv_fwd_f32(const float *query, const float *support, cons
 
 P3D_EXPORT size_t p3d_kpconv_bwd_ws_bytes(int64_t n, int M, int K, int Cin, int Cout) {
     (void)M;
-    (void)Cout;
-    return (size_t)2 * (size_t)n * (size_t)K * (size_t)Cin * sizeof(float);
+    // wf + dwf  [n, K, Cin] each, then the bf16 hi/lo image of W^T for the tensor-core dwf GEMM (0 if unsupported)
+    return (size_t)2 * (size_t)n * (size_t)K * (size_t)Cin * sizeof(float) + gemm_tc_ws_bytes(Cout, K * Cin);
 }
 
 P3D_EXPORT int p3d_kpconv_bwd_f32(const float *query, const float *support, const int64_t *neighbors,
@@ -367,6 +372,8 @@ P3D_EXPORT int p3d_kpconv_bwd_f32(const float *query, const float *support, cons
             if (int e = finish_launch("kpconv_wf")) return e;
         }
         // dW[kc][o] += sum_p wf[p][kc] * dout[p][o]
+        if (dw_accumulate(wf, dout, n, (int)KC, Cout, dweights, st) == 0) goto dw_done;
+        {
         const int64_t tiles = ((KC + 63) / 64) * ((Cout + 63) / 64);
         int64_t split = (2 * kNumSMs + tiles - 1) / tiles;
         int64_t kps = (n + split - 1) / split;
@@ -376,12 +383,20 @@ P3D_EXPORT int p3d_kpconv_bwd_f32(const float *query, const float *support, cons
         dim3 gd((unsigned)((Cout + 63) / 64), (unsigned)((KC + 63) / 64), (unsigned)split);
         sgemm_strided_kernel<<<gd, 256, 0, st>>>(wf, 1, KC, dout, Cout, 1, dweights, Cout, KC, Cout, n, kps, 1);
         if (int e = finish_launch("kpconv_dW_gemm")) return e;
+        }
+    dw_done:;
     }
     if (dfeat) {
-        // dwf[p][kc] = sum_o dout[p][o] * W[kc][o]
-        dim3 gd((unsigned)((KC + 63) / 64), (unsigned)((n + 63) / 64), 1);
-        sgemm_strided_kernel<<<gd, 256, 0, st>>>(dout, Cout, 1, k_values, 1, Cout, dwf, KC, n, KC, Cout, Cout, 0);
-        if (int e = finish_launch("kpconv_dwf_gemm")) return e;
+        // dwf[p][kc] = sum_o dout[p][o] * W[kc][o]: tcgen05 GEMM (bf16 hi+lo operands) when the shape allows it
+        void *bimg = (char *)ws + (size_t)2 * n * K * Cin * sizeof(float);
+        const size_t bimg_bytes = ws_bytes - (size_t)2 * n * K * Cin * sizeof(float);
+        const int r = gemm_tc(dout, Cout, k_values, 1, Cout, n, Cout, (int)KC, dwf, KC, bimg, bimg_bytes, st);
+        if (r < 0) return r;
+        if (r == 1) {
+            dim3 gd((unsigned)((KC + 63) / 64), (unsigned)((n + 63) / 64), 1);
+            sgemm_strided_kernel<<<gd, 256, 0, st>>>(dout, Cout, 1, k_values, 1, Cout, dwf, KC, n, KC, Cout, Cout, 0);
+            if (int e = finish_launch("kpconv_dwf_gemm")) return e;
+        }
         if (sparse) {
             if (int e = kpconv_scatter_sparse(query, support, neighbors, k_points, dwf, n, N0, M, K, Cin, extent,
                                               influence, aggregation, dfeat, st))

@@ -573,6 +573,351 @@ int kpconv_scatter_sparse(const float *query, const float *support, const int64_
     return finish_launch("kpconv_scatter_sparse");
 }
 
+// ---- generic tcgen05 GEMM  C[R x N] = A[R x Kd] * B[Kd x N]  (fp32 in HBM, bf16 hi+lo on the tensor cores) --------
+// Used by the KPConv backward for dwf = dout * W^T.  Same machinery as the forward kernel: 64-row tiles in the
+// canonical UMMA layout, weight pieces by TMA, TMEM accumulators, tcgen05.ld epilogue; the producers here are plain
+// row loaders (16 consecutive K elements per lane, split into bf16 hi + lo).
+// B image: piece(s, nc, qq) as in kpconv_prep_w_kernel but with the plain K index: kidx = k - 512 * s.
+__global__ void __launch_bounds__(256)
+gemm_prep_b_kernel(const float *__restrict__ B, int64_t sbk, int64_t sbj, int Kd, int N, uint8_t *__restrict__ img) {
+    const int piece = blockIdx.x;  // ((s * ncs + nc) * 4 + q)
+    const int ncs = N / TC_NCH;
+    const int qq = piece & 3, nc = (piece >> 2) % ncs, s = (piece >> 2) / ncs;
+    uint8_t *base = img + (size_t)piece * TC_W_PIECE;
+    for (int i = threadIdx.x; i < TC_WCH * TC_NCH * 64; i += 256) {
+        const int e = i & 63, r = (i >> 6) & 31, kc = i >> 11;
+        const int k = s * 512 + (qq * TC_WCH + kc) * 64 + e;
+        const float v = k < Kd ? __ldg(B + (int64_t)k * sbk + (int64_t)(nc * TC_NCH + r) * sbj) : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        const int off = (kc * TC_NCH + r) * 128 + (((e >> 3) ^ (r & 7)) << 4) + ((e & 7) << 1);
+        *reinterpret_cast<__nv_bfloat16 *>(base + off) = hi;
+        *reinterpret_cast<__nv_bfloat16 *>(base + TC_WCH * TC_NCH * 128 + off) = lo;
+    }
+}
+
+// resident = 1: the whole B image of this CTA's output-channel chunks (ncl x chunks x 8 KB) is loaded into shared
+// memory ONCE (small Kd: the backward's dwf GEMM has Kd = Cout), so a tile costs no TMA round trips at all;
+// resident = 0: weight pieces are streamed per tile as in the forward kernel.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const float *__restrict__ A, int64_t lda, const uint8_t *__restrict__ bimg, int64_t R, int Kd, int N,
+               uint32_t tmem_cols, int ncpc, int resident, float *__restrict__ C, int64_t ldc) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *a_tile = smem;
+    uint8_t *w_tile = smem + TC_A_BYTES;
+    __shared__ __align__(8) uint64_t bar_a_empty, bar_w_full, bar_w_empty, bar_d_full;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slabs = (Kd + 511) / 512, ncs = N / TC_NCH;
+    const int nc0 = blockIdx.y * ncpc;
+    const int ncl = (ncs - nc0 < ncpc) ? (ncs - nc0) : ncpc;
+    const int64_t ntiles = (R + TC_TILE - 1) / TC_TILE;
+    if (tid == 0) {
+        mbar_init(&bar_a_empty, 1);
+        mbar_init(&bar_w_full, 1);
+        mbar_init(&bar_w_empty, 1);
+        mbar_init(&bar_d_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == TC_PWARPS) tmem_alloc(&tmem_base_s, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    uint32_t pass = 0, wloads = 0, tile_iter = 0;
+    constexpr int PPW = TC_TILE / TC_PWARPS;
+    const bool vec = ((lda & 3) == 0) && ((((uintptr_t)A) & 15) == 0);
+    const int kchunks = (Kd + 63) / 64;  // resident mode: Kd <= 512, one slab
+    if (resident) {
+        // B_res[ncq][chunk][hi 4 KB | lo 4 KB] right after the part of the A tile that is used
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&bar_w_full, (uint32_t)(ncl * kchunks * 2 * TC_NCH * 128));
+            for (int ncq = 0; ncq < ncl; ++ncq)
+                for (int ch = 0; ch < kchunks; ++ch) {
+                    const uint8_t *piece = bimg + ((size_t)(nc0 + ncq) * 4 + (ch >> 1)) * TC_W_PIECE;
+                    uint8_t *dst = w_tile + (size_t)(ncq * kchunks + ch) * (2 * TC_NCH * 128);
+                    bulk_g2s(dst, piece + (ch & 1) * (TC_NCH * 128), TC_NCH * 128, &bar_w_full);
+                    bulk_g2s(dst + TC_NCH * 128, piece + TC_W_PIECE / 2 + (ch & 1) * (TC_NCH * 128), TC_NCH * 128,
+                             &bar_w_full);
+                }
+        }
+        mbar_wait(&bar_w_full, 0);
+    }
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
+        const int64_t r_base = tile * TC_TILE;
+        for (int sl = 0; sl < slabs; ++sl, ++pass) {
+            const int kleft = Kd - sl * 512;                       // K elements of this slab (<= 512 used)
+            const int pieces = kleft >= 512 ? 4 : (kleft + 127) / 128;  // 128-K weight pieces that hold data
+            if (warp < TC_PWARPS) {
+                if (pass > 0) mbar_wait(&bar_a_empty, (pass - 1) & 1);
+                for (int pi = 0; pi < PPW; ++pi) {
+                    const int row = warp * PPW + pi;
+                    const int64_t r = r_base + row;
+                    const int k0 = sl * 512 + lane * 16;
+                    float v[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = 0.f;
+                    if (r < R && lane * 16 < pieces * 128) {
+                        const float *src = A + r * lda + k0;
+                        if (vec && k0 + 16 <= Kd) {
+#pragma unroll
+                            for (int g4 = 0; g4 < 4; ++g4) {
+                                const float4 t4 = __ldg(reinterpret_cast<const float4 *>(src) + g4);
+                                v[4 * g4] = t4.x; v[4 * g4 + 1] = t4.y; v[4 * g4 + 2] = t4.z; v[4 * g4 + 3] = t4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e)
+                                if (k0 + e < Kd) v[e] = __ldg(src + e);
+                        }
+                    }
+                    if (lane * 16 < pieces * 128) {
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const float h0 = __bfloat162float(__float2bfloat16_rn(v[2 * u]));
+                            const float h1 = __bfloat162float(__float2bfloat16_rn(v[2 * u + 1]));
+                            hi[u] = pack_bf16(h0, h1);
+                            lo[u] = pack_bf16(v[2 * u] - h0, v[2 * u + 1] - h1);
+                        }
+                        uint8_t *rowp = a_tile + (lane >> 2) * TC_A_CHUNK + row * 128;
+                        const int g0 = (lane & 3) * 2, sw = row & 7;
+                        *reinterpret_cast<uint4 *>(rowp + ((g0 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4 *>(rowp + (((g0 + 1) ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                        rowp += TC_A_BYTES / 2;
+                        *reinterpret_cast<uint4 *>(rowp + ((g0 ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<uint4 *>(rowp + (((g0 + 1) ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    }
+                }
+                fence_proxy_async();
+            }
+            __syncthreads();
+            if (warp == TC_PWARPS) {
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t idesc = tc_idesc(TC_MMA_M, TC_NCH);
+                    const uint32_t a_addr = smem_u32(a_tile), w_addr = smem_u32(w_tile);
+                    for (int ncq = 0; ncq < ncl; ++ncq) {
+                        const int nc = nc0 + ncq;
+                        const uint32_t d = tmem_base + (uint32_t)(ncq * TC_NCH);
+                        if (resident) {
+                            for (int ch = 0; ch < kchunks; ++ch) {
+                                const uint32_t wb = w_addr + (uint32_t)((ncq * kchunks + ch) * (2 * TC_NCH * 128));
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    const uint32_t ko = (uint32_t)(ks * 32);
+                                    const uint32_t ac = a_addr + (uint32_t)(ch * TC_A_CHUNK) + ko;
+                                    const uint64_t a_hi = tc_smem_desc(ac);
+                                    const uint64_t a_lo = tc_smem_desc(ac + TC_A_BYTES / 2);
+                                    const uint64_t b_hi = tc_smem_desc(wb + ko);
+                                    const uint64_t b_lo = tc_smem_desc(wb + TC_NCH * 128 + ko);
+                                    const uint32_t first = (ch == 0 && ks == 0) ? 0u : 1u;
+                                    tc_mma_bf16(d, a_hi, b_hi, idesc, first);
+                                    tc_mma_bf16(d, a_lo, b_hi, idesc, 1u);
+                                    tc_mma_bf16(d, a_hi, b_lo, idesc, 1u);
+                                }
+                            }
+                            continue;
+                        }
+                        for (int qq = 0; qq < pieces; ++qq, ++wloads) {
+                            if (wloads > 0) mbar_wait(&bar_w_empty, (wloads - 1) & 1);
+                            mbar_arrive_expect_tx(&bar_w_full, TC_W_PIECE);
+                            bulk_g2s(w_tile, bimg + ((size_t)(sl * ncs + nc) * 4 + qq) * TC_W_PIECE, TC_W_PIECE,
+                                     &bar_w_full);
+                            mbar_wait(&bar_w_full, wloads & 1);
+                            tc_fence_after();
+#pragma unroll
+                            for (int kc = 0; kc < TC_WCH; ++kc) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    const uint32_t ko = (uint32_t)(ks * 32);
+                                    const uint32_t ac = a_addr + (uint32_t)((qq * TC_WCH + kc) * TC_A_CHUNK) + ko;
+                                    const uint64_t a_hi = tc_smem_desc(ac);
+                                    const uint64_t a_lo = tc_smem_desc(ac + TC_A_BYTES / 2);
+                                    const uint64_t b_hi = tc_smem_desc(w_addr + kc * (TC_NCH * 128) + ko);
+                                    const uint64_t b_lo = tc_smem_desc(w_addr + TC_W_PIECE / 2 + kc * (TC_NCH * 128) + ko);
+                                    const uint32_t first = (sl == 0 && qq == 0 && kc == 0 && ks == 0) ? 0u : 1u;
+                                    tc_mma_bf16(d, a_hi, b_hi, idesc, first);
+                                    tc_mma_bf16(d, a_lo, b_hi, idesc, 1u);
+                                    tc_mma_bf16(d, a_hi, b_lo, idesc, 1u);
+                                }
+                            }
+                            tc_commit(&bar_w_empty);
+                        }
+                    }
+                    tc_commit(&bar_a_empty);
+                    if (sl == slabs - 1) tc_commit(&bar_d_full);
+                }
+                __syncwarp();
+            }
+        }
+        if (warp < TC_TILE / 32) {
+            mbar_wait(&bar_d_full, tile_iter & 1);
+            tc_fence_after();
+            const int64_t r = r_base + warp * 32 + lane;
+            for (int ncq = 0; ncq < ncl; ++ncq) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ncq * TC_NCH), v);
+                if (r < R) {
+                    float *dst = C + r * ldc + (nc0 + ncq) * TC_NCH;
+                    if ((ldc & 3) == 0 && ((((uintptr_t)C) & 15) == 0)) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            reinterpret_cast<float4 *>(dst)[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 32; ++u) dst[u] = v[u];
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    __syncthreads();
+    if (warp == TC_PWARPS) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+size_t gemm_tc_ws_bytes(int Kd, int N) {
+    if (N % TC_NCH != 0 || N > 512) return 0;
+    return (size_t)((Kd + 511) / 512) * (N / TC_NCH) * 4 * TC_W_PIECE;
+}
+
+// C[R x N] = A[R x Kd] * B, B(k, j) = Bp[k * sbk + j * sbj]; returns 1 when the shape is not supported
+int gemm_tc(const float *A, int64_t lda, const float *Bp, int64_t sbk, int64_t sbj, int64_t R, int Kd, int N, float *C,
+            int64_t ldc, void *ws, size_t ws_bytes, cudaStream_t st) {
+    const size_t need = gemm_tc_ws_bytes(Kd, N);
+    if (need == 0 || ws == nullptr || ws_bytes < need || (((uintptr_t)ws) & 15) != 0) return 1;
+    const int ncs = N / TC_NCH;
+    gemm_prep_b_kernel<<<((Kd + 511) / 512) * ncs * 4, 256, 0, st>>>(Bp, sbk, sbj, Kd, N, (uint8_t *)ws);
+    if (int e = finish_launch("gemm_prep_b")) return e;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
+        attr_done = true;
+    }
+    const int64_t ntiles = (R + TC_TILE - 1) / TC_TILE;
+    int ygroups = 1;
+    if (ntiles < kNumSMs) {
+        ygroups = (int)((kNumSMs + ntiles - 1) / ntiles);
+        if (ygroups > ncs) ygroups = ncs;
+    }
+    int ncpc = (ncs + ygroups - 1) / ygroups;
+    // resident-B mode: one K slab and the B chunks of a CTA fit beside the A tile
+    const int kchunks = (Kd + 63) / 64;
+    int resident = 0;
+    if (Kd <= 512) {
+        const int fit = (int)((size_t)(92 * 1024) / ((size_t)kchunks * 2 * TC_NCH * 128));  // chunks of 8 KB in 92 KB
+        if (fit >= 1) {
+            resident = 1;
+            if (ncpc > fit) ncpc = fit;
+        }
+    }
+    ygroups = (ncs + ncpc - 1) / ncpc;
+    uint32_t cols = 32;
+    while ((int)cols < ncpc * TC_NCH) cols <<= 1;
+    const size_t smem = TC_A_BYTES + (resident ? (size_t)ncpc * kchunks * 2 * TC_NCH * 128 : (size_t)TC_W_PIECE) + 1024;
+    const dim3 grid((unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs), (unsigned)ygroups);
+    gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(A, lda, (const uint8_t *)ws, R, Kd, N, cols, ncpc, resident, C, ldc);
+    return finish_launch("gemm_tc");
+}
+
+// ---- dW[R x Cn] += A^T B over the points:  A = wf [n x R], B = dout [n x Cn]  (fp32 SIMT, split over points) -------
+// CTA = 256 threads = 32 row groups x 8 column groups, thread tile 8 x 4 -> a 256 x 32 block of dW in registers;
+// the CTA walks its share of the points in sub-chunks of 16 staged in shared memory and finishes with one fp32
+// reduction per output element.
+constexpr int DW_SUB = 32;
+
+__global__ void __launch_bounds__(256)
+dw_accumulate_kernel(const float *__restrict__ A, const float *__restrict__ B, int64_t n, int R, int Cn, int64_t p_per_cta,
+                     float *__restrict__ dW) {
+    extern __shared__ __align__(16) float dsm[];  // [2][DW_SUB][256 + 32]: double-buffered wf rows | dout rows
+    constexpr int ROW = 256 + 32;
+    const int tid = threadIdx.x, tr = tid >> 3, tc = tid & 7;  // row group (32), column group (8)
+    const int r0 = blockIdx.y * 256, c0 = blockIdx.z * 32;
+    const int64_t p_lo = (int64_t)blockIdx.x * p_per_cta;
+    const int64_t p_hi = (p_lo + p_per_cta < n) ? p_lo + p_per_cta : n;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    // stage DW_SUB points: thread t copies element t of every wf row (coalesced 4-byte cp.async), threads 0-31 the dout row
+    auto stage_in = [&](int64_t pb, int buf) {
+        float *base = dsm + (size_t)buf * DW_SUB * ROW;
+        for (int pp = 0; pp < DW_SUB; ++pp) {
+            const int64_t p = pb + pp;
+            float *dst = base + pp * ROW;
+            if (p < p_hi && r0 + tid < R)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + tid)), "l"(A + p * R + r0 + tid) : "memory");
+            else
+                dst[tid] = 0.f;
+            if (tid < 32) {
+                if (p < p_hi && c0 + tid < Cn)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + 256 + tid)), "l"(B + p * Cn + c0 + tid) : "memory");
+                else
+                    dst[256 + tid] = 0.f;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int it = 0;
+    if (p_lo < p_hi) stage_in(p_lo, 0);
+    for (int64_t pb = p_lo; pb < p_hi; pb += DW_SUB, ++it) {
+        if (pb + DW_SUB < p_hi) {
+            stage_in(pb + DW_SUB, (it + 1) & 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const float *base = dsm + (size_t)(it & 1) * DW_SUB * ROW;
+#pragma unroll 8
+        for (int pp = 0; pp < DW_SUB; ++pp) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(base + pp * ROW + tr * 8);
+            const float4 a1 = *reinterpret_cast<const float4 *>(base + pp * ROW + tr * 8 + 4);
+            const float4 b = *reinterpret_cast<const float4 *>(base + pp * ROW + 256 + tc * 4);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();  // the buffer is refilled two iterations later
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = r0 + tr * 8 + i, c = c0 + tc * 4 + j;
+            if (r < R && c < Cn) atomicAdd(dW + (int64_t)r * Cn + c, acc[i][j]);
+        }
+}
+
+int dw_accumulate(const float *A, const float *B, int64_t n, int R, int Cn, float *dW, cudaStream_t st) {
+    const int rb = (R + 255) / 256, cb = (Cn + 31) / 32;
+    int64_t chunks = (2 * kNumSMs + rb * cb - 1) / (rb * cb);
+    if (chunks < 1) chunks = 1;
+    int64_t ppc = (n + chunks - 1) / chunks;
+    ppc = (ppc + DW_SUB - 1) / DW_SUB * DW_SUB;
+    if (ppc < 4 * DW_SUB) ppc = 4 * DW_SUB;
+    chunks = (n + ppc - 1) / ppc;
+    if (rb > 65535 || cb > 65535) return 1;
+    static bool attr_done = false;
+    const size_t smem = (size_t)2 * DW_SUB * (256 + 32) * sizeof(float);
+    if (!attr_done) {
+        cudaFuncSetAttribute(dw_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_done = true;
+    }
+    dw_accumulate_kernel<<<dim3((unsigned)chunks, (unsigned)rb, (unsigned)cb), 256, smem, st>>>(A, B, n, R, Cn, ppc, dW);
+    return finish_launch("kpconv_dW");
+}
+
 size_t kpconv_tc_ws_bytes(int K, int Cin, int Cout) {
     if (K > KP_K || Cin % 32 != 0 || Cout % TC_NCH != 0 || Cout > 512) return 0;
     return (size_t)(Cin / 32) * (Cout / TC_NCH) * 4 * TC_W_PIECE;
