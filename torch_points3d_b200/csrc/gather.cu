@@ -270,7 +270,7 @@ invert_kernel(const int64_t *__restrict__ keys, int64_t E, int N, int EC, int nc
               uint16_t *__restrict__ order, int *__restrict__ seg, uint32_t *__restrict__ runs,
               int *__restrict__ nruns) {
     extern __shared__ int ism[];
-    int *hist = ism;                  // [N][INV_WARPS]
+    int *hist = ism;                  // [INV_WARPS][N]  (warp-major: key-strided accesses are conflict-free)
     int *rowsum = ism + (size_t)N * INV_WARPS;  // [N]
     __shared__ int warp_tot[INV_WARPS];
     __shared__ int warp_runs[INV_WARPS];
@@ -313,7 +313,7 @@ invert_kernel(const int64_t *__restrict__ keys, int64_t E, int N, int EC, int nc
             headm[s] = __ballot_sync(0xffffffffu, head);
             // headbits marks every slot that BREAKS a run: heads and slots with an out-of-range index
             const unsigned breakm = headm[s] | __ballot_sync(0xffffffffu, key[s] < 0);
-            if (head) atomicAdd(&hist[key[s] * INV_WARPS + warp], 1);
+            if (head) atomicAdd(&hist[warp * N + key[s]], 1);
             carry = __shfl_sync(0xffffffffu, key[s], 31);
             if (lane == 0 && w0 + s * 32 < EC) headbits[(w0 >> 5) + s] = breakm;
         }
@@ -342,7 +342,7 @@ invert_kernel(const int64_t *__restrict__ keys, int64_t E, int N, int EC, int nc
     for (int j = tid; j < N; j += INV_WARPS * 32) {
         int t = 0;
 #pragma unroll
-        for (int w = 0; w < INV_WARPS; ++w) t += hist[j * INV_WARPS + w];
+        for (int w = 0; w < INV_WARPS; ++w) t += hist[w * N + j];
         rowsum[j] = t;
     }
     __syncthreads();
@@ -362,21 +362,27 @@ invert_kernel(const int64_t *__restrict__ keys, int64_t E, int N, int EC, int nc
     __syncthreads();
     int base = incl - local;
     for (int w = 0; w < warp; ++w) base += warp_tot[w];
-    for (int i = 0; i < per; ++i) {
+    for (int i = 0; i < per; ++i) {  // rowsum[j] <- exclusive prefix (in place: each thread owns its block)
         const int j = j0 + i;
         if (j < N) {
-            sb[j] = base;
-            int run = base;
-#pragma unroll
-            for (int w = 0; w < INV_WARPS; ++w) {
-                const int c = hist[j * INV_WARPS + w];
-                hist[j * INV_WARPS + w] = run;
-                run += c;
-            }
-            base = run;
+            const int c = rowsum[j];
+            rowsum[j] = base;
+            base += c;
         }
     }
     if (tid == INV_WARPS * 32 - 1) sb[N] = base;  // the last thread ends on the total count
+    __syncthreads();
+    // per-(warp, key) start offsets and the segment table, key-strided (coalesced, conflict-free)
+    for (int j = tid; j < N; j += INV_WARPS * 32) {
+        int run = rowsum[j];
+        sb[j] = run;
+#pragma unroll
+        for (int w = 0; w < INV_WARPS; ++w) {
+            const int c = hist[w * N + j];
+            hist[w * N + j] = run;
+            run += c;
+        }
+    }
     int run_base = 0;
     for (int w = 0; w < warp; ++w) run_base += warp_runs[w];
     if (tid == INV_WARPS * 32 - 1) nruns[(int64_t)b * nchunks + chunk] = run_base + my_runs;
@@ -398,8 +404,8 @@ invert_kernel(const int64_t *__restrict__ keys, int64_t E, int N, int EC, int nc
                 const int leader = __ffs(peers) - 1;
                 int pos = 0;
                 if (lane == leader) {
-                    pos = hist[key[s] * INV_WARPS + warp];
-                    hist[key[s] * INV_WARPS + warp] = pos + __popc(peers);
+                    pos = hist[warp * N + key[s]];
+                    hist[warp * N + key[s]] = pos + __popc(peers);
                 }
                 pos = __shfl_sync(peers, pos, leader);
                 ob[pos + rank] = (uint16_t)e;
