@@ -177,6 +177,115 @@ fps_reg_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr, i
     }
 }
 
+// Single-CTA variant (clouds of up to 8192 points): besides the register copy used for the distance update, the
+// coordinates sit in shared memory, so a round tracks only (best, slot) per point -- 12 instructions per point --
+// the per-warp record is 8 bytes, and every thread fetches the winner's coordinates by index after the one
+// barrier of the round.  A round is issue-bound inside its SM (warps x instructions), so every instruction shaved
+// off the per-point update shortens all S-1 dependent rounds.
+template <int T, int PPT, typename IdxT>
+__global__ void __launch_bounds__(T, 1)
+fps_cta_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr, int64_t n_dense,
+               const int64_t *__restrict__ out_ptr, int64_t s_dense, IdxT *__restrict__ out,
+               const int64_t *__restrict__ first, float *__restrict__ new_xyz) {
+    constexpr int NW = T / 32;
+    extern __shared__ float fsm[];  // sx | sy | sz, T * PPT floats each
+    float *sx = fsm, *sy = fsm + T * PPT, *sz = fsm + 2 * T * PPT;
+    __shared__ uint2 rec[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cloud = blockIdx.x;
+    int64_t start, n64, s64, obase, add;
+    if (ptr != nullptr) {
+        start = ptr[cloud];
+        n64 = ptr[cloud + 1] - start;
+        obase = out_ptr[cloud];
+        s64 = out_ptr[cloud + 1] - obase;
+        add = start;
+    } else {
+        start = (int64_t)cloud * n_dense;
+        n64 = n_dense;
+        obase = (int64_t)cloud * s_dense;
+        s64 = s_dense;
+        add = 0;
+    }
+    if (s64 > n64) s64 = n64;
+    const int n = (int)n64, s = (int)s64;
+    const float *__restrict__ p = xyz + 3 * start;
+    float px[PPT], py[PPT], pz[PPT], md[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int i = j * T + tid;
+        if (i < n) {
+            px[j] = p[3 * i]; py[j] = p[3 * i + 1]; pz[j] = p[3 * i + 2];
+            md[j] = 1e10f;
+            sx[i] = px[j]; sy[i] = py[j]; sz[i] = pz[j];
+        } else {
+            px[j] = py[j] = pz[j] = 0.f;
+            md[j] = -1.f;  // never selected
+        }
+    }
+    int f0 = 0;
+    if (n > 0 && first != nullptr) {
+        const int64_t f = first[cloud];
+        f0 = f < 0 ? 0 : (f >= n ? n - 1 : (int)f);
+    }
+    __syncthreads();
+    float lx = 0.f, ly = 0.f, lz = 0.f;
+    if (n > 0) { lx = sx[f0]; ly = sy[f0]; lz = sz[f0]; }
+    IdxT *__restrict__ orow = out + obase;
+    float *__restrict__ xrow = new_xyz ? new_xyz + 3 * obase : nullptr;
+    if (tid == 0 && s > 0) {
+        orow[0] = (IdxT)(add + f0);
+        if (xrow) { xrow[0] = lx; xrow[1] = ly; xrow[2] = lz; }
+    }
+    for (int r = 1; r < s; ++r) {
+        const int buf = r & 1;
+        float best = -1.f;
+        int bj = 0;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const float d = sqdist3(px[j], py[j], pz[j], lx, ly, lz);
+            const float m = fminf(md[j], d);
+            md[j] = m;
+            if (m > best) { best = m; bj = j; }  // strict: the lowest index wins inside a thread
+        }
+        const unsigned bi = best >= 0.f ? (unsigned)(bj * T + tid) : 0xffffffffu;
+        const unsigned key = best >= 0.f ? __float_as_uint(best) : 0u;
+        unsigned wkey, widx;
+        warp_argmax(key, bi, wkey, widx);
+        if (lane == 0) rec[buf][warp] = make_uint2(wkey, widx);
+        __syncthreads();
+        unsigned k2 = 0u, i2 = 0xffffffffu;
+        if (lane < NW) {
+            const uint2 rr = rec[buf][lane];
+            k2 = rr.x;
+            i2 = rr.y;
+        }
+        unsigned ckey, cidx;
+        warp_argmax(k2, i2, ckey, cidx);
+        lx = sx[cidx]; ly = sy[cidx]; lz = sz[cidx];
+        if (tid == 0) {
+            orow[r] = (IdxT)(add + (int64_t)cidx);
+            if (xrow) { xrow[3 * r] = lx; xrow[3 * r + 1] = ly; xrow[3 * r + 2] = lz; }
+        }
+    }
+}
+
+template <int T, int PPT, typename IdxT>
+static int launch_cta(const float *xyz, const int64_t *ptr, int64_t n_dense, const int64_t *out_ptr, int64_t s_dense,
+                      IdxT *out, const int64_t *first, float *new_xyz, int clouds, cudaStream_t st) {
+    auto kern = fps_cta_kernel<T, PPT, IdxT>;
+    const size_t smem = (size_t)3 * T * PPT * sizeof(float);
+    if (smem + 2048 > 48 * 1024) {  // static shared memory counts against the 48 KB default as well
+        static bool done = false;
+        if (!done) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            done = true;
+        }
+    }
+    kern<<<clouds, T, smem, st>>>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz);
+    return finish_launch("fps_cta");
+}
+
 // Fallback for clouds larger than 131072 points: one 1024-thread CTA per cloud, points read
 // from global/L2 every round, min-distances in a caller-provided workspace.
 template <typename IdxT>
@@ -307,6 +416,30 @@ static int fps_dispatch(const float *xyz, const int64_t *ptr, int64_t n_dense, c
     }
 #define P3D_FPS_CASE(LIM, T, PPT, CL) \
     if (max_n <= (LIM)) return launch_reg<T, PPT, CL, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
+#define P3D_FPS_CTA(LIM, T, PPT) \
+    if (max_n <= (LIM)) return launch_cta<T, PPT, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
+    if (const char *force = getenv("P3D_FPS_CTA")) {  // tuning hook: "T,PPT"
+        int ft = 0, fp = 0;
+        if (sscanf(force, "%d,%d", &ft, &fp) == 2 && (int64_t)ft * fp >= max_n) {
+#define P3D_FPS_CTAF(T, PPT) \
+    if (ft == T && fp == PPT) return launch_cta<T, PPT, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
+            P3D_FPS_CTAF(64, 8) P3D_FPS_CTAF(64, 16) P3D_FPS_CTAF(128, 4) P3D_FPS_CTAF(128, 8) P3D_FPS_CTAF(128, 16)
+            P3D_FPS_CTAF(256, 4) P3D_FPS_CTAF(256, 8) P3D_FPS_CTAF(512, 4) P3D_FPS_CTAF(512, 2) P3D_FPS_CTAF(1024, 2)
+            P3D_FPS_CTAF(256, 16) P3D_FPS_CTAF(512, 8) P3D_FPS_CTAF(1024, 4) P3D_FPS_CTAF(512, 16)
+#undef P3D_FPS_CTAF
+        }
+    }
+    if (getenv("P3D_FPS_OLD") == nullptr) {
+        // variants picked by bench_tools/tune_fps_cta.py on B200 (profiles/r1_fps_tuning.md): few fat threads win,
+        // a round is bound by warps x instructions issued inside the one SM
+        P3D_FPS_CTA(256, 64, 4)
+        P3D_FPS_CTA(512, 128, 4)
+        P3D_FPS_CTA(1024, 128, 8)
+        P3D_FPS_CTA(2048, 128, 16)
+        P3D_FPS_CTA(4096, 256, 16)
+        P3D_FPS_CTA(8192, 512, 16)
+    }
+#undef P3D_FPS_CTA
     P3D_FPS_CASE(256, 64, 4, 1)
     P3D_FPS_CASE(512, 128, 4, 1)
     P3D_FPS_CASE(1024, 256, 4, 1)
