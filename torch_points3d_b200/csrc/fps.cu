@@ -44,6 +44,8 @@ fps_reg_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr, i
                const int64_t *__restrict__ out_ptr, int64_t s_dense, IdxT *__restrict__ out,
                const int64_t *__restrict__ first, float *__restrict__ new_xyz) {
     constexpr int NW = T / 32;
+    extern __shared__ float csm[];  // this CTA's coordinates: cx | cy | cz, T * PPT floats each (slot = j * T + tid)
+    float *cx = csm, *cy = csm + T * PPT, *cz = csm + 2 * T * PPT;
     __shared__ FpsRec rec[2][32];
     __shared__ FpsRec crec[2][CLUSTER];
 
@@ -83,6 +85,9 @@ fps_reg_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr, i
             px[j] = py[j] = pz[j] = 0.f;
             md[j] = -1.f;  // never selected: min(-1, d) stays -1 and -1 > best is false
         }
+        cx[j * T + tid] = px[j];
+        cy[j * T + tid] = py[j];
+        cz[j * T + tid] = pz[j];
     }
     float lx = 0.f, ly = 0.f, lz = 0.f;
     int64_t f0 = 0;
@@ -102,27 +107,23 @@ fps_reg_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr, i
 
     for (int64_t r = 1; r < s; ++r) {
         const int buf = (int)(r & 1);
-        float best = -1.f, bx = 0.f, by = 0.f, bz = 0.f;
-        unsigned bi = 0xffffffffu;
+        float best = -1.f;
+        int bj = 0;
 #pragma unroll
         for (int j = 0; j < PPT; ++j) {
             const float d = sqdist3(px[j], py[j], pz[j], lx, ly, lz);
             const float m = fminf(md[j], d);
             md[j] = m;
-            if (m > best) {  // strict: the lowest index wins inside a thread (indices ascend with j)
-                best = m;
-                bi = (unsigned)(j * (CLUSTER * T) + rank * T + tid);
-                bx = px[j];
-                by = py[j];
-                bz = pz[j];
-            }
+            if (m > best) { best = m; bj = j; }  // strict: the lowest index wins inside a thread (indices ascend with j)
         }
+        const unsigned bi = best >= 0.f ? (unsigned)(bj * (CLUSTER * T) + rank * T + tid) : 0xffffffffu;
         const unsigned key = best >= 0.f ? __float_as_uint(best) : 0u;
         unsigned wkey, widx;
         warp_argmax(key, bi, wkey, widx);
-        if (key == wkey && bi == widx) {
+        if (key == wkey && bi == widx) {  // the winning lane fetches its point's coordinates from shared memory
             FpsRec rr;
-            rr.key = wkey; rr.idx = widx; rr.x = bx; rr.y = by; rr.z = bz; rr.pad = 0;
+            const int slot = bj * T + tid;
+            rr.key = wkey; rr.idx = widx; rr.x = cx[slot]; rr.y = cy[slot]; rr.z = cz[slot]; rr.pad = 0;
             rec[buf][warp] = rr;
         }
         __syncthreads();
@@ -356,7 +357,14 @@ static int launch_reg(const float *xyz, const int64_t *ptr, int64_t n_dense, con
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(clouds * CLUSTER));
     cfg.blockDim = dim3(T);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = (size_t)3 * T * PPT * sizeof(float);
+    if (cfg.dynamicSmemBytes + 4096 > 48 * 1024) {
+        static bool smem_done = false;
+        if (!smem_done) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+            smem_done = true;
+        }
+    }
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
