@@ -545,16 +545,28 @@ bwd_sorted_kernel(const float *__restrict__ dout, const float *__restrict__ weig
             // fold every run of repeated indices into its head slot: one warp per run, lanes stride
             // the run, fixed xor tree -> deterministic
             const uint32_t *rt = reinterpret_cast<const uint32_t *>(ob + EC);
+#pragma unroll 1
             for (int r = warp; r < nr_cur; r += SB_THREADS / 32) {
                 const uint32_t rr = rt[r];
                 const int st = (int)(rr >> 16), ln = (int)(rr & 0xffffu) + 1;
+                float v[SB_CC];
 #pragma unroll
-                for (int c = 0; c < SB_CC; ++c) {
-                    float v = 0.f;
-                    for (int i = lane; i < ln; i += 32) v += cur[c * Wd + st + i];
+                for (int c = 0; c < SB_CC; ++c) v[c] = 0.f;
+#pragma unroll 1
+                for (int i = lane; i < ln; i += 32) {
 #pragma unroll
-                    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                    if (lane == 0) cur[c * Wd + st] = v;
+                    for (int c = 0; c < SB_CC; ++c) v[c] += cur[c * Wd + st + i];
+                }
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) {
+#pragma unroll
+                    for (int c = 0; c < SB_CC; ++c) v[c] += __shfl_xor_sync(0xffffffffu, v[c], d);
+                }
+                if (lane < SB_CC) {
+                    float mine = v[0];
+#pragma unroll
+                    for (int c = 1; c < SB_CC; ++c) mine = lane == c ? v[c] : mine;
+                    cur[lane * Wd + st] = mine;
                 }
             }
             __syncthreads();
