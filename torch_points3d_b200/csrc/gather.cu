@@ -574,27 +574,9 @@ bwd_sorted_kernel(const float *__restrict__ dout, const float *__restrict__ weig
 #pragma unroll
         for (int k = 0; k < SB_KPT; ++k) {
             if (k >= kpt) break;
-            int t = a0[k];
             const int te = a1[k];
-            for (; t + 1 < te; t += 2) {  // two independent gathers in flight, summed in slot order
-                const int ea = ob[t], eb = ob[t + 1];
-                if (INTERP) {
-                    const float wa = wst[ea], wv = wst[eb];
-                    const int pa = ea / 3, pb = eb / 3;
-#pragma unroll
-                    for (int c = 0; c < SB_CC; ++c) {
-                        const float va = cur[c * Wd + pa], vb = cur[c * Wd + pb];
-                        acc[k][c] = fmaf(vb, wv, fmaf(va, wa, acc[k][c]));
-                    }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < SB_CC; ++c) {
-                        const float va = cur[c * Wd + ea], vb = cur[c * Wd + eb];
-                        acc[k][c] = (acc[k][c] + va) + vb;
-                    }
-                }
-            }
-            if (t < te) {
+#pragma unroll 1
+            for (int t = a0[k]; t < te; ++t) {  // slot order: deterministic
                 const int ea = ob[t];
                 if (INTERP) {
                     const float wa = wst[ea];
