@@ -86,18 +86,19 @@ ball_query_kernel(const float *__restrict__ x, const float *__restrict__ y, cons
                   float r2, int K, int strict, int64_t shadow, int64_t *__restrict__ idx,
                   float *__restrict__ dist2) {
     constexpr int QPC = NB_WARPS * QPW;
-    __shared__ float sx[NB_TILE], sy[NB_TILE], sz[NB_TILE];
+    __shared__ float4 tile[NB_TILE];  // packed xyz_: one LDS.128 per candidate and lane
     __shared__ RangeCache rc;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t q0 = (int64_t)blockIdx.x * QPC;
     const int64_t q1 = (q0 + QPC < Ny) ? q0 + QPC : Ny;
+    // d <= r2  <=>  d < nextafter(r2): one compare for both membership rules
+    const float r2x = strict ? r2 : __uint_as_float(__float_as_uint(r2) + 1u);
 
     cta_ranges<DENSE>(q0, q1, batch_x, batch_y, Nx, rc, warp, lane);
 
     float qx[QPW], qy[QPW], qz[QPW];
     int64_t x0[QPW], x1[QPW];
-    int cnt[QPW];
-    int64_t first[QPW];
+    int cnt[QPW], first[QPW];
     int64_t X0 = INT64_MAX, X1 = 0;
 #pragma unroll
     for (int u = 0; u < QPW; ++u) {
@@ -134,15 +135,21 @@ ball_query_kernel(const float *__restrict__ x, const float *__restrict__ y, cons
         }
         first_tile = false;
         const int tn = (int)((X1 - tb < NB_TILE) ? (X1 - tb) : NB_TILE);
-        load_tile(x, tb, tn, sx, sy, sz, tid, NB_WARPS * 32);
+        {
+            const float *__restrict__ src = x + 3 * tb;
+#pragma unroll 2
+            for (int p = tid; p < tn; p += NB_WARPS * 32)
+                tile[p] = make_float4(__ldg(src + 3 * p), __ldg(src + 3 * p + 1), __ldg(src + 3 * p + 2), 0.f);
+        }
         __syncthreads();
 #pragma unroll
         for (int u = 0; u < QPW; ++u) {
             if (cnt[u] >= K) continue;
             const int64_t q = q0 + warp * QPW + u;
-            const int64_t off = DENSE ? x0[u] : 0;  // dense mode reports indices local to the cloud
-            int lo = (int)((x0[u] > tb ? x0[u] : tb) - tb);
-            int hi = (int)((x1[u] < tb + tn ? x1[u] : tb + tn) - tb);
+            const int lo = (int)((x0[u] > tb ? x0[u] : tb) - tb);
+            const int hi = (int)((x1[u] < tb + tn ? x1[u] : tb + tn) - tb);
+            // index reported for tile slot i (32-bit arithmetic inside the loop): dense mode is cloud-local
+            const int ibase = (int)(tb - (DENSE ? x0[u] : 0));
             int64_t *__restrict__ row = idx + q * K;
             float *__restrict__ drow = dist2 ? dist2 + q * K : nullptr;
             int c = cnt[u];
@@ -156,9 +163,9 @@ ball_query_kernel(const float *__restrict__ x, const float *__restrict__ y, cons
                 for (int v = 0; v < 4; ++v) {
                     const int i = i0 + 32 * v + lane;
                     const bool ok = i < hi;
-                    const int ii = ok ? i : lo;
-                    d[v] = sqdist3(sx[ii], sy[ii], sz[ii], qx[u], qy[u], qz[u]);
-                    hit[v] = ok && (strict ? (d[v] < r2) : (d[v] <= r2));
+                    const float4 cnd = tile[ok ? i : lo];
+                    d[v] = sqdist3(cnd.x, cnd.y, cnd.z, qx[u], qy[u], qz[u]);
+                    hit[v] = ok && d[v] < r2x;
                     m[v] = __ballot_sync(0xffffffffu, hit[v]);
                 }
 #pragma unroll
@@ -166,10 +173,10 @@ ball_query_kernel(const float *__restrict__ x, const float *__restrict__ y, cons
                     if (m[v]) {
                         const int pos = c + __popc(m[v] & lanemask_lt());
                         if (hit[v] && pos < K) {
-                            row[pos] = tb + i0 + 32 * v + lane - off;
+                            row[pos] = (int64_t)(ibase + i0 + 32 * v + lane);
                             if (drow) drow[pos] = d[v];
                         }
-                        if (c == 0) first[u] = tb + i0 + 32 * v + (__ffs(m[v]) - 1) - off;
+                        if (c == 0) first[u] = ibase + i0 + 32 * v + (__ffs(m[v]) - 1);
                         c += __popc(m[v]);
                     }
                 }
@@ -183,7 +190,7 @@ ball_query_kernel(const float *__restrict__ x, const float *__restrict__ y, cons
         const int64_t q = q0 + warp * QPW + u;
         if (q >= q1) continue;
         const int c = cnt[u] < K ? cnt[u] : K;
-        const int64_t padv = DENSE ? (c > 0 ? first[u] : 0) : shadow;
+        const int64_t padv = DENSE ? (c > 0 ? (int64_t)first[u] : 0) : shadow;
         for (int e = c + lane; e < K; e += 32) {
             idx[q * K + e] = padv;
             if (dist2) dist2[q * K + e] = -1.f;
@@ -578,6 +585,7 @@ P3D_EXPORT int p3d_ball_query_batch_f32(const float *x, const float *y, const in
                                         const int64_t *batch_y, int64_t Nx, int64_t Ny, float radius, int nsample,
                                         int strict, int64_t shadow, int64_t *idx, float *dist2, void *stream) {
     P3D_REQUIRE(Nx >= 0 && Ny >= 0 && nsample >= 0, "ball_query_batch: negative dimension");
+    P3D_REQUIRE(Nx < ((int64_t)1 << 31), "ball_query_batch: more than 2^31 candidate points");
     if (Ny == 0 || nsample == 0) return P3D_OK;
     P3D_REQUIRE(y && idx && (x || Nx == 0), "ball_query_batch: null pointer");
     P3D_REQUIRE((batch_x == nullptr) == (batch_y == nullptr), "ball_query_batch: give both batch vectors or none");
