@@ -189,6 +189,39 @@ int p3d_kpconv_bwd_f32(const float *query, const float *support, const int64_t *
 int p3d_neighbor_max_f32(const float *x, const int64_t *neighbors, int64_t n, int64_t N0, int M, int C,
                          float *out, int64_t *arg, void *stream);
 
+/* ------------------------------------------------------ GridSampling3D ------
+ * Replaces the position side of GridSampling3D._process (core/data_transform/grid_transform.py:110-126):
+ *     coords = torch.round(pos / size); cluster = voxel_grid(coords, batch, 1)   [torch_cluster.grid_cluster]
+ *     cluster, unique_pos_indices = consecutive_cluster(cluster)                 [torch_geometric 1.7.2]
+ *   reference call sites: modules/KPConv/blocks.py:74-77 (strided blocks), core/data_transform/transforms.py:603-651
+ *   (MultiScaleTransform), core/spatial_ops/sampling.py:75 (RandomSampler/GridSampler).
+ * batch (nullable) [N] int64.  Voxels are numbered in increasing (batch, z, y, x) order of their rounded
+ * coordinates (grid_cluster strides: x fastest, batch slowest; sorted unique ids).  Outputs:
+ *   cluster[N]      consecutive voxel id of every point;
+ *   last_index[N]   first n rows: highest point index inside voxel c (what consecutive_cluster's sequential
+ *                   scatter_ leaves in `perm`; group_data mode="last" and the `batch` key select these rows);
+ *   order[N], seg_start[N+1]  points sorted by (voxel, point index) and the first slot of every voxel
+ *                   (seg_start[n] = N): the segment list the two companion entry points below consume;
+ *   mean_pos (nullable) [N,3]   first n rows: scatter_mean of pos, fp32 sums in ascending point index;
+ *   out_batch (nullable) [N]    first n rows: batch[last_index];
+ *   coords_out (nullable) [N,3] int32, first n rows: the rounded coordinates of last_index (quantize_coords=True);
+ *   n_out           device scalar: number of voxels n.
+ * One cooperative persistent kernel (needs all of its <= 148 CTAs co-resident). N < 2^31. */
+size_t p3d_grid_cluster_ws_bytes(int64_t N);
+int p3d_grid_cluster_f32(const float *pos, const int64_t *batch, int64_t N, float size, int64_t *cluster,
+                         int64_t *last_index, int32_t *order, int32_t *seg_start, float *mean_pos,
+                         int64_t *out_batch, int32_t *coords_out, int64_t *n_out, void *ws, size_t ws_bytes,
+                         void *stream);
+/* scatter_mean(item, cluster, dim=0) of group_data (grid_transform.py:76): out[c,:] = mean of x[p,:] over the
+ * voxel's points, summed in ascending point index.  n_rows = rows to produce; n_dev (nullable) = device
+ * scalar clamping it (lets a caller launch before it has read n back). */
+int p3d_segment_mean_f32(const float *x, const int32_t *order, const int32_t *seg_start, const int64_t *n_dev,
+                         int64_t n_rows, int C, float *out, void *stream);
+/* majority label per voxel (grid_transform.py:70-74: one_hot(item - min) -> scatter_add -> argmax + min; ties
+ * go to the lowest label).  hist [n, num_labels] int32 must be zeroed by the caller. */
+int p3d_segment_vote_i64(const int64_t *labels, const int64_t *cluster, int64_t N, int64_t n, int64_t label_min,
+                         int num_labels, int32_t *hist, int64_t *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -260,3 +260,53 @@ def neighbor_max(x, nb):
     out = np.zeros((n, C), dtype=np.float32)
     lib().orc_neighbor_max(px, pn, ctypes.c_int64(n), ctypes.c_int64(N0), M, C, out.ctypes.data_as(_F), None)
     return out
+
+
+# ------------------------------------------------------- GridSampling3D ----
+# numpy restatement of GridSampling3D._process (core/data_transform/grid_transform.py:110-126) and
+# group_data (:33-81).  The arithmetic of the three third-party calls is restated from their published
+# sources (not under /root/reference; "parity unpinned" except for the reference tests named below):
+#   torch_cluster.grid_cluster 1.5.9 (cpu/grid_cpu.cpp): pos -= start; num_voxels = ((end - start) / size).long()
+#       + 1; strides = exclusive cumprod (x fastest); cluster = sum((pos / size).long() * strides)
+#   torch_geometric 1.7.2 voxel_grid: appends batch (cast to pos.dtype) as a 4th coordinate with size 1
+#   torch_geometric 1.7.2 consecutive_cluster: unique(sorted, return_inverse); perm = empty.scatter_(0, inv, arange)
+#       (sequential on the CPU: the LAST point of a voxel wins)
+#   torch_scatter 2.0.8 scatter_mean: sequential fp32 scatter_add, then true_divide by the count
+# Pinned by the reference's own tests: majority label (test/test_grid_sampling.py:30-36), idempotence of a
+# second pass (:38-58), int32 quantised coordinates (:60-67), MultiScaleTransform consistency
+# (test/test_transform.py:67-93).
+def grid_cluster(pos, size, batch=None):
+    """returns (cluster [N] int64 consecutive ids, unique_pos_indices [n] int64, coords [N,3] float32)."""
+    pos = np.ascontiguousarray(pos, dtype=np.float32)
+    coords = np.rint(pos / np.float32(size)).astype(np.float32)  # torch.round: half to even
+    if batch is None:
+        full = coords
+    else:
+        full = np.concatenate([coords, np.asarray(batch).astype(np.float32)[:, None]], axis=1)
+    if full.shape[0] == 0:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64), coords
+    start, end = full.min(0), full.max(0)
+    num_voxels = (end - start).astype(np.float32).astype(np.int64) + 1
+    strides = np.concatenate([[1], np.cumprod(num_voxels)[:-1]]).astype(np.int64)
+    key = ((full - start[None, :]).astype(np.float32).astype(np.int64) * strides[None, :]).sum(1)
+    _, inv = np.unique(key, return_inverse=True)
+    perm = np.empty(int(inv.max()) + 1, dtype=np.int64)
+    perm[inv] = np.arange(inv.shape[0], dtype=np.int64)  # numpy assigns in order: last write wins
+    return inv.astype(np.int64), perm, coords
+
+
+def scatter_mean(x, cluster, n):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.zeros((n,) + x.shape[1:], dtype=np.float32)
+    np.add.at(out, cluster, x)  # unbuffered, in index order, fp32
+    cnt = np.bincount(cluster, minlength=n).astype(np.float32)
+    cnt = np.maximum(cnt, 1)
+    return out / cnt.reshape((n,) + (1,) * (x.ndim - 1))
+
+
+def label_vote(labels, cluster, n):
+    labels = np.asarray(labels, dtype=np.int64)
+    lmin = labels.min()
+    hist = np.zeros((n, int(labels.max() - lmin) + 1), dtype=np.int64)
+    np.add.at(hist, (cluster, labels - lmin), 1)
+    return hist.argmax(1) + lmin

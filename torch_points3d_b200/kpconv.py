@@ -95,24 +95,12 @@ class Cloud:
 
 
 def grid_subsample(pos, batch, size):
-    """GridSampling3D(size, mode="mean") on the device (core/data_transform/grid_transform.py:84-141: voxel id per
-    point, consecutive cluster ids, per-voxel mean position; the batch id is constant inside a voxel).  Plain torch
-    ops: this is the strided blocks' query-set construction, a 'next' row of SURVEY.md section 8f, not a hot kernel.
-    Returns (q_pos [n,3], q_batch [n]) sorted by (batch, voxel)."""
-    vox = torch.floor(pos / size).to(torch.int64)
-    vox = vox - vox.min(0, keepdim=True).values
-    dims = vox.max(0).values + 1
-    key = ((batch.to(torch.int64) * dims[0] + vox[:, 0]) * dims[1] + vox[:, 1]) * dims[2] + vox[:, 2]
-    uniq, inv, cnt = torch.unique(key, return_inverse=True, return_counts=True)
-    # deterministic per-voxel mean: stable sort by voxel, fp64 running sum, differences at the voxel ends
-    order = torch.argsort(inv, stable=True)
-    csum = torch.cumsum(pos[order].t().contiguous().to(torch.float64), 1)  # [3, N]: scan along the fast dimension
-    ends = torch.cumsum(cnt, 0) - 1
-    seg = csum[:, ends]
-    seg[:, 1:] = seg[:, 1:] - csum[:, ends[:-1]]
-    q_pos = (seg / cnt.unsqueeze(0).to(torch.float64)).t().contiguous().to(pos.dtype)
-    q_batch = (uniq // (dims[0] * dims[1] * dims[2])).to(batch.dtype)  # the batch id is the top digit of the key
-    return q_pos, q_batch
+    """GridSampling3D(size, mode="mean") restricted to what the strided blocks read back (blocks.py:74-87:
+    `query_data.pos`, `query_data.batch`): one launch of the voxel-clustering kernel (csrc/grid.cu).  Voxels come out
+    in the reference's order, increasing (batch, z, y, x) of the rounded coordinates; positions are fp32 means summed
+    in point order.  Returns (q_pos [n,3], q_batch [n])."""
+    vox = ops.grid_cluster(pos, size, batch, want_mean=True)
+    return vox.mean_pos, vox.batch
 
 
 class GridSampler:

@@ -568,3 +568,71 @@ def neighbor_max(x: torch.Tensor, neighbors: torch.Tensor) -> torch.Tensor:
     """strided-shortcut max-pool of ResnetBBlock (modules/KPConv/blocks.py:206-210):
     max over the neighbour rows of cat(x, zeros(1,C))."""
     return _NeighborMax.apply(x, neighbors)
+
+
+# ------------------------------------------------------------ GridSampling3D ---------------
+class VoxelClusters:
+    """result of `grid_cluster`: consecutive voxel ids plus the segment list the mean / vote kernels consume"""
+
+    def __init__(self, cluster, unique_pos_indices, order, seg_start, n, mean_pos, batch, coords):
+        self.cluster, self.unique_pos_indices, self.order, self.seg_start = cluster, unique_pos_indices, order, seg_start
+        self.n, self.mean_pos, self.batch, self.coords = n, mean_pos, batch, coords
+
+
+def grid_cluster(pos: torch.Tensor, size: float, batch: Optional[torch.Tensor] = None, want_mean: bool = True,
+                 want_coords: bool = False) -> VoxelClusters:
+    """`consecutive_cluster(voxel_grid(torch.round(pos / size), batch, 1))` of GridSampling3D._process
+    (core/data_transform/grid_transform.py:110-120) in one cooperative kernel, together with the per-voxel
+    mean position (group_data mode="mean"), the voxel's batch id and, on request, the int32 quantised
+    coordinates.  One D2H read of the voxel count sizes the outputs (the reference's torch.unique does the same)."""
+    dev = _require_cuda("grid_cluster", pos, batch)
+    if pos.dim() != 2 or pos.shape[1] != 3:
+        raise ValueError("grid_cluster expects pos of shape [N, 3]")
+    pos = _f32(pos)
+    N = pos.shape[0]
+    b = None if batch is None else _i64(batch)
+    cluster = torch.empty(N, dtype=torch.int64, device=dev)
+    last = torch.empty(N, dtype=torch.int64, device=dev)
+    order = torch.empty(N, dtype=torch.int32, device=dev)
+    seg = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    mean = torch.empty(N, 3, dtype=torch.float32, device=dev) if want_mean else None
+    ob = torch.empty(N, dtype=torch.int64, device=dev) if b is not None else None
+    co = torch.empty(N, 3, dtype=torch.int32, device=dev) if want_coords else None
+    n_dev = torch.empty(1, dtype=torch.int64, device=dev)
+    ws_bytes = _cabi.lib().p3d_grid_cluster_ws_bytes(N)
+    ws = _workspace(ws_bytes, dev)
+    _call(dev, "p3d_grid_cluster_f32", pos.data_ptr(), _ptr(b), N, float(size), cluster.data_ptr(), last.data_ptr(),
+          order.data_ptr(), seg.data_ptr(), _ptr(mean), _ptr(ob), _ptr(co), n_dev.data_ptr(), ws.data_ptr(), ws_bytes)
+    n = int(n_dev.item())
+    return VoxelClusters(cluster, last[:n], order, seg[:n + 1], n, None if mean is None else mean[:n],
+                         None if ob is None else ob[:n].to(batch.dtype), None if co is None else co[:n])
+
+
+def segment_mean(x: torch.Tensor, vc: VoxelClusters) -> torch.Tensor:
+    """`scatter_mean(x, cluster, dim=0)` (grid_transform.py:76) over the voxels of `vc`; sums run in ascending
+    point index in fp32, which is what the sequential CPU scatter_add of the reference produces."""
+    dev = _require_cuda("segment_mean", x, vc.order)
+    if x.shape[0] != vc.cluster.shape[0]:
+        raise ValueError("segment_mean: x has %d rows, the clustering %d" % (x.shape[0], vc.cluster.shape[0]))
+    shape = x.shape[1:]
+    x2 = _f32(x).reshape(x.shape[0], -1)
+    C = x2.shape[1]
+    out = torch.empty(vc.n, C, dtype=torch.float32, device=dev)
+    _call(dev, "p3d_segment_mean_f32", x2.data_ptr(), vc.order.data_ptr(), vc.seg_start.data_ptr(), None, vc.n, C,
+          out.data_ptr())
+    return out.reshape((vc.n,) + tuple(shape))
+
+
+def segment_vote(labels: torch.Tensor, vc: VoxelClusters) -> torch.Tensor:
+    """majority label per voxel (grid_transform.py:70-74); ties go to the lowest label"""
+    dev = _require_cuda("segment_vote", labels, vc.cluster)
+    lab = _i64(labels)
+    if lab.numel() == 0:
+        return lab.clone()
+    lmin, lmax = int(lab.min().item()), int(lab.max().item())
+    L = lmax - lmin + 1
+    hist = torch.zeros(vc.n, L, dtype=torch.int32, device=dev)
+    out = torch.empty(vc.n, dtype=torch.int64, device=dev)
+    _call(dev, "p3d_segment_vote_i64", lab.data_ptr(), vc.cluster.data_ptr(), lab.shape[0], vc.n, lmin, L,
+          hist.data_ptr(), out.data_ptr())
+    return out.to(labels.dtype)
