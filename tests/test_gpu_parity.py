@@ -303,6 +303,26 @@ def test_grouping_forward_bit_exact_and_backward(B, C, n, S, K):
     assert relerr(N(f.grad), oracle.group_bwd(dout, idx, n)) <= RTOL
 
 
+@pytest.mark.parametrize("B,C,n,S,K,r", [(3, 70, 500, 37, 29, 0.3), (16, 320, 512, 128, 128, 0.8), (1, 16, 1024, 4, 3, 0.2),
+                                         (5, 33, 700, 64, 48, 0.25), (2, 40, 64, 300, 16, 0.5), (149, 32, 96, 8, 64, 0.4)])
+def test_grouping_backward_wide_channels_on_ball_query_tables(B, C, n, S, K, r):
+    """wide-channel backward (lanes = channels, run-compressed lists, CTA ranges cut across units) on real
+    ball-query tables: rows padded with their first hit give long runs of one index; sizes that are not multiples
+    of the chunk, the channel block or the warp's point block; the result is deterministic"""
+    xyz = synthetic.surface_clouds(B, n, seed=60 + C)
+    pos = T(xyz)
+    new_pos = pos[:, torch.linspace(0, n - 1, S, device=DEV).long()].contiguous()
+    idx = ops.ball_query(r, K, pos, new_pos)[0]
+    rng = np.random.default_rng(43)
+    feat = T(rng.standard_normal((B, C, n)).astype(np.float32)).requires_grad_(True)
+    out = ops.grouping_operation(feat, idx)
+    dout = T(rng.standard_normal(tuple(out.shape)).astype(np.float32))
+    (g1,) = torch.autograd.grad(out, feat, dout, retain_graph=True)
+    (g2,) = torch.autograd.grad(out, feat, dout)
+    assert torch.equal(g1, g2)
+    assert relerr(N(g1), oracle.group_bwd(N(dout), N(idx), n)) <= RTOL
+
+
 def test_group_features_matches_reference_formulation():
     """fused _prepare_features == the reference's op-by-op chain (modules/pointnet2/dense.py:36-54)"""
     B, n, S, K, C = 4, 1024, 256, 32, 16
