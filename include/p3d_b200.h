@@ -183,6 +183,35 @@ int p3d_kpconv_bwd_f32(const float *query, const float *support, const int64_t *
                        int M, int K, int Cin, int Cout, float extent, int influence, int aggregation,
                        float *dfeat, float *dweights, void *ws, size_t ws_bytes, void *stream);
 
+/* ------------------------------------------------------ deformable KPConv ------
+ * Replaces KPConv_deform_ops(query, support, neighbors, features, K_points, offsets, modulations, K_values,
+ *                            KP_extent, KP_influence, "sum") -> (out [n,Cout], sq_distances [n,M,K], K_points + offsets)
+ *   reference: torch_points3d/modules/KPConv/convolution_ops.py:110-235, called from
+ *   KPConvDeformableLayer.forward (modules/KPConv/kernels.py:228-241).
+ * offsets [n,K,3]; modulations (nullable) [n,K].  Neighbours in range (d2 < extent^2) of no deformed kernel point are
+ * dropped (the reference's topk re-compaction).  aggregation_mode "closest" cannot run in the reference (it passes a
+ * TensorFlow keyword to torch.argmin, :196) and is not offered.
+ * wf [n,K,Cin] (required): modulated weighted features, out = wf . K_values; keep it for the backward pass.
+ * sq_distances (nullable) [n,M,K]; kpmin (nullable) [n,K] + argmin (nullable) [n,K] int32: min over the neighbours of
+ * sq_distances, which is all fitting_loss (modules/KPConv/losses.py:4-16) reads -- saves writing and re-reading the
+ * [n,M,K] tensor.  deformed_K_points is K_points + offsets (caller side). */
+int p3d_kpconv_deform_fwd_f32(const float *query, const float *support, const int64_t *neighbors, const float *feat,
+                              const float *k_points, const float *offsets, const float *modulations,
+                              const float *k_values, int64_t n, int64_t N0, int M, int K, int Cin, int Cout,
+                              float extent, int influence, float *out, float *wf, float *sq_distances, float *kpmin,
+                              int32_t *argmin, void *stream);
+/* autograd backward.  Cotangents: dout [n,Cout]; d_sq_distances (nullable) [n,M,K]; d_kpmin (nullable) [n,K] with the
+ * forward's argmin.  Gradients (all nullable): dfeat [N0,Cin] and dweights [K,Cin,Cout] are ACCUMULATED into (zero them
+ * first); doffsets [n,K,3] and dmodulations [n,K] are overwritten (the cotangent of deformed_K_points adds to doffsets
+ * on the caller side). */
+size_t p3d_kpconv_deform_bwd_ws_bytes(int64_t n, int K, int Cin);
+int p3d_kpconv_deform_bwd_f32(const float *query, const float *support, const int64_t *neighbors, const float *feat,
+                              const float *k_points, const float *offsets, const float *modulations,
+                              const float *k_values, const float *wf, const float *dout, const float *d_sq_distances,
+                              const float *d_kpmin, const int32_t *argmin, int64_t n, int64_t N0, int M, int K, int Cin,
+                              int Cout, float extent, int influence, float *dfeat, float *dweights, float *doffsets,
+                              float *dmodulations, void *ws, size_t ws_bytes, void *stream);
+
 /* Strided-shortcut neighbour max-pool (modules/KPConv/blocks.py:206-210):
  * out[p,c] = max_m x'[neighbors[p,m], c], x' = cat(x, zeros); arg (nullable) = winning row
  * (N0 for the shadow row) for the backward pass. */

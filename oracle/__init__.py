@@ -310,3 +310,75 @@ def label_vote(labels, cluster, n):
     hist = np.zeros((n, int(labels.max() - lmin) + 1), dtype=np.int64)
     np.add.at(hist, (cluster, labels - lmin), 1)
     return hist.argmax(1) + lmin
+
+
+# --------------------------------------------------- deformable KPConv ----
+# numpy restatement of KPConv_deform_ops (torch_points3d/modules/KPConv/convolution_ops.py:110-235) and of its
+# autograd gradients.  PINNED by tests/golden/kpdeform_*.npz, generated by running the reference function and
+# torch autograd in this container (tests/golden/make_golden.py).  The topk re-compaction of :158-185 is restated
+# as what it computes: neighbours in range of no kernel point contribute nothing.
+def _deform_tables(q, s, nb, Kp, offsets, extent, influence):
+    q, s, Kp, offsets = (np.asarray(t, np.float32) for t in (q, s, Kp, offsets))
+    N0 = s.shape[0]
+    s1 = np.concatenate([s, np.full((1, 3), 1e6, np.float32)])
+    nbc = np.where((nb < 0) | (nb >= N0), N0, nb)
+    rel = s1[nbc] - q[:, None, :]
+    kpd = offsets + Kp[None]
+    diff = rel[:, :, None, :] - kpd[:, None, :, :]
+    sqd = (diff[..., 0] * diff[..., 0] + diff[..., 1] * diff[..., 1]) + diff[..., 2] * diff[..., 2]
+    thr = np.float32(float(extent) ** 2)
+    in_range = (sqd < thr).any(2)
+    ext = np.float32(extent)
+    if influence == "constant":
+        w = (sqd < thr).astype(np.float32)
+        slope = np.zeros_like(w)
+    elif influence == "linear":
+        r = np.sqrt(sqd)
+        w = np.maximum(np.float32(1) - r / ext, np.float32(0))
+        with np.errstate(divide="ignore"):
+            slope = np.where(w > 0, np.float32(-1) / (np.float32(2) * ext * r), np.float32(0)).astype(np.float32)
+    elif influence == "gaussian":
+        den = np.float32(2.0 * (float(extent) * 0.3) ** 2 + 1e-9)
+        w = np.exp(-sqd / den).astype(np.float32)
+        slope = -w / den
+    else:
+        raise ValueError("Unknown influence function type (config.KP_influence)")
+    w = w * in_range[:, :, None]
+    slope = slope * in_range[:, :, None]
+    return nbc, diff, sqd, w.astype(np.float32), slope.astype(np.float32), kpd
+
+
+def kpconv_deform_fwd(q, s, nb, x, Kp, offsets, mods, W, extent, influence="linear"):
+    """returns (out [n,Cout], sq_distances [n,M,K], deformed_K_points [n,K,3])"""
+    x, W = np.asarray(x, np.float32), np.asarray(W, np.float32)
+    nbc, _, sqd, w, _, kpd = _deform_tables(q, s, nb, Kp, offsets, extent, influence)
+    x1 = np.concatenate([x, np.zeros((1, x.shape[1]), np.float32)])
+    wf = np.einsum("nmk,nmc->nkc", w, x1[nbc])
+    if mods is not None:
+        wf = wf * np.asarray(mods, np.float32)[:, :, None]
+    return np.einsum("nkc,kco->no", wf, W).astype(np.float32), sqd, kpd
+
+
+def kpconv_deform_bwd(q, s, nb, x, Kp, offsets, mods, W, extent, influence, dout, dsq=None, ddef=None):
+    """gradients of sum(out*dout) + sum(sq_distances*dsq) + sum(deformed*ddef): (dx, dW, doffsets, dmods)"""
+    x, W, dout = np.asarray(x, np.float32), np.asarray(W, np.float32), np.asarray(dout, np.float32)
+    nbc, diff, sqd, w, slope, _ = _deform_tables(q, s, nb, Kp, offsets, extent, influence)
+    N0 = x.shape[0]
+    x1 = np.concatenate([x, np.zeros((1, x.shape[1]), np.float32)])
+    fnb = x1[nbc]
+    wf0 = np.einsum("nmk,nmc->nkc", w, fnb)
+    m = np.ones(wf0.shape[:2], np.float32) if mods is None else np.asarray(mods, np.float32)
+    dwfm = np.einsum("no,kco->nkc", dout, W)
+    dW = np.einsum("nkc,no->kco", wf0 * m[:, :, None], dout)
+    dmods = (dwfm * wf0).sum(2)
+    dwf0 = dwfm * m[:, :, None]
+    dx1 = np.zeros_like(x1)
+    np.add.at(dx1, nbc, np.einsum("nmk,nkc->nmc", w, dwf0))
+    gw = np.einsum("nkc,nmc->nmk", dwf0, fnb)
+    dd2 = gw * slope
+    if dsq is not None:
+        dd2 = dd2 + np.asarray(dsq, np.float32)
+    doff = np.einsum("nmk,nmkd->nkd", dd2, -2.0 * diff)
+    if ddef is not None:
+        doff = doff + np.asarray(ddef, np.float32)
+    return dx1[:N0], dW, doff.astype(np.float32), (None if mods is None else dmods)

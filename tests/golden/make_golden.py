@@ -77,6 +77,50 @@ def make_case(ops, seed, n, N0, M, Cin, Cout, influence, aggregation, extent=0.0
     )
 
 
+def make_deform_case(ops, seed, n, N0, M, Cin, Cout, influence, modulated, extent=0.05, shadow_frac=0.2, K=15):
+    """KPConv_deform_ops (convolution_ops.py:110-235) forward + autograd gradients w.r.t. features, K_values,
+    offsets and modulations, for a loss that uses all three outputs the way KPConvDeformableLayer does
+    (kernels.py:228-246: new_feat, fitting_loss(sq_distances), repulsion over deformed_K_points) plus a dense
+    cotangent on sq_distances restricted to the real (non-shadow) neighbours."""
+    g = torch.Generator().manual_seed(seed)
+    kp = read_kernel_ply(os.path.join(REF, "torch_points3d/modules/KPConv/kernels/dispositions/k_015_center.ply"))
+    K_points = torch.from_numpy((kp[:K] * 1.5 * extent).astype(np.float32))
+    support = torch.rand((N0, 3), generator=g) * 0.3
+    qsel = torch.randperm(N0, generator=g)[:n]
+    query = support[qsel] + 0.002 * torch.randn((n, 3), generator=g)
+    d = torch.cdist(query, support)
+    nb = d.topk(M, largest=False).indices
+    mask = torch.rand((n, M), generator=g) < shadow_frac
+    nb = torch.where(mask, torch.full_like(nb, N0), nb)
+    nb[0, :] = N0
+    x = torch.randn((N0, Cin), generator=g)
+    W = torch.randn((K, Cin, Cout), generator=g) * 0.1
+    offsets = torch.randn((n, K, 3), generator=g) * (0.3 * extent)
+    mods = (2 * torch.sigmoid(torch.randn((n, K), generator=g))) if modulated else None
+    dout = torch.randn((n, Cout), generator=g)
+    dsq = torch.randn((n, M, K), generator=g) * (nb != N0).unsqueeze(-1).float()
+    ddef = torch.randn((n, K, 3), generator=g)
+    for t in (x, W, offsets) + ((mods,) if modulated else ()):
+        t.requires_grad_(True)
+    out, sqd, deformed = ops.KPConv_deform_ops(query, support, nb.clone(), x, K_points, offsets, mods, W, extent,
+                                               influence, "sum")
+    kpmin = sqd.min(dim=1)[0]
+    fitting = torch.mean(kpmin / (1.5 * extent) ** 2)
+    loss = (out * dout).sum() + 3.0 * fitting + (sqd * dsq).sum() + (deformed * ddef).sum()
+    loss.backward()
+    case = dict(
+        query=query.numpy(), support=support.numpy(), neighbors=nb.numpy().astype(np.int64), x=x.detach().numpy(),
+        K_points=K_points.numpy(), W=W.detach().numpy(), offsets=offsets.detach().numpy(), dout=dout.numpy(),
+        dsq=dsq.numpy(), ddef=ddef.numpy(), extent=np.float32(extent), influence=influence,
+        out=out.detach().numpy(), sqd=sqd.detach().numpy(), deformed=deformed.detach().numpy(),
+        fitting=np.float32(fitting.item()), dx=x.grad.numpy(), dW=W.grad.numpy(), doffsets=offsets.grad.numpy(),
+    )
+    if modulated:
+        case["modulations"] = mods.detach().numpy()
+        case["dmodulations"] = mods.grad.numpy()
+    return case
+
+
 def main():
     ops = _load_reference_kpconv_ops()
     cases = [
@@ -90,6 +134,16 @@ def main():
         case = make_case(ops, **kw)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **case)
         print(name, case["out"].shape, float(np.abs(case["out"]).mean()))
+    deform_cases = [
+        ("kpdeform_linear_mod", dict(seed=21, n=96, N0=160, M=20, Cin=8, Cout=12, influence="linear", modulated=True)),
+        ("kpdeform_linear", dict(seed=22, n=120, N0=200, M=34, Cin=32, Cout=32, influence="linear", modulated=False)),
+        ("kpdeform_gaussian_mod", dict(seed=23, n=64, N0=128, M=16, Cin=5, Cout=7, influence="gaussian", modulated=True)),
+        ("kpdeform_constant", dict(seed=24, n=64, N0=128, M=16, Cin=6, Cout=6, influence="constant", modulated=False)),
+    ]
+    for name, kw in deform_cases:
+        case = make_deform_case(ops, **kw)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **case)
+        print(name, case["out"].shape, float(np.abs(case["out"]).mean()), float(np.abs(case["doffsets"]).mean()))
     kp = read_kernel_ply(os.path.join(REF, "torch_points3d/modules/KPConv/kernels/dispositions/k_015_center.ply"))
     # the 15 kernel-point disposition is DATA of the reference model (k_015_center.ply); kept as a fixture
     np.save(os.path.join(HERE, "k_015_center.npy"), kp)

@@ -191,3 +191,30 @@ def test_fps_properties():
     assert sorted(oracle.fps_dense(xyz[:1, :9], 9)[0].tolist()) == list(range(9))
     with pytest.raises(ValueError):
         oracle.fps_dense(xyz[:, :4], 5)
+
+
+# ------------------------------------------------------------ deformable KPConv ----
+@pytest.mark.parametrize("name", ["kpdeform_linear_mod", "kpdeform_linear", "kpdeform_gaussian_mod", "kpdeform_constant"])
+def test_kpconv_deform_oracle_against_reference_golden(name):
+    """forward and all four gradients of the numpy restatement against the reference's own KPConv_deform_ops +
+    torch autograd (tests/golden/make_golden.py); the loss there feeds all three outputs, including the
+    fitting-loss min over neighbours"""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    mods = g["modulations"] if "modulations" in g.files else None
+    infl, ext = str(g["influence"]), float(g["extent"])
+    args = (g["query"], g["support"], g["neighbors"], g["x"], g["K_points"], g["offsets"], mods, g["W"], ext, infl)
+    out, sqd, kpd = oracle.kpconv_deform_fwd(*args)
+    assert np.abs(out - g["out"]).max() <= 1e-5 * np.abs(g["out"]).max()
+    assert np.array_equal(sqd, g["sqd"]) and np.array_equal(kpd, g["deformed"])
+    n, M, K = sqd.shape
+    kpmin = sqd.min(1)
+    assert abs(float(np.mean(kpmin / np.float32((1.5 * ext) ** 2))) - float(g["fitting"])) <= 1e-5 * abs(float(g["fitting"]))
+    # cotangent of sq_distances = the golden's dense one + the fitting term through the first argmin
+    dsq = g["dsq"].copy()
+    am = sqd.argmin(1)
+    np.add.at(dsq, (np.arange(n)[:, None], am, np.arange(K)[None, :]), np.float32(3.0 / ((1.5 * ext) ** 2) / (n * K)))
+    dx, dW, doff, dm = oracle.kpconv_deform_bwd(*args, g["dout"], dsq, g["ddef"])
+    for got, key in ((dx, "dx"), (dW, "dW"), (doff, "doffsets")):
+        assert np.abs(got - g[key]).max() <= 2e-5 * np.abs(g[key]).max(), key
+    if mods is not None:
+        assert np.abs(dm - g["dmodulations"]).max() <= 2e-5 * np.abs(g["dmodulations"]).max()

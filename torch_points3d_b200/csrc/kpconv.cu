@@ -277,6 +277,27 @@ int kpconv_fwd_simt(const float *query, const float *support, const int64_t *nei
     return finish_launch("kpconv_fwd_simt");
 }
 
+// host-side launchers of the plain SGEMM, shared with kpconv_deform.cu
+int sgemm_strided(const float *A, int64_t sai, int64_t sak, const float *B, int64_t sbk, int64_t sbj, float *C,
+                  int64_t ldc, int64_t Mr, int64_t Nc, int64_t Kd, cudaStream_t st) {
+    dim3 gd((unsigned)((Nc + 63) / 64), (unsigned)((Mr + 63) / 64), 1);
+    sgemm_strided_kernel<<<gd, 256, 0, st>>>(A, sai, sak, B, sbk, sbj, C, ldc, Mr, Nc, Kd, Kd, 0);
+    return finish_launch("sgemm_strided");
+}
+
+// dW[kc][o] += sum_p A[p][kc] * B[p][o]: split over p, fp32 reductions into the (zeroed) dW
+int sgemm_splitk_atomic(const float *A, const float *B, int64_t n, int64_t KC, int Cout, float *dW, cudaStream_t st) {
+    const int64_t tiles = ((KC + 63) / 64) * ((Cout + 63) / 64);
+    int64_t split = (2 * kNumSMs + tiles - 1) / tiles;
+    int64_t kps = (n + split - 1) / split;
+    kps = (kps + 15) / 16 * 16;
+    if (kps < 64) kps = 64;
+    split = (n + kps - 1) / kps;
+    dim3 gd((unsigned)((Cout + 63) / 64), (unsigned)((KC + 63) / 64), (unsigned)split);
+    sgemm_strided_kernel<<<gd, 256, 0, st>>>(A, 1, KC, B, Cout, 1, dW, Cout, KC, Cout, n, kps, 1);
+    return finish_launch("sgemm_splitk_atomic");
+}
+
 }  // namespace p3d
 
 using namespace p3d;

@@ -83,6 +83,99 @@ class KPConvLayer(torch.nn.Module):
             self.add_one)
 
 
+def fitting_loss(sq_distance, radius):
+    """losses.py:4-16"""
+    kpmin = sq_distance.min(dim=1)[0]
+    return torch.mean(kpmin / (radius ** 2))
+
+
+def repulsion_loss(deformed_kpoints, radius):
+    """losses.py:19-36 (the division by the radius in the reference discards its result, :26: kept that way)"""
+    n_points = deformed_kpoints.shape[1]
+    repulsive_loss = 0
+    for i in range(n_points):
+        with torch.no_grad():
+            other_points = torch.cat([deformed_kpoints[:, :i, :], deformed_kpoints[:, i + 1:, :]], dim=1)
+        distances = torch.sqrt(torch.sum((other_points - deformed_kpoints[:, i:i + 1, :]) ** 2, dim=-1))
+        repulsion_force = torch.sum(torch.pow(torch.relu(1.5 - distances), 2), dim=1)
+        repulsive_loss += torch.mean(repulsion_force)
+    return repulsive_loss
+
+
+def permissive_loss(deformed_kpoints, radius):
+    """losses.py:39-45"""
+    norm_deformed_normalized = torch.norm(deformed_kpoints, p=2, dim=-1) / float(radius)
+    return torch.mean(norm_deformed_normalized[norm_deformed_normalized > 1.0])
+
+
+class KPConvDeformableLayer(torch.nn.Module):
+    """modules/KPConv/kernels.py:107-256: a rigid KPConv (offset_weights) predicts per-point kernel offsets (and
+    modulations), the deformable operator applies them; fitting / repulsion (or permissive) regularisers are kept
+    in `internal_losses`.  The fitting loss reads the fused min over neighbours instead of the [n,M,K] tensor."""
+
+    PERMISSIVE_LOSS_KEY = "permissive_loss"
+    FITTING_LOSS_KEY = "fitting_loss"
+    REPULSION_LOSS_KEY = "repulsion_loss"
+    _INFLUENCE_TO_RADIUS = 1.5
+
+    def __init__(self, num_inputs, num_outputs, point_influence, n_kernel_points=15, fixed="center",
+                 KP_influence="linear", aggregation_mode="sum", dimension=3, modulated=False, loss_mode="fitting",
+                 add_one=False, random_rotation=True, **kwargs):
+        super().__init__()
+        assert dimension == 3
+        self.kernel_radius = self._INFLUENCE_TO_RADIUS * point_influence
+        self.point_influence = point_influence
+        self.add_one = add_one
+        self.num_inputs = num_inputs + self.add_one * 1
+        self.num_outputs = num_outputs
+        self.KP_influence, self.n_kernel_points, self.aggregation_mode = KP_influence, n_kernel_points, aggregation_mode
+        self.modulated, self.loss_mode = modulated, loss_mode
+        self.internal_losses = {self.PERMISSIVE_LOSS_KEY: 0.0, self.FITTING_LOSS_KEY: 0.0, self.REPULSION_LOSS_KEY: 0.0}
+        kp = load_kernels(self.kernel_radius, n_kernel_points, fixed=fixed, random_rotation=random_rotation)
+        self.K_points = torch.nn.Parameter(torch.from_numpy(kp.reshape(n_kernel_points, 3)).to(torch.float),
+                                           requires_grad=False)
+        offset_dim = (4 if modulated else 3) * n_kernel_points
+        offset_weights = torch.empty([n_kernel_points, self.num_inputs, offset_dim], dtype=torch.float)
+        torch.nn.init.xavier_normal_(offset_weights)
+        self.offset_weights = torch.nn.Parameter(offset_weights)
+        self.offset_bias = torch.nn.Parameter(torch.zeros(offset_dim, dtype=torch.float))
+        weights = torch.empty([n_kernel_points, self.num_inputs, num_outputs], dtype=torch.float)
+        torch.nn.init.xavier_normal_(weights)
+        self.weight = torch.nn.Parameter(weights)
+
+    def forward(self, query_points, support_points, neighbors, x):
+        x = add_ones(support_points, x, self.add_one)
+        offset_feat = ops.KPConv_ops(query_points, support_points, neighbors, x, self.K_points, self.offset_weights,
+                                     self.point_influence, self.KP_influence, self.aggregation_mode) + self.offset_bias
+        nk = self.n_kernel_points
+        if self.modulated:
+            offsets = offset_feat[:, :3 * nk].reshape((-1, nk, 3))
+            modulations = 2 * torch.sigmoid(offset_feat[:, 3 * nk:])
+        else:
+            offsets = offset_feat.reshape((-1, nk, 3))
+            modulations = None
+        offsets = offsets * self.point_influence
+        new_feat, kpmin, K_points_deformed = ops.KPConv_deform_fitting(
+            query_points, support_points, neighbors, x, self.K_points, offsets, modulations, self.weight,
+            self.point_influence, self.KP_influence, self.aggregation_mode)
+        if self.loss_mode == "fitting":
+            self.internal_losses[self.FITTING_LOSS_KEY] = torch.mean(kpmin / (self.kernel_radius ** 2))
+            self.internal_losses[self.REPULSION_LOSS_KEY] = repulsion_loss(K_points_deformed, self.point_influence)
+        elif self.loss_mode == "permissive":
+            self.internal_losses[self.PERMISSIVE_LOSS_KEY] = permissive_loss(K_points_deformed, self.kernel_radius)
+        else:
+            raise NotImplementedError("Loss mode %s not recognised. Only permissive and fitting are valid"
+                                      % self.loss_mode)
+        return new_feat
+
+    def get_internal_losses(self):
+        return self.internal_losses
+
+    def __repr__(self):
+        return "KPConvDeformableLayer(InF: %i, OutF: %i, kernel_pts: %i, radius: %.2f, KP_influence: %s)" % (
+            self.num_inputs, self.num_outputs, self.n_kernel_points, self.kernel_radius, self.KP_influence)
+
+
 class Cloud:
     """minimal stand-in for the torch_geometric `Data` objects the reference blocks pass around"""
 

@@ -540,6 +540,101 @@ def KPConv_ops(query_points, support_points, neighbors_indices, features, K_poin
                          PRECISION[precision or KPCONV_PRECISION])
 
 
+
+# --------------------------------------------------------- deformable KPConv ---------------
+class _KPConvDeform(torch.autograd.Function):
+    """outputs (out [n,Cout], sq_distances [n,M,K] or empty, kpmin [n,K] or empty)"""
+
+    @staticmethod
+    def forward(ctx, query, support, neighbors, feat, k_points, offsets, mods, k_values, extent, influence, want_sqd,
+                want_kpmin):
+        dev = _require_cuda("KPConv_deform_ops", query, support, neighbors, feat, k_points, offsets, mods, k_values)
+        query, support, feat, offsets = _f32(query), _f32(support), _f32(feat), _f32(offsets)
+        k_points, k_values, neighbors = _f32(k_points), _f32(k_values), _i64(neighbors)
+        mods = None if mods is None else _f32(mods)
+        n, M = neighbors.shape
+        N0, Cin = feat.shape
+        K, _, Cout = k_values.shape
+        out = torch.empty((n, Cout), dtype=torch.float32, device=dev)
+        wf = torch.empty((n, K, Cin), dtype=torch.float32, device=dev)
+        sqd = torch.empty((n, M, K) if want_sqd else (0,), dtype=torch.float32, device=dev)
+        kpmin = torch.empty((n, K) if want_kpmin else (0,), dtype=torch.float32, device=dev)
+        argmin = torch.empty((n, K), dtype=torch.int32, device=dev) if want_kpmin else None
+        _call(dev, "p3d_kpconv_deform_fwd_f32", query.data_ptr(), support.data_ptr(), neighbors.data_ptr(),
+              feat.data_ptr(), k_points.data_ptr(), offsets.data_ptr(), _ptr(mods), k_values.data_ptr(), n, N0, M, K,
+              Cin, Cout, float(extent), influence, out.data_ptr(), wf.data_ptr(), sqd.data_ptr() if want_sqd else None,
+              kpmin.data_ptr() if want_kpmin else None, _ptr(argmin))
+        ctx.save_for_backward(query, support, neighbors, feat, k_points, offsets, mods, k_values, wf, argmin)
+        ctx.cfg = (float(extent), influence)
+        ctx.set_materialize_grads(False)
+        return out, sqd, kpmin
+
+    @staticmethod
+    def backward(ctx, g_out, g_sqd, g_kpmin):
+        query, support, neighbors, feat, k_points, offsets, mods, k_values, wf, argmin = ctx.saved_tensors
+        extent, influence = ctx.cfg
+        dev = query.device
+        n, M = neighbors.shape
+        N0, Cin = feat.shape
+        K, _, Cout = k_values.shape
+        need = ctx.needs_input_grad
+        g_out = torch.zeros((n, Cout), dtype=torch.float32, device=dev) if g_out is None else _f32(g_out)
+        g_sqd = None if g_sqd is None or g_sqd.numel() == 0 else _f32(g_sqd)
+        g_kpmin = None if g_kpmin is None or g_kpmin.numel() == 0 else _f32(g_kpmin)
+        dfeat = torch.zeros_like(feat) if need[3] else None
+        dW = torch.zeros_like(k_values) if need[7] else None
+        doff = torch.empty_like(offsets) if need[5] else None
+        dmod = torch.empty_like(mods) if (mods is not None and need[6]) else None
+        ws_bytes = _cabi.lib().p3d_kpconv_deform_bwd_ws_bytes(n, K, Cin)
+        ws = torch.empty(max(ws_bytes // 4, 1), dtype=torch.float32, device=dev)
+        _call(dev, "p3d_kpconv_deform_bwd_f32", query.data_ptr(), support.data_ptr(), neighbors.data_ptr(),
+              feat.data_ptr(), k_points.data_ptr(), offsets.data_ptr(), _ptr(mods), k_values.data_ptr(), wf.data_ptr(),
+              g_out.data_ptr(), _ptr(g_sqd), _ptr(g_kpmin), _ptr(argmin), n, N0, M, K, Cin, Cout, extent, influence,
+              _ptr(dfeat), _ptr(dW), _ptr(doff), _ptr(dmod), ws.data_ptr(), ws_bytes)
+        return None, None, None, dfeat, None, doff, dmod, dW, None, None, None, None
+
+
+def _check_deform(features, K_points, offsets, modulations, K_values, KP_influence, aggregation_mode):
+    if KP_influence not in INFLUENCE:
+        raise ValueError("Unknown influence function type (config.KP_influence)")
+    if aggregation_mode == "closest":
+        # convolution_ops.py:196 calls torch.argmin(..., output_type=torch.long): the reference cannot run this mode
+        raise TypeError("argmin() received an invalid combination of arguments - got output_type (the reference's "
+                        "deformable 'closest' aggregation does not run; only 'sum' is offered)")
+    if aggregation_mode != "sum":
+        raise ValueError("Unknown convolution mode. Should be 'closest' or 'sum'")
+    K = K_points.shape[0]
+    if K_values.dim() != 3 or K_values.shape[0] != K or K_values.shape[1] != features.shape[1]:
+        raise AssertionError("K_values must be [n_kernel_points, Cin, Cout]")
+    if offsets.dim() != 3 or offsets.shape[1] != K or offsets.shape[2] != 3:
+        raise AssertionError("offsets must be [n_points, n_kernel_points, 3]")
+    if modulations is not None and tuple(modulations.shape) != tuple(offsets.shape[:2]):
+        raise AssertionError("modulations must be [n_points, n_kernel_points]")
+
+
+def KPConv_deform_ops(query_points, support_points, neighbors_indices, features, K_points, offsets, modulations,
+                      K_values, KP_extent, KP_influence, aggregation_mode):
+    """KPConv_deform_ops (torch_points3d/modules/KPConv/convolution_ops.py:110-235), same positional signature and
+    return value: (output_features [n,Cout], sq_distances [n,M,K], deformed_K_points [n,K,3]).  Differentiable
+    w.r.t. features, offsets, modulations and K_values; sq_distances and deformed_K_points carry gradients to
+    offsets like the reference's (they feed the regularisers of modules/KPConv/losses.py)."""
+    _check_deform(features, K_points, offsets, modulations, K_values, KP_influence, aggregation_mode)
+    out, sqd, _ = _KPConvDeform.apply(query_points, support_points, neighbors_indices, features, K_points, offsets,
+                                      modulations, K_values, float(KP_extent), INFLUENCE[KP_influence], True, False)
+    return out, sqd, torch.add(offsets, K_points)
+
+
+def KPConv_deform_fitting(query_points, support_points, neighbors_indices, features, K_points, offsets, modulations,
+                          K_values, KP_extent, KP_influence, aggregation_mode):
+    """Same operator for callers that only reduce sq_distances the way fitting_loss does (losses.py:4-16):
+    returns (output_features, kpmin [n,K] = sq_distances.min(dim=1)[0], deformed_K_points) without ever writing the
+    [n,M,K] tensor; kpmin is differentiable w.r.t. offsets through the first argmin, like torch.min."""
+    _check_deform(features, K_points, offsets, modulations, K_values, KP_influence, aggregation_mode)
+    out, _, kpmin = _KPConvDeform.apply(query_points, support_points, neighbors_indices, features, K_points, offsets,
+                                        modulations, K_values, float(KP_extent), INFLUENCE[KP_influence], False, True)
+    return out, kpmin, torch.add(offsets, K_points)
+
+
 class _NeighborMax(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, neighbors):
