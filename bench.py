@@ -341,6 +341,12 @@ def run_b200(args):
                 "algorithmic_bytes": dom_bytes, "avg_launch_ms": round(dom_ms, 5), "peak_source": peaks_src}
 
     kp = bench_kpconv(dev, args) if not args.skip_extras else None
+    operators = None
+    if not args.skip_extras:
+        try:
+            operators = bench_operators(dev)
+        except Exception as e:  # noqa: BLE001
+            operators = {"error": str(e)[:200]}
     cpu = cpu_baseline(max_seconds=12.0) if not args.skip_extras else None
 
     clouds = B_CLOUDS * world * args.steps
@@ -362,6 +368,7 @@ def run_b200(args):
         "gpu_launches": int(launches_per_step * args.steps),
         "launches_per_step": int(launches_per_step),
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "kpconv": kp, "kpconv_stack": stack, "c4": c4,
+        "operators": operators,
     }
     print(json.dumps(line))
     if world > 1:
@@ -442,6 +449,131 @@ def bench_kpconv(dev, args):
                 res["tensor_pipe"] = json.load(f)
         except Exception:  # noqa: BLE001
             pass
+    return res
+
+
+def bench_operators(dev):
+    """Per-operator device times on the C2 / C3 / C4 shapes with the figures SURVEY.md section 8d asks for: dependent
+    rounds/s for FPS (latency bound), pair tests/s for the neighbour searches (FP32 ALU bound; the FP32 peak of
+    148 SMs x 128 lanes x 1.965 GHz = 37.2 T tests/s would need one instruction per test, a test is ~8), achieved
+    GB/s on algorithmic bytes for the gather / scatter kernels (HBM bound), points/s for voxel clustering and the
+    deformable KPConv.  Every call is captured in a CUDA graph and replayed (device time, no launch overhead)."""
+    import torch
+    from torch_points3d_b200 import _cabi, kpconv, ops, synthetic
+    peaks, _ = _peaks()
+    res = {}
+
+    def timed(fn, reps=10):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        run = fn
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                keep = fn()  # noqa: F841
+            run = graph.replay
+            run()
+        except Exception:  # noqa: BLE001
+            run = fn
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e3  # us
+
+    def put(name, us, **kw):
+        d = {"us": round(us, 2)}
+        for k, v in kw.items():
+            d[k] = float("%.4g" % v)
+        if "gb_s" in d:
+            d["hbm_frac"] = round(d["gb_s"] / peaks["hbm_gbs"], 3)
+        res[name] = d
+
+    B = B_CLOUDS
+    g = torch.Generator(device=dev).manual_seed(0)
+    xyz = torch.from_numpy(synthetic.surface_clouds(B, N_PTS, 1002)).to(dev)
+    us = timed(lambda: ops.furthest_point_sample(xyz, 512))
+    put("fps 16x2048->512", us, rounds_per_s=511 / (us * 1e-6), us_per_round=us / 511)
+    idx1 = ops.furthest_point_sample(xyz, 512)
+    pos1 = xyz.gather(1, idx1.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    idx2 = ops.furthest_point_sample(pos1, 128)
+    pos2 = pos1.gather(1, idx2.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    x1 = torch.randn((B, 320, 512), device=dev, generator=g)
+    for (p, q, r, k) in [(xyz, pos1, 0.2, 64), (pos1, pos2, 0.8, 128)]:
+        n, s_ = p.shape[1], q.shape[1]
+        us = timed(lambda: ops.ball_query(r, k, p, q, return_dist=False))
+        put("ball_query N=%d S=%d r=%.1f K=%d" % (n, s_, r, k), us, pair_tests_per_s=B * n * s_ / (us * 1e-6),
+            gb_s=B * (12 * (n + s_) + 8 * s_ * k) / us / 1e3)
+    ridx = ops.ball_query(0.8, 128, pos1, pos2, return_dist=False)[0]
+    C, S, K, n = 320, 128, 128, 512
+    us = timed(lambda: ops.group_features(x1, pos1, pos2, ridx))
+    put("group_features fwd SA2 K=128 C=320", us, gb_s=B * (4 * C * n + 8 * S * K + 4 * (C + 3) * S * K) / us / 1e3)
+    gout = torch.randn((B, C + 3, S, K), device=dev, generator=g)
+    ws_b = _cabi.lib().p3d_group_bwd_ws_bytes(B, C, n, S, K)
+    ws = torch.empty(max(ws_b, 1), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream
+    _cabi.call("p3d_group_bwd_prepare", ridx.data_ptr(), B, C, n, S, K, ws.data_ptr(), ws_b, st().cuda_stream)
+    dfe = torch.empty((B, C, n), device=dev)
+    us = timed(lambda: _cabi.call("p3d_group_bwd_f32", gout.data_ptr(), ridx.data_ptr(), B, C, n, S, K, dfe.data_ptr(),
+                                  (C + 3) * S * K, 3, ws.data_ptr(), ws_b, 1, st().cuda_stream))
+    put("grouping bwd SA2 K=128 C=320 (inverse index prepared)", us, gb_s=B * (4 * C * S * K + 8 * S * K + 4 * C * n) / us / 1e3)
+    us = timed(lambda: ops.three_nn(xyz, pos1))
+    put("three_nn n=2048 m=512", us, pair_tests_per_s=B * 2048 * 512 / (us * 1e-6))
+    dist, i3 = ops.three_nn(xyz, pos1)
+    w3 = torch.rand_like(dist)
+    f3 = torch.randn((B, 128, 512), device=dev, generator=g)
+    us = timed(lambda: ops.three_interpolate(f3, i3, w3))
+    put("three_interpolate fwd C=128 512->2048", us, gb_s=B * (4 * 128 * 512 + 36 * 2048 + 4 * 128 * 2048) / us / 1e3)
+    # C3: partial-dense search, voxel clustering, deformable KPConv
+    pos_h, batch_h = synthetic.indoor_spheres()
+    pos, batch = torch.from_numpy(pos_h).to(dev), torch.from_numpy(batch_h).to(dev)
+    npts = pos.shape[0]
+    us = timed(lambda: ops.ball_query(0.1, 34, pos, pos, mode="partial_dense", batch_x=batch, batch_y=batch,
+                                      return_dist=False))
+    pairs = float((torch.bincount(batch).double() ** 2).sum())
+    put("ball_query partial n=%d r=0.1 M=34" % npts, us, pair_tests_per_s=pairs / (us * 1e-6), points_per_s=npts / (us * 1e-6))
+    nb = ops.ball_query(0.1, 34, pos, pos, mode="partial_dense", batch_x=batch, batch_y=batch, return_dist=False)[0]
+    N_ = pos.shape[0]
+    cl = torch.empty(N_, dtype=torch.int64, device=dev)
+    la = torch.empty(N_, dtype=torch.int64, device=dev)
+    od = torch.empty(N_, dtype=torch.int32, device=dev)
+    sg = torch.empty(N_ + 1, dtype=torch.int32, device=dev)
+    mp = torch.empty(N_, 3, device=dev)
+    ob = torch.empty(N_, dtype=torch.int64, device=dev)
+    nd = torch.empty(1, dtype=torch.int64, device=dev)
+    gb = _cabi.lib().p3d_grid_cluster_ws_bytes(N_)
+    gws = torch.empty(gb, dtype=torch.uint8, device=dev)
+    us = timed(lambda: _cabi.call("p3d_grid_cluster_f32", pos.data_ptr(), batch.data_ptr(), N_, 0.08, cl.data_ptr(),
+                                  la.data_ptr(), od.data_ptr(), sg.data_ptr(), mp.data_ptr(), ob.data_ptr(), None,
+                                  nd.data_ptr(), gws.data_ptr(), gb, st().cuda_stream))
+    put("grid_cluster n=%d size=0.08 (GridSampling3D)" % npts, us, points_per_s=npts / (us * 1e-6), voxels=float(nd.item()))
+    kp = torch.from_numpy(kpconv.load_kernels(0.06, random_rotation=False)).to(dev)
+    xk = torch.randn((npts, 32), device=dev, generator=g, requires_grad=True)
+    W = (torch.randn((15, 32, 32), device=dev, generator=g) * 0.1).requires_grad_(True)
+    off = (torch.randn((npts, 15, 3), device=dev, generator=g) * 0.012).requires_grad_(True)
+    dout = torch.randn((npts, 32), device=dev, generator=g)
+
+    def dfwd():
+        with torch.no_grad():
+            return ops.KPConv_deform_fitting(pos, pos, nb, xk, kp, off, None, W, 0.04, "linear", "sum")[0]
+
+    def dfb():
+        out, kpmin, _ = ops.KPConv_deform_fitting(pos, pos, nb, xk, kp, off, None, W, 0.04, "linear", "sum")
+        return torch.autograd.grad([out, kpmin], (xk, W, off), [dout, torch.ones_like(kpmin)])
+
+    us = timed(dfwd, reps=5)
+    put("kpconv_deform fwd 32->32 n=%d M=34 (fp32)" % npts, us, points_per_s=npts / (us * 1e-6))
+    us = timed(dfb, reps=5)
+    put("kpconv_deform fwd+bwd 32->32 n=%d M=34 (fp32)" % npts, us, points_per_s=npts / (us * 1e-6))
     return res
 
 
