@@ -251,6 +251,28 @@ int p3d_segment_mean_f32(const float *x, const int32_t *order, const int32_t *se
 int p3d_segment_vote_i64(const int64_t *labels, const int64_t *cluster, int64_t N, int64_t n, int64_t label_min,
                          int num_labels, int32_t *hist, int64_t *out, void *stream);
 
+/* ------------------------------------------------ MESSAGE_PASSING operators ------
+ * Edge lists [2,E] come from radius / knn (core/spatial_ops/neighbour_finder.py:32-33,47): src[e] indexes the
+ * support set, dst[e] the query set, sorted by dst (BaseConvolutionDown.forward, core/base_conv/message_passing.py:44-58
+ * stacks them as edge_index = [col, row]).
+ * p3d_edge_message: input of PointConv's local_nn (torch_geometric 1.7.2 PointConv.message, used by
+ *   modules/pointnet2/message_passing.py:9-26): out[e] = [x[src[e]] (C, may be 0), pos_src[src[e]] - pos_dst[dst[e]]].
+ * p3d_edge_message_bwd: dx[src[e]] += dout[e, 0:C] (dx zeroed by the caller).
+ * p3d_edge_encoding: RandlaKernel.message (modules/RandLANet/modules.py:28-40) relative point position encoding
+ *   out[e] = [pos_i, pos_j, pos_i - pos_j, |pos_i - pos_j|] (10 floats), i = dst, j = src.
+ * p3d_segment_reduce: MessagePassing.aggregate over the contiguous edges of every target t in [0,T):
+ *   mode 0 = max (PointConv; arg (nullable) [T,C] = winning edge, -1 and value 0 for a target without edges),
+ *   mode 1 = sum in edge order (RandlaKernel).  p3d_segment_reduce_bwd: dmsg [E,C] from dout [T,C]. */
+int p3d_edge_message_f32(const float *x, const float *pos_src, const float *pos_dst, const int64_t *src,
+                         const int64_t *dst, int64_t E, int C, float *out, void *stream);
+int p3d_edge_message_bwd_f32(const float *dout, const int64_t *src, int64_t E, int C, float *dx, void *stream);
+int p3d_edge_encoding_f32(const float *pos_src, const float *pos_dst, const int64_t *src, const int64_t *dst, int64_t E,
+                          float *out, void *stream);
+int p3d_segment_reduce_f32(const float *msg, const int64_t *dst, int64_t E, int64_t T, int C, int mode, float *out,
+                           int64_t *arg, void *stream);
+int p3d_segment_reduce_bwd_f32(const float *dout, const int64_t *dst, const int64_t *arg, int64_t E, int64_t T, int C,
+                               int mode, float *dmsg, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

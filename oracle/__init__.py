@@ -382,3 +382,35 @@ def kpconv_deform_bwd(q, s, nb, x, Kp, offsets, mods, W, extent, influence, dout
     if ddef is not None:
         doff = doff + np.asarray(ddef, np.float32)
     return dx1[:N0], dW, doff.astype(np.float32), (None if mods is None else dmods)
+
+
+# ------------------------------------------------ MESSAGE_PASSING operators ----
+# numpy restatement of what torch_geometric 1.7.2 executes around the per-edge MLP of PointConv (message: cat([x_j,
+# pos_j - pos_i]); aggregate: scatter max, 0 for targets without edges) and RandlaKernel
+# (modules/RandLANet/modules.py:34-40; aggregate: scatter add).  torch_geometric / torch_scatter are not under
+# /root/reference and not installable here: "parity unpinned", the spec is the published operator definition.
+def edge_message(x, pos_src, pos_dst, src, dst):
+    rel = np.asarray(pos_src, np.float32)[src] - np.asarray(pos_dst, np.float32)[dst]
+    return rel if x is None else np.concatenate([np.asarray(x, np.float32)[src], rel], axis=1)
+
+
+def edge_encoding(pos_src, pos_dst, src, dst):
+    pi, pj = np.asarray(pos_dst, np.float32)[dst], np.asarray(pos_src, np.float32)[src]
+    v = pi - pj
+    d = np.sqrt((v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]) + v[:, 2] * v[:, 2])[:, None]
+    return np.concatenate([pi, pj, v, d], axis=1).astype(np.float32)
+
+
+def segment_max(msg, dst, T):
+    msg = np.asarray(msg, np.float32)
+    out = np.full((T, msg.shape[1]), -np.inf, np.float32)
+    np.maximum.at(out, dst, msg)
+    out[np.isinf(out)] = 0
+    return out
+
+
+def segment_sum(msg, dst, T):
+    msg = np.asarray(msg, np.float32)
+    out = np.zeros((T, msg.shape[1]), np.float32)
+    np.add.at(out, dst, msg)  # in edge order
+    return out

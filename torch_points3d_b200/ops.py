@@ -731,3 +731,84 @@ def segment_vote(labels: torch.Tensor, vc: VoxelClusters) -> torch.Tensor:
     _call(dev, "p3d_segment_vote_i64", lab.data_ptr(), vc.cluster.data_ptr(), lab.shape[0], vc.n, lmin, L,
           hist.data_ptr(), out.data_ptr())
     return out.to(labels.dtype)
+
+
+# ------------------------------------------------- MESSAGE_PASSING operators ---------------
+class _EdgeMessage(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pos_src, pos_dst, src, dst):
+        dev = _require_cuda("edge_message", x, pos_src, pos_dst, src, dst)
+        pos_src, pos_dst, src, dst = _f32(pos_src), _f32(pos_dst), _i64(src), _i64(dst)
+        x = None if x is None else _f32(x)
+        C = 0 if x is None else x.shape[1]
+        E = src.shape[0]
+        out = torch.empty((E, C + 3), dtype=torch.float32, device=dev)
+        _call(dev, "p3d_edge_message_f32", _ptr(x), pos_src.data_ptr(), pos_dst.data_ptr(), src.data_ptr(),
+              dst.data_ptr(), E, C, out.data_ptr())
+        ctx.save_for_backward(src)
+        ctx.shape = None if x is None else tuple(x.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (src,) = ctx.saved_tensors
+        if ctx.shape is None or not ctx.needs_input_grad[0]:
+            return None, None, None, None, None
+        grad_out = _f32(grad_out)
+        dx = torch.zeros(ctx.shape, dtype=torch.float32, device=grad_out.device)
+        _call(grad_out.device, "p3d_edge_message_bwd_f32", grad_out.data_ptr(), src.data_ptr(), src.shape[0],
+              ctx.shape[1], dx.data_ptr())
+        return dx, None, None, None, None
+
+
+def edge_message(x: Optional[torch.Tensor], pos_src: torch.Tensor, pos_dst: torch.Tensor, src: torch.Tensor,
+                 dst: torch.Tensor) -> torch.Tensor:
+    """PointConv.message before its local_nn (torch_geometric 1.7.2): cat([x_j, pos_j - pos_i], dim=1) for every
+    edge, j = src (support index), i = dst (query index); x may be None.  Differentiable w.r.t. x."""
+    return _EdgeMessage.apply(x, pos_src, pos_dst, src, dst)
+
+
+def edge_encoding(pos_src: torch.Tensor, pos_dst: torch.Tensor, src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """RandlaKernel.message relative point position encoding (modules/RandLANet/modules.py:34-40):
+    cat([pos_i, pos_j, pos_i - pos_j, |pos_i - pos_j|]) -> [E, 10]"""
+    dev = _require_cuda("edge_encoding", pos_src, pos_dst, src, dst)
+    pos_src, pos_dst, src, dst = _f32(pos_src), _f32(pos_dst), _i64(src), _i64(dst)
+    out = torch.empty((src.shape[0], 10), dtype=torch.float32, device=dev)
+    _call(dev, "p3d_edge_encoding_f32", pos_src.data_ptr(), pos_dst.data_ptr(), src.data_ptr(), dst.data_ptr(),
+          src.shape[0], out.data_ptr())
+    return out
+
+
+class _SegmentReduce(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, msg, dst, T, mode):
+        dev = _require_cuda("segment_reduce", msg, dst)
+        msg, dst = _f32(msg), _i64(dst)
+        E, C = msg.shape
+        out = torch.empty((T, C), dtype=torch.float32, device=dev)
+        arg = torch.empty((T, C), dtype=torch.int64, device=dev) if mode == 0 else None
+        _call(dev, "p3d_segment_reduce_f32", msg.data_ptr(), dst.data_ptr(), E, T, C, mode, out.data_ptr(), _ptr(arg))
+        ctx.save_for_backward(dst, arg)
+        ctx.cfg = (E, T, C, mode)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dst, arg = ctx.saved_tensors
+        E, T, C, mode = ctx.cfg
+        grad_out = _f32(grad_out)
+        dmsg = torch.empty((E, C), dtype=torch.float32, device=grad_out.device)
+        _call(grad_out.device, "p3d_segment_reduce_bwd_f32", grad_out.data_ptr(), dst.data_ptr(), _ptr(arg), E, T, C,
+              mode, dmsg.data_ptr())
+        return dmsg, None, None, None
+
+
+def segment_max(msg: torch.Tensor, dst: torch.Tensor, num_targets: int) -> torch.Tensor:
+    """aggr="max" of MessagePassing over edges sorted by target: [E,C] -> [T,C]; a target without edges gets 0
+    (torch_scatter's fill value)."""
+    return _SegmentReduce.apply(msg, dst, int(num_targets), 0)
+
+
+def segment_sum(msg: torch.Tensor, dst: torch.Tensor, num_targets: int) -> torch.Tensor:
+    """aggr="add" of MessagePassing over edges sorted by target, summed in edge order (deterministic)."""
+    return _SegmentReduce.apply(msg, dst, int(num_targets), 1)
