@@ -322,6 +322,46 @@ class _Prepared:
         torch.cuda.current_stream(dev).wait_event(self.event)
 
 
+class PreparedInverse:
+    """inverse index of a neighbour table, built ahead of time on the caller's stream (`prepare_grouping`,
+    `prepare_three_interpolate`).  It depends on the indices only, so a pipeline can build it together with the
+    neighbour search -- e.g. for the NEXT batch while the current one is in its feature stage -- and hand it to
+    `group_features` / `grouping_operation` / `three_interpolate` through their `prepared=` argument."""
+
+    def __init__(self, ws, ws_bytes):
+        self.ws, self.ws_bytes = ws, ws_bytes
+
+    def join(self, dev):  # same-stream (or caller-synchronised) producer: nothing to wait for
+        pass
+
+
+def prepare_grouping(idx: torch.Tensor, C: int, N: int) -> Optional[PreparedInverse]:
+    """inverse index for the backward of grouping `C` channels of an `N`-point table through idx[B,S,K]
+    (None when the shape uses the workspace-free path)"""
+    dev = _require_cuda("prepare_grouping", idx)
+    idx = _i64(idx)
+    B, S, K = idx.shape
+    ws_bytes = _cabi.lib().p3d_group_bwd_ws_bytes(B, C, N, S, K)
+    if not ws_bytes:
+        return None
+    ws = _workspace(ws_bytes, dev)
+    _call(dev, "p3d_group_bwd_prepare", idx.data_ptr(), B, C, N, S, K, ws.data_ptr(), ws_bytes)
+    return PreparedInverse(ws, ws_bytes)
+
+
+def prepare_three_interpolate(idx: torch.Tensor, C: int, m: int) -> Optional[PreparedInverse]:
+    """inverse index for the backward of three_interpolate(features[B,C,m], idx[B,n,3], ...)"""
+    dev = _require_cuda("prepare_three_interpolate", idx)
+    idx = _i64(idx)
+    B, n, _ = idx.shape
+    ws_bytes = _cabi.lib().p3d_three_interp_bwd_ws_bytes(B, C, m, n)
+    if not ws_bytes:
+        return None
+    ws = _workspace(ws_bytes, dev)
+    _call(dev, "p3d_three_interp_bwd_prepare", idx.data_ptr(), B, C, m, n, ws.data_ptr(), ws_bytes)
+    return PreparedInverse(ws, ws_bytes)
+
+
 def _prepare_group(idx, B, C, N, S, K):
     if not PREPARE_INVERSE_IN_FORWARD:
         return None
@@ -347,7 +387,7 @@ def _group_bwd(grad_out, idx, B, C, N, S, K, batch_stride, c_off, prepared=None)
 
 class _Grouping(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, features, idx):
+    def forward(ctx, features, idx, prepared=None):
         dev = _require_cuda("grouping_operation", features, idx)
         features, idx = _f32(features), _i64(idx)
         B, C, N = features.shape
@@ -357,7 +397,9 @@ class _Grouping(torch.autograd.Function):
               C * S * K, 0)
         ctx.save_for_backward(idx)
         ctx.N = N
-        ctx.prepared = _prepare_group(idx, B, C, N, S, K) if ctx.needs_input_grad[0] else None
+        if prepared is None and ctx.needs_input_grad[0]:
+            prepared = _prepare_group(idx, B, C, N, S, K)
+        ctx.prepared = prepared
         return out
 
     @staticmethod
@@ -366,15 +408,15 @@ class _Grouping(torch.autograd.Function):
         grad_out = _f32(grad_out)
         B, C, S, K = grad_out.shape
         dfeat = _group_bwd(grad_out, idx, B, C, ctx.N, S, K, C * S * K, 0, ctx.prepared)
-        return dfeat, None
+        return dfeat, None, None
 
 
-def grouping_operation(features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+def grouping_operation(features: torch.Tensor, idx: torch.Tensor, prepared=None) -> torch.Tensor:
     """tp.grouping_operation(features[B,C,N], idx[B,S,K]) -> [B,C,S,K]
     (reference call sites modules/pointnet2/dense.py:38,45; modules/RSConv/dense.py:147,...)."""
     if features.dim() != 3 or idx.dim() != 3 or features.shape[0] != idx.shape[0]:
         raise AssertionError("grouping_operation expects features[B,C,N] and idx[B,S,K]")
-    return _Grouping.apply(features, idx)
+    return _Grouping.apply(features, idx, prepared)
 
 
 class _GroupXyzFeat(torch.autograd.Function):
@@ -383,7 +425,7 @@ class _GroupXyzFeat(torch.autograd.Function):
     grouped_pos temporary, no torch.cat copy."""
 
     @staticmethod
-    def forward(ctx, x, pos, new_pos, idx, norm, use_xyz):
+    def forward(ctx, x, pos, new_pos, idx, norm, use_xyz, prepared=None):
         dev = _require_cuda("group_features", pos, new_pos, idx, x)
         pos, new_pos, idx = _f32(pos), _f32(new_pos), _i64(idx)
         B, N, _ = pos.shape
@@ -401,7 +443,9 @@ class _GroupXyzFeat(torch.autograd.Function):
                   c_xyz)
         ctx.save_for_backward(idx)
         ctx.dims = (B, C, N, S, K, c_xyz)
-        ctx.prepared = _prepare_group(idx, B, C, N, S, K) if (C > 0 and ctx.needs_input_grad[0]) else None
+        if prepared is None and C > 0 and ctx.needs_input_grad[0]:
+            prepared = _prepare_group(idx, B, C, N, S, K)
+        ctx.prepared = prepared
         return out
 
     @staticmethod
@@ -412,22 +456,22 @@ class _GroupXyzFeat(torch.autograd.Function):
         if C > 0 and ctx.needs_input_grad[0]:
             grad_out = _f32(grad_out)
             dx = _group_bwd(grad_out, idx, B, C, N, S, K, (c_xyz + C) * S * K, c_xyz, ctx.prepared)
-        return dx, None, None, None, None, None
+        return dx, None, None, None, None, None, None
 
 
-def group_features(x, pos, new_pos, idx, normalize_by: Optional[float] = None, use_xyz: bool = True):
+def group_features(x, pos, new_pos, idx, normalize_by: Optional[float] = None, use_xyz: bool = True, prepared=None):
     """fused `_prepare_features`: cat([(pos[idx] - new_pos) / r, x[idx]], dim=1) -> [B,3+C,S,K].
     Positions carry no gradient (as in the reference, where pos never requires grad)."""
     if x is None and not use_xyz:
         raise AssertionError("Cannot have not features and not use xyz as a feature!")
     norm = 1.0 if normalize_by is None else float(normalize_by)
-    return _GroupXyzFeat.apply(x, pos, new_pos, idx, norm, use_xyz)
+    return _GroupXyzFeat.apply(x, pos, new_pos, idx, norm, use_xyz, prepared)
 
 
 # --------------------------------------------------------- three_interpolate ---------------
 class _ThreeInterpolate(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, features, idx, weight):
+    def forward(ctx, features, idx, weight, prepared=None):
         dev = _require_cuda("three_interpolate", features, idx, weight)
         features, idx, weight = _f32(features), _i64(idx), _f32(weight)
         B, C, m = features.shape
@@ -437,8 +481,8 @@ class _ThreeInterpolate(torch.autograd.Function):
               out.data_ptr())
         ctx.save_for_backward(idx, weight)
         ctx.m = m
-        ctx.prepared = None
-        if PREPARE_INVERSE_IN_FORWARD and ctx.needs_input_grad[0]:
+        ctx.prepared = prepared
+        if prepared is None and PREPARE_INVERSE_IN_FORWARD and ctx.needs_input_grad[0]:
             ws_bytes = _cabi.lib().p3d_three_interp_bwd_ws_bytes(B, C, m, n)
             if ws_bytes:
                 ctx.prepared = _Prepared("p3d_three_interp_bwd_prepare", dev, ws_bytes, idx.data_ptr(), B, C, m, n)
@@ -458,15 +502,15 @@ class _ThreeInterpolate(torch.autograd.Function):
             ws, flag = _workspace(ws_bytes, grad_out.device), 0
         _call(grad_out.device, "p3d_three_interp_bwd_f32", grad_out.data_ptr(), idx.data_ptr(), weight.data_ptr(), B,
               C, ctx.m, n, dfeat.data_ptr(), _ptr(ws), ws_bytes, flag)
-        return dfeat, None, None
+        return dfeat, None, None, None
 
 
-def three_interpolate(features: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+def three_interpolate(features: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor, prepared=None) -> torch.Tensor:
     """tp.three_interpolate(features[B,C,m], idx[B,n,3], weight[B,n,3]) -> [B,C,n]
     (reference call site core/base_conv/dense.py:140); differentiable w.r.t. features."""
     if features.dim() != 3 or idx.dim() != 3 or weight.shape != idx.shape or idx.shape[2] != 3:
         raise AssertionError("three_interpolate expects features[B,C,m], idx[B,n,3], weight[B,n,3]")
-    return _ThreeInterpolate.apply(features, idx, weight)
+    return _ThreeInterpolate.apply(features, idx, weight, prepared)
 
 
 def knn_interpolate(x, pos_x, pos_y, batch_x=None, batch_y=None, k: int = 3, num_workers: int = 1):
