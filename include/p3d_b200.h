@@ -144,6 +144,13 @@ int p3d_group_bwd_f32(const float *dout, const int64_t *idx, int B, int C, int N
 int p3d_group_xyz_f32(const float *pos, const float *new_pos, const int64_t *idx, int B, int N, int S, int K,
                       float norm, float *out, int64_t out_batch_stride, void *stream);
 
+/* Both halves of _prepare_features in ONE launch: out [B,3+C,S,K] = cat([(pos[idx] - new_pos) / norm, feat[idx]], 1)
+ * (modules/pointnet2/dense.py:36-54).  The relative-coordinate channels are one more channel block of the staged
+ * gather kernel (positions transposed into shared memory once per CTA).  Tables too large to stage (N > 8192) run
+ * the two kernels above. */
+int p3d_group_xyz_feat_f32(const float *pos, const float *new_pos, const float *feat, const int64_t *idx, int B, int C,
+                           int N, int S, int K, float norm, float *out, void *stream);
+
 /* ---------------------------------------------------- three_interpolate ----
  * Replaces tp.three_interpolate(features[B,C,m], idx[B,n,3], weight[B,n,3]) -> [B,C,n]
  *   reference call site: core/base_conv/dense.py:140 */

@@ -304,11 +304,13 @@ def test_grouping_forward_bit_exact_and_backward(B, C, n, S, K):
 
 
 @pytest.mark.parametrize("B,C,n,S,K,r", [(3, 70, 500, 37, 29, 0.3), (16, 320, 512, 128, 128, 0.8), (1, 16, 1024, 4, 3, 0.2),
-                                         (5, 33, 700, 64, 48, 0.25), (2, 40, 64, 300, 16, 0.5), (149, 32, 96, 8, 64, 0.4)])
-def test_grouping_backward_wide_channels_on_ball_query_tables(B, C, n, S, K, r):
-    """wide-channel backward (lanes = channels, run-compressed lists, CTA ranges cut across units) on real
-    ball-query tables: rows padded with their first hit give long runs of one index; sizes that are not multiples
-    of the chunk, the channel block or the warp's point block; the result is deterministic"""
+                                         (5, 33, 700, 64, 48, 0.25), (2, 40, 64, 300, 16, 0.5), (149, 32, 96, 8, 64, 0.4),
+                                         (16, 3, 2048, 512, 64, 0.2), (4, 6, 1024, 256, 32, 0.2), (3, 8, 700, 37, 29, 0.3),
+                                         (1, 1, 6144, 700, 9, 0.15), (200, 2, 50, 3, 5, 0.6)])
+def test_grouping_backward_on_ball_query_tables(B, C, n, S, K, r):
+    """backward kernels (sorted lists with run compression for wide tables, per-warp shared-memory tables for the
+    narrow first-level ones) on real ball-query tables: rows padded with their first hit give long runs of one
+    index; sizes that are not multiples of the chunk or the warp step; the result is deterministic"""
     xyz = synthetic.surface_clouds(B, n, seed=60 + C)
     pos = T(xyz)
     new_pos = pos[:, torch.linspace(0, n - 1, S, device=DEV).long()].contiguous()
@@ -352,6 +354,26 @@ def test_group_features_matches_reference_formulation():
     plain = ops.group_features(T(feat), pos, new_pos, ridx)
     assert np.array_equal(N(plain)[:, :3], want)
     assert np.array_equal(N(plain)[:, 3:], oracle.group_fwd(feat, gi))
+
+
+@pytest.mark.parametrize("S,K,C", [(37, 29, 5), (64, 30, 16), (50, 6, 40)])
+def test_group_features_fused_rows_crossing_vector_boundaries(S, K, C):
+    """fused relative-coordinate + feature grouping when a 4-slot vector straddles two centroids (K % 4 != 0) and
+    when the slot count is not a multiple of 4 (scalar tail path)"""
+    B, n = 3, 777
+    xyz = synthetic.surface_clouds(B, n, seed=52)
+    feat = np.random.default_rng(53).standard_normal((B, C, n)).astype(np.float32)
+    pos = T(xyz)
+    new_pos = pos[:, torch.linspace(0, n - 1, S, device=DEV).long()].contiguous()
+    ridx = ops.ball_query(0.3, K, pos, new_pos)[0]
+    gi = N(ridx)
+    for normalize in (None, 0.3):
+        fused = N(ops.group_features(T(feat), pos, new_pos, ridx, normalize_by=normalize))
+        want = np.stack([xyz[b][gi[b]] - N(new_pos)[b][:, None] for b in range(B)]).transpose(0, 3, 1, 2)
+        if normalize:
+            want = want * (np.float32(1.0) / np.float32(normalize))
+        assert np.array_equal(fused[:, :3], want.astype(np.float32))
+        assert np.array_equal(fused[:, 3:], oracle.group_fwd(feat, gi))
 
 
 # -------------------------------------------------------------------- interpolation ---------

@@ -36,6 +36,7 @@ SIGNATURES = {
     "p3d_group_bwd_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64, c_int, c_vp, c_sz,
                                   c_int, c_vp]),
     "p3d_group_xyz_f32": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_vp, c_i64, c_vp]),
+    "p3d_group_xyz_feat_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp]),
     "p3d_three_interp_fwd_f32": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "p3d_three_interp_bwd_ws_bytes": (c_sz, [c_int, c_int, c_int, c_int]),
     "p3d_three_interp_bwd_prepare": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_sz, c_vp]),

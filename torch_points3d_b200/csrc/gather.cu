@@ -23,24 +23,42 @@ constexpr int GR_THREADS = 256;
 constexpr int GR_VEC = 4;                        // output positions per thread per step
 constexpr int GR_SMEM_FLOATS = 24 * 1024;        // 96 KB of staged feature rows per CTA (2 CTAs / SM)
 
+// optional fused relative-coordinate channels of group_fwd_kernel (pos == nullptr: plain gather)
+struct GroupXyz {
+    const float *pos;      // [B,N,3]
+    const float *new_pos;  // [B,S,3]
+    int S, K;
+    float norm;
+    int do_norm;
+};
+
 // out[b, c_off+c, e] = feat[b, c, idx[b, e]],   e in [0, E = S*K)
 template <bool STAGED>
 __global__ void __launch_bounds__(GR_THREADS)
 group_fwd_kernel(const float *__restrict__ feat, const int64_t *__restrict__ idx, int C, int N, int64_t E,
-                 int CC, int e_per_cta, float *__restrict__ out, int64_t out_batch_stride, int c_off) {
+                 int CC, int e_per_cta, float *__restrict__ out, int64_t out_batch_stride, int c_off,
+                 GroupXyz xyz) {
     extern __shared__ __align__(16) float rows[];  // [CC][N] when STAGED
     const int b = blockIdx.z;
-    const int c0 = blockIdx.y * CC;
-    const int cc = (C - c0 < CC) ? (C - c0) : CC;
+    // fused _prepare_features: the first channel block of the grid (when xyz.pos is set) produces the three
+    // relative-coordinate channels (pos[idx] - new_pos) * scale from the point-major position tensor
+    const bool xyz_block = STAGED && xyz.pos != nullptr && blockIdx.y == 0;
+    const int fy = blockIdx.y - ((STAGED && xyz.pos != nullptr) ? 1 : 0);
+    const int c0 = xyz_block ? 0 : fy * CC;
+    const int cc = xyz_block ? 3 : ((C - c0 < CC) ? (C - c0) : CC);
     const int64_t e0 = (int64_t)blockIdx.x * e_per_cta;
     const int64_t e1 = (e0 + e_per_cta < E) ? e0 + e_per_cta : E;
     const float *__restrict__ fb = feat + ((int64_t)b * C + c0) * N;
     const int64_t *__restrict__ ib = idx + (int64_t)b * E;
-    float *__restrict__ ob = out + (int64_t)b * out_batch_stride + (int64_t)(c_off + c0) * E;
+    float *__restrict__ ob = out + (int64_t)b * out_batch_stride + (int64_t)(xyz_block ? 0 : c_off + c0) * E;
+    const float *__restrict__ nb = xyz_block ? xyz.new_pos + (int64_t)b * xyz.S * 3 : nullptr;
 
     if (STAGED) {
         const int total = cc * N;
-        if ((((uintptr_t)fb) & 15) == 0 && (total & 3) == 0) {
+        if (xyz_block) {
+            const float *__restrict__ pb = xyz.pos + (int64_t)b * N * 3;
+            for (int i = threadIdx.x; i < 3 * N; i += GR_THREADS) rows[(i % 3) * N + i / 3] = __ldg(pb + i);
+        } else if ((((uintptr_t)fb) & 15) == 0 && (total & 3) == 0) {
             const float4 *__restrict__ s4 = reinterpret_cast<const float4 *>(fb);
             float4 *d4 = reinterpret_cast<float4 *>(rows);
             for (int i = threadIdx.x; i < total / 4; i += GR_THREADS) d4[i] = __ldg(s4 + i);
@@ -62,6 +80,22 @@ group_fwd_kernel(const float *__restrict__ feat, const int64_t *__restrict__ idx
                 float4 v;
                 if (STAGED) { v.x = r[j[0]]; v.y = r[j[1]]; v.z = r[j[2]]; v.w = r[j[3]]; }
                 else { v.x = __ldg(r + j[0]); v.y = __ldg(r + j[1]); v.z = __ldg(r + j[2]); v.w = __ldg(r + j[3]); }
+                if (xyz_block) {
+                    const int s0 = (int)(e / xyz.K), s3 = (int)((e + 3) / xyz.K);
+                    const float n0 = __ldg(nb + 3 * s0 + ch);
+                    if (s0 == s3) {
+                        v.x = __fsub_rn(v.x, n0); v.y = __fsub_rn(v.y, n0); v.z = __fsub_rn(v.z, n0); v.w = __fsub_rn(v.w, n0);
+                    } else {
+                        v.x = __fsub_rn(v.x, n0);
+                        v.y = __fsub_rn(v.y, __ldg(nb + 3 * (int)((e + 1) / xyz.K) + ch));
+                        v.z = __fsub_rn(v.z, __ldg(nb + 3 * (int)((e + 2) / xyz.K) + ch));
+                        v.w = __fsub_rn(v.w, __ldg(nb + 3 * s3 + ch));
+                    }
+                    if (xyz.do_norm) {  // norm = 1/r: ATen divides by a scalar as a multiply by 1/r
+                        v.x = __fmul_rn(v.x, xyz.norm); v.y = __fmul_rn(v.y, xyz.norm);
+                        v.z = __fmul_rn(v.z, xyz.norm); v.w = __fmul_rn(v.w, xyz.norm);
+                    }
+                }
                 st_cs_f4(ob + (int64_t)ch * E + e, v);
             }
         } else {
@@ -69,7 +103,12 @@ group_fwd_kernel(const float *__restrict__ feat, const int64_t *__restrict__ idx
                 const int jj = (int)__ldg(ib + e + t);
                 for (int ch = 0; ch < cc; ++ch) {
                     const float *__restrict__ r = STAGED ? rows + ch * N : fb + (int64_t)ch * N;
-                    ob[(int64_t)ch * E + e + t] = STAGED ? r[jj] : __ldg(r + jj);
+                    float v = STAGED ? r[jj] : __ldg(r + jj);
+                    if (xyz_block) {
+                        v = __fsub_rn(v, __ldg(nb + 3 * (int)((e + t) / xyz.K) + ch));
+                        if (xyz.do_norm) v = __fmul_rn(v, xyz.norm);
+                    }
+                    ob[(int64_t)ch * E + e + t] = v;
                 }
             }
         }
@@ -613,6 +652,132 @@ reduce_partials_kernel(const float *__restrict__ part, int splits, int64_t n, fl
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Narrow grouping backward (C * N <= 6144 floats, i.e. the first set-abstraction level: C = 3 normals / colours
+// gathered from N = 2048 raw points into up to 65 536 slots per cloud).  The sorted kernel above spends most of its
+// time on per-chunk bookkeeping there (three channel rows cannot amortise it: 91 us per C2 step for 22 MB of
+// gradient, plus three inverse-index builds).  Here the WHOLE gradient table of a cloud, [C][N] floats, fits in
+// shared memory once per warp: a CTA owns a contiguous slot range of one cloud, each of its 8 warps walks its own
+// sub-range in slot order, 32 consecutive slots per step (coalesced gradient and index loads), and adds into its
+// private table.  Duplicate indices inside a step (ball-query padding) are found with __match_any_sync and summed
+// by a fixed shuffle tree, so no two lanes ever touch the same word; the 8 warp tables are added in warp order,
+// the CTAs' partial tables in split order (reduce_partials_kernel): atomic-free and deterministic, and it needs
+// no inverse index at all.
+constexpr int DS_WARPS = 8;
+constexpr int DS_MAX_FLOATS = 6144;  // C * N per warp table: 8 x 24 KB = 192 KB of shared memory
+constexpr int DS_MAX_C = 8;
+constexpr int DS_U = 4;
+
+__global__ void __launch_bounds__(DS_WARPS * 32, 1)
+bwd_direct_kernel(const float *__restrict__ dout, const int64_t *__restrict__ idx, int C, int N, int64_t E,
+                  int64_t slots_per_cta, float *__restrict__ dst_base, int64_t split_stride, int64_t dout_batch_stride,
+                  int c_off) {
+    extern __shared__ __align__(16) float ds_acc[];  // [DS_WARPS][C*N]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y, split = blockIdx.x;
+    const int CN = C * N;
+    for (int i = tid; i < DS_WARPS * CN; i += DS_WARPS * 32) ds_acc[i] = 0.f;
+    __syncthreads();
+    float *acc = ds_acc + (size_t)warp * CN;
+    const int64_t r0 = (int64_t)split * slots_per_cta;
+    const int64_t r1 = (r0 + slots_per_cta < E) ? r0 + slots_per_cta : E;
+    const int64_t per = ((r1 - r0 + DS_WARPS - 1) / DS_WARPS + 31) / 32 * 32;  // slots per warp, multiple of 32
+    const int64_t w0 = r0 + (int64_t)warp * per;
+    const int64_t w1 = (w0 + per < r1) ? w0 + per : r1;
+    const int64_t *__restrict__ ib = idx + (int64_t)b * E;
+    const float *__restrict__ gb = dout + (int64_t)b * dout_batch_stride + (int64_t)c_off * E;
+    // DS_U steps (32 slots each) per iteration: all of their index and gradient loads are issued before the first
+    // one is consumed -- a warp otherwise pays two dependent DRAM round trips per step with nothing else in flight
+    for (int64_t e0 = w0; e0 < w1; e0 += 32 * DS_U) {
+        int64_t j[DS_U];
+        float v[DS_U][DS_MAX_C];
+#pragma unroll
+        for (int u = 0; u < DS_U; ++u) {
+            const int64_t e = e0 + u * 32 + lane;
+            j[u] = (e < w1) ? __ldg(ib + e) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < DS_U; ++u) {
+            const int64_t e = e0 + u * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < DS_MAX_C; ++c) v[u][c] = (c < C && e < w1) ? __ldcs(gb + (int64_t)c * E + e) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < DS_U; ++u) {
+            if (e0 + u * 32 >= w1) break;  // warp-uniform
+            const bool valid = j[u] >= 0 && j[u] < N;
+            const int jj = (int)j[u];
+            const unsigned peers = __match_any_sync(0xffffffffu, valid ? jj : N + lane);
+            const bool single = peers == (1u << lane);
+            const unsigned leaders = __ballot_sync(0xffffffffu, valid && !single && (__ffs(peers) - 1) == lane);
+#pragma unroll
+            for (int c = 0; c < DS_MAX_C; ++c) {
+                if (c >= C) break;
+                const float val = v[u][c];
+                if (valid && single) acc[c * N + jj] += val;
+                unsigned m = leaders;
+                while (m) {  // groups of equal indices inside this step: fixed shuffle tree over the members
+                    const int L = __ffs(m) - 1;
+                    m &= m - 1;
+                    const unsigned members = __shfl_sync(0xffffffffu, peers, L);
+                    float x = ((members >> lane) & 1u) ? val : 0.f;
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                    if (lane == L) acc[c * N + jj] += x;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    float *__restrict__ dst = dst_base + (int64_t)split * split_stride + (int64_t)b * CN;
+    for (int i = tid; i < CN; i += DS_WARPS * 32) {
+        float sacc = ds_acc[i];
+#pragma unroll
+        for (int w = 1; w < DS_WARPS; ++w) sacc += ds_acc[(size_t)w * CN + i];
+        dst[i] = sacc;
+    }
+}
+
+static bool use_direct_path(int C, int N) {
+    if (const char *e = getenv("P3D_BWD_DIRECT")) return atoi(e) != 0 && C <= DS_MAX_C && (int64_t)C * N <= DS_MAX_FLOATS;
+    return C <= DS_MAX_C && (int64_t)C * N <= DS_MAX_FLOATS;
+}
+
+static int direct_splits(int B, int64_t E) {
+    int splits = (kNumSMs + B - 1) / B;  // one CTA per SM
+    const int64_t max_splits = (E + DS_WARPS * 32 - 1) / (DS_WARPS * 32);
+    if (splits > max_splits) splits = (int)max_splits;
+    if (B * splits > kNumSMs && splits > 1) --splits;
+    return splits < 1 ? 1 : splits;
+}
+
+static int launch_bwd_direct(const float *dout, const int64_t *keys, int B, int C, int N, int64_t E, float *dfeat,
+                             int64_t dout_batch_stride, int c_off, void *ws, cudaStream_t st) {
+    const int splits = direct_splits(B, E);
+    const int64_t total = (int64_t)B * C * N;
+    int64_t spc = (E + splits - 1) / splits;
+    spc = (spc + 31) / 32 * 32;
+    const size_t smem = (size_t)DS_WARPS * C * N * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(bwd_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             DS_WARPS * DS_MAX_FLOATS * (int)sizeof(float));
+        attr_done = true;
+    }
+    float *part = (float *)ws;
+    bwd_direct_kernel<<<dim3((unsigned)splits, (unsigned)B), DS_WARPS * 32, smem, st>>>(
+        dout, keys, C, N, E, spc, splits > 1 ? part : dfeat, total, dout_batch_stride, c_off);
+    if (int e = finish_launch("group_bwd_direct")) return e;
+    if (splits > 1) {
+        int64_t gr = (total + 255) / 256;
+        if (gr > 4 * kNumSMs) gr = 4 * kNumSMs;
+        reduce_partials_kernel<<<(unsigned)gr, 256, 0, st>>>(part, splits, total, dfeat);
+        return finish_launch("reduce_partials");
+    }
+    return P3D_OK;
+}
+
 static int pick_splits(int B, int C, int N, int nchunks) {
     const int64_t ctas = (int64_t)((C + SB_CC - 1) / SB_CC) * B * ((N + SB_KPT * SB_THREADS - 1) / (SB_KPT * SB_THREADS));
     int splits = 1;
@@ -736,16 +901,54 @@ P3D_EXPORT int p3d_group_fwd_f32(const float *feat, const int64_t *idx, int B, i
             attr_done = true;
         }
         group_fwd_kernel<true><<<grid, GR_THREADS, smem, st>>>(feat, idx, C, N, E, CC, (int)e_per_cta, out,
-                                                               out_batch_stride, c_off);
+                                                               out_batch_stride, c_off, GroupXyz{});
     } else {
         group_fwd_kernel<false><<<grid, GR_THREADS, 0, st>>>(feat, idx, C, N, E, CC, (int)e_per_cta, out,
-                                                             out_batch_stride, c_off);
+                                                             out_batch_stride, c_off, GroupXyz{});
     }
     return finish_launch("group_fwd");
 }
 
+P3D_EXPORT int p3d_group_xyz_feat_f32(const float *pos, const float *new_pos, const float *feat, const int64_t *idx,
+                                      int B, int C, int N, int S, int K, float norm, float *out, void *stream) {
+    P3D_REQUIRE(B >= 0 && C >= 1 && N >= 0 && S >= 0 && K >= 0, "group_xyz_feat: bad dimension");
+    P3D_REQUIRE(norm > 0.f, "group_xyz_feat: norm must be positive");
+    const int64_t E = (int64_t)S * K;
+    if (B == 0 || E == 0) return P3D_OK;
+    P3D_REQUIRE(pos && new_pos && feat && idx && out, "group_xyz_feat: null pointer");
+    P3D_REQUIRE(N > 0, "group_xyz_feat: empty point table");
+    const int64_t stride = (int64_t)(3 + C) * E;
+    bool staged;
+    const int CC = pick_cc(C, N, staged);
+    if (!staged || 3 * N > GR_SMEM_FLOATS) {  // tables too large to stage: the two plain kernels
+        if (int e = p3d_group_xyz_f32(pos, new_pos, idx, B, N, S, K, norm, out, stride, stream)) return e;
+        return p3d_group_fwd_f32(feat, idx, B, C, N, S, K, out, stride, 3, stream);
+    }
+    const int cchunks = (C + CC - 1) / CC + 1;  // + the relative-coordinate block
+    int64_t e_per_cta = (int64_t)GR_THREADS * GR_VEC * 8;
+    while (e_per_cta > GR_THREADS * GR_VEC && ((E + e_per_cta - 1) / e_per_cta) * cchunks * B < 4 * kNumSMs)
+        e_per_cta /= 2;
+    dim3 grid((unsigned)((E + e_per_cta - 1) / e_per_cta), (unsigned)cchunks, (unsigned)B);
+    const size_t smem = (size_t)((CC > 3 ? CC : 3)) * N * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(group_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             GR_SMEM_FLOATS * (int)sizeof(float));
+        attr_done = true;
+    }
+    GroupXyz xyz{pos, new_pos, S, K, 1.0f / norm, norm != 1.0f ? 1 : 0};
+    group_fwd_kernel<true><<<grid, GR_THREADS, smem, (cudaStream_t)stream>>>(feat, idx, C, N, E, CC, (int)e_per_cta, out,
+                                                                            stride, 3, xyz);
+    return finish_launch("group_xyz_feat");
+}
+
 P3D_EXPORT size_t p3d_group_bwd_ws_bytes(int B, int C, int N, int S, int K) {
-    if (N > INV_MAX_N || B > 65535) return 0;  // atomic path needs no workspace
+    if (B > 65535) return 0;
+    if (use_direct_path(C, N)) {  // partial tables of the narrow path: [splits][B*C*N]
+        const int splits = direct_splits(B, (int64_t)S * K);
+        return splits > 1 ? (size_t)splits * B * C * N * sizeof(float) : 256;
+    }
+    if (N > INV_MAX_N) return 0;  // atomic path needs no workspace
     return inverse_layout(B, C, N, (int64_t)S * K, SB_EC_GROUP).total;
 }
 
@@ -759,6 +962,7 @@ P3D_EXPORT int p3d_group_bwd_prepare(const int64_t *idx, int B, int C, int N, in
         set_error("group_bwd_prepare: workspace of %zu bytes required (p3d_group_bwd_ws_bytes)", need);
         return P3D_ERR_WORKSPACE;
     }
+    if (use_direct_path(C, N)) return P3D_OK;  // the narrow path reads the index tensor directly
     return launch_bwd_sorted<false>(nullptr, nullptr, idx, B, C, N, (int64_t)S * K, nullptr, 0, 0, ws,
                                     (cudaStream_t)stream, BWD_PREPARE);
 }
@@ -777,9 +981,12 @@ P3D_EXPORT int p3d_group_bwd_f32(const float *dout, const int64_t *idx, int B, i
     }
     P3D_REQUIRE(dout && idx, "group_bwd: null pointer");
     const size_t need = p3d_group_bwd_ws_bytes(B, C, N, S, K);
-    if (need > 0 && ws != nullptr && ws_bytes >= need)
+    if (need > 0 && ws != nullptr && ws_bytes >= need) {
+        if (use_direct_path(C, N))
+            return launch_bwd_direct(dout, idx, B, C, N, E, dfeat, dout_batch_stride, c_off, ws, st);
         return launch_bwd_sorted<false>(dout, nullptr, idx, B, C, N, E, dfeat, dout_batch_stride, c_off, ws, st,
                                         prepared ? BWD_PREPARED : BWD_ALL);
+    }
     if (need > 0) {
         set_error("group_bwd: workspace of %zu bytes required (p3d_group_bwd_ws_bytes)", need);
         return P3D_ERR_WORKSPACE;

@@ -434,10 +434,14 @@ class _GroupXyzFeat(torch.autograd.Function):
         c_xyz = 3 if use_xyz else 0
         out = torch.empty((B, c_xyz + C, S, K), dtype=torch.float32, device=dev)
         stride = (c_xyz + C) * S * K
-        if use_xyz:
+        if use_xyz and x is not None:  # both halves in one launch
+            x = _f32(x)
+            _call(dev, "p3d_group_xyz_feat_f32", pos.data_ptr(), new_pos.data_ptr(), x.data_ptr(), idx.data_ptr(), B,
+                  C, N, S, K, float(norm), out.data_ptr())
+        elif use_xyz:
             _call(dev, "p3d_group_xyz_f32", pos.data_ptr(), new_pos.data_ptr(), idx.data_ptr(), B, N, S, K,
                   float(norm), out.data_ptr(), stride)
-        if x is not None:
+        else:
             x = _f32(x)
             _call(dev, "p3d_group_fwd_f32", x.data_ptr(), idx.data_ptr(), B, C, N, S, K, out.data_ptr(), stride,
                   c_xyz)
