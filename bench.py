@@ -131,13 +131,15 @@ class Chain:
         g1.wait_stream(g0)
         with torch.cuda.stream(g1):
             t["idx2"], t["pos2"] = ops.furthest_point_sample(t["pos1"], sa2["npoint"], return_xyz=True)
-            for si, (r, k) in enumerate(zip(sa2["radii"], sa2["nsample"])):
-                t["ridx2_%d" % si] = ops.ball_query(r, k, t["pos1"], t["pos2"], return_dist=False)[0]
+            tables = ops.ball_query_multi(sa2["radii"], sa2["nsample"], t["pos1"], t["pos2"])  # all scales, one sweep
+            for si in range(len(tables)):
+                t["ridx2_%d" % si] = tables[si]
                 t["prep2_%d" % si] = ops.prepare_grouping(t["ridx2_%d" % si], sa2["cin"], sa1["npoint"]).ws
             _, t["nn0_idx"], t["nn0_w"] = ops.three_nn(t["pos1"], t["pos2"], return_weight=True)
             t["prepi0"] = ops.prepare_three_interpolate(t["nn0_idx"], 256, sa2["npoint"]).ws
-        for si, (r, k) in enumerate(zip(sa1["radii"], sa1["nsample"])):
-            t["ridx1_%d" % si] = ops.ball_query(r, k, pos, t["pos1"], return_dist=False)[0]
+        tables = ops.ball_query_multi(sa1["radii"], sa1["nsample"], pos, t["pos1"])
+        for si in range(len(tables)):
+            t["ridx1_%d" % si] = tables[si]
             t["prep1_%d" % si] = ops.prepare_grouping(t["ridx1_%d" % si], sa1["cin"], N_PTS).ws
         _, t["nn1_idx"], t["nn1_w"] = ops.three_nn(pos, t["pos1"], return_weight=True)
         t["prepi1"] = ops.prepare_three_interpolate(t["nn1_idx"], 128, sa1["npoint"]).ws

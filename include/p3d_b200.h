@@ -86,6 +86,15 @@ int p3d_fps_csr_f32(const float *xyz, const int64_t *ptr, int num_clouds, const 
 int p3d_ball_query_dense_f32(const float *x, const float *y, int B, int N, int S, float radius, int nsample,
                              int strict, int64_t *idx, float *dist2, void *stream);
 
+/* All scales of a multi-scale-grouping layer in one sweep: DenseRadiusNeighbourFinder is called once per scale on
+ * the same (x, y) pair (core/base_conv/dense.py:78-82 over neighbour_finder.py:156-178; PointNet++ MSG uses 2-3
+ * radii per level).  Every squared distance is computed once and tested against each radius; idx of scale s is
+ * bit-identical to p3d_ball_query_dense_f32(radius[s], nsample[s]).  h_radii, h_nsamples, h_idx are HOST arrays of
+ * num_scales (<= 4) entries; h_idx[s] is the device pointer of idx_s [B,S,nsample[s]]. */
+int p3d_ball_query_dense_multi_f32(const float *x, const float *y, int B, int N, int S, int num_scales,
+                                   const float *h_radii, const int *h_nsamples, int strict, int64_t *const *h_idx,
+                                   void *stream);
+
 /* Replaces tp.ball_query(..., mode="partial_dense", batch_x, batch_y)
  *   reference call site: core/spatial_ops/neighbour_finder.py:35-37
  * batch_x[Nx], batch_y[Ny]: sorted cloud ids (int64).  GLOBAL indices into x, unfilled

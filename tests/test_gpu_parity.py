@@ -151,6 +151,20 @@ def test_ball_query_dense_spec_cases():
     assert N(ops.ball_query(0.25, 1, T(xb[0]), T(yb[0]), mode="partial_dense", batch_x=z, batch_y=z)[0])[0, 0] == 0
 
 
+@pytest.mark.parametrize("B,n,S,radii,ks", [(16, 2048, 512, [0.1, 0.2, 0.4], [32, 64, 128]), (16, 512, 128, [0.4, 0.8], [64, 128]),
+                                            (3, 2500, 77, [0.3, 0.05, 0.6, 0.2], [16, 5, 200, 1]), (2, 40, 9, [0.5], [7])])
+def test_ball_query_multi_scale_equals_single_scale(B, n, S, radii, ks):
+    """one sweep for all scales of an MSG layer == one single-scale query per radius, bit for bit (candidate tiles
+    of 2048 points: n = 2500 crosses a tile boundary; unsorted radii; rows that never fill)"""
+    xyz = synthetic.surface_clouds(B, n, seed=33)
+    pos = T(xyz)
+    ctr = pos[:, torch.linspace(0, n - 1, S, device=DEV).long()].contiguous()
+    multi = ops.ball_query_multi(radii, ks, pos, ctr)
+    for r, k, got in zip(radii, ks, multi):
+        assert torch.equal(got, ops.ball_query(r, k, pos, ctr)[0]), (r, k)
+        assert np.array_equal(N(got), oracle.ball_query_dense(r, k, xyz, N(ctr))[0])
+
+
 def test_ball_query_partial_reference_grid():
     # reference test/test_transform.py:67-113: 10x10 grid, widths 100/150/200, shadow = N
     n = 10

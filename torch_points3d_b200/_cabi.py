@@ -25,6 +25,7 @@ SIGNATURES = {
     "p3d_fps_csr_ws_bytes": (c_sz, [c_i64, c_i64]),
     "p3d_fps_csr_f32": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_sz, c_vp]),
     "p3d_ball_query_dense_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_f32, c_int, c_int, c_vp, c_vp, c_vp]),
+    "p3d_ball_query_dense_multi_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp]),
     "p3d_ball_query_batch_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_int, c_int, c_i64, c_vp,
                                          c_vp, c_vp]),
     "p3d_knn_batch_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp]),

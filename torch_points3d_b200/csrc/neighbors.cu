@@ -515,6 +515,108 @@ knn_lane_kernel(const float *__restrict__ x, const float *__restrict__ y, const 
     }
 }
 
+// ---------------------------------------------------- multi-scale dense ball query -----------
+// PointNet++ MSG layers query the SAME (points, centroids) pair at several radii (pointnet2.yaml:95-130:
+// r = [.1,.2,.4] with K = [32,64,128]).  One sweep serves all scales: every squared distance is computed once
+// and tested against each radius; a scale stops taking hits when its row is full, the warp stops when all rows
+// are.  Each scale's output is exactly what the single-scale kernel produces (same candidate order, same
+// fp32 distance, same padding rule).
+constexpr int BQ_MAX_SCALES = 4;
+
+struct MultiScaleArgs {
+    float r2x[BQ_MAX_SCALES];  // exclusive upper bound on d2 (strict: r2, otherwise nextafter(r2))
+    int K[BQ_MAX_SCALES];
+    int64_t *idx[BQ_MAX_SCALES];
+    int ns;
+};
+
+template <int NS>
+__global__ void __launch_bounds__(NB_WARPS * 32)
+ball_query_multi_kernel(const float *__restrict__ x, const float *__restrict__ y, int64_t Ny, int64_t n_dense,
+                        int64_t s_dense, MultiScaleArgs a) {
+    __shared__ float4 tile[NB_TILE];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q0 = (int64_t)blockIdx.x * NB_WARPS;
+    const int64_t q1 = (q0 + NB_WARPS < Ny) ? q0 + NB_WARPS : Ny;
+    const int64_t q = q0 + warp;
+    const bool live = q < q1;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    int64_t x0 = 0, x1 = 0;
+    int cnt[NS], first[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) cnt[s] = live ? 0 : a.K[s], first[s] = 0;
+    if (live) {
+        qx = __ldg(y + 3 * q), qy = __ldg(y + 3 * q + 1), qz = __ldg(y + 3 * q + 2);
+        x0 = (q / s_dense) * n_dense, x1 = x0 + n_dense;
+    }
+    const int64_t X0 = (q0 / s_dense) * n_dense, X1 = ((q1 - 1) / s_dense) * n_dense + n_dense;
+    bool first_tile = true;
+    for (int64_t tb = X0; tb < X1; tb += NB_TILE) {
+        bool mydone = tb >= x1;
+        if (!mydone) {
+            mydone = true;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) mydone = mydone && cnt[s] >= a.K[s];
+        }
+        if (!first_tile) {
+            if (__syncthreads_and(mydone)) break;
+        }
+        first_tile = false;
+        const int tn = (int)((X1 - tb < NB_TILE) ? (X1 - tb) : NB_TILE);
+        {
+            const float *__restrict__ src = x + 3 * tb;
+#pragma unroll 2
+            for (int p = tid; p < tn; p += NB_WARPS * 32)
+                tile[p] = make_float4(__ldg(src + 3 * p), __ldg(src + 3 * p + 1), __ldg(src + 3 * p + 2), 0.f);
+        }
+        __syncthreads();
+        if (mydone) continue;
+        const int lo = (int)((x0 > tb ? x0 : tb) - tb);
+        const int hi = (int)((x1 < tb + tn ? x1 : tb + tn) - tb);
+        const int ibase = (int)(tb - x0);
+        for (int i0 = lo; i0 < hi; i0 += 128) {
+            bool open = false;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) open = open || cnt[s] < a.K[s];
+            if (!open) break;
+            float d[4];
+            bool ok[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const int i = i0 + 32 * v + lane;
+                ok[v] = i < hi;
+                const float4 cnd = tile[ok[v] ? i : lo];
+                d[v] = sqdist3(cnd.x, cnd.y, cnd.z, qx, qy, qz);
+            }
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                int c = cnt[s];
+                if (c >= a.K[s]) continue;  // warp-uniform
+                int64_t *__restrict__ row = a.idx[s] + q * a.K[s];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const bool hit = ok[v] && d[v] < a.r2x[s];
+                    const unsigned m = __ballot_sync(0xffffffffu, hit);
+                    if (m) {
+                        const int pos = c + __popc(m & lanemask_lt());
+                        if (hit && pos < a.K[s]) row[pos] = (int64_t)(ibase + i0 + 32 * v + lane);
+                        if (c == 0) first[s] = ibase + i0 + 32 * v + (__ffs(m) - 1);
+                        c += __popc(m);
+                    }
+                }
+                cnt[s] = c;
+            }
+        }
+    }
+    if (!live) return;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {  // padding: first hit, or 0 for an empty ball
+        const int c = cnt[s] < a.K[s] ? cnt[s] : a.K[s];
+        const int64_t padv = c > 0 ? (int64_t)first[s] : 0;
+        for (int e = c + lane; e < a.K[s]; e += 32) a.idx[s][q * a.K[s] + e] = padv;
+    }
+}
+
 template <bool DENSE>
 static int launch_ball_query(const float *x, const float *y, const int64_t *bx, const int64_t *by, int64_t Nx,
                              int64_t Ny, int64_t n_dense, int64_t s_dense, float radius, int K, int strict,
@@ -579,6 +681,36 @@ P3D_EXPORT int p3d_ball_query_dense_f32(const float *x, const float *y, int B, i
     P3D_REQUIRE(x && y && idx, "ball_query_dense: null pointer");
     return launch_ball_query<true>(x, y, nullptr, nullptr, (int64_t)B * N, (int64_t)B * S, N, S, radius, nsample,
                                    strict, 0, idx, dist2, (cudaStream_t)stream);
+}
+
+P3D_EXPORT int p3d_ball_query_dense_multi_f32(const float *x, const float *y, int B, int N, int S, int num_scales,
+                                              const float *h_radii, const int *h_nsamples, int strict,
+                                              int64_t *const *h_idx, void *stream) {
+    P3D_REQUIRE(B >= 0 && N >= 0 && S >= 0, "ball_query_dense_multi: negative dimension");
+    P3D_REQUIRE(num_scales >= 1 && num_scales <= BQ_MAX_SCALES, "ball_query_dense_multi: 1..%d scales", BQ_MAX_SCALES);
+    P3D_REQUIRE(h_radii && h_nsamples && h_idx, "ball_query_dense_multi: null host array");
+    if (B == 0 || S == 0) return P3D_OK;
+    P3D_REQUIRE(x && y, "ball_query_dense_multi: null pointer");
+    MultiScaleArgs a;
+    a.ns = num_scales;
+    for (int s = 0; s < BQ_MAX_SCALES; ++s) {
+        const int t = s < num_scales ? s : 0;  // unused slots repeat scale 0 (never read)
+        P3D_REQUIRE(h_nsamples[t] >= 1 && h_idx[t], "ball_query_dense_multi: scale %d: nsample >= 1 and idx required", t);
+        const float r2 = h_radii[t] * h_radii[t];
+        a.r2x[s] = strict ? r2 : __builtin_nextafterf(r2, __builtin_inff());
+        a.K[s] = h_nsamples[t];
+        a.idx[s] = h_idx[t];
+    }
+    const int64_t Ny = (int64_t)B * S;
+    const unsigned grid = (unsigned)((Ny + NB_WARPS - 1) / NB_WARPS);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (num_scales) {
+        case 1: ball_query_multi_kernel<1><<<grid, NB_WARPS * 32, 0, st>>>(x, y, Ny, N, S, a); break;
+        case 2: ball_query_multi_kernel<2><<<grid, NB_WARPS * 32, 0, st>>>(x, y, Ny, N, S, a); break;
+        case 3: ball_query_multi_kernel<3><<<grid, NB_WARPS * 32, 0, st>>>(x, y, Ny, N, S, a); break;
+        default: ball_query_multi_kernel<4><<<grid, NB_WARPS * 32, 0, st>>>(x, y, Ny, N, S, a); break;
+    }
+    return finish_launch("ball_query_multi");
 }
 
 P3D_EXPORT int p3d_ball_query_batch_f32(const float *x, const float *y, const int64_t *batch_x,

@@ -181,6 +181,29 @@ def ball_query(radius: float, nsample: int, x: torch.Tensor, y: torch.Tensor, mo
     raise Exception("unrecognized mode {}".format(mode))
 
 
+def ball_query_multi(radii, nsamples, x: torch.Tensor, y: torch.Tensor, strict: bool = True):
+    """every scale of a multi-scale-grouping layer in one sweep over the candidates: returns [idx_s [B,S,nsample_s]]
+    with idx_s == ball_query(radii[s], nsamples[s], x, y)[0] bit for bit (DenseRadiusNeighbourFinder is called
+    once per scale on the same pair, core/base_conv/dense.py:78-82)."""
+    import ctypes
+    dev = _require_cuda("ball_query_multi", x, y)
+    if x.dim() != 3 or y.dim() != 3 or x.shape[0] != y.shape[0]:
+        raise AssertionError("ball_query_multi expects x[B,N,3] and y[B,S,3]")
+    if len(radii) != len(nsamples) or not 1 <= len(radii) <= 4:
+        raise ValueError("ball_query_multi: 1..4 scales, one radius and one nsample per scale")
+    x, y = _f32(x), _f32(y)
+    B, N, _ = x.shape
+    S = y.shape[1]
+    ns = len(radii)
+    out = [torch.empty((B, S, int(k)), dtype=torch.int64, device=dev) for k in nsamples]
+    h_r = (ctypes.c_float * ns)(*[float(r) for r in radii])
+    h_k = (ctypes.c_int * ns)(*[int(k) for k in nsamples])
+    h_i = (ctypes.c_void_p * ns)(*[t.data_ptr() for t in out])
+    _call(dev, "p3d_ball_query_dense_multi_f32", x.data_ptr(), y.data_ptr(), B, N, S, ns, ctypes.cast(h_r, ctypes.c_void_p),
+          ctypes.cast(h_k, ctypes.c_void_p), 1 if strict else 0, ctypes.cast(h_i, ctypes.c_void_p))
+    return out
+
+
 def radius(x: torch.Tensor, y: torch.Tensor, r: float, batch_x: Optional[torch.Tensor] = None,
            batch_y: Optional[torch.Tensor] = None, max_num_neighbors: int = 32, num_workers: int = 1) -> torch.Tensor:
     """torch_geometric.nn.radius == torch_cluster.radius (reference call sites

@@ -78,9 +78,14 @@ class PointNetMSGDown(nn.Module):
             idx = idx.unsqueeze(-1).repeat(1, 1, pos.shape[-1]).long()
             new_pos = pos.gather(1, idx)
         ms_x = []
-        for scale_idx in range(self.neighbour_finder.num_scales):
-            radius_idx = self.neighbour_finder(pos, new_pos, scale_idx=scale_idx)
-            ms_x.append(self.conv(x, pos, new_pos, radius_idx, scale_idx))
+        nf = self.neighbour_finder
+        if self.fused_grouping and 1 < nf.num_scales <= 4:
+            # every scale queries the same (pos, new_pos) pair: one sweep, distances computed once
+            tables = ops.ball_query_multi(nf._radius, nf._max_num_neighbors, pos, new_pos)
+        else:
+            tables = [nf(pos, new_pos, scale_idx=s) for s in range(nf.num_scales)]
+        for scale_idx in range(nf.num_scales):
+            ms_x.append(self.conv(x, pos, new_pos, tables[scale_idx], scale_idx))
         return SimpleNamespace(pos=new_pos, x=torch.cat(ms_x, 1), sampling_id=idx[:, :, 0])
 
 
