@@ -670,42 +670,87 @@ def bench_kpconv_stack(dev, world, rank):
                 super().__init__()
                 self.enc, self.head = enc, head
 
-            def forward(self, pos, x, batch):
-                return self.head(self.enc(pos, x, batch).x)
+            def forward(self, pos, x, batch, ms):
+                return self.head(self.enc(pos, x, batch, precomputed=ms).x)
         ddp = torch.nn.parallel.DistributedDataParallel(Wrapper(enc, head), device_ids=[dev.index])
     opt = torch.optim.SGD([p for p in params if p.requires_grad], lr=0.01, momentum=0.98)
     g = torch.Generator(device=dev).manual_seed(7 + rank)
     feats = torch.cat([torch.ones(n, 1, device=dev), torch.randn(n, 4, device=dev, generator=g)], 1)
 
-    def step():
+    transform = kpconv.MultiScaleTransform(enc.strategies())
+    labels_cache = {}
+
+    def step(ms=None):
         opt.zero_grad(set_to_none=True)
-        logits = ddp(pos, feats, batch) if ddp is not None else head(enc(pos, feats, batch).x)
-        labels = (torch.arange(logits.shape[0], device=dev) % 13)
-        loss = torch.nn.functional.cross_entropy(logits, labels)
+        if ms is None:  # geometry of this batch on the device, then the network (what a training loop pays per batch)
+            ms = transform(pos, batch)
+        logits = ddp(pos, feats, batch, ms) if ddp is not None else head(enc(pos, feats, batch, precomputed=ms).x)
+        if logits.shape[0] not in labels_cache:
+            labels_cache[logits.shape[0]] = torch.arange(logits.shape[0], device=dev) % 13
+        loss = torch.nn.functional.cross_entropy(logits, labels_cache[logits.shape[0]])
         loss.backward()
         opt.step()
         return loss
 
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10
-    e0.record()
-    for _ in range(reps):
-        loss = step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
-    return {"workload": "C3/C5: KPConvPaper encoder stack (10 KPConv blocks, %.1f M params), ~%d points/rank in 8 spheres, "
-                        "fwd+bwd+SGD%s" % (nparams / 1e6, n, ", DDP over NCCL" if world > 1 else ""),
-            "ms_per_step": round(ms, 3), "points_per_s": round(world * n / (ms * 1e-3), 1),
-            "loss": round(float(loss.item()), 4), "unit": "points/s"}
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_ = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms_, op=dist.ReduceOp.MAX)
+        # only a float leaves: a live loss tensor would keep this step's autograd graph (and its AccumulateGrad
+        # nodes, bound to the eager stream) alive into the graph capture below
+        val = float(out.detach().item()) if torch.is_tensor(out) and out.numel() == 1 else None
+        del out
+        return float(ms_.item()), val
+
+    ms_full, loss = timed(step)
+    # the reference's configuration: the pyramid is precomputed (DataLoader workers there, one call here), the timed
+    # step is the network alone
+    pyramid = transform(pos, batch)
+    ms_geo, _ = timed(lambda: transform(pos, batch))
+    ms_pre, _ = timed(lambda: step(pyramid))
+    res = {"workload": "C3/C5: KPConvPaper encoder stack (10 KPConv blocks, %.1f M params), ~%d points/rank in 8 spheres, "
+                       "fwd+bwd+SGD%s" % (nparams / 1e6, n, ", DDP over NCCL" if world > 1 else ""),
+           "ms_per_step": round(ms_full, 3), "points_per_s": round(world * n / (ms_full * 1e-3), 1),
+           "geometry_ms": round(ms_geo, 3), "precomputed_geometry_ms_per_step": round(ms_pre, 3),
+           "loss": round(loss, 4), "unit": "points/s"}
+    if world == 1:
+        # with the pyramid given, every shape of the step is static: capture forward + backward + SGD in one graph
+        try:
+            opt.zero_grad(set_to_none=False)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    opt.zero_grad(set_to_none=False)
+                    lg = head(enc(pos, feats, batch, precomputed=pyramid).x)
+                    torch.nn.functional.cross_entropy(lg, labels_cache[lg.shape[0]]).backward()
+                    opt.step()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                opt.zero_grad(set_to_none=False)
+                lg = head(enc(pos, feats, batch, precomputed=pyramid).x)
+                gloss = torch.nn.functional.cross_entropy(lg, labels_cache[lg.shape[0]])
+                gloss.backward()
+                opt.step()
+            ms_graph, _ = timed(lambda: graph.replay() or None)
+            res["precomputed_geometry_cuda_graph_ms_per_step"] = round(ms_graph, 3)
+            res["points_per_s_graph"] = round(n / ((ms_graph + ms_geo) * 1e-3), 1)
+            res["graph_loss"] = round(float(gloss.item()), 4)
+        except Exception as e:  # noqa: BLE001
+            res["cuda_graph_error"] = str(e)[:160]
+    return res
 
 
 def bench_c4(dev):

@@ -199,6 +199,17 @@ int p3d_kpconv_bwd_f32(const float *query, const float *support, const int64_t *
                        int M, int K, int Cin, int Cout, float extent, int influence, int aggregation,
                        float *dfeat, float *dweights, void *ws, size_t ws_bytes, void *stream);
 
+/* The geometric halves of KPConv_ops on their own (convolution_ops.py:49-98 and its adjoint), for shapes where the
+ * dense contraction is better run as a plain GEMM by the caller (few query points, wide channels):
+ *   wf[n,K,Cin] = sum_m influence(p,m,k) * feat[neighbors[p,m]]            out = wf.view(n, K*Cin) @ K_values.view(K*Cin, Cout)
+ *   dfeat[neighbors[p,m]] += sum_k influence(p,m,k) * dwf[p,k,:]           (dfeat zeroed by the caller) */
+int p3d_kpconv_wf_f32(const float *query, const float *support, const int64_t *neighbors, const float *feat,
+                      const float *k_points, int64_t n, int64_t N0, int M, int K, int Cin, float extent, int influence,
+                      int aggregation, float *wf, void *stream);
+int p3d_kpconv_scatter_f32(const float *query, const float *support, const int64_t *neighbors, const float *k_points,
+                           const float *dwf, int64_t n, int64_t N0, int M, int K, int Cin, float extent, int influence,
+                           int aggregation, float *dfeat, void *stream);
+
 /* ------------------------------------------------------ deformable KPConv ------
  * Replaces KPConv_deform_ops(query, support, neighbors, features, K_points, offsets, modulations, K_values,
  *                            KP_extent, KP_influence, "sum") -> (out [n,Cout], sq_distances [n,M,K], K_points + offsets)

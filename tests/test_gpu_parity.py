@@ -498,6 +498,30 @@ def test_kpconv_vs_oracle(cin, cout, M, influence, agg):
     assert relerr(N(tW.grad), dW) <= RTOL
 
 
+@pytest.mark.parametrize("n,N0,M,cin,cout,influence,agg", [(114, 464, 38, 256, 256, "linear", "sum"), (464, 2580, 34, 128, 128, "linear", "sum"),
+                                                           (300, 900, 20, 64, 96, "gaussian", "closest"), (64, 64, 45, 70, 64, "linear", "sum")])
+def test_kpconv_split_path_small_point_sets(n, N0, M, cin, cout, influence, agg):
+    """deep-level shapes: aggregation kernel + library GEMM (exact fp32) against the oracle, forward and gradients"""
+    rng = np.random.default_rng(n + cin)
+    sup = (rng.random((N0, 3)) * 0.6).astype(np.float32)
+    qry = sup[rng.permutation(N0)[:n]]
+    d = ((qry[:, None] - sup[None]) ** 2).sum(-1)
+    nb = np.argsort(d, 1)[:, :M].astype(np.int64)
+    nb[rng.random((n, M)) < 0.2] = N0
+    Kp = kpconv.load_kernels(0.09, random_rotation=False).astype(np.float32)
+    x = rng.standard_normal((N0, cin)).astype(np.float32)
+    W = (rng.standard_normal((15, cin, cout)) * 0.1).astype(np.float32)
+    dout = rng.standard_normal((n, cout)).astype(np.float32)
+    tx, tW = T(x).requires_grad_(True), T(W).requires_grad_(True)
+    assert n <= ops.KPCONV_SPLIT_MAX_POINTS and W.size >= ops.KPCONV_SPLIT_MIN_WEIGHTS
+    out = ops.KPConv_ops(T(qry), T(sup), T(nb), tx, T(Kp), tW, 0.06, influence, agg)
+    assert out.grad_fn.name().startswith("_KPConvSplit")
+    assert relerr(N(out), oracle.kpconv_fwd(qry, sup, nb, x, Kp, W, 0.06, influence, agg)) <= RTOL
+    out.backward(T(dout))
+    dx, dW = oracle.kpconv_bwd(qry, sup, nb, x, Kp, W, dout, 0.06, influence, agg)
+    assert relerr(N(tx.grad), dx) <= RTOL and relerr(N(tW.grad), dW) <= RTOL
+
+
 def test_kpconv_layer_module_and_linearity():
     """KPConvLayer (kernels.py:20-104) + size-independent properties at the C3 size: linear in the
     features, all-shadow rows give exactly 0, shard-by-cloud == whole batch."""
@@ -570,15 +594,45 @@ def test_kpconv_encoder_stack_forward_backward():
     assert sum(float(g.abs().sum()) > 0 for g in grads) >= len(grads) - 2
 
 
-def test_neighbor_max():
+def test_multiscale_transform_precomputed_path_equals_on_the_fly():
+    """MultiScaleTransform (core/data_transform/transforms.py:579-651) on the device: the `precomputed=` path of the
+    blocks (modules/KPConv/blocks.py:70-79) reproduces the on-the-fly path bit for bit, and the pyramid obeys the
+    reference test's consistency checks (test/test_transform.py:67-113: level positions chain through the samplers,
+    neighbour tables have the finder's width, shadow index = support count)"""
+    torch.manual_seed(6)
+    pos_h, batch_h = synthetic.indoor_spheres(num_spheres=2, raw_points=20000, radius=0.6, seed=93)
+    pos, batch = T(pos_h), T(batch_h)
+    enc = kpconv.KPConvEncoder(5, max_nn_cap=34, random_rotation=False).to(DEV).eval()
+    feats = torch.randn(pos.shape[0], 5, device=DEV)
+    ms = kpconv.MultiScaleTransform(enc.strategies())(pos, batch)
+    assert len(ms) == len(enc.blocks) == 10
+    support, s_batch = pos, batch
+    for level, block in zip(ms, enc.blocks):
+        if block.sampler is None:
+            assert torch.equal(level.pos, support)
+        else:
+            q_pos, q_batch = block.sampler(support, s_batch)
+            assert torch.equal(level.pos, q_pos) and torch.equal(level.batch, q_batch)
+        nf = block.neighbour_finder
+        assert level.idx_neighboors.shape == (level.pos.shape[0], nf._max_num_neighbors)
+        assert int(level.idx_neighboors.max()) <= support.shape[0] and int(level.idx_neighboors.min()) >= 0
+        support, s_batch = level.pos, level.batch
+    with torch.no_grad():
+        a = enc(pos, feats, batch)
+        b = enc(pos, feats, batch, precomputed=ms)
+    assert torch.equal(a.x, b.x) and torch.equal(a.pos, b.pos) and b.block_idx == 10
+
+
+@pytest.mark.parametrize("C,n,M", [(70, 300, 20), (128, 300, 38), (1024, 57, 38), (36, 1000, 5)])
+def test_neighbor_max(C, n, M):
     rng = np.random.default_rng(81)
-    x = rng.standard_normal((500, 70)).astype(np.float32)
-    nb = rng.integers(0, 501, (300, 20))
+    x = rng.standard_normal((500, C)).astype(np.float32)
+    nb = rng.integers(0, 501, (n, M))
     tx = T(x).requires_grad_(True)
     out = ops.neighbor_max(tx, T(nb))
     assert np.array_equal(N(out), oracle.neighbor_max(x, nb))
     out.sum().backward()
-    x1 = torch.cat([T(x), torch.zeros(1, 70, device=DEV)]).requires_grad_(True)
+    x1 = torch.cat([T(x), torch.zeros(1, C, device=DEV)]).requires_grad_(True)
     x1[T(nb)].max(1)[0].sum().backward()
     assert torch.equal(tx.grad, x1.grad[:-1])
 

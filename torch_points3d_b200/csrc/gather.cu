@@ -262,6 +262,54 @@ neighbor_max_kernel(const float *__restrict__ x, const int64_t *__restrict__ nb,
     }
 }
 
+// C % 4 == 0: a warp owns (point, block of 128 channels), every lane four channels (one 16-byte load per neighbour
+// row and lane, eight rows in flight); deep KPConv levels have ~100 query points x 1024 channels, so the channel
+// blocks -- not the points -- provide the parallelism.
+__global__ void __launch_bounds__(GR_THREADS)
+neighbor_max_vec_kernel(const float *__restrict__ x, const int64_t *__restrict__ nb, int64_t n, int64_t N0, int M,
+                        int C, int chunks, float *__restrict__ out, int64_t *__restrict__ arg) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * (GR_THREADS / 32) + (threadIdx.x >> 5);
+    const int64_t p = w / chunks;
+    if (p >= n) return;
+    const int c = (int)(w - p * chunks) * 128 + lane * 4;
+    const bool cok = c < C;
+    float best[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    int64_t bi[4] = {N0, N0, N0, N0};
+    for (int m0 = 0; m0 < M; m0 += 32) {
+        int64_t jl = (m0 + lane < M) ? __ldg(nb + p * M + m0 + lane) : -1;
+        if (jl < 0 || jl >= N0) jl = -1;  // shadow row (zeros)
+        const int cnt = (M - m0 < 32) ? (M - m0) : 32;
+        for (int mm = 0; mm < cnt; mm += 8) {
+            int64_t j[8];
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                j[u] = __shfl_sync(0xffffffffu, jl, (mm + u) & 31);
+                v[u] = (mm + u < cnt && j[u] >= 0 && cok) ? __ldg(reinterpret_cast<const float4 *>(x + j[u] * C + c))
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (mm + u < cnt) {
+                    const int64_t jj = j[u] < 0 ? N0 : j[u];
+                    if (v[u].x > best[0]) { best[0] = v[u].x; bi[0] = jj; }
+                    if (v[u].y > best[1]) { best[1] = v[u].y; bi[1] = jj; }
+                    if (v[u].z > best[2]) { best[2] = v[u].z; bi[2] = jj; }
+                    if (v[u].w > best[3]) { best[3] = v[u].w; bi[3] = jj; }
+                }
+            }
+        }
+    }
+    if (cok) {
+        *reinterpret_cast<float4 *>(out + p * C + c) = make_float4(best[0], best[1], best[2], best[3]);
+        if (arg) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) arg[p * C + c + u] = bi[u];
+        }
+    }
+}
+
 // ------------------------------------------------- atomic-free backward (inverse index) ----
 // Both scatter-type gradients (grouping, three_interpolate) are sums over "all output slots e
 // that read source point j".  Instead of fp32 atomics at L2 (one RED per element: the bound of
@@ -1099,6 +1147,14 @@ P3D_EXPORT int p3d_neighbor_max_f32(const float *x, const int64_t *neighbors, in
     P3D_REQUIRE(n >= 0 && N0 >= 0 && M >= 1 && C >= 0, "neighbor_max: bad dimension");
     if (n == 0 || C == 0) return P3D_OK;
     P3D_REQUIRE(neighbors && out && (x || N0 == 0), "neighbor_max: null pointer");
+    if ((C & 3) == 0 && (((uintptr_t)x) & 15) == 0 && (((uintptr_t)out) & 15) == 0) {
+        const int chunks = (C + 127) / 128;
+        const int64_t warps = n * chunks;
+        const int64_t grid = (warps + GR_THREADS / 32 - 1) / (GR_THREADS / 32);
+        neighbor_max_vec_kernel<<<(unsigned)grid, GR_THREADS, 0, (cudaStream_t)stream>>>(x, neighbors, n, N0, M, C,
+                                                                                        chunks, out, arg);
+        return finish_launch("neighbor_max_vec");
+    }
     const int64_t grid = (n + GR_THREADS / 32 - 1) / (GR_THREADS / 32);
     neighbor_max_kernel<<<(unsigned)grid, GR_THREADS, 0, (cudaStream_t)stream>>>(x, neighbors, n, N0, M, C, out, arg);
     return finish_launch("neighbor_max");

@@ -347,6 +347,53 @@ P3D_EXPORT int p3d_kpconv_fwd_f32(const float *query, const float *support, cons
                            influence, aggregation, out, (cudaStream_t)stream);
 }
 
+// The two geometric halves of the operator on their own, for callers that run the dense contraction
+// out = wf . K_values as a plain library GEMM: with a few hundred query points and 512 x 512 weights per kernel
+// point (the deep levels of the KPConv encoder) the work is streaming 16 MB of weights, which a split-K GEMM
+// spreads over the SMs and the fused kernel (2 point tiles x Cout/32 CTAs) does not.
+P3D_EXPORT int p3d_kpconv_wf_f32(const float *query, const float *support, const int64_t *neighbors, const float *feat,
+                                 const float *k_points, int64_t n, int64_t N0, int M, int K, int Cin, float extent,
+                                 int influence, int aggregation, float *wf, void *stream) {
+    if (int e = check_common("kpconv_wf", n, N0, M, K, Cin, 1, influence, aggregation)) return e;
+    if (n == 0) return P3D_OK;
+    P3D_REQUIRE(query && neighbors && k_points && wf && (N0 == 0 || (support && feat)), "kpconv_wf: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (kpconv_sparse_supported(M, K, Cin))
+        return kpconv_wf_sparse(query, support, neighbors, feat, k_points, n, N0, M, K, Cin, extent, influence,
+                                aggregation, wf, st);
+    const int Mpad = (M + 31) / 32 * 32;
+    const size_t smem = (size_t)KPF_WARPS * (Mpad * KP_K + Mpad) * sizeof(float);
+    cudaFuncSetAttribute(kpconv_wf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    int64_t grid = (n + KPF_WARPS - 1) / KPF_WARPS;
+    if (grid > 16 * kNumSMs) grid = 16 * kNumSMs;
+    kpconv_wf_kernel<<<(unsigned)grid, KPF_WARPS * 32, smem, st>>>(query, support, neighbors, feat, k_points, n, N0, M,
+                                                                 Mpad, K, Cin, make_geom(extent, influence, aggregation),
+                                                                 wf);
+    return finish_launch("kpconv_wf");
+}
+
+P3D_EXPORT int p3d_kpconv_scatter_f32(const float *query, const float *support, const int64_t *neighbors,
+                                      const float *k_points, const float *dwf, int64_t n, int64_t N0, int M, int K,
+                                      int Cin, float extent, int influence, int aggregation, float *dfeat,
+                                      void *stream) {
+    if (int e = check_common("kpconv_scatter", n, N0, M, K, Cin, 1, influence, aggregation)) return e;
+    if (n == 0) return P3D_OK;
+    P3D_REQUIRE(query && neighbors && k_points && dwf && dfeat && (N0 == 0 || support), "kpconv_scatter: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (kpconv_sparse_supported(M, K, Cin))
+        return kpconv_scatter_sparse(query, support, neighbors, k_points, dwf, n, N0, M, K, Cin, extent, influence,
+                                     aggregation, dfeat, st);
+    const int Mpad = (M + 31) / 32 * 32;
+    const size_t smem = (size_t)KPF_WARPS * (Mpad * KP_K + Mpad) * sizeof(float);
+    cudaFuncSetAttribute(kpconv_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    int64_t grid = (n + KPF_WARPS - 1) / KPF_WARPS;
+    if (grid > 16 * kNumSMs) grid = 16 * kNumSMs;
+    kpconv_scatter_kernel<<<(unsigned)grid, KPF_WARPS * 32, smem, st>>>(query, support, neighbors, k_points, dwf, n, N0,
+                                                                      M, Mpad, K, Cin,
+                                                                      make_geom(extent, influence, aggregation), dfeat);
+    return finish_launch("kpconv_scatter");
+}
+
 P3D_EXPORT size_t p3d_kpconv_bwd_ws_bytes(int64_t n, int M, int K, int Cin, int Cout) {
     (void)M;
     // wf + dwf  [n, K, Cin] each, then the bf16 hi/lo image of W^T for the tensor-core dwf GEMM (0 if unsupported)

@@ -179,12 +179,13 @@ class KPConvDeformableLayer(torch.nn.Module):
 class Cloud:
     """minimal stand-in for the torch_geometric `Data` objects the reference blocks pass around"""
 
-    def __init__(self, pos, x, batch, idx_neighboors=None, nb_key=None):
+    def __init__(self, pos, x, batch, idx_neighboors=None, nb_key=None, block_idx=0):
         self.pos, self.x, self.batch, self.idx_neighboors = pos, x, batch, idx_neighboors
         self.nb_key = nb_key  # (radius, max_num_neighbors) of a self-neighbour table of `pos`, if one is attached
+        self.block_idx = block_idx  # position in the precomputed multiscale list (blocks.py:67-68,93)
 
     def clone(self):
-        return Cloud(self.pos, self.x, self.batch, self.idx_neighboors, self.nb_key)
+        return Cloud(self.pos, self.x, self.batch, self.idx_neighboors, self.nb_key, self.block_idx)
 
 
 def grid_subsample(pos, batch, size):
@@ -226,21 +227,27 @@ class SimpleBlock(torch.nn.Module):
         self.activation = activation if activation is not None else torch.nn.LeakyReLU(negative_slope=0.1)
         self.sampler = GridSampler(grid_size) if prev_grid_size != grid_size else None
 
-    def forward(self, data, **kwargs):
-        if self.sampler is not None:
-            q_pos, q_batch = self.sampler(data.pos, data.batch)
+    def forward(self, data, precomputed=None, **kwargs):
+        if precomputed:  # blocks.py:70-79: geometry of this block was built ahead of time (MultiScaleTransform)
+            query = precomputed[data.block_idx]
+            q_pos, q_batch, idx_neighboors = query.pos, query.batch, query.idx_neighboors
+            key = query.nb_key
         else:
-            q_pos, q_batch = data.pos, data.batch
-        key = (self.neighbour_finder._radius, self.neighbour_finder._max_num_neighbors)
-        if self.sampler is None and data.idx_neighboors is not None and data.nb_key == key:
-            idx_neighboors = data.idx_neighboors  # same points, radius and width as the previous block: same table
-        else:
-            idx_neighboors = self.neighbour_finder(data.pos, q_pos, batch_x=data.batch, batch_y=q_batch)
+            if self.sampler is not None:
+                q_pos, q_batch = self.sampler(data.pos, data.batch)
+            else:
+                q_pos, q_batch = data.pos, data.batch
+            key = (self.neighbour_finder._radius, self.neighbour_finder._max_num_neighbors)
+            if self.sampler is None and data.idx_neighboors is not None and data.nb_key == key:
+                idx_neighboors = data.idx_neighboors  # same points, radius and width as the previous block: same table
+            else:
+                idx_neighboors = self.neighbour_finder(data.pos, q_pos, batch_x=data.batch, batch_y=q_batch)
+            if self.sampler is not None:
+                key = None  # the table describes self-neighbourhoods of q_pos only when this block was not strided
         x = self.kp_conv(q_pos, data.pos, idx_neighboors, data.x)
         if self.bn is not None:
             x = self.bn(x)
-        # the table describes self-neighbourhoods of q_pos only when this block was not strided
-        return Cloud(q_pos, self.activation(x), q_batch, idx_neighboors, key if self.sampler is None else None)
+        return Cloud(q_pos, self.activation(x), q_batch, idx_neighboors, key, data.block_idx + 1)
 
 
 class ResnetBBlock(torch.nn.Module):
@@ -280,12 +287,12 @@ class ResnetBBlock(torch.nn.Module):
             self.shortcut_op = torch.nn.Identity()
         self.activation = act
 
-    def forward(self, data, **kwargs):
+    def forward(self, data, precomputed=None, **kwargs):
         shortcut_x = data.x
         inner = data.clone()
         if self.has_bottleneck:
             inner.x = self.unary_1(inner.x)
-        output = self.kp_conv(inner)
+        output = self.kp_conv(inner, precomputed=precomputed)
         if self.has_bottleneck:
             output.x = self.unary_2(output.x)
         if self.is_strided:  # max over the neighbour rows of cat(x, zeros): one gather+max kernel
@@ -328,8 +335,47 @@ class KPConvEncoder(torch.nn.Module):
                                                 max_num_neighbors=nn_[1], **kwargs))
         self.out_channels = in_feat * 2 ** levels
 
-    def forward(self, pos, x, batch):
+    def forward(self, pos, x, batch, precomputed=None):
         data = Cloud(pos, x, batch)
         for block in self.blocks:
-            data = block(data)
+            data = block(data, precomputed=precomputed)
         return data
+
+    def strategies(self):
+        """samplers and neighbour finders of the blocks in order -- what the reference hands to MultiScaleTransform
+        (models/base_architectures/unet.py collects the same lists from its down modules)"""
+        return {"sampler": [b.sampler for b in self.blocks], "neighbour_finder": [b.neighbour_finder for b in self.blocks]}
+
+
+class MultiScaleTransform:
+    """core/data_transform/transforms.py:579-651 on the device: runs every block's sampler and neighbour finder once,
+    ahead of the network, and returns the `multiscale` list the blocks read through `precomputed=`
+    (modules/KPConv/blocks.py:70-79).  Differences from the reference's DataLoader-worker version: the whole batch is
+    processed at once by the batched operators (no per-sample loop, so MultiScaleBatch.from_data_list's index
+    shifting -- and its aliasing of every sample's shadow index with the first point of the next sample,
+    datasets/multiscale_data.py:128-136 -- does not arise: the shadow index is the support count of the batch), and a
+    block that repeats the previous block's search on unchanged points shares its table."""
+
+    def __init__(self, strategies):
+        self.strategies = strategies
+        self.num_layers = len(strategies["sampler"])
+
+    @torch.no_grad()
+    def __call__(self, pos, batch):
+        multiscale = []
+        s_pos, s_batch = pos, batch
+        prev_key, prev_table = None, None
+        for sampler, finder in zip(self.strategies["sampler"], self.strategies["neighbour_finder"]):
+            if sampler is not None:
+                q_pos, q_batch = sampler(s_pos, s_batch)
+            else:
+                q_pos, q_batch = s_pos, s_batch
+            key = (finder._radius, finder._max_num_neighbors)
+            if sampler is None and prev_key == key:
+                table = prev_table
+            else:
+                table = finder(s_pos, q_pos, batch_x=s_batch, batch_y=q_batch)
+            multiscale.append(Cloud(q_pos, None, q_batch, table, key if sampler is None else None))
+            prev_key, prev_table = (key, table) if sampler is None else (None, None)
+            s_pos, s_batch = q_pos, q_batch
+        return multiscale

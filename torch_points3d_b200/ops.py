@@ -594,6 +594,50 @@ class _KPConv(torch.autograd.Function):
         return None, None, None, dfeat, None, dW, None, None, None, None
 
 
+class _KPConvSplit(torch.autograd.Function):
+    """KPConv_ops as (influence-weighted neighbour aggregation kernel) + (plain library GEMM): used for the deep
+    encoder levels, a few hundred query points against 15 x 512 x 512 weights, where the contraction is a
+    weight-streaming GEMM (exact fp32)."""
+
+    @staticmethod
+    def forward(ctx, query, support, neighbors, feat, k_points, k_values, extent, influence, aggregation):
+        dev = _require_cuda("KPConv_ops", query, support, neighbors, feat, k_points, k_values)
+        query, support, feat = _f32(query), _f32(support), _f32(feat)
+        k_points, k_values, neighbors = _f32(k_points), _f32(k_values), _i64(neighbors)
+        n, M = neighbors.shape
+        N0, Cin = feat.shape
+        K, _, Cout = k_values.shape
+        wf = torch.empty((n, K * Cin), dtype=torch.float32, device=dev)
+        _call(dev, "p3d_kpconv_wf_f32", query.data_ptr(), support.data_ptr(), neighbors.data_ptr(), feat.data_ptr(),
+              k_points.data_ptr(), n, N0, M, K, Cin, float(extent), influence, aggregation, wf.data_ptr())
+        ctx.save_for_backward(query, support, neighbors, k_points, k_values, wf)
+        ctx.cfg = (float(extent), influence, aggregation, N0, Cin)
+        return wf @ k_values.reshape(K * Cin, Cout)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        query, support, neighbors, k_points, k_values, wf = ctx.saved_tensors
+        extent, influence, aggregation, N0, Cin = ctx.cfg
+        grad_out = _f32(grad_out)
+        n, M = neighbors.shape
+        K, _, Cout = k_values.shape
+        dW = dfeat = None
+        if ctx.needs_input_grad[5]:
+            dW = (wf.t() @ grad_out).reshape(K, Cin, Cout)
+        if ctx.needs_input_grad[3]:
+            dwf = (grad_out @ k_values.reshape(K * Cin, Cout).t()).contiguous()
+            dfeat = torch.zeros((N0, Cin), dtype=torch.float32, device=grad_out.device)
+            _call(grad_out.device, "p3d_kpconv_scatter_f32", query.data_ptr(), support.data_ptr(), neighbors.data_ptr(),
+                  k_points.data_ptr(), dwf.data_ptr(), n, N0, M, K, Cin, extent, influence, aggregation,
+                  dfeat.data_ptr())
+        return None, None, None, dfeat, None, dW, None, None, None
+
+
+# query-point count below which KPConv_ops runs as aggregation kernel + library GEMM (see _KPConvSplit)
+KPCONV_SPLIT_MAX_POINTS = 4096
+KPCONV_SPLIT_MIN_WEIGHTS = 15 * 64 * 64
+
+
 def KPConv_ops(query_points, support_points, neighbors_indices, features, K_points, K_values, KP_extent,
                KP_influence, aggregation_mode, precision=None):
     """KPConv_ops (torch_points3d/modules/KPConv/convolution_ops.py:19-107), same positional
@@ -606,6 +650,10 @@ def KPConv_ops(query_points, support_points, neighbors_indices, features, K_poin
         raise ValueError("Unknown convolution mode. Should be 'closest' or 'sum'")
     if K_values.dim() != 3 or K_values.shape[0] != K_points.shape[0] or K_values.shape[1] != features.shape[1]:
         raise AssertionError("K_values must be [n_kernel_points, Cin, Cout]")
+    if (precision is None and neighbors_indices.shape[0] <= KPCONV_SPLIT_MAX_POINTS
+            and K_values.numel() >= KPCONV_SPLIT_MIN_WEIGHTS):
+        return _KPConvSplit.apply(query_points, support_points, neighbors_indices, features, K_points, K_values,
+                                  float(KP_extent), INFLUENCE[KP_influence], AGGREGATION[aggregation_mode])
     return _KPConv.apply(query_points, support_points, neighbors_indices, features, K_points, K_values,
                          float(KP_extent), INFLUENCE[KP_influence], AGGREGATION[aggregation_mode],
                          PRECISION[precision or KPCONV_PRECISION])
