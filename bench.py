@@ -672,7 +672,11 @@ def bench_kpconv_stack(dev, world, rank):
 
             def forward(self, pos, x, batch, ms):
                 return self.head(self.enc(pos, x, batch, precomputed=ms).x)
-        ddp = torch.nn.parallel.DistributedDataParallel(Wrapper(enc, head), device_ids=[dev.index])
+        # BatchNorm statistics stay per rank (the reference has no SyncBN): no buffer broadcast every forward;
+        # gradients live in the all-reduce buckets (no copy in / out), two ~25 MB buckets overlap the backward pass
+        ddp = torch.nn.parallel.DistributedDataParallel(Wrapper(enc, head), device_ids=[dev.index],
+                                                        broadcast_buffers=False, gradient_as_bucket_view=True,
+                                                        bucket_cap_mb=25)
     opt = torch.optim.SGD([p for p in params if p.requires_grad], lr=0.01, momentum=0.98)
     g = torch.Generator(device=dev).manual_seed(7 + rank)
     feats = torch.cat([torch.ones(n, 1, device=dev), torch.randn(n, 4, device=dev, generator=g)], 1)

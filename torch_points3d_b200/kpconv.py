@@ -362,14 +362,20 @@ class MultiScaleTransform:
 
     @torch.no_grad()
     def __call__(self, pos, batch):
-        multiscale = []
+        # pass 1: every level's query set.  Each grid sampling reads its voxel count back (it sizes the outputs), so
+        # the samplers run first, back to back, while the stream is nearly empty; the neighbour searches -- the bulk
+        # of the work -- are queued afterwards and never sit in front of one of those reads.
+        levels = []
         s_pos, s_batch = pos, batch
+        for sampler in self.strategies["sampler"]:
+            q_pos, q_batch = sampler(s_pos, s_batch) if sampler is not None else (s_pos, s_batch)
+            levels.append((s_pos, s_batch, q_pos, q_batch))
+            s_pos, s_batch = q_pos, q_batch
+        # pass 2: neighbour tables
+        multiscale = []
         prev_key, prev_table = None, None
-        for sampler, finder in zip(self.strategies["sampler"], self.strategies["neighbour_finder"]):
-            if sampler is not None:
-                q_pos, q_batch = sampler(s_pos, s_batch)
-            else:
-                q_pos, q_batch = s_pos, s_batch
+        for (s_pos, s_batch, q_pos, q_batch), sampler, finder in zip(levels, self.strategies["sampler"],
+                                                                    self.strategies["neighbour_finder"]):
             key = (finder._radius, finder._max_num_neighbors)
             if sampler is None and prev_key == key:
                 table = prev_table
@@ -377,5 +383,4 @@ class MultiScaleTransform:
                 table = finder(s_pos, q_pos, batch_x=s_batch, batch_y=q_batch)
             multiscale.append(Cloud(q_pos, None, q_batch, table, key if sampler is None else None))
             prev_key, prev_table = (key, table) if sampler is None else (None, None)
-            s_pos, s_batch = q_pos, q_batch
         return multiscale
