@@ -140,3 +140,65 @@ def test_kernel_points_fixture_matches_reference_disposition(golden_dir):
     layer = kpconv.KPConvLayer(8, 16, point_influence=0.04, add_one=True)
     assert layer.weight.shape == (15, 9, 16) and not layer.K_points.requires_grad
     assert "K_points" in layer.state_dict()            # checkpoints carry the kernel points (kernels.py:66-68)
+
+
+def test_new_entry_points_validate_before_any_cuda_call(cabi):
+    lib = cabi.lib()
+    assert lib.p3d_grid_cluster_f32(None, None, 4, 0.0, None, None, None, None, None, None, None, None, None, 0, None) == -1
+    assert b"voxel size" in lib.p3d_last_error()
+    assert lib.p3d_grid_cluster_ws_bytes(0) == 256 and lib.p3d_grid_cluster_ws_bytes(1000) >= 40 * 1000
+    assert lib.p3d_ball_query_dense_multi_f32(None, None, 1, 4, 2, 5, None, None, 1, None, None) == -1
+    assert b"scales" in lib.p3d_last_error()
+    assert lib.p3d_segment_reduce_f32(None, None, 4, 2, 3, 7, None, None, None) == -1
+    assert lib.p3d_kpconv_deform_fwd_f32(None, None, None, None, None, None, None, None, 4, 4, 500, 15, 8, 8, 0.1, 1,
+                                         None, None, None, None, None, None) == -1
+    assert lib.p3d_kpconv_deform_bwd_ws_bytes(10, 15, 32) == 10 * 15 * 32 * 4
+    assert lib.p3d_group_xyz_feat_f32(None, None, None, None, 1, 0, 4, 2, 2, 1.0, None, None) == -1
+    # narrow first-level backward: per-split partial tables; wide tables: the inverse-index layout
+    assert lib.p3d_group_bwd_ws_bytes(16, 3, 2048, 512, 32) == 9 * 16 * 3 * 2048 * 4
+    assert lib.p3d_group_bwd_ws_bytes(16, 320, 512, 128, 128) > 16 * 16384 * 2
+    # empty problems are a successful no-op
+    assert lib.p3d_edge_message_f32(None, None, None, None, None, 0, 8, None, None) == 0
+    assert lib.p3d_kpconv_wf_f32(None, None, None, None, None, 0, 0, 4, 15, 8, 0.1, 1, 0, None, None) == 0
+
+
+def test_host_logic_of_the_next_row_mirrors():
+    """argument checking and bookkeeping that never reaches the device"""
+    from torch_points3d_b200 import grid_transform as gt, kpconv, message_passing as mp, ops
+    d = gt.Data(pos=torch.rand(6, 3), x=torch.rand(6, 2), y=torch.zeros(6, dtype=torch.long))
+    assert sorted(d.keys) == ["pos", "x", "y"] and d.num_nodes == 6 and "batch" not in d
+    c = d.clone()
+    c["x"] = c["x"] + 1
+    assert not torch.equal(c.x, d.x)
+    with pytest.raises(ValueError):
+        gt.group_data(d, mode="mean")                          # grid_transform.py:53-54
+    with pytest.raises(ValueError):
+        gt.group_data(d, cluster=torch.zeros(6, dtype=torch.long), mode="last")   # :55-56
+    with pytest.raises(AssertionError):
+        gt.group_data(d, mode="median")
+    with pytest.raises(ValueError, match="Edges not supported"):
+        gt.group_data(gt.Data(pos=torch.rand(3, 3), edge_index=torch.zeros(2, 3)), cluster=torch.zeros(3),
+                      unique_pos_indices=torch.zeros(1, dtype=torch.long), mode="last")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gt.GridSampling3D(0.1)(d)
+    assert "grid_size=0.1" in repr(gt.GridSampling3D(0.1))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.ball_query_multi([0.1], [4], torch.rand(1, 8, 3), torch.rand(1, 2, 3))
+    with pytest.raises(TypeError):
+        ops.KPConv_deform_ops(None, None, None, torch.rand(4, 8), torch.rand(15, 3), torch.rand(4, 15, 3), None,
+                              torch.rand(15, 8, 8), 0.1, "linear", "closest")
+    with pytest.raises(AssertionError):
+        ops.KPConv_deform_ops(None, None, None, torch.rand(4, 8), torch.rand(15, 3), torch.rand(4, 14, 3), None,
+                              torch.rand(15, 8, 8), 0.1, "linear", "sum")
+    enc = kpconv.KPConvEncoder(5, max_nn_cap=34)
+    st = enc.strategies()
+    assert len(st["sampler"]) == len(st["neighbour_finder"]) == 10
+    assert [s is not None for s in st["sampler"]] == [False, False, True, False, True, False, True, False, True, False]
+    assert st["neighbour_finder"][2]._radius == pytest.approx(2.5 * 0.04)   # blocks.py:52: 2.5 * sigma * prev_grid
+    layer = kpconv.KPConvDeformableLayer(8, 16, point_influence=0.04, modulated=True)
+    assert layer.offset_weights.shape == (15, 8, 60) and layer.weight.shape == (15, 8, 16)
+    assert set(layer.get_internal_losses()) == {"permissive_loss", "fitting_loss", "repulsion_loss"}
+    conv = mp.PointConv(local_nn=mp.MLP([6, 8]), global_nn=None)
+    assert conv.add_self_loops and isinstance(conv.local_nn, torch.nn.Sequential)
+    sa = mp.SAModule(ratio=0.5, radius=[0.1, 0.2], radius_num_point=[8, 16], down_conv_nn=[6, 8])
+    assert sa.neighbour_finder.num_scales == 2
