@@ -328,12 +328,18 @@ knn_kernel(const float *__restrict__ x, const float *__restrict__ y, const int64
 constexpr int TNN_THREADS = 128;
 constexpr int TNN_TILE = 1024;
 
+// SPLIT consecutive lanes share one unknown point and scan interleaved candidates (lane s takes candidates
+// s, s + SPLIT, ...); their sorted triples are merged by (distance, index) -- the order the sequential strict-<
+// cascade produces -- with two shuffle rounds.  Small problems (C2: 8k-32k unknown points) would otherwise put
+// 1-2 CTAs on an SM and run at ~10 % occupancy.
+template <int SPLIT>
 __global__ void __launch_bounds__(TNN_THREADS)
 three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ known, int n, int m,
                 float *__restrict__ dist, int64_t *__restrict__ idx, float *__restrict__ weight) {
     __shared__ float4 tile[TNN_TILE];
     const int b = blockIdx.y;
-    const int q = blockIdx.x * TNN_THREADS + threadIdx.x;
+    const int q = (blockIdx.x * TNN_THREADS + threadIdx.x) / SPLIT;
+    const int sub = threadIdx.x % SPLIT;
     const bool live = q < n;
     const float *__restrict__ u = unknown + ((int64_t)b * n + (live ? q : 0)) * 3;
     const float qx = __ldg(u), qy = __ldg(u + 1), qz = __ldg(u + 2);
@@ -349,10 +355,10 @@ three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ kno
         }
         __syncthreads();
 #pragma unroll 4
-        for (int i = 0; i < tn; ++i) {
+        for (int i = sub; i < tn; i += SPLIT) {
             const float4 c = tile[i];
             const float d = sqdist3(qx, qy, qz, c.x, c.y, c.z);
-            if (d < b3) {
+            if (d < b3) {  // within one lane candidates arrive in index order: strict < keeps the lower index on ties
                 const int k = tb + i;
                 if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k; }
                 else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = k; }
@@ -360,7 +366,28 @@ three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ kno
             }
         }
     }
-    if (live) {
+    if (SPLIT > 1) {
+        auto lt = [](float d, int k, float e, int l) { return d < e || (d == e && k < l); };
+#pragma unroll
+        for (int o = 1; o < SPLIT; o <<= 1) {
+            float pd[3];
+            int pi[3];
+            pd[0] = __shfl_xor_sync(0xffffffffu, b1, o), pi[0] = __shfl_xor_sync(0xffffffffu, i1, o);
+            pd[1] = __shfl_xor_sync(0xffffffffu, b2, o), pi[1] = __shfl_xor_sync(0xffffffffu, i2, o);
+            pd[2] = __shfl_xor_sync(0xffffffffu, b3, o), pi[2] = __shfl_xor_sync(0xffffffffu, i3, o);
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const float d = pd[t];
+                const int k = pi[t];
+                if (d < CUDART_INF_F && lt(d, k, b3, i3)) {
+                    if (lt(d, k, b1, i1)) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k; }
+                    else if (lt(d, k, b2, i2)) { b3 = b2; i3 = i2; b2 = d; i2 = k; }
+                    else { b3 = d; i3 = k; }
+                }
+            }
+        }
+    }
+    if (live && sub == 0) {
         float *__restrict__ dd = dist + ((int64_t)b * n + q) * 3;
         int64_t *__restrict__ ii = idx + ((int64_t)b * n + q) * 3;
         const float d1 = __fsqrt_rn(b1), d2 = __fsqrt_rn(b2), d3 = __fsqrt_rn(b3);
@@ -752,7 +779,12 @@ P3D_EXPORT int p3d_three_nn_f32(const float *unknown, const float *known, int B,
     if (B == 0 || n == 0) return P3D_OK;
     P3D_REQUIRE(unknown && known && dist && idx, "three_nn: null pointer");
     P3D_REQUIRE(B <= 65535, "three_nn: batch size must be <= 65535");
-    dim3 grid((unsigned)((n + TNN_THREADS - 1) / TNN_THREADS), (unsigned)B);
-    three_nn_kernel<<<grid, TNN_THREADS, 0, (cudaStream_t)stream>>>(unknown, known, n, m, dist, idx, weight);
+    if ((int64_t)B * n < (int64_t)kNumSMs * 512) {  // too few unknown points to fill the GPU one thread each
+        dim3 grid((unsigned)(((int64_t)n * 4 + TNN_THREADS - 1) / TNN_THREADS), (unsigned)B);
+        three_nn_kernel<4><<<grid, TNN_THREADS, 0, (cudaStream_t)stream>>>(unknown, known, n, m, dist, idx, weight);
+    } else {
+        dim3 grid((unsigned)((n + TNN_THREADS - 1) / TNN_THREADS), (unsigned)B);
+        three_nn_kernel<1><<<grid, TNN_THREADS, 0, (cudaStream_t)stream>>>(unknown, known, n, m, dist, idx, weight);
+    }
     return finish_launch("three_nn");
 }
