@@ -31,6 +31,9 @@ if ROOT not in sys.path:
 
 B_CLOUDS, N_PTS = 16, 2048
 METRIC = "PointNet++ MSG SA/FP operator chain fwd+bwd (FPS + ball_query + grouping + three_nn/interpolate)"
+WORKLOAD = ("C2: PointNet++ MSG part-seg op chain fwd+bwd, batch 16 x 2048 pts per GPU "
+            "(SA1 512 pts r[.1,.2,.4] k[32,64,128] C=3; SA2 128 pts r[.4,.8] k[64,128] C=320; "
+            "FP 128->512 C=256, 512->2048 C=128)")
 UNIT = "clouds/s"
 
 
@@ -420,9 +423,7 @@ def run_b200(args):
         "metric": METRIC, "value": round(clouds / (ms_total * 1e-3), 2), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: PointNet++ MSG part-seg op chain fwd+bwd, batch 16 x 2048 pts per GPU "
-                               "(SA1 512 pts r[.1,.2,.4] k[32,64,128] C=3; SA2 128 pts r[.4,.8] k[64,128] C=320; "
-                               "FP 128->512 C=256, 512->2048 C=128)",
+        "config": {"workload": WORKLOAD,
                    "clouds_per_gpu": B_CLOUDS, "points_per_cloud": N_PTS, "parallelism": "clouds sharded x%d" % world,
                    "cuda_graph": bool(use_graph),
                    "streams": "software-pipelined: each step runs the feature stage (grouping, interpolation, all "
@@ -866,7 +867,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": args.warmup, "ms_per_step": round(dt / steps * 1e3, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: PointNet++ MSG part-seg op chain fwd+bwd, batch 16 x 2048 pts (CPU sample)"},
+            "config": {"workload": WORKLOAD, "clouds_per_gpu": B_CLOUDS, "points_per_cloud": N_PTS,
+                       "parallelism": "host cores (the same batch of 16 clouds per step, %d steps)" % steps},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
                              "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
