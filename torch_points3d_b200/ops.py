@@ -654,9 +654,17 @@ def KPConv_ops(query_points, support_points, neighbors_indices, features, K_poin
             and K_values.numel() >= KPCONV_SPLIT_MIN_WEIGHTS):
         return _KPConvSplit.apply(query_points, support_points, neighbors_indices, features, K_points, K_values,
                                   float(KP_extent), INFLUENCE[KP_influence], AGGREGATION[aggregation_mode])
+    prec = precision or KPCONV_PRECISION
+    cin, cout = features.shape[1], K_values.shape[2]
+    if (prec == "tensor" and cin % 32 != 0 and cin < 32 and cout % 32 == 0 and cout <= 512
+            and neighbors_indices.shape[1] <= 40 and features.is_cuda):
+        # first layer of a network (a handful of raw channels): zero-pad Cin to 32 so the layer runs on the tcgen05
+        # path and the sparse backward kernels instead of the generic fp32 ones; the padding contributes exact zeros
+        pad = 32 - cin
+        features = torch.nn.functional.pad(features, (0, pad))
+        K_values = torch.nn.functional.pad(K_values, (0, 0, 0, pad))
     return _KPConv.apply(query_points, support_points, neighbors_indices, features, K_points, K_values,
-                         float(KP_extent), INFLUENCE[KP_influence], AGGREGATION[aggregation_mode],
-                         PRECISION[precision or KPCONV_PRECISION])
+                         float(KP_extent), INFLUENCE[KP_influence], AGGREGATION[aggregation_mode], PRECISION[prec])
 
 
 
