@@ -187,7 +187,14 @@ three_interp_fwd_kernel(const float *__restrict__ feat, const int64_t *__restric
     const int j1 = (j0 + n_per_cta < n) ? j0 + n_per_cta : n;
     const float *__restrict__ fb = feat + ((int64_t)b * C + c0) * m;
     if (STAGED) {
-        for (int i = threadIdx.x; i < cc * m; i += GR_THREADS) rows[i] = __ldg(fb + i);
+        const int total = cc * m;
+        if ((((uintptr_t)fb) & 15) == 0 && (total & 3) == 0) {
+            const float4 *__restrict__ s4 = reinterpret_cast<const float4 *>(fb);
+            float4 *d4 = reinterpret_cast<float4 *>(rows);
+            for (int i = threadIdx.x; i < total / 4; i += GR_THREADS) d4[i] = __ldg(s4 + i);
+        } else {
+            for (int i = threadIdx.x; i < total; i += GR_THREADS) rows[i] = __ldg(fb + i);
+        }
         __syncthreads();
     }
     const int64_t *__restrict__ ib = idx + (int64_t)b * n * 3;
@@ -1073,9 +1080,18 @@ P3D_EXPORT int p3d_three_interp_fwd_f32(const float *feat, const int64_t *idx, c
     P3D_REQUIRE(feat && idx && weight && out, "three_interpolate: null pointer");
     P3D_REQUIRE(m > 0, "three_interpolate: empty feature table");
     bool staged;
-    const int CC = pick_cc(C, m, staged);
-    const int cchunks = (C + CC - 1) / CC;
+    int CC = pick_cc(C, m, staged);
+    // CTA tile = CC staged rows x n_per_cta output columns.  The fill (CC * m floats) is amortised over the columns,
+    // so tiles are tall in n (>= 4 m columns when n allows) and the CTA count is made up with narrower channel
+    // blocks -- 32 rows x 256 columns re-read the table 8 times on the C2 shapes.
     int n_per_cta = GR_THREADS * 8;
+    if (staged) {
+        while (n_per_cta > GR_THREADS && n_per_cta / 2 >= 4 * m) n_per_cta /= 2;
+        while (n_per_cta / 2 >= n && n_per_cta > GR_THREADS) n_per_cta /= 2;
+        const int64_t col_tiles = (n + n_per_cta - 1) / n_per_cta;
+        while (CC > 4 && col_tiles * ((C + CC - 1) / CC) * B < 2 * kNumSMs) CC = (CC + 1) / 2;
+    }
+    const int cchunks = (C + CC - 1) / CC;
     while (n_per_cta > GR_THREADS && (int64_t)((n + n_per_cta - 1) / n_per_cta) * cchunks * B < 2 * kNumSMs)
         n_per_cta /= 2;
     dim3 grid((unsigned)((n + n_per_cta - 1) / n_per_cta), (unsigned)cchunks, (unsigned)B);
