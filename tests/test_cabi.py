@@ -202,3 +202,32 @@ def test_host_logic_of_the_next_row_mirrors():
     assert conv.add_self_loops and isinstance(conv.local_nn, torch.nn.Sequential)
     sa = mp.SAModule(ratio=0.5, radius=[0.1, 0.2], radius_num_point=[8, 16], down_conv_nn=[6, 8])
     assert sa.neighbour_finder.num_scales == 2
+
+
+def test_sass_uses_the_blackwell_units_the_design_names(cabi):
+    """DESIGN.md section 4 in SASS (B200_PROFILING.md mnemonics): tcgen05 MMAs with TMEM loads in the KPConv tensor
+    path, TMA bulk copies + mbarrier transaction waits in the staged kernels, warp redux in FPS, cluster barriers
+    in the large-cloud FPS"""
+    out = subprocess.run(["cuobjdump", "-sass", cabi.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    sass = out.stdout
+    per_kernel = {}
+    name = None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            per_kernel[name] = []
+        elif name is not None:
+            per_kernel[name].append(line)
+
+    def has(kernel_substr, mnemonic):
+        return any(kernel_substr in k and any(mnemonic in l for l in body) for k, body in per_kernel.items())
+
+    assert has("kpconv_fwd_tc_kernel", "UTCHMMA") and has("kpconv_fwd_tc_kernel", "LDTM")      # tcgen05.mma / tcgen05.ld
+    assert has("kpconv_fwd_tc_kernel", "UBLKCP") and has("kpconv_fwd_tc_kernel", "UTCBAR")     # TMA weights, tcgen05.commit
+    assert has("gemm_tc_kernel", "UTCHMMA")
+    assert has("bwd_sorted_kernel", "UBLKCP") and has("bwd_sorted_kernel", "SYNCS.PHASECHK")   # TMA ring + mbarrier wait
+    assert has("fps_cta_kernel", "REDUX") and has("fps_reg_kernel", "UCGABAR")                 # warp redux, cluster barrier
+    assert has("kpconv_fwd_tc_kernel", "LDGSTS")                                               # cp.async row staging
