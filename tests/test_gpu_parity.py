@@ -621,6 +621,20 @@ def test_multiscale_transform_precomputed_path_equals_on_the_fly():
         a = enc(pos, feats, batch)
         b = enc(pos, feats, batch, precomputed=ms)
     assert torch.equal(a.x, b.x) and torch.equal(a.pos, b.pos) and b.block_idx == 10
+    # upsample half (transforms.py:616-629): one precompute per strided level, innermost first, and
+    # "precomputed == direct" (test/test_interpolateop.py:10-35)
+    st = dict(enc.strategies(), upsample_op=[spatial_ops.KNNInterpolate(3) for _ in range(4)])
+    tr = kpconv.MultiScaleTransform(st)
+    ups = tr.upsample(pos, batch, ms)
+    assert len(ups) == 4
+    assert [u.num_nodes for u in ups] == [ms[7].pos.shape[0], ms[5].pos.shape[0], ms[3].pos.shape[0], pos.shape[0]]
+    query = kpconv.Cloud(ms[2].pos, torch.randn(ms[2].pos.shape[0], 8, device=DEV), ms[2].batch)
+    support = kpconv.Cloud(pos, None, batch)
+    direct = spatial_ops.KNNInterpolate(3)(query, support)
+    pre = spatial_ops.KNNInterpolate(3)(query, support, precomputed=ups[-1])
+    assert relerr(N(pre), N(direct)) <= 1e-5
+    with pytest.raises(ValueError):
+        kpconv.MultiScaleTransform(dict(enc.strategies(), upsample_op=[spatial_ops.KNNInterpolate(1)])).upsample(pos, batch, ms)
 
 
 @pytest.mark.parametrize("C,n,M", [(70, 300, 20), (128, 300, 38), (1024, 57, 38), (36, 1000, 5)])

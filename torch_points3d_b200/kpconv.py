@@ -357,8 +357,25 @@ class MultiScaleTransform:
     block that repeats the previous block's search on unchanged points shares its table."""
 
     def __init__(self, strategies):
-        self.strategies = strategies
+        self.strategies = strategies  # {"sampler": [...], "neighbour_finder": [...], optional "upsample_op": [...]}
         self.num_layers = len(strategies["sampler"])
+
+    @torch.no_grad()
+    def upsample(self, pos, batch, multiscale):
+        """the `upsample` half of the pyramid (transforms.py:616-629, 649-650): one KNNInterpolate.precompute per
+        strided level -- query = the subsampled level, support = the level above it -- innermost level first"""
+        ups = self.strategies.get("upsample_op") or []
+        out, k = [], 0
+        support = Cloud(pos, None, batch)
+        for sampler, level in zip(self.strategies["sampler"], multiscale):
+            if sampler is not None and ups:
+                if k >= len(ups):
+                    raise ValueError("You are missing some upsample blocks in your network")
+                out.append(ups[k].precompute(level, support))
+                k += 1
+            support = level
+        out.reverse()
+        return out
 
     @torch.no_grad()
     def __call__(self, pos, batch):
