@@ -144,6 +144,23 @@ def main():
         case = make_deform_case(ops, **kw)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **case)
         print(name, case["out"].shape, float(np.abs(case["out"]).mean()), float(np.abs(case["doffsets"]).mean()))
+    # the deformable-KPConv regularisers (modules/KPConv/losses.py), values and gradients
+    spec = importlib.util.spec_from_file_location("ref_kpconv_losses",
+                                                  os.path.join(REF, "torch_points3d/modules/KPConv/losses.py"))
+    losses = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(losses)
+    g = torch.Generator().manual_seed(31)
+    deformed = (torch.randn((40, 15, 3), generator=g) * 0.9).requires_grad_(True)
+    sqd = (torch.rand((40, 20, 15), generator=g) * 0.01).requires_grad_(True)
+    vals = {"fitting": losses.fitting_loss(sqd, 0.06), "repulsion": losses.repulsion_loss(deformed, 0.04),
+            "permissive": losses.permissive_loss(deformed, 1.2)}
+    grads = {"fitting": torch.autograd.grad(vals["fitting"], sqd)[0],
+             "repulsion": torch.autograd.grad(vals["repulsion"], deformed)[0],
+             "permissive": torch.autograd.grad(vals["permissive"], deformed)[0]}
+    np.savez_compressed(os.path.join(HERE, "kpconv_losses.npz"), deformed=deformed.detach().numpy(),
+                        sqd=sqd.detach().numpy(), **{k: np.float32(v.item()) for k, v in vals.items()},
+                        **{"d" + k: v.numpy() for k, v in grads.items()})
+    print("losses", {k: float(v) for k, v in vals.items()})
     kp = read_kernel_ply(os.path.join(REF, "torch_points3d/modules/KPConv/kernels/dispositions/k_015_center.ply"))
     # the 15 kernel-point disposition is DATA of the reference model (k_015_center.ply); kept as a fixture
     np.save(os.path.join(HERE, "k_015_center.npy"), kp)

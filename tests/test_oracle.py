@@ -218,3 +218,19 @@ def test_kpconv_deform_oracle_against_reference_golden(name):
         assert np.abs(got - g[key]).max() <= 2e-5 * np.abs(g[key]).max(), key
     if mods is not None:
         assert np.abs(dm - g["dmodulations"]).max() <= 2e-5 * np.abs(g["dmodulations"]).max()
+
+
+def test_kpconv_regularisers_against_reference_golden():
+    """fitting / repulsion / permissive losses of the deformable layer (mirrors in torch_points3d_b200/kpconv.py)
+    against values and gradients produced by the reference's modules/KPConv/losses.py (make_golden.py)"""
+    import torch
+    from torch_points3d_b200 import kpconv
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "kpconv_losses.npz"))
+    deformed = torch.from_numpy(g["deformed"]).requires_grad_(True)
+    sqd = torch.from_numpy(g["sqd"]).requires_grad_(True)
+    for name, fn, arg, rad in (("fitting", kpconv.fitting_loss, sqd, 0.06), ("repulsion", kpconv.repulsion_loss, deformed, 0.04),
+                               ("permissive", kpconv.permissive_loss, deformed, 1.2)):
+        val = fn(arg, rad)
+        assert abs(float(val.detach()) - float(g[name])) <= 1e-6 * abs(float(g[name])), name
+        (grad,) = torch.autograd.grad(val, arg)
+        assert np.abs(grad.numpy() - g["d" + name]).max() <= 1e-6 * np.abs(g["d" + name]).max(), name
