@@ -731,6 +731,10 @@ def bench_kpconv_stack(dev, world, rank):
            "loss": round(loss, 4), "unit": "points/s"}
     if world == 1:
         # with the pyramid given, every shape of the step is static: capture forward + backward + SGD in one graph
+        # (the parameters' AccumulateGrad nodes were created on the eager stream: the mismatch is intended here)
+        quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if quiet is not None:
+            quiet(False)
         try:
             opt.zero_grad(set_to_none=False)
             side = torch.cuda.Stream(device=dev)
