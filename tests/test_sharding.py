@@ -102,3 +102,26 @@ def test_two_rank_sharding_equals_single_process():
     ref_col, _ = oracle.knn_csr(pos, pos, 4, ptr, ptr)
     assert np.array_equal(np.concatenate(cols), ref_col)
     assert slowest == 11.0  # max over ranks
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """bench.py --impl reference launched like the driver launches it for N > 1: rank 0 alone measures and prints
+    ONE JSON line carrying the same metric / unit / workload as the b200 arm; the other rank exits 0 silently"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29617", os.path.join(root, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    sys.path.insert(0, root)
+    import bench
+    assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["unit"] == bench.UNIT
+    assert line["config"]["workload"] == bench.WORKLOAD and line["n_gpus"] == 2 and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
