@@ -721,8 +721,9 @@ reduce_partials_kernel(const float *__restrict__ part, int splits, int64_t n, fl
 constexpr int DS_WARPS = 8;
 constexpr int DS_MAX_FLOATS = 6144;  // C * N per warp table: 8 x 24 KB = 192 KB of shared memory
 constexpr int DS_MAX_C = 8;
-constexpr int DS_U = 4;
 
+// CC = channel rows held in registers per step (>= C), U = 32-slot steps whose loads are in flight together
+template <int CC, int U>
 __global__ void __launch_bounds__(DS_WARPS * 32, 1)
 bwd_direct_kernel(const float *__restrict__ dout, const int64_t *__restrict__ idx, int C, int N, int64_t E,
                   int64_t slots_per_cta, float *__restrict__ dst_base, int64_t split_stride, int64_t dout_batch_stride,
@@ -741,24 +742,24 @@ bwd_direct_kernel(const float *__restrict__ dout, const int64_t *__restrict__ id
     const int64_t w1 = (w0 + per < r1) ? w0 + per : r1;
     const int64_t *__restrict__ ib = idx + (int64_t)b * E;
     const float *__restrict__ gb = dout + (int64_t)b * dout_batch_stride + (int64_t)c_off * E;
-    // DS_U steps (32 slots each) per iteration: all of their index and gradient loads are issued before the first
+    // U steps (32 slots each) per iteration: all of their index and gradient loads are issued before the first
     // one is consumed -- a warp otherwise pays two dependent DRAM round trips per step with nothing else in flight
-    for (int64_t e0 = w0; e0 < w1; e0 += 32 * DS_U) {
-        int64_t j[DS_U];
-        float v[DS_U][DS_MAX_C];
+    for (int64_t e0 = w0; e0 < w1; e0 += 32 * U) {
+        int64_t j[U];
+        float v[U][CC];
 #pragma unroll
-        for (int u = 0; u < DS_U; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int64_t e = e0 + u * 32 + lane;
             j[u] = (e < w1) ? __ldg(ib + e) : -1;
         }
 #pragma unroll
-        for (int u = 0; u < DS_U; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int64_t e = e0 + u * 32 + lane;
 #pragma unroll
-            for (int c = 0; c < DS_MAX_C; ++c) v[u][c] = (c < C && e < w1) ? __ldcs(gb + (int64_t)c * E + e) : 0.f;
+            for (int c = 0; c < CC; ++c) v[u][c] = (c < C && e < w1) ? __ldcs(gb + (int64_t)c * E + e) : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < DS_U; ++u) {
+        for (int u = 0; u < U; ++u) {
             if (e0 + u * 32 >= w1) break;  // warp-uniform
             const bool valid = j[u] >= 0 && j[u] < N;
             const int jj = (int)j[u];
@@ -766,7 +767,7 @@ bwd_direct_kernel(const float *__restrict__ dout, const int64_t *__restrict__ id
             const bool single = peers == (1u << lane);
             const unsigned leaders = __ballot_sync(0xffffffffu, valid && !single && (__ffs(peers) - 1) == lane);
 #pragma unroll
-            for (int c = 0; c < DS_MAX_C; ++c) {
+            for (int c = 0; c < CC; ++c) {
                 if (c >= C) break;
                 const float val = v[u][c];
                 if (valid && single) acc[c * N + jj] += val;
@@ -816,13 +817,21 @@ static int launch_bwd_direct(const float *dout, const int64_t *keys, int B, int 
     const size_t smem = (size_t)DS_WARPS * C * N * sizeof(float);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(bwd_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(bwd_direct_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             DS_WARPS * DS_MAX_FLOATS * (int)sizeof(float));
+        cudaFuncSetAttribute(bwd_direct_kernel<DS_MAX_C, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              DS_WARPS * DS_MAX_FLOATS * (int)sizeof(float));
         attr_done = true;
     }
     float *part = (float *)ws;
-    bwd_direct_kernel<<<dim3((unsigned)splits, (unsigned)B), DS_WARPS * 32, smem, st>>>(
-        dout, keys, C, N, E, spc, splits > 1 ? part : dfeat, total, dout_batch_stride, c_off);
+    const dim3 grid((unsigned)splits, (unsigned)B);
+    if (C <= 4)  // the usual case (3 normals / colours): half the value registers, twice the steps in flight
+        bwd_direct_kernel<4, 8><<<grid, DS_WARPS * 32, smem, st>>>(dout, keys, C, N, E, spc, splits > 1 ? part : dfeat,
+                                                                  total, dout_batch_stride, c_off);
+    else
+        bwd_direct_kernel<DS_MAX_C, 4><<<grid, DS_WARPS * 32, smem, st>>>(dout, keys, C, N, E, spc,
+                                                                         splits > 1 ? part : dfeat, total,
+                                                                         dout_batch_stride, c_off);
     if (int e = finish_launch("group_bwd_direct")) return e;
     if (splits > 1) {
         int64_t gr = (total + 255) / 256;
