@@ -33,7 +33,8 @@ struct GroupXyz {
 };
 
 // out[b, c_off+c, e] = feat[b, c, idx[b, e]],   e in [0, E = S*K)
-template <bool STAGED>
+// XYZ = false compiles the relative-coordinate block out of the plain gather
+template <bool STAGED, bool XYZ = false>
 __global__ void __launch_bounds__(GR_THREADS)
 group_fwd_kernel(const float *__restrict__ feat, const int64_t *__restrict__ idx, int C, int N, int64_t E,
                  int CC, int e_per_cta, float *__restrict__ out, int64_t out_batch_stride, int c_off,
@@ -42,8 +43,8 @@ group_fwd_kernel(const float *__restrict__ feat, const int64_t *__restrict__ idx
     const int b = blockIdx.z;
     // fused _prepare_features: the first channel block of the grid (when xyz.pos is set) produces the three
     // relative-coordinate channels (pos[idx] - new_pos) * scale from the point-major position tensor
-    const bool xyz_block = STAGED && xyz.pos != nullptr && blockIdx.y == 0;
-    const int fy = blockIdx.y - ((STAGED && xyz.pos != nullptr) ? 1 : 0);
+    const bool xyz_block = XYZ && blockIdx.y == 0;
+    const int fy = blockIdx.y - (XYZ ? 1 : 0);
     const int c0 = xyz_block ? 0 : fy * CC;
     const int cc = xyz_block ? 3 : ((C - c0 < CC) ? (C - c0) : CC);
     const int64_t e0 = (int64_t)blockIdx.x * e_per_cta;
@@ -996,13 +997,13 @@ P3D_EXPORT int p3d_group_xyz_feat_f32(const float *pos, const float *new_pos, co
     const size_t smem = (size_t)((CC > 3 ? CC : 3)) * N * sizeof(float);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(group_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(group_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              GR_SMEM_FLOATS * (int)sizeof(float));
         attr_done = true;
     }
     GroupXyz xyz{pos, new_pos, S, K, 1.0f / norm, norm != 1.0f ? 1 : 0};
-    group_fwd_kernel<true><<<grid, GR_THREADS, smem, (cudaStream_t)stream>>>(feat, idx, C, N, E, CC, (int)e_per_cta, out,
-                                                                            stride, 3, xyz);
+    group_fwd_kernel<true, true><<<grid, GR_THREADS, smem, (cudaStream_t)stream>>>(feat, idx, C, N, E, CC,
+                                                                                  (int)e_per_cta, out, stride, 3, xyz);
     return finish_launch("group_xyz_feat");
 }
 
