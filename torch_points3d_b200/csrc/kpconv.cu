@@ -277,6 +277,94 @@ int kpconv_fwd_simt(const float *query, const float *support, const int64_t *nei
     return finish_launch("kpconv_fwd_simt");
 }
 
+// C[R x N] = A[R x Kd] * B, B(k, j) = Bp[k * sbk + j * sbj], for SHORT reductions (Kd <= 64): the backward's
+// dwf = dout . W^T at the shallow levels (Kd = Cout = 32 or 64, N = K * Cin = 480..960, R = 15-50 k points) is a
+// write-bound problem -- 97 MB of output for 1.5 GFLOP -- that the tcgen05 GEMM spends on operand conversion and
+// its epilogue (121 us).  Plain fp32: a CTA keeps a 256-column block of B in shared memory and walks row tiles of
+// 64; thread tile 8 x 8 (two float4 column groups, so shared-memory reads are conflict-free and every row is
+// stored as two coalesced 512-byte runs per warp).
+constexpr int SK_ROWS = 64, SK_COLS = 256, SK_KD = 64, SK_APITCH = SK_ROWS + 4;
+
+__global__ void __launch_bounds__(256, 2)
+gemm_smallk_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__ Bp, int64_t sbk, int64_t sbj,
+                   int64_t R, int Kd, int N, float *__restrict__ C, int64_t ldc) {
+    extern __shared__ __align__(16) float sk_smem[];
+    float *Bs = sk_smem;                  // [Kd][SK_COLS]
+    float *As = sk_smem + Kd * SK_COLS;   // [Kd][SK_APITCH]
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int col0 = blockIdx.y * SK_COLS;
+    for (int i = tid; i < Kd * SK_COLS; i += 256) {
+        const int j = i / Kd, k = i - j * Kd;  // k fastest: contiguous when sbk == 1
+        Bs[k * SK_COLS + j] = (col0 + j < N) ? __ldg(Bp + (int64_t)k * sbk + (int64_t)(col0 + j) * sbj) : 0.f;
+    }
+    const int64_t tiles = (R + SK_ROWS - 1) / SK_ROWS;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * SK_ROWS;
+        __syncthreads();  // previous tile's As reads are done (and, first time, Bs is complete)
+        for (int i = tid; i < SK_ROWS * Kd; i += 256) {
+            const int r = i / Kd, k = i - r * Kd;
+            As[k * SK_APITCH + r] = (row0 + r < R) ? __ldg(A + (row0 + r) * lda + k) : 0.f;
+        }
+        __syncthreads();
+        float acc[8][8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int v = 0; v < 8; ++v) acc[u][v] = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < Kd; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(As + k * SK_APITCH + ty * 8);
+            const float4 a1 = *reinterpret_cast<const float4 *>(As + k * SK_APITCH + ty * 8 + 4);
+            const float4 b0 = *reinterpret_cast<const float4 *>(Bs + k * SK_COLS + tx * 4);
+            const float4 b1 = *reinterpret_cast<const float4 *>(Bs + k * SK_COLS + 128 + tx * 4);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int v = 0; v < 8; ++v) acc[u][v] = fmaf(a[u], b[v], acc[u][v]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int64_t r = row0 + ty * 8 + u;
+            if (r >= R) continue;
+            float *crow = C + r * ldc + col0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = h * 128 + tx * 4;
+                if (col0 + j + 3 < N && ((((uintptr_t)(crow + j)) & 15) == 0)) {
+                    __stcs(reinterpret_cast<float4 *>(crow + j),
+                           make_float4(acc[u][4 * h], acc[u][4 * h + 1], acc[u][4 * h + 2], acc[u][4 * h + 3]));
+                } else {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v)
+                        if (col0 + j + v < N) crow[j + v] = acc[u][4 * h + v];
+                }
+            }
+        }
+    }
+}
+
+// returns 1 when the shape is outside this kernel (Kd > 64)
+int gemm_smallk(const float *A, int64_t lda, const float *Bp, int64_t sbk, int64_t sbj, int64_t R, int Kd, int N,
+                float *C, int64_t ldc, cudaStream_t st) {
+    if (Kd > SK_KD || Kd < 1) return 1;
+    const size_t smem = (size_t)Kd * (SK_COLS + SK_APITCH) * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(gemm_smallk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(SK_KD * (SK_COLS + SK_APITCH) * sizeof(float)));
+        attr_done = true;
+    }
+    const int64_t tiles = (R + SK_ROWS - 1) / SK_ROWS;
+    const int cblocks = (N + SK_COLS - 1) / SK_COLS;
+    int64_t gx = (2 * kNumSMs + cblocks - 1) / cblocks;
+    if (gx > tiles) gx = tiles;
+    if (gx < 1) gx = 1;
+    gemm_smallk_kernel<<<dim3((unsigned)gx, (unsigned)cblocks), 256, smem, st>>>(A, lda, Bp, sbk, sbj, R, Kd, N, C, ldc);
+    return finish_launch("gemm_smallk");
+}
+
 // host-side launchers of the plain SGEMM, shared with kpconv_deform.cu
 int sgemm_strided(const float *A, int64_t sai, int64_t sak, const float *B, int64_t sbk, int64_t sbj, float *C,
                   int64_t ldc, int64_t Mr, int64_t Nc, int64_t Kd, cudaStream_t st) {
@@ -458,7 +546,8 @@ P3D_EXPORT int p3d_kpconv_bwd_f32(const float *query, const float *support, cons
         // dwf[p][kc] = sum_o dout[p][o] * W[kc][o]: tcgen05 GEMM (bf16 hi+lo operands) when the shape allows it
         void *bimg = (char *)ws + (size_t)2 * n * K * Cin * sizeof(float);
         const size_t bimg_bytes = ws_bytes - (size_t)2 * n * K * Cin * sizeof(float);
-        const int r = gemm_tc(dout, Cout, k_values, 1, Cout, n, Cout, (int)KC, dwf, KC, bimg, bimg_bytes, st);
+        int r = gemm_smallk(dout, Cout, k_values, 1, Cout, n, Cout, (int)KC, dwf, KC, st);  // Cout <= 64: write-bound
+        if (r == 1) r = gemm_tc(dout, Cout, k_values, 1, Cout, n, Cout, (int)KC, dwf, KC, bimg, bimg_bytes, st);
         if (r < 0) return r;
         if (r == 1) {
             dim3 gd((unsigned)((KC + 63) / 64), (unsigned)((n + 63) / 64), 1);
