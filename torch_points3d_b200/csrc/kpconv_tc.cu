@@ -901,7 +901,7 @@ dw_accumulate_kernel(const float *__restrict__ A, const float *__restrict__ B, i
 
 int dw_accumulate(const float *A, const float *B, int64_t n, int R, int Cn, float *dW, cudaStream_t st) {
     const int rb = (R + 255) / 256, cb = (Cn + 31) / 32;
-    int64_t chunks = (2 * kNumSMs + rb * cb - 1) / (rb * cb);
+    int64_t chunks = (3 * kNumSMs + rb * cb - 1) / (rb * cb);  // 72 KB of staging per CTA: three CTAs per SM
     if (chunks < 1) chunks = 1;
     int64_t ppc = (n + chunks - 1) / chunks;
     ppc = (ppc + DW_SUB - 1) / DW_SUB * DW_SUB;
