@@ -239,6 +239,19 @@ int p3d_kpconv_deform_bwd_f32(const float *query, const float *support, const in
                               int Cout, float extent, int influence, float *dfeat, float *dweights, float *doffsets,
                               float *dmodulations, void *ws, size_t ws_bytes, void *stream);
 
+/* Training pair: the tensor-path forward also stores the fp32 weighted features wf [n,K,Cin] it holds in registers
+ * (one extra 4*K*Cin-byte row per point), and the backward reads them for dW = wf^T dout instead of recomputing the
+ * influence-weighted aggregation (a third of the backward at the shallow levels).  p3d_kpconv_fwd_wf_f32 fails with
+ * P3D_ERR_INVALID for shapes outside the tensor path; wf = NULL in p3d_kpconv_bwd_wf_f32 recomputes. */
+int p3d_kpconv_fwd_wf_f32(const float *query, const float *support, const int64_t *neighbors, const float *feat,
+                          const float *k_points, const float *k_values, int64_t n, int64_t N0, int M, int K, int Cin,
+                          int Cout, float extent, int influence, int aggregation, float *out, float *wf, void *ws,
+                          size_t ws_bytes, void *stream);
+int p3d_kpconv_bwd_wf_f32(const float *query, const float *support, const int64_t *neighbors, const float *feat,
+                          const float *k_points, const float *k_values, const float *dout, const float *wf, int64_t n,
+                          int64_t N0, int M, int K, int Cin, int Cout, float extent, int influence, int aggregation,
+                          float *dfeat, float *dweights, void *ws, size_t ws_bytes, void *stream);
+
 /* Strided-shortcut neighbour max-pool (modules/KPConv/blocks.py:206-210):
  * out[p,c] = max_m x'[neighbors[p,m], c], x' = cat(x, zeros); arg (nullable) = winning row
  * (N0 for the shadow row) for the backward pass. */

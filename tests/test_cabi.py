@@ -231,3 +231,49 @@ def test_sass_uses_the_blackwell_units_the_design_names(cabi):
     assert has("bwd_sorted_kernel", "UBLKCP") and has("bwd_sorted_kernel", "SYNCS.PHASECHK")   # TMA ring + mbarrier wait
     assert has("fps_cta_kernel", "REDUX") and has("fps_reg_kernel", "UCGABAR")                 # warp redux, cluster barrier
     assert has("kpconv_fwd_tc_kernel", "LDGSTS")                                               # cp.async row staging
+
+
+def test_kpconv_autograd_plumbing_with_stubbed_device_calls(monkeypatch):
+    """which entry points a training / inference / frozen-weight KPConv call reaches, and that every autograd
+    Function returns one gradient per input -- checked on the CPU with the device calls stubbed out"""
+    from torch_points3d_b200 import ops
+    calls = []
+    monkeypatch.setattr(ops, "_call", lambda dev, name, *args: calls.append(name))
+    monkeypatch.setattr(ops, "_require_cuda", lambda name, *t: torch.device("cpu"))
+
+    class FakeLib:
+        def p3d_kpconv_fwd_ws_bytes(self, K, Cin, Cout):
+            return 1024 if Cin % 32 == 0 and Cout % 32 == 0 else 0
+
+        def p3d_kpconv_bwd_ws_bytes(self, *a):
+            return 1024
+
+        def p3d_kpconv_deform_bwd_ws_bytes(self, *a):
+            return 1024
+
+    monkeypatch.setattr(ops._cabi, "lib", lambda: FakeLib())
+    monkeypatch.setattr(ops, "KPCONV_SPLIT_MAX_POINTS", 0)
+    q, nb, kp = torch.rand(6, 3), torch.zeros(6, 4, dtype=torch.long), torch.rand(15, 3)
+    x = torch.rand(6, 32, requires_grad=True)
+    W = torch.rand(15, 32, 32, requires_grad=True)
+    out = ops.KPConv_ops(q, q, nb, x, kp, W, 0.1, "linear", "sum")
+    out.sum().backward()
+    assert calls == ["p3d_kpconv_fwd_wf_f32", "p3d_kpconv_bwd_wf_f32"]      # training: the forward keeps wf
+    assert x.grad.shape == x.shape and W.grad.shape == W.shape
+    calls.clear()
+    with torch.no_grad():
+        ops.KPConv_ops(q, q, nb, x, kp, W, 0.1, "linear", "sum")
+    assert calls == ["p3d_kpconv_fwd_f32"]                                  # inference: nothing extra is written
+    calls.clear()
+    ops.KPConv_ops(q, q, nb, x, kp, W.detach(), 0.1, "linear", "sum").sum().backward()
+    assert calls == ["p3d_kpconv_fwd_f32", "p3d_kpconv_bwd_wf_f32"]         # frozen weights: wf is not needed
+    calls.clear()
+    ops.KPConv_ops(q, q, nb, x, kp, W, 0.1, "linear", "sum", precision="fp32").sum().backward()
+    assert calls == ["p3d_kpconv_fwd_f32", "p3d_kpconv_bwd_wf_f32"]
+    calls.clear()
+    off = torch.zeros(6, 15, 3, requires_grad=True)
+    mods = torch.ones(6, 15, requires_grad=True)
+    o, sqd, dk = ops.KPConv_deform_ops(q, q, nb, x, kp, off, mods, W, 0.1, "linear", "sum")
+    (o.sum() + sqd.sum() + dk.sum()).backward()
+    assert calls == ["p3d_kpconv_deform_fwd_f32", "p3d_kpconv_deform_bwd_f32"]
+    assert off.grad.shape == off.shape and mods.grad.shape == mods.shape

@@ -49,6 +49,10 @@ SIGNATURES = {
     "p3d_kpconv_bwd_ws_bytes": (c_sz, [c_i64, c_int, c_int, c_int, c_int]),
     "p3d_kpconv_bwd_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int,
                                    c_int, c_f32, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "p3d_kpconv_fwd_wf_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_int,
+                                      c_f32, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "p3d_kpconv_bwd_wf_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int,
+                                      c_int, c_f32, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "p3d_kpconv_wf_f32": (c_int, [c_vp] * 5 + [c_i64, c_i64, c_int, c_int, c_int, c_f32, c_int, c_int, c_vp, c_vp]),
     "p3d_kpconv_scatter_f32": (c_int, [c_vp] * 5 + [c_i64, c_i64, c_int, c_int, c_int, c_f32, c_int, c_int, c_vp, c_vp]),
     "p3d_kpconv_deform_fwd_f32": (c_int, [c_vp] * 8 + [c_i64, c_i64, c_int, c_int, c_int, c_int, c_f32, c_int] +

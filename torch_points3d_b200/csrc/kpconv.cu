@@ -396,7 +396,7 @@ namespace p3d {
 int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neighbors, const float *feat,
                   const float *k_points, const float *k_values, int64_t n, int64_t N0, int M, int K, int Cin,
                   int Cout, float extent, int influence, int aggregation, float *out, void *ws, size_t ws_bytes,
-                  cudaStream_t st);
+                  cudaStream_t st, float *wf_out = nullptr);
 size_t kpconv_tc_ws_bytes(int K, int Cin, int Cout);
 // tensor-core / register-tiled GEMMs of the backward (kpconv_tc.cu)
 size_t gemm_tc_ws_bytes(int Kd, int N);
@@ -482,6 +482,30 @@ P3D_EXPORT int p3d_kpconv_scatter_f32(const float *query, const float *support, 
     return finish_launch("kpconv_scatter");
 }
 
+// Training forward: the tensor path also stores the fp32 weighted features wf [n, K, Cin] it builds in registers, so
+// the backward pass (p3d_kpconv_bwd_wf_f32) does not recompute them.  Only shapes the tensor path covers.
+P3D_EXPORT int p3d_kpconv_fwd_wf_f32(const float *query, const float *support, const int64_t *neighbors,
+                                     const float *feat, const float *k_points, const float *k_values, int64_t n,
+                                     int64_t N0, int M, int K, int Cin, int Cout, float extent, int influence,
+                                     int aggregation, float *out, float *wf, void *ws, size_t ws_bytes, void *stream) {
+    if (int e = check_common("kpconv_fwd_wf", n, N0, M, K, Cin, Cout, influence, aggregation)) return e;
+    if (n == 0) return P3D_OK;
+    P3D_REQUIRE(query && neighbors && k_points && k_values && out && wf && (N0 == 0 || (support && feat)),
+                "kpconv_fwd_wf: null pointer");
+    const int r = kpconv_fwd_tc(query, support, neighbors, feat, k_points, k_values, n, N0, M, K, Cin, Cout, extent,
+                                influence, aggregation, out, ws, ws_bytes, (cudaStream_t)stream, wf);
+    if (r == 1) {
+        set_error("kpconv_fwd_wf: shape outside the tensor path (Cin %% 32, Cout %% 32, Cout <= 512, M <= 40, workspace)");
+        return P3D_ERR_INVALID;
+    }
+    return r;
+}
+
+static int kpconv_bwd_impl(const float *query, const float *support, const int64_t *neighbors, const float *feat,
+                           const float *k_points, const float *k_values, const float *dout, const float *wf_saved,
+                           int64_t n, int64_t N0, int M, int K, int Cin, int Cout, float extent, int influence,
+                           int aggregation, float *dfeat, float *dweights, void *ws, size_t ws_bytes, void *stream);
+
 P3D_EXPORT size_t p3d_kpconv_bwd_ws_bytes(int64_t n, int M, int K, int Cin, int Cout) {
     (void)M;
     // wf + dwf  [n, K, Cin] each, then the bf16 hi/lo image of W^T for the tensor-core dwf GEMM (0 if unsupported)
@@ -493,6 +517,24 @@ P3D_EXPORT int p3d_kpconv_bwd_f32(const float *query, const float *support, cons
                                   int64_t n, int64_t N0, int M, int K, int Cin, int Cout, float extent,
                                   int influence, int aggregation, float *dfeat, float *dweights, void *ws,
                                   size_t ws_bytes, void *stream) {
+    return kpconv_bwd_impl(query, support, neighbors, feat, k_points, k_values, dout, nullptr, n, N0, M, K, Cin, Cout,
+                           extent, influence, aggregation, dfeat, dweights, ws, ws_bytes, stream);
+}
+
+// same, with the weighted features saved by p3d_kpconv_fwd_wf_f32 (wf [n, K, Cin]; nullptr = recompute)
+P3D_EXPORT int p3d_kpconv_bwd_wf_f32(const float *query, const float *support, const int64_t *neighbors,
+                                     const float *feat, const float *k_points, const float *k_values,
+                                     const float *dout, const float *wf, int64_t n, int64_t N0, int M, int K, int Cin,
+                                     int Cout, float extent, int influence, int aggregation, float *dfeat,
+                                     float *dweights, void *ws, size_t ws_bytes, void *stream) {
+    return kpconv_bwd_impl(query, support, neighbors, feat, k_points, k_values, dout, wf, n, N0, M, K, Cin, Cout, extent,
+                           influence, aggregation, dfeat, dweights, ws, ws_bytes, stream);
+}
+
+static int kpconv_bwd_impl(const float *query, const float *support, const int64_t *neighbors, const float *feat,
+                           const float *k_points, const float *k_values, const float *dout, const float *wf_saved,
+                           int64_t n, int64_t N0, int M, int K, int Cin, int Cout, float extent, int influence,
+                           int aggregation, float *dfeat, float *dweights, void *ws, size_t ws_bytes, void *stream) {
     if (int e = check_common("kpconv_bwd", n, N0, M, K, Cin, Cout, influence, aggregation)) return e;
     if (n == 0 || (dfeat == nullptr && dweights == nullptr)) return P3D_OK;
     P3D_REQUIRE(query && neighbors && k_points && k_values && dout && (N0 == 0 || (support && feat)),
@@ -517,7 +559,11 @@ P3D_EXPORT int p3d_kpconv_bwd_f32(const float *query, const float *support, cons
     int64_t grid = (n + KPF_WARPS - 1) / KPF_WARPS;
     if (grid > 16 * kNumSMs) grid = 16 * kNumSMs;
     const bool sparse = kpconv_sparse_supported(M, K, Cin);
-    if (dweights) {
+    if (dweights && wf_saved != nullptr) {
+        // dW[kc][o] += sum_p wf[p][kc] * dout[p][o] straight from the forward's slab
+        if (dw_accumulate(wf_saved, dout, n, (int)KC, Cout, dweights, st) != 0)
+            if (int e = sgemm_splitk_atomic(wf_saved, dout, n, KC, Cout, dweights, st)) return e;
+    } else if (dweights) {
         if (sparse) {
             if (int e = kpconv_wf_sparse(query, support, neighbors, feat, k_points, n, N0, M, K, Cin, extent, influence,
                                          aggregation, wf, st))

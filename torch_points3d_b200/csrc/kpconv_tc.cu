@@ -218,12 +218,12 @@ __device__ __forceinline__ void tc_weights(const TcPoint &P, const float4 *kps, 
     }
 }
 
-template <int INFL, bool CLOSEST>
+template <int INFL, bool CLOSEST, bool SAVE_WF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, const int64_t *__restrict__ nb,
                      const float *__restrict__ x, const float *__restrict__ kp, const uint8_t *__restrict__ wimg,
                      int64_t n, int64_t N0, int M, int K, int Cin, int Cout, KpGeom g, uint32_t tmem_cols, int ncpc,
-                     float *__restrict__ out) {
+                     float *__restrict__ out, float *__restrict__ wf_out) {
     extern __shared__ uint8_t smem_raw[];
     // the UMMA 128-byte swizzle atoms need 1024-byte aligned tiles (the launch adds 1 KB of slack)
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -336,6 +336,14 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                                 a = fmaf(__shfl_sync(0xffffffffu, w1[k >> 2], mm + 8 * (k & 3)), xs[(32 + mm) * 32 + lane], a);
                             }
                             acc[k] = a;
+                        }
+                        if (SAVE_WF && nc0 == 0) {
+                            // training: keep the fp32 weighted features (dW = wf^T dout needs them) instead of
+                            // recomputing them in the backward pass: 15 coalesced 128-byte stores per point and slab
+                            float *wrow = wf_out + (p * K) * Cin + sl * 32 + lane;
+#pragma unroll
+                            for (int k = 0; k < KP_K - 1; ++k)
+                                if (k < K) __stcs(wrow + (int64_t)k * Cin, acc[k]);
                         }
                         P = Pn;
                     }
@@ -927,7 +935,7 @@ size_t kpconv_tc_ws_bytes(int K, int Cin, int Cout) {
 int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neighbors, const float *feat,
                   const float *k_points, const float *k_values, int64_t n, int64_t N0, int M, int K, int Cin,
                   int Cout, float extent, int influence, int aggregation, float *out, void *ws, size_t ws_bytes,
-                  cudaStream_t st) {
+                  cudaStream_t st, float *wf_out) {
     const size_t need = kpconv_tc_ws_bytes(K, Cin, Cout);
     if (need == 0 || M > TC_MCAP || ws == nullptr || ws_bytes < need) return 1;
     if ((((uintptr_t)out) & 15) != 0 || (((uintptr_t)ws) & 15) != 0) return 1;  // float4 row stores, TMA source
@@ -942,16 +950,20 @@ int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neigh
     if (int e = finish_launch("kpconv_prep_w")) return e;
     const size_t smem = TC_A_BYTES + TC_W_PIECE + (size_t)TC_PWARPS * TC_SCRATCH_FLOATS * sizeof(float) + 1024;
     using Kern = void (*)(const float *, const float *, const int64_t *, const float *, const float *, const uint8_t *,
-                          int64_t, int64_t, int, int, int, int, KpGeom, uint32_t, int, float *);
-    static const Kern kerns[3][2] = {
-        {kpconv_fwd_tc_kernel<P3D_INFLUENCE_CONSTANT, false>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_CONSTANT, true>},
-        {kpconv_fwd_tc_kernel<P3D_INFLUENCE_LINEAR, false>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_LINEAR, true>},
-        {kpconv_fwd_tc_kernel<P3D_INFLUENCE_GAUSSIAN, false>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_GAUSSIAN, true>}};
+                          int64_t, int64_t, int, int, int, int, KpGeom, uint32_t, int, float *, float *);
+    static const Kern kerns[2][3][2] = {
+        {{kpconv_fwd_tc_kernel<P3D_INFLUENCE_CONSTANT, false, false>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_CONSTANT, true, false>},
+         {kpconv_fwd_tc_kernel<P3D_INFLUENCE_LINEAR, false, false>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_LINEAR, true, false>},
+         {kpconv_fwd_tc_kernel<P3D_INFLUENCE_GAUSSIAN, false, false>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_GAUSSIAN, true, false>}},
+        {{kpconv_fwd_tc_kernel<P3D_INFLUENCE_CONSTANT, false, true>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_CONSTANT, true, true>},
+         {kpconv_fwd_tc_kernel<P3D_INFLUENCE_LINEAR, false, true>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_LINEAR, true, true>},
+         {kpconv_fwd_tc_kernel<P3D_INFLUENCE_GAUSSIAN, false, true>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_GAUSSIAN, true, true>}}};
     static bool attr_done = false;
     if (!attr_done) {
-        for (int a = 0; a < 3; ++a)
-            for (int b = 0; b < 2; ++b)
-                cudaFuncSetAttribute(kerns[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
+        for (int w = 0; w < 2; ++w)
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 2; ++b)
+                    cudaFuncSetAttribute(kerns[w][a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
         attr_done = true;
     }
     const int64_t ntiles = (n + TC_TILE - 1) / TC_TILE;
@@ -966,9 +978,9 @@ int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neigh
     uint32_t cols = 32;
     while ((int)cols < ncpc * TC_NCH) cols <<= 1;
     const dim3 grid((unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs), (unsigned)ygroups);
-    kerns[influence][aggregation]<<<grid, TC_THREADS, smem, st>>>(query, support, neighbors, feat, k_points,
+    kerns[wf_out != nullptr ? 1 : 0][influence][aggregation]<<<grid, TC_THREADS, smem, st>>>(query, support, neighbors, feat, k_points,
                                                                   (const uint8_t *)ws, n, N0, M, K, Cin, Cout, g, cols,
-                                                                  ncpc, out);
+                                                                  ncpc, out, wf_out);
     return finish_launch("kpconv_fwd_tc");
 }
 

@@ -25,6 +25,9 @@ PRECISION = {"fp32": 0, "tensor": 1}
 # fp32 accumulate; <= 2e-5 of max|out| against the fp32 oracle) where the shape allows it,
 # "fp32" = exact fp32 SIMT kernel everywhere (<= 1e-5).
 KPCONV_PRECISION = "tensor"
+# keep the fp32 weighted features of a tensor-path forward for the backward pass (n*K*Cin floats per layer) instead
+# of recomputing them there
+SAVE_KPCONV_WF = True
 
 
 # ------------------------------------------------------------------ plumbing ---------------
@@ -556,7 +559,7 @@ def knn_interpolate(x, pos_x, pos_y, batch_x=None, batch_y=None, k: int = 3, num
 class _KPConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, query, support, neighbors, feat, k_points, k_values, extent, influence, aggregation,
-                precision):
+                precision, save_wf=False):
         dev = _require_cuda("KPConv_ops", query, support, neighbors, feat, k_points, k_values)
         query, support, feat = _f32(query), _f32(support), _f32(feat)
         k_points, k_values, neighbors = _f32(k_points), _f32(k_values), _i64(neighbors)
@@ -566,9 +569,18 @@ class _KPConv(torch.autograd.Function):
         out = torch.empty((n, Cout), dtype=torch.float32, device=dev)
         ws_bytes = _cabi.lib().p3d_kpconv_fwd_ws_bytes(K, Cin, Cout) if precision else 0
         ws = _workspace(ws_bytes, dev)
-        _call(dev, "p3d_kpconv_fwd_f32", query.data_ptr(), support.data_ptr(), neighbors.data_ptr(), feat.data_ptr(),
-              k_points.data_ptr(), k_values.data_ptr(), n, N0, M, K, Cin, Cout, float(extent), influence,
-              aggregation, precision, out.data_ptr(), _ptr(ws), ws_bytes)
+        wf = None
+        if save_wf and ws_bytes and M <= 40 and n > 0 and ctx.needs_input_grad[5]:
+            # training on the tensor path: keep the weighted features the kernel builds anyway (n*K*Cin floats)
+            wf = torch.empty((n, K, Cin), dtype=torch.float32, device=dev)
+            _call(dev, "p3d_kpconv_fwd_wf_f32", query.data_ptr(), support.data_ptr(), neighbors.data_ptr(),
+                  feat.data_ptr(), k_points.data_ptr(), k_values.data_ptr(), n, N0, M, K, Cin, Cout, float(extent),
+                  influence, aggregation, out.data_ptr(), wf.data_ptr(), ws.data_ptr(), ws_bytes)
+        else:
+            _call(dev, "p3d_kpconv_fwd_f32", query.data_ptr(), support.data_ptr(), neighbors.data_ptr(),
+                  feat.data_ptr(), k_points.data_ptr(), k_values.data_ptr(), n, N0, M, K, Cin, Cout, float(extent),
+                  influence, aggregation, precision, out.data_ptr(), _ptr(ws), ws_bytes)
+        ctx.wf = wf
         ctx.save_for_backward(query, support, neighbors, feat, k_points, k_values)
         ctx.cfg = (float(extent), influence, aggregation)
         return out
@@ -588,10 +600,11 @@ class _KPConv(torch.autograd.Function):
         if need_x or need_w:
             ws_bytes = _cabi.lib().p3d_kpconv_bwd_ws_bytes(n, M, K, Cin, Cout)
             ws = torch.empty(max(ws_bytes // 4, 1), dtype=torch.float32, device=dev)
-            _call(dev, "p3d_kpconv_bwd_f32", query.data_ptr(), support.data_ptr(), neighbors.data_ptr(),
-                  feat.data_ptr(), k_points.data_ptr(), k_values.data_ptr(), grad_out.data_ptr(), n, N0, M, K, Cin,
-                  Cout, extent, influence, aggregation, _ptr(dfeat), _ptr(dW), ws.data_ptr(), ws_bytes)
-        return None, None, None, dfeat, None, dW, None, None, None, None
+            _call(dev, "p3d_kpconv_bwd_wf_f32", query.data_ptr(), support.data_ptr(), neighbors.data_ptr(),
+                  feat.data_ptr(), k_points.data_ptr(), k_values.data_ptr(), grad_out.data_ptr(), _ptr(ctx.wf), n, N0,
+                  M, K, Cin, Cout, extent, influence, aggregation, _ptr(dfeat), _ptr(dW), ws.data_ptr(), ws_bytes)
+            ctx.wf = None
+        return None, None, None, dfeat, None, dW, None, None, None, None, None
 
 
 class _KPConvSplit(torch.autograd.Function):
@@ -663,8 +676,11 @@ def KPConv_ops(query_points, support_points, neighbors_indices, features, K_poin
         pad = 32 - cin
         features = torch.nn.functional.pad(features, (0, pad))
         K_values = torch.nn.functional.pad(K_values, (0, 0, 0, pad))
+    # (grad mode is always off inside Function.forward, so "is this a training forward" is decided here)
+    save_wf = SAVE_KPCONV_WF and prec == "tensor" and torch.is_grad_enabled() and K_values.requires_grad
     return _KPConv.apply(query_points, support_points, neighbors_indices, features, K_points, K_values,
-                         float(KP_extent), INFLUENCE[KP_influence], AGGREGATION[aggregation_mode], PRECISION[prec])
+                         float(KP_extent), INFLUENCE[KP_influence], AGGREGATION[aggregation_mode], PRECISION[prec],
+                         save_wf)
 
 
 
