@@ -277,3 +277,26 @@ def test_kpconv_autograd_plumbing_with_stubbed_device_calls(monkeypatch):
     (o.sum() + sqd.sum() + dk.sum()).backward()
     assert calls == ["p3d_kpconv_deform_fwd_f32", "p3d_kpconv_deform_bwd_f32"]
     assert off.grad.shape == off.shape and mods.grad.shape == mods.shape
+
+
+def test_integration_md_stub_matches_the_header(cabi):
+    """INTEGRATION.md section 2 shows the ctypes binding a maintainer would add.  Execute that text against the
+    built library: the argtypes must have one entry per parameter of the header's declaration and the documented
+    call must reach the library's own argument validation (npoint > N is rejected before any CUDA call)."""
+    import types
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"```python\n(# torch_points3d/core/spatial_ops/_p3d_b200\.py.*?)```", text, flags=re.S)
+    assert m, "INTEGRATION.md lost its binding stub"
+    src = m.group(1).replace('ctypes.CDLL("libp3d_b200.so")', "ctypes.CDLL(%r)" % cabi.LIB_PATH)
+    mod = types.ModuleType("_p3d_b200_stub")
+    exec(compile(src, "INTEGRATION.md:stub", "exec"), mod.__dict__)
+    header = open(os.path.join(ROOT, "include", "p3d_b200.h")).read()
+    decl = re.search(r"int p3d_fps_dense_f32\((.*?)\);", header, flags=re.S).group(1)
+    assert len(mod._lib.p3d_fps_dense_f32.argtypes) == len(decl.split(","))
+    assert cabi.SIGNATURES["p3d_fps_dense_f32"][1] == list(mod._lib.p3d_fps_dense_f32.argtypes)
+    with pytest.raises(ValueError):
+        mod.furthest_point_sample(torch.zeros(1, 4, 3), 5)          # the stub's own check (reference message)
+    rc = mod._lib.p3d_fps_dense_f32(None, 1, 4, 5, None, 1, None, None, 0, None)
+    assert rc == -1 and b"npoint" in mod._lib.p3d_last_error()
+    # an empty problem goes through the documented call path end to end without a device
+    assert mod.furthest_point_sample(torch.zeros(0, 4, 3), 2).shape == (0, 2)

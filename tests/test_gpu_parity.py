@@ -522,6 +522,33 @@ def test_kpconv_split_path_small_point_sets(n, N0, M, cin, cout, influence, agg)
     assert relerr(N(tx.grad), dx) <= RTOL and relerr(N(tW.grad), dW) <= RTOL
 
 
+@pytest.mark.parametrize("K,cin,cout,n", [(16, 32, 32, 3000), (16, 64, 64, 900), (16, 128, 128, 400), (7, 32, 64, 1500),
+                                          (16, 24, 40, 700)])
+def test_kpconv_kernel_point_counts(K, cin, cout, n):
+    """kernel-point counts other than the usual 15 -- in particular the full 16 the padded layout holds -- on every
+    path: exact fp32, tcgen05 forward, training forward that keeps wf + its backward, and the small-point-set path"""
+    rng = np.random.default_rng(K * 100 + cin)
+    N0, M = 2 * n, 30
+    sup = (rng.random((N0, 3)) * 0.5).astype(np.float32)
+    qry = sup[rng.permutation(N0)[:n]]
+    bz = np.zeros(N0, dtype=np.int64)
+    nb = N(ops.ball_query(0.09, M, T(sup), T(qry), mode="partial_dense", batch_x=T(bz), batch_y=T(bz[:n]))[0])
+    Kp = (rng.standard_normal((K, 3)) * 0.035).astype(np.float32)
+    Kp[0] = 0
+    x = rng.standard_normal((N0, cin)).astype(np.float32)
+    W = (rng.standard_normal((K, cin, cout)) / np.sqrt(cin)).astype(np.float32)
+    dout = rng.standard_normal((n, cout)).astype(np.float32)
+    ref = oracle.kpconv_fwd(qry, sup, nb, x, Kp, W, 0.05, "linear", "sum")
+    dx, dW = oracle.kpconv_bwd(qry, sup, nb, x, Kp, W, dout, 0.05, "linear", "sum")
+    for prec, tol in (("fp32", RTOL), ("tensor", RTOL_TENSOR), (None, RTOL_TENSOR)):
+        tx, tW = T(x).requires_grad_(True), T(W).requires_grad_(True)
+        out = ops.KPConv_ops(T(qry), T(sup), T(nb), tx, T(Kp), tW, 0.05, "linear", "sum", precision=prec)
+        assert relerr(N(out), ref) <= tol, prec
+        out.backward(T(dout))
+        assert relerr(N(tx.grad), dx) <= RTOL, prec
+        assert relerr(N(tW.grad), dW) <= RTOL, prec
+
+
 def test_kpconv_layer_module_and_linearity():
     """KPConvLayer (kernels.py:20-104) + size-independent properties at the C3 size: linear in the
     features, all-shadow rows give exactly 0, shard-by-cloud == whole batch."""

@@ -1,0 +1,192 @@
+"""CPU tests of the host-side mirrors added for the decoder / chains / wire format: parameter names a reference
+checkpoint uses, the index bookkeeping of the reference's pyramid collation (datasets/multiscale_data.py:107-165), the
+gathers of BasePartialDenseConvolutionDown.forward (core/base_conv/partial_dense.py:60-81) and the call order of the
+RandLA chain -- no device needed (searches are replaced by numpy restatements where a chain needs one)."""
+import numpy as np
+import pytest
+import torch
+
+from torch_points3d_b200 import kpconv, message_passing as mp, multiscale, partial_dense as pd, spatial_ops
+
+
+def test_state_dict_keys_are_the_reference_names():
+    """key names written down from the reference's module tree: UnwrappedUnetBasedModel (`down_modules`, `up_modules`),
+    KPDualBlock.blocks, SimpleBlock (`kp_conv`, `bn` = FastBatchNorm1d -> `.batch_norm`), ResnetBBlock (`unary_1`,
+    `unary_2`, `shortcut_op` Sequentials), FPModule_PD.nn = MLP (Sequential of Sequential(Linear, FastBatchNorm1d,
+    act)), KPConvPaper.FC_layer (kpconv.py:52-71)."""
+    model = kpconv.KPConvPaper(4, 13)
+    keys = set(model.state_dict().keys())
+    for k in ["down_modules.0.blocks.0.kp_conv.K_points", "down_modules.0.blocks.0.kp_conv.weight",
+              "down_modules.0.blocks.0.bn.batch_norm.weight", "down_modules.0.blocks.0.bn.batch_norm.running_var",
+              "down_modules.0.blocks.1.unary_1.0.weight", "down_modules.0.blocks.1.unary_1.1.batch_norm.bias",
+              "down_modules.0.blocks.1.kp_conv.kp_conv.weight", "down_modules.0.blocks.1.kp_conv.bn.batch_norm.weight",
+              "down_modules.0.blocks.1.unary_2.1.batch_norm.running_mean",
+              "down_modules.0.blocks.1.shortcut_op.0.weight", "down_modules.0.blocks.1.shortcut_op.1.batch_norm.weight",
+              "down_modules.4.blocks.1.kp_conv.kp_conv.K_points", "up_modules.0.nn.0.0.weight",
+              "up_modules.3.nn.0.1.batch_norm.num_batches_tracked", "FC_layer.1.0.weight",
+              "FC_layer.1.1.batch_norm.weight", "FC_layer.Class.weight"]:
+        assert k in keys, k
+    assert not any(".bn.weight" in k or "unary_1.1.weight" in k for k in keys)  # plain BatchNorm1d names
+    # shapes of the yaml (in_feat = 64): last down block 1024 -> 2048 with a 512-wide KPConv, first up 3072 -> 512
+    sd = model.state_dict()
+    assert sd["down_modules.4.blocks.1.kp_conv.kp_conv.weight"].shape == (15, 512, 512)
+    assert sd["up_modules.0.nn.0.0.weight"].shape == (512, 2048 + 1024)
+    assert sd["up_modules.3.nn.0.0.weight"].shape == (64, 128 + 128)
+    assert sd["down_modules.0.blocks.0.kp_conv.weight"].shape == (15, 5, 64)     # FEAT + 1 (the ones column)
+    # a reference-shaped state dict loads strictly
+    other = kpconv.KPConvPaper(4, 13)
+    other.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=True)
+    st = model.strategies()
+    assert len(st["sampler"]) == len(st["neighbour_finder"]) == 10 and len(st["upsample_op"]) == 4
+    assert all(u.k == 1 for u in st["upsample_op"])
+    rl = mp.RandLANetRes(3, 32, [1, 1], [[10, 8, 3], [10, 16, 16]], [[6, 8, 6], [32, 64, 32]], [[6, 8, 16], [32, 64, 32]])
+    rk = set(rl.state_dict().keys())
+    assert "_conv.conv1._conv.point_pos_nn.0.0.weight" in rk and "_conv.conv2._conv.global_nn.1.1.batch_norm.bias" in rk
+    assert "_conv.shortcut_feature_resize_nn.0.0.weight" in rk
+
+
+def test_fast_batch_norm_is_the_reference_arithmetic():
+    """FastBatchNorm1d._forward_sparse (base_modules.py:136-145) reshapes [N,C] -> [1,C,N] around BatchNorm1d; the direct
+    2-D call gives the same numbers"""
+    torch.manual_seed(0)
+    bn = pd.FastBatchNorm1d(7, momentum=0.02)
+    x = torch.randn(50, 7)
+    ref = torch.nn.BatchNorm1d(7, momentum=0.02)
+    y_ref = ref(x.unsqueeze(2).transpose(0, 2)).transpose(0, 2).squeeze(2)
+    assert torch.allclose(bn(x), y_ref, atol=1e-6)
+    assert torch.allclose(bn.batch_norm.running_var, ref.running_var, atol=1e-6)
+    with pytest.raises(ValueError):
+        bn(torch.randn(7))
+
+
+def _level(pos, table, inc):
+    d = pd._Data(pos=pos, idx_neighboors=table)
+    d._inc = {"idx_neighboors": inc}
+    return d
+
+
+def test_pyramid_collation_index_rule():
+    """from_data_list_token: non-negative entries of sample i move by the cumulated SUPPORT counts -- the per-sample
+    shadow index included, so it aliases the next sample's first point; negative entries stay; x_idx / y_idx move
+    by query / support counts; `batch` numbers the samples"""
+    rng = np.random.default_rng(0)
+    sup = [5, 3, 4]      # support points per sample
+    qry = [2, 2, 1]      # query points per sample
+    levels, ups = [], []
+    for s, q in zip(sup, qry):
+        t = torch.from_numpy(rng.integers(0, s + 1, (q, 3)))   # entries == s are shadows
+        t[0, 0] = -1
+        levels.append(_level(torch.rand(q, 3), t, s))
+        u = pd._Data(x_idx=torch.from_numpy(rng.integers(0, q, (s,))), y_idx=torch.arange(s),
+                     weights=torch.rand(s, 1), normalisation=torch.rand(s, 1), num_nodes=s)
+        u._inc = {"x_idx": q, "y_idx": s}
+        ups.append(u)
+    before = [l.idx_neighboors.clone() for l in levels]
+    out = multiscale.from_data_list_token(levels)
+    assert all(torch.equal(a, l.idx_neighboors) for a, l in zip(before, levels))   # inputs untouched
+    off = np.concatenate([[0], np.cumsum(sup)])
+    want = torch.cat([torch.where(b >= 0, b + int(o), b) for b, o in zip(before, off[:-1])])
+    assert torch.equal(out.idx_neighboors, want)
+    assert out.batch.tolist() == [0, 0, 1, 1, 2] and out.pos.shape == (5, 3)
+    # the aliasing: a shadow of sample 0 (value 5) is now index 5 = first support point of sample 1
+    shadow0 = before[0] == sup[0]
+    if shadow0.any():
+        assert (out.idx_neighboors[:qry[0]][shadow0] == off[1]).all()
+    assert (out.idx_neighboors[0, 0] == -1)
+    last_shadow = before[2] == sup[2]
+    assert (out.idx_neighboors[-qry[2]:][last_shadow] == sum(sup)).all()          # only the last one is the real N
+    up = multiscale.from_data_list_token(ups)
+    qoff = np.concatenate([[0], np.cumsum(qry)])
+    assert torch.equal(up.x_idx, torch.cat([u.x_idx + int(o) for u, o in zip(ups, qoff[:-1])]))
+    assert torch.equal(up.y_idx, torch.cat([u.y_idx + int(o) for u, o in zip(ups, off[:-1])]))
+    assert up.num_nodes == sum(sup) and up.batch.shape[0] == sum(sup) and up.weights.shape == (sum(sup), 1)
+    # MultiScaleBatch: per-scale lists collated scale by scale, plain attributes like a Batch
+    samples = []
+    for i, (s, q) in enumerate(zip(sup, qry)):
+        d = multiscale.MultiScaleData(pos=torch.rand(s, 3), x=torch.rand(s, 2), y=torch.full((s,), i))
+        d.multiscale, d.upsample = [levels[i]], [ups[i]]
+        samples.append(d)
+    b = multiscale.MultiScaleBatch.from_data_list(samples)
+    assert b.num_scales == 1 and b.num_upsample == 1 and b.pos.shape == (sum(sup), 3)
+    assert b.batch.tolist() == np.repeat(np.arange(3), sup).tolist() and b.y.tolist() == b.batch.tolist()
+    assert torch.equal(b.multiscale[0].idx_neighboors, want)
+    with pytest.raises(AssertionError):
+        samples[1].multiscale = []
+        multiscale.MultiScaleBatch.from_data_list(samples)
+
+
+def _np_ball(pos, batch, r, M):
+    n = pos.shape[0]
+    out = np.full((n, M), n, dtype=np.int64)
+    for i in range(n):
+        c = 0
+        for j in range(n):
+            if batch[j] == batch[i] and ((pos[i] - pos[j]) ** 2).sum() <= r * r and c < M:
+                out[i, c] = j
+                c += 1
+    return out
+
+
+def test_partial_dense_conv_down_gathers():
+    """BasePartialDenseConvolutionDown.forward with a numpy neighbour finder: shadow rows, centred neighbour positions,
+    sampled outputs (partial_dense.py:60-81)"""
+    rng = np.random.default_rng(1)
+    pos = rng.random((12, 3)).astype(np.float32)
+    batch = np.repeat([0, 1], 6)
+    x = rng.standard_normal((12, 4)).astype(np.float32)
+    seen = {}
+
+    class Conv(pd.BasePartialDenseConvolutionDown):
+        def conv(self, x, pos, x_neighbour, pos_centered_neighbour, idx_neighbour, idx_sampler):
+            seen.update(x=x, pos=pos, xn=x_neighbour, pc=pos_centered_neighbour, idx=idx_neighbour)
+            return x_neighbour.sum(1)[idx_sampler]
+
+    finder = lambda a, b, batch_x, batch_y: torch.from_numpy(_np_ball(a.numpy(), batch_x.numpy(), 0.5, 5))  # noqa: E731
+    sampler = lambda pos, x, batch: torch.tensor([0, 3, 7, 11])  # noqa: E731
+    out = Conv(sampler, finder)(pd._Data(x=torch.from_numpy(x), pos=torch.from_numpy(pos), batch=torch.from_numpy(batch),
+                                         y=torch.arange(12)))
+    nb = _np_ball(pos, batch, 0.5, 5)
+    xs = np.concatenate([x, np.zeros((1, 4), np.float32)])
+    ps = np.concatenate([pos, np.full((1, 3), 1e6, np.float32)])
+    assert seen["x"].shape == (13, 4) and seen["pos"].shape == (13, 3)
+    assert np.array_equal(seen["xn"].numpy(), xs[nb])
+    assert np.array_equal(seen["pc"].numpy(), ps[nb] - pos[:, None])
+    assert np.allclose(out.x.numpy(), xs[nb].sum(1)[[0, 3, 7, 11]])
+    assert out.pos.shape == (4, 3) and out.batch.tolist() == [0, 0, 1, 1] and out.y.shape == (12,)  # copy_from_to
+
+
+def test_randla_chain_call_order_and_shapes(monkeypatch):
+    """BaseConvolutionDown.forward as RandlaConv drives it (message_passing.py:44-58, RandLANet/modules.py:57-67):
+    sampler -> knn(pos, pos[idx]) -> edge_index [support, query] -> kernel on (pos, pos[idx])"""
+    calls = []
+    n, k = 40, 4
+    pos = torch.rand(n, 3)
+    batch = torch.zeros(n, dtype=torch.long)
+
+    def fake_knn(x, y, kk, bx, by, *a, **kw):
+        calls.append(("knn", x.shape[0], y.shape[0], kk))
+        d = torch.cdist(y, x)
+        col = d.topk(kk, largest=False).indices
+        row = torch.arange(y.shape[0]).view(-1, 1).expand_as(col)
+        return torch.stack([row.reshape(-1), col.reshape(-1)])
+
+    monkeypatch.setattr(spatial_ops.ops, "knn_edges", fake_knn)
+    conv = mp.RandlaConv(ratio=0.5, k=k, point_pos_nn=[10, 8, 3], attention_nn=[6, 8, 6], down_conv_nn=[6, 8, 16])
+    got = {}
+
+    def fake_kernel(x, p, edge_index):
+        got.update(x=x, pos=p, ei=edge_index)
+        return torch.zeros(p[1].shape[0], 16)
+
+    conv._conv.forward = fake_kernel
+    out = conv(pd._Data(x=torch.rand(n, 3), pos=pos, batch=batch))
+    assert calls == [("knn", n, n // 2, k)]
+    assert out.idx.shape == (n // 2,) and (out.idx[1:] >= out.idx[:-1]).all()      # sorted draw: batch stays sorted
+    assert got["pos"][0] is pos and torch.equal(got["pos"][1], pos[out.idx])        # (source, target) positions
+    assert got["ei"].shape == (2, n // 2 * k) and int(got["ei"][0].max()) < n and int(got["ei"][1].max()) < n // 2
+    assert torch.equal(out.edge_index, got["ei"]) and out.x.shape == (n // 2, 16)
+    lit = mp.RandlaConv(ratio=1.0, k=k, point_pos_nn=[10, 8, 3], attention_nn=[6, 8, 6], down_conv_nn=[6, 8, 16],
+                        reference_pos_order=True)
+    lit._conv.forward = fake_kernel
+    lit(pd._Data(x=torch.rand(n, 3), pos=pos, batch=batch))
+    assert got["pos"][1] is pos                                                      # the reference's literal order

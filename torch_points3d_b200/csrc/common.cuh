@@ -29,6 +29,20 @@ inline int finish_launch(const char *what) {
     return P3D_OK;
 }
 
+// One-time kernel opt-ins (cudaFuncSetAttribute) are PER DEVICE: a process that drives several GPUs must repeat them
+// on each.  `done()` / `mark()` keep one bit per device ordinal; a racing second thread at worst repeats the
+// (idempotent) attribute call.
+struct DeviceOnce {
+    std::atomic<uint64_t> bits[4] = {};
+    static int dev() {
+        int d = 0;
+        cudaGetDevice(&d);
+        return d & 255;
+    }
+    bool done() const { const int d = dev(); return (bits[d >> 6].load(std::memory_order_acquire) >> (d & 63)) & 1u; }
+    void mark() { const int d = dev(); bits[d >> 6].fetch_or((uint64_t)1 << (d & 63), std::memory_order_release); }
+};
+
 #define P3D_REQUIRE(cond, ...)          \
     do {                                \
         if (!(cond)) {                  \

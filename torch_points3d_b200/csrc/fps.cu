@@ -17,8 +17,6 @@
 //     DSMEM, then one barrier.cluster per round.
 #include <cooperative_groups.h>
 
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -277,10 +275,10 @@ static int launch_cta(const float *xyz, const int64_t *ptr, int64_t n_dense, con
     auto kern = fps_cta_kernel<T, PPT, IdxT>;
     const size_t smem = (size_t)3 * T * PPT * sizeof(float);
     if (smem + 2048 > 48 * 1024) {  // static shared memory counts against the 48 KB default as well
-        static bool done = false;
-        if (!done) {
+        static DeviceOnce done;
+        if (!done.done()) {
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            done = true;
+            done.mark();
         }
     }
     kern<<<clouds, T, smem, st>>>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz);
@@ -359,10 +357,10 @@ static int launch_reg(const float *xyz, const int64_t *ptr, int64_t n_dense, con
     cfg.blockDim = dim3(T);
     cfg.dynamicSmemBytes = (size_t)3 * T * PPT * sizeof(float);
     if (cfg.dynamicSmemBytes + 4096 > 48 * 1024) {
-        static bool smem_done = false;
-        if (!smem_done) {
+        static DeviceOnce smem_done;
+        if (!smem_done.done()) {
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
-            smem_done = true;
+            smem_done.mark();
         }
     }
     cfg.stream = st;
@@ -394,66 +392,19 @@ static int fps_dispatch(const float *xyz, const int64_t *ptr, int64_t n_dense, c
                         int64_t s_dense, IdxT *out, const int64_t *first, float *new_xyz, int clouds, int64_t max_n,
                         float *ws, size_t ws_bytes, int64_t total_rows, cudaStream_t st) {
     if (clouds == 0) return P3D_OK;
-    // tuning hook (bench/tune_fps.py): P3D_FPS_FORCE="T,PPT" selects a single-CTA variant by hand
-    if (const char *force = getenv("P3D_FPS_FORCE")) {
-        int ft = 0, fp = 0, fc = 1;
-        const int nf = sscanf(force, "%d,%d,%d", &ft, &fp, &fc);
-        if (nf == 3 && fc > 1 && (int64_t)ft * fp * fc >= max_n) {
-#define P3D_FPS_FORCED_CL(T, PPT, CL) \
-    if (ft == T && fp == PPT && fc == CL) \
-        return launch_reg<T, PPT, CL, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
-            P3D_FPS_FORCED_CL(1024, 8, 16) P3D_FPS_FORCED_CL(512, 16, 16) P3D_FPS_FORCED_CL(256, 32, 16)
-            P3D_FPS_FORCED_CL(1024, 8, 8) P3D_FPS_FORCED_CL(512, 16, 8) P3D_FPS_FORCED_CL(512, 8, 8)
-            P3D_FPS_FORCED_CL(512, 8, 16) P3D_FPS_FORCED_CL(256, 16, 16) P3D_FPS_FORCED_CL(512, 32, 8)
-            P3D_FPS_FORCED_CL(1024, 16, 8) P3D_FPS_FORCED_CL(256, 8, 8) P3D_FPS_FORCED_CL(256, 8, 4)
-            P3D_FPS_FORCED_CL(128, 16, 8) P3D_FPS_FORCED_CL(256, 4, 2) P3D_FPS_FORCED_CL(128, 8, 2)
-            P3D_FPS_FORCED_CL(256, 4, 4) P3D_FPS_FORCED_CL(128, 4, 4) P3D_FPS_FORCED_CL(128, 8, 4)
-#undef P3D_FPS_FORCED_CL
-        }
-        if (nf == 2 && (int64_t)ft * fp >= max_n) {
-#define P3D_FPS_FORCED(T, PPT) \
-    if (ft == T && fp == PPT)  \
-        return launch_reg<T, PPT, 1, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
-            P3D_FPS_FORCED(64, 8) P3D_FPS_FORCED(64, 16) P3D_FPS_FORCED(64, 32)
-            P3D_FPS_FORCED(128, 4) P3D_FPS_FORCED(128, 8) P3D_FPS_FORCED(128, 16)
-            P3D_FPS_FORCED(256, 4) P3D_FPS_FORCED(256, 8) P3D_FPS_FORCED(512, 4) P3D_FPS_FORCED(1024, 2)
-            P3D_FPS_FORCED(1024, 4) P3D_FPS_FORCED(512, 2) P3D_FPS_FORCED(256, 2) P3D_FPS_FORCED(32, 32)
-            P3D_FPS_FORCED(32, 16)
-#undef P3D_FPS_FORCED
-        }
-    }
 #define P3D_FPS_CASE(LIM, T, PPT, CL) \
     if (max_n <= (LIM)) return launch_reg<T, PPT, CL, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
 #define P3D_FPS_CTA(LIM, T, PPT) \
     if (max_n <= (LIM)) return launch_cta<T, PPT, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
-    if (const char *force = getenv("P3D_FPS_CTA")) {  // tuning hook: "T,PPT"
-        int ft = 0, fp = 0;
-        if (sscanf(force, "%d,%d", &ft, &fp) == 2 && (int64_t)ft * fp >= max_n) {
-#define P3D_FPS_CTAF(T, PPT) \
-    if (ft == T && fp == PPT) return launch_cta<T, PPT, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
-            P3D_FPS_CTAF(64, 8) P3D_FPS_CTAF(64, 16) P3D_FPS_CTAF(128, 4) P3D_FPS_CTAF(128, 8) P3D_FPS_CTAF(128, 16)
-            P3D_FPS_CTAF(256, 4) P3D_FPS_CTAF(256, 8) P3D_FPS_CTAF(512, 4) P3D_FPS_CTAF(512, 2) P3D_FPS_CTAF(1024, 2)
-            P3D_FPS_CTAF(256, 16) P3D_FPS_CTAF(512, 8) P3D_FPS_CTAF(1024, 4) P3D_FPS_CTAF(512, 16)
-#undef P3D_FPS_CTAF
-        }
-    }
-    if (getenv("P3D_FPS_OLD") == nullptr) {
-        // variants picked by bench_tools/tune_fps_cta.py on B200 (profiles/r1_fps_tuning.md): few fat threads win,
-        // a round is bound by warps x instructions issued inside the one SM
-        P3D_FPS_CTA(256, 64, 4)
-        P3D_FPS_CTA(512, 128, 4)
-        P3D_FPS_CTA(1024, 128, 8)
-        P3D_FPS_CTA(2048, 128, 16)
-        P3D_FPS_CTA(4096, 256, 16)
-        P3D_FPS_CTA(8192, 512, 16)
-    }
+    // variants picked on B200 (profiles/r1_fps_tuning.md): few fat threads win, a round is bound by
+    // warps x instructions issued inside the one SM
+    P3D_FPS_CTA(256, 64, 4)
+    P3D_FPS_CTA(512, 128, 4)
+    P3D_FPS_CTA(1024, 128, 8)
+    P3D_FPS_CTA(2048, 128, 16)
+    P3D_FPS_CTA(4096, 256, 16)
+    P3D_FPS_CTA(8192, 512, 16)
 #undef P3D_FPS_CTA
-    P3D_FPS_CASE(256, 64, 4, 1)
-    P3D_FPS_CASE(512, 128, 4, 1)
-    P3D_FPS_CASE(1024, 256, 4, 1)
-    P3D_FPS_CASE(2048, 512, 4, 1)
-    P3D_FPS_CASE(4096, 1024, 4, 1)
-    P3D_FPS_CASE(8192, 1024, 8, 1)
     P3D_FPS_CASE(16384, 1024, 8, 2)
     P3D_FPS_CASE(32768, 1024, 8, 4)
     P3D_FPS_CASE(65536, 1024, 8, 8)

@@ -797,7 +797,6 @@ bwd_direct_kernel(const float *__restrict__ dout, const int64_t *__restrict__ id
 }
 
 static bool use_direct_path(int C, int N) {
-    if (const char *e = getenv("P3D_BWD_DIRECT")) return atoi(e) != 0 && C <= DS_MAX_C && (int64_t)C * N <= DS_MAX_FLOATS;
     return C <= DS_MAX_C && (int64_t)C * N <= DS_MAX_FLOATS;
 }
 
@@ -816,13 +815,13 @@ static int launch_bwd_direct(const float *dout, const int64_t *keys, int B, int 
     int64_t spc = (E + splits - 1) / splits;
     spc = (spc + 31) / 32 * 32;
     const size_t smem = (size_t)DS_WARPS * C * N * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_done;
+    if (!attr_done.done()) {
         cudaFuncSetAttribute(bwd_direct_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              DS_WARPS * DS_MAX_FLOATS * (int)sizeof(float));
         cudaFuncSetAttribute(bwd_direct_kernel<DS_MAX_C, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              DS_WARPS * DS_MAX_FLOATS * (int)sizeof(float));
-        attr_done = true;
+        attr_done.mark();
     }
     float *part = (float *)ws;
     const dim3 grid((unsigned)splits, (unsigned)B);
@@ -887,12 +886,12 @@ static int launch_bwd_sorted(const float *dout, const float *weight, const int64
     uint32_t *runs = (uint32_t *)(w8 + L.runs);
     int *nruns = (int *)(w8 + L.nruns);
     float *part = (float *)(w8 + L.nruns + align256((size_t)B * nchunks * sizeof(int)));
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_done;
+    if (!attr_done.done()) {
         cudaFuncSetAttribute(invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         cudaFuncSetAttribute(bwd_sorted_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(bwd_sorted_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_done = true;
+        attr_done.mark();
     }
     if (mode != BWD_PREPARED) {
         const size_t inv_smem = ((size_t)N * INV_WARPS + N) * sizeof(int);
@@ -902,11 +901,7 @@ static int launch_bwd_sorted(const float *dout, const float *weight, const int64
         if (mode == BWD_PREPARE) return P3D_OK;
     }
     const int Wd = INTERP ? EC / 3 : EC;
-    int SB_STAGES = 2, use_tma = 1;
-    if (const char *e = getenv("P3D_BWD_STAGES")) SB_STAGES = atoi(e);   // tuning hooks
-    if (const char *e = getenv("P3D_BWD_TMA")) use_tma = atoi(e);
-    if (SB_STAGES < 2) SB_STAGES = 2;
-    if (SB_STAGES > SB_MAX_STAGES) SB_STAGES = SB_MAX_STAGES;
+    const int SB_STAGES = 2, use_tma = 1;
     const size_t smem =
         (size_t)SB_STAGES * (SB_CC * Wd + (INTERP ? EC : 0) + EC / 2 + (INTERP ? 0 : EC / 2)) * sizeof(float);
     const int splits = L.splits;
@@ -959,11 +954,11 @@ P3D_EXPORT int p3d_group_fwd_f32(const float *feat, const int64_t *idx, int B, i
     cudaStream_t st = (cudaStream_t)stream;
     if (staged) {
         const size_t smem = (size_t)CC * N * sizeof(float);
-        static bool attr_done = false;
-        if (!attr_done) {
+        static DeviceOnce attr_done;
+        if (!attr_done.done()) {
             cudaFuncSetAttribute(group_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  GR_SMEM_FLOATS * (int)sizeof(float));
-            attr_done = true;
+            attr_done.mark();
         }
         group_fwd_kernel<true><<<grid, GR_THREADS, smem, st>>>(feat, idx, C, N, E, CC, (int)e_per_cta, out,
                                                                out_batch_stride, c_off, GroupXyz{});
@@ -995,11 +990,11 @@ P3D_EXPORT int p3d_group_xyz_feat_f32(const float *pos, const float *new_pos, co
         e_per_cta /= 2;
     dim3 grid((unsigned)((E + e_per_cta - 1) / e_per_cta), (unsigned)cchunks, (unsigned)B);
     const size_t smem = (size_t)((CC > 3 ? CC : 3)) * N * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_done;
+    if (!attr_done.done()) {
         cudaFuncSetAttribute(group_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              GR_SMEM_FLOATS * (int)sizeof(float));
-        attr_done = true;
+        attr_done.mark();
     }
     GroupXyz xyz{pos, new_pos, S, K, 1.0f / norm, norm != 1.0f ? 1 : 0};
     group_fwd_kernel<true, true><<<grid, GR_THREADS, smem, (cudaStream_t)stream>>>(feat, idx, C, N, E, CC,
@@ -1107,11 +1102,11 @@ P3D_EXPORT int p3d_three_interp_fwd_f32(const float *feat, const int64_t *idx, c
     dim3 grid((unsigned)((n + n_per_cta - 1) / n_per_cta), (unsigned)cchunks, (unsigned)B);
     cudaStream_t st = (cudaStream_t)stream;
     if (staged) {
-        static bool attr_done = false;
-        if (!attr_done) {
+        static DeviceOnce attr_done;
+        if (!attr_done.done()) {
             cudaFuncSetAttribute(three_interp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  GR_SMEM_FLOATS * (int)sizeof(float));
-            attr_done = true;
+            attr_done.mark();
         }
         three_interp_fwd_kernel<true><<<grid, GR_THREADS, (size_t)CC * m * sizeof(float), st>>>(
             feat, idx, weight, C, m, n, CC, n_per_cta, out);

@@ -263,10 +263,10 @@ int kpconv_fwd_simt(const float *query, const float *support, const int64_t *nei
                     int Cout, float extent, int influence, int aggregation, float *out, cudaStream_t st) {
     const int Mpad = (M + 31) / 32 * 32;
     const size_t smem = (size_t)KPF_WARPS * (Mpad * KP_K + Mpad + KP_K * 32 * KPF_T) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_done;
+    if (!attr_done.done()) {
         cudaFuncSetAttribute(kpconv_fwd_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_done = true;
+        attr_done.mark();
     }
     const int64_t tiles = (n + KPF_T - 1) / KPF_T;
     int64_t grid = (tiles + KPF_WARPS - 1) / KPF_WARPS;
@@ -350,11 +350,11 @@ int gemm_smallk(const float *A, int64_t lda, const float *Bp, int64_t sbk, int64
                 float *C, int64_t ldc, cudaStream_t st) {
     if (Kd > SK_KD || Kd < 1) return 1;
     const size_t smem = (size_t)Kd * (SK_COLS + SK_APITCH) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_done;
+    if (!attr_done.done()) {
         cudaFuncSetAttribute(gemm_smallk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(SK_KD * (SK_COLS + SK_APITCH) * sizeof(float)));
-        attr_done = true;
+        attr_done.mark();
     }
     const int64_t tiles = (R + SK_ROWS - 1) / SK_ROWS;
     const int cblocks = (N + SK_COLS - 1) / SK_COLS;
@@ -547,11 +547,11 @@ static int kpconv_bwd_impl(const float *query, const float *support, const int64
     const KpGeom g = make_geom(extent, influence, aggregation);
     const int Mpad = (M + 31) / 32 * 32;
     const size_t smem = (size_t)KPF_WARPS * (Mpad * KP_K + Mpad) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_done;
+    if (!attr_done.done()) {
         cudaFuncSetAttribute(kpconv_wf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         cudaFuncSetAttribute(kpconv_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        attr_done = true;
+        attr_done.mark();
     }
     float *wf = (float *)ws;
     float *dwf = wf + (size_t)n * K * Cin;
@@ -561,7 +561,9 @@ static int kpconv_bwd_impl(const float *query, const float *support, const int64
     const bool sparse = kpconv_sparse_supported(M, K, Cin);
     if (dweights && wf_saved != nullptr) {
         // dW[kc][o] += sum_p wf[p][kc] * dout[p][o] straight from the forward's slab
-        if (dw_accumulate(wf_saved, dout, n, (int)KC, Cout, dweights, st) != 0)
+        const int r = dw_accumulate(wf_saved, dout, n, (int)KC, Cout, dweights, st);
+        if (r < 0) return r;
+        if (r == 1)  // shape outside the register-tiled kernel
             if (int e = sgemm_splitk_atomic(wf_saved, dout, n, KC, Cout, dweights, st)) return e;
     } else if (dweights) {
         if (sparse) {
@@ -574,7 +576,11 @@ static int kpconv_bwd_impl(const float *query, const float *support, const int64
             if (int e = finish_launch("kpconv_wf")) return e;
         }
         // dW[kc][o] += sum_p wf[p][kc] * dout[p][o]
-        if (dw_accumulate(wf, dout, n, (int)KC, Cout, dweights, st) == 0) goto dw_done;
+        {
+        const int r = dw_accumulate(wf, dout, n, (int)KC, Cout, dweights, st);
+        if (r < 0) return r;
+        if (r == 0) goto dw_done;
+        }
         {
         const int64_t tiles = ((KC + 63) / 64) * ((Cout + 63) / 64);
         int64_t split = (2 * kNumSMs + tiles - 1) / tiles;

@@ -350,11 +350,11 @@ P3D_EXPORT int p3d_kpconv_deform_fwd_f32(const float *query, const float *suppor
                                      extent, influence);
     const int warps = 8;
     const size_t smem = (size_t)warps * deform_warp_floats(a.Mpad, false) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_done;
+    if (!attr_done.done()) {
         cudaFuncSetAttribute(kpconv_deform_wf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         cudaFuncSetAttribute(kpconv_deform_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_done = true;
+        attr_done.mark();
     }
     int64_t grid = (n + warps - 1) / warps;
     if (grid > 16 * kNumSMs) grid = 16 * kNumSMs;
@@ -398,11 +398,11 @@ P3D_EXPORT int p3d_kpconv_deform_bwd_f32(const float *query, const float *suppor
                                      extent, influence);
     const int warps = a.Mpad <= 64 ? 8 : 4;
     const size_t smem = (size_t)warps * deform_warp_floats(a.Mpad, true) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_done;
+    if (!attr_done.done()) {
         cudaFuncSetAttribute(kpconv_deform_wf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         cudaFuncSetAttribute(kpconv_deform_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_done = true;
+        attr_done.mark();
     }
     int64_t grid = (n + warps - 1) / warps;
     if (grid > 16 * kNumSMs) grid = 16 * kNumSMs;

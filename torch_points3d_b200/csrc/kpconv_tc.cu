@@ -303,7 +303,8 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                         tc_weights<INFL, CLOSEST>(P, kps, K, M, g, inv_extent, w0, w1, mask0, mask1, lane);
                         asm volatile("cp.async.wait_group 0;" ::: "memory");  // each lane reads only what it copied
 #pragma unroll
-                        for (int k = 0; k < KP_K - 1; ++k) {  // kernel point 15 is padding
+                        for (int k = 0; k < KP_K; ++k) {
+                            if (k == KP_K - 1 && K < KP_K) break;  // the usual 15 kernel points: slot 15 is padding
                             // ~2.3 influencing neighbours per kernel point: the first three are taken without a
                             // branch (an absent one reads row 0 with weight 0; rows never hold NaNs, see the
                             // zero fill at kernel start), so the loads of a point are independent and pipeline;
@@ -321,9 +322,11 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                             const float w1s = __shfl_sync(0xffffffffu, w0[k], m1);
                             const float w2s = __shfl_sync(0xffffffffu, w0[k], m2);
                             const float w3s = __shfl_sync(0xffffffffu, w0[k], m3);
-                            float a = (h1 ? w1s : 0.f) * xs[m1 * 32 + lane];
-                            a = fmaf(h2 ? w2s : 0.f, xs[m2 * 32 + lane], a);
-                            a = fmaf(h3 ? w3s : 0.f, xs[m3 * 32 + lane], a);
+                            // absent taps are SELECTED away (0 * stale row could be NaN if another point's
+                            // neighbour held a non-finite feature)
+                            float a = h1 ? w1s * xs[m1 * 32 + lane] : 0.f;
+                            a = h2 ? fmaf(w2s, xs[m2 * 32 + lane], a) : a;
+                            a = h3 ? fmaf(w3s, xs[m3 * 32 + lane], a) : a;
                             while (mk) {
                                 const int m = __ffs(mk) - 1;
                                 mk &= mk - 1;
@@ -342,7 +345,7 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                             // recomputing them in the backward pass: 15 coalesced 128-byte stores per point and slab
                             float *wrow = wf_out + (p * K) * Cin + sl * 32 + lane;
 #pragma unroll
-                            for (int k = 0; k < KP_K - 1; ++k)
+                            for (int k = 0; k < KP_K; ++k)
                                 if (k < K) __stcs(wrow + (int64_t)k * Cin, acc[k]);
                         }
                         P = Pn;
@@ -470,7 +473,8 @@ kpconv_wf_sparse_kernel(const float *__restrict__ q, const float *__restrict__ s
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
-            for (int k = 0; k < KP_K - 1; ++k) {
+            for (int k = 0; k < KP_K; ++k) {
+                if (k == KP_K - 1 && K < KP_K) break;  // slot 15 is padding unless the layer has 16 kernel points
                 unsigned mk = mask0[k];
                 float a = 0.f;
                 while (mk) {
@@ -514,7 +518,8 @@ kpconv_scatter_sparse_kernel(const float *__restrict__ q, const float *__restric
 #pragma unroll
             for (int k = 0; k < KP_K; ++k) d[k] = k < K ? __ldg(dwf + (p * K + k) * Cin + c) : 0.f;
 #pragma unroll
-            for (int k = 0; k < KP_K - 1; ++k) {
+            for (int k = 0; k < KP_K; ++k) {
+                if (k == KP_K - 1 && K < KP_K) break;
                 unsigned mk = mask0[k];
                 while (mk) {
                     const int m = __ffs(mk) - 1;
@@ -803,10 +808,10 @@ int gemm_tc(const float *A, int64_t lda, const float *Bp, int64_t sbk, int64_t s
     const int ncs = N / TC_NCH;
     gemm_prep_b_kernel<<<((Kd + 511) / 512) * ncs * 4, 256, 0, st>>>(Bp, sbk, sbj, Kd, N, (uint8_t *)ws);
     if (int e = finish_launch("gemm_prep_b")) return e;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_done;
+    if (!attr_done.done()) {
         cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
-        attr_done = true;
+        attr_done.mark();
     }
     const int64_t ntiles = (R + TC_TILE - 1) / TC_TILE;
     int ygroups = 1;
@@ -916,11 +921,11 @@ int dw_accumulate(const float *A, const float *B, int64_t n, int R, int Cn, floa
     if (ppc < 4 * DW_SUB) ppc = 4 * DW_SUB;
     chunks = (n + ppc - 1) / ppc;
     if (rb > 65535 || cb > 65535) return 1;
-    static bool attr_done = false;
+    static DeviceOnce attr_done;
     const size_t smem = (size_t)2 * DW_SUB * (256 + 32) * sizeof(float);
-    if (!attr_done) {
+    if (!attr_done.done()) {
         cudaFuncSetAttribute(dw_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
+        attr_done.mark();
     }
     dw_accumulate_kernel<<<dim3((unsigned)chunks, (unsigned)rb, (unsigned)cb), 256, smem, st>>>(A, B, n, R, Cn, ppc, dW);
     return finish_launch("kpconv_dW");
@@ -958,13 +963,13 @@ int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neigh
         {{kpconv_fwd_tc_kernel<P3D_INFLUENCE_CONSTANT, false, true>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_CONSTANT, true, true>},
          {kpconv_fwd_tc_kernel<P3D_INFLUENCE_LINEAR, false, true>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_LINEAR, true, true>},
          {kpconv_fwd_tc_kernel<P3D_INFLUENCE_GAUSSIAN, false, true>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_GAUSSIAN, true, true>}}};
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_done;
+    if (!attr_done.done()) {
         for (int w = 0; w < 2; ++w)
             for (int a = 0; a < 3; ++a)
                 for (int b = 0; b < 2; ++b)
                     cudaFuncSetAttribute(kerns[w][a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
-        attr_done = true;
+        attr_done.mark();
     }
     const int64_t ntiles = (n + TC_TILE - 1) / TC_TILE;
     const int ncs = Cout / TC_NCH;

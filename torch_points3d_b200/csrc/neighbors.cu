@@ -651,7 +651,6 @@ static int launch_ball_query(const float *x, const float *y, const int64_t *bx, 
     if (Ny == 0 || K == 0) return P3D_OK;
     const float r2 = radius * radius;
     int qpw = Ny >= (int64_t)NB_WARPS * 4 * 2 * kNumSMs ? 4 : 1;
-    if (const char *e = getenv("P3D_BQ_QPW")) qpw = atoi(e);  // tuning hook
     if (qpw == 4) {
         const int64_t grid = (Ny + NB_WARPS * 4 - 1) / (NB_WARPS * 4);
         ball_query_kernel<DENSE, 4><<<(unsigned)grid, NB_WARPS * 32, 0, st>>>(

@@ -1,9 +1,11 @@
 """Host-side mirror of the rigid KPConv layer:
   KPConv_ops     torch_points3d/modules/KPConv/convolution_ops.py:19-107
   KPConvLayer    torch_points3d/modules/KPConv/kernels.py:20-104
-  SimpleBlock    torch_points3d/modules/KPConv/blocks.py:15-97 (rigid, on-device neighbour search)
-Same constructor arguments; K_points stays a non-trainable Parameter so that reference
-checkpoints load.
+  SimpleBlock    torch_points3d/modules/KPConv/blocks.py:15-97 (on-device neighbour search)
+  ResnetBBlock   blocks.py:100-225        KPDualBlock  blocks.py:228-292
+  KPConvPaper    torch_points3d/models/segmentation/kpconv.py:22-140 with conf/models/segmentation/kpconv.yaml:4-76
+Same constructor arguments and parameter names (K_points stays a non-trainable Parameter, BatchNorm sits inside
+FastBatchNorm1d as `.batch_norm`), so a reference state_dict loads key for key.
 """
 import os
 
@@ -13,6 +15,7 @@ from torch.nn.parameter import Parameter
 
 from . import ops
 from .ops import KPConv_ops  # noqa: F401  (re-export under the reference's name)
+from .partial_dense import FastBatchNorm1d, FPModule_PD
 from .spatial_ops import PARTIAL_DENSE, RadiusNeighbourFinder
 
 # 15 kernel points of k_015_center.ply (unit radius): DATA of the reference model, stored next to
@@ -177,15 +180,23 @@ class KPConvDeformableLayer(torch.nn.Module):
 
 
 class Cloud:
-    """minimal stand-in for the torch_geometric `Data` objects the reference blocks pass around"""
+    """minimal stand-in for the torch_geometric `Data` objects the reference blocks pass around: an attribute bag
+    (`pos`, `x`, `batch`, `idx_neighboors`, `block_idx`, `up_idx`, ...) whose `clone` copies the attribute table"""
 
-    def __init__(self, pos, x, batch, idx_neighboors=None, nb_key=None, block_idx=0):
+    def __init__(self, pos=None, x=None, batch=None, idx_neighboors=None, nb_key=None, block_idx=0, **extra):
         self.pos, self.x, self.batch, self.idx_neighboors = pos, x, batch, idx_neighboors
         self.nb_key = nb_key  # (radius, max_num_neighbors) of a self-neighbour table of `pos`, if one is attached
         self.block_idx = block_idx  # position in the precomputed multiscale list (blocks.py:67-68,93)
+        self.__dict__.update(extra)
+
+    @property
+    def keys(self):
+        return [k for k, v in self.__dict__.items() if v is not None]
 
     def clone(self):
-        return Cloud(self.pos, self.x, self.batch, self.idx_neighboors, self.nb_key, self.block_idx)
+        out = Cloud()
+        out.__dict__.update(self.__dict__)
+        return out
 
 
 def grid_subsample(pos, batch, size):
@@ -209,29 +220,38 @@ class GridSampler:
 
 
 class SimpleBlock(torch.nn.Module):
-    """blocks.py:15-97 (rigid): [grid subsampling of the queries when strided] -> neighbour search
-    (partial-dense ball query, radius 2.5 * sigma * prev_grid_size) -> KPConv -> BN -> LeakyReLU(0.1)."""
+    """blocks.py:15-97: [grid subsampling of the queries when strided] -> neighbour search (partial-dense ball query,
+    radius 2.5 (rigid) / 5.0 (deformable) * sigma * prev_grid_size) -> KPConv -> BN -> LeakyReLU(0.1)."""
 
+    DEFORMABLE_DENSITY = 5.0
     RIGID_DENSITY = 2.5
 
     def __init__(self, down_conv_nn=None, grid_size=None, prev_grid_size=None, sigma=1.0, max_num_neighbors=16,
-                 activation=None, bn_momentum=0.02, bn=True, add_one=False, **kwargs):
+                 activation=None, bn_momentum=0.02, bn=FastBatchNorm1d, deformable=False, add_one=False, **kwargs):
         super().__init__()
         assert len(down_conv_nn) == 2
         num_inputs, num_outputs = down_conv_nn
-        self.kp_conv = KPConvLayer(num_inputs, num_outputs, point_influence=prev_grid_size * sigma,
-                                   add_one=add_one, **kwargs)
-        search_radius = self.RIGID_DENSITY * sigma * prev_grid_size
+        if deformable:
+            density_parameter = self.DEFORMABLE_DENSITY
+            self.kp_conv = KPConvDeformableLayer(num_inputs, num_outputs, point_influence=prev_grid_size * sigma,
+                                                 add_one=add_one, **kwargs)
+        else:
+            density_parameter = self.RIGID_DENSITY
+            self.kp_conv = KPConvLayer(num_inputs, num_outputs, point_influence=prev_grid_size * sigma,
+                                       add_one=add_one, **kwargs)
+        search_radius = density_parameter * sigma * prev_grid_size
         self.neighbour_finder = RadiusNeighbourFinder(search_radius, max_num_neighbors, conv_type=PARTIAL_DENSE)
-        self.bn = torch.nn.BatchNorm1d(num_outputs, momentum=bn_momentum) if bn else None
+        if bn is True:
+            bn = FastBatchNorm1d
+        self.bn = bn(num_outputs, momentum=bn_momentum) if bn else None
         self.activation = activation if activation is not None else torch.nn.LeakyReLU(negative_slope=0.1)
         self.sampler = GridSampler(grid_size) if prev_grid_size != grid_size else None
 
     def forward(self, data, precomputed=None, **kwargs):
         if precomputed:  # blocks.py:70-79: geometry of this block was built ahead of time (MultiScaleTransform)
             query = precomputed[data.block_idx]
-            q_pos, q_batch, idx_neighboors = query.pos, query.batch, query.idx_neighboors
-            key = query.nb_key
+            q_pos, q_batch, idx_neighboors = query.pos, getattr(query, "batch", None), query.idx_neighboors
+            key = getattr(query, "nb_key", None)  # absent on a reference-format pyramid (multiscale.py)
         else:
             if self.sampler is not None:
                 q_pos, q_batch = self.sampler(data.pos, data.batch)
@@ -255,8 +275,11 @@ class ResnetBBlock(torch.nn.Module):
     (max over the neighbour rows when strided, a Linear+BN when the width changes)."""
 
     def __init__(self, down_conv_nn=None, grid_size=None, prev_grid_size=None, sigma=1, max_num_neighbors=16,
-                 activation=None, has_bottleneck=True, bn_momentum=0.02, bn=True, add_one=False, **kwargs):
+                 activation=None, has_bottleneck=True, bn_momentum=0.02, bn=FastBatchNorm1d, deformable=False,
+                 add_one=False, **kwargs):
         super().__init__()
+        if bn is True:
+            bn = FastBatchNorm1d
         assert len(down_conv_nn) == 2 or len(down_conv_nn) == 3, "down_conv_nn should be of size 2 or 3"
         if len(down_conv_nn) == 2:
             num_inputs, num_outputs = down_conv_nn
@@ -269,8 +292,8 @@ class ResnetBBlock(torch.nn.Module):
         kp_size = [d_2, d_2] if has_bottleneck else [num_inputs, num_outputs]
         self.kp_conv = SimpleBlock(down_conv_nn=kp_size, grid_size=grid_size, prev_grid_size=prev_grid_size,
                                    sigma=sigma, max_num_neighbors=max_num_neighbors, activation=act,
-                                   bn_momentum=bn_momentum, bn=bn, add_one=add_one, **kwargs)
-        Lin, BN = torch.nn.Linear, torch.nn.BatchNorm1d
+                                   bn_momentum=bn_momentum, bn=bn, deformable=deformable, add_one=add_one, **kwargs)
+        Lin, BN = torch.nn.Linear, bn
         if has_bottleneck:
             if bn:
                 self.unary_1 = torch.nn.Sequential(Lin(num_inputs, d_2, bias=False), BN(d_2, momentum=bn_momentum), act)
@@ -345,6 +368,109 @@ class KPConvEncoder(torch.nn.Module):
         """samplers and neighbour finders of the blocks in order -- what the reference hands to MultiScaleTransform
         (models/base_architectures/unet.py collects the same lists from its down modules)"""
         return {"sampler": [b.sampler for b in self.blocks], "neighbour_finder": [b.neighbour_finder for b in self.blocks]}
+
+
+def _is_list(v):
+    return isinstance(v, (list, tuple))
+
+
+class KPDualBlock(torch.nn.Module):
+    """blocks.py:228-292: a pair of KPConv blocks (usually strided + non strided) built by name."""
+
+    def __init__(self, block_names=None, down_conv_nn=None, grid_size=None, prev_grid_size=None, has_bottleneck=None,
+                 max_num_neighbors=None, deformable=False, add_one=False, **kwargs):
+        super().__init__()
+        assert len(block_names) == len(down_conv_nn)
+        self.blocks = torch.nn.ModuleList()
+        classes = {"SimpleBlock": SimpleBlock, "ResnetBBlock": ResnetBBlock}
+        for i, class_name in enumerate(block_names):
+            block_kwargs = {key: (arg[i] if _is_list(arg) else arg) for key, arg in kwargs.items()}
+            self.blocks.append(classes[class_name](
+                down_conv_nn=down_conv_nn[i], grid_size=grid_size[i], prev_grid_size=prev_grid_size[i],
+                has_bottleneck=has_bottleneck[i], max_num_neighbors=max_num_neighbors[i],
+                deformable=deformable[i] if _is_list(deformable) else deformable,
+                add_one=add_one[i] if _is_list(add_one) else add_one, **block_kwargs))
+
+    def forward(self, data, precomputed=None, **kwargs):
+        for block in self.blocks:
+            data = block(data, precomputed=precomputed)
+        return data
+
+    @property
+    def sampler(self):
+        return [b.sampler for b in self.blocks]
+
+    @property
+    def neighbour_finder(self):
+        return [b.neighbour_finder for b in self.blocks]
+
+
+class KPConvPaper(torch.nn.Module):
+    """The KPConv segmentation network (models/segmentation/kpconv.py:22-140) with its architecture file
+    (conf/models/segmentation/kpconv.yaml:4-76) resolved: five KPDualBlocks down (the yaml's down_conv_nn /
+    grid_size / prev_grid_size / block_names / has_bottleneck / max_num_neighbors lists), no innermost module, four
+    FPModule_PD up (KNNInterpolate(k = 1) + skip + MLP, core/base_conv/partial_dense.py:103-146), then the mlp_cls
+    head (Linear -> FastBatchNorm1d -> LeakyReLU(0.2), Linear to the classes, LogSoftmax).  Module names follow
+    UnwrappedUnetBasedModel (`down_modules`, `up_modules`, `FC_layer`).
+
+    forward(pos, x, batch, multiscale=None, upsample=None) mirrors set_input + forward: a ones column is prepended to
+    the features (kpconv.py:88), the down modules push their outputs on a stack, the up modules pop them.
+    `multiscale` / `upsample` are the precomputed pyramid halves (MultiScaleTransform); without them every block
+    searches on the fly."""
+
+    MAX_NN = [[25, 25], [25, 30], [30, 38], [38, 38], [38, 38]]
+
+    def __init__(self, feat_dim, num_classes, in_feat=64, first_subsampling=0.04, bn_momentum=0.02, levels=5,
+                 max_nn_cap=None, deformable=False, **kwargs):
+        super().__init__()
+        g, f = first_subsampling, in_feat
+        self.down_modules = torch.nn.ModuleList()
+        for lv in range(levels):
+            nn_ = [min(v, max_nn_cap) if max_nn_cap else v for v in self.MAX_NN[lv]]
+            w = f * 2 ** lv
+            if lv == 0:
+                args = dict(block_names=["SimpleBlock", "ResnetBBlock"], down_conv_nn=[[feat_dim + 1, f], [f, 2 * f]],
+                            grid_size=[g, g], prev_grid_size=[g, g], has_bottleneck=[False, True])
+            else:
+                args = dict(block_names=["ResnetBBlock", "ResnetBBlock"], down_conv_nn=[[w, w], [w, 2 * w]],
+                            grid_size=[g * 2 ** lv, g * 2 ** lv], prev_grid_size=[g * 2 ** (lv - 1), g * 2 ** lv],
+                            has_bottleneck=[True, True])
+            self.down_modules.append(KPDualBlock(max_num_neighbors=nn_, deformable=deformable, n_kernel_points=15,
+                                                 bn_momentum=bn_momentum, **args, **kwargs))
+        self.up_modules = torch.nn.ModuleList()
+        for lv in range(levels - 1, 0, -1):  # yaml up_conv_nn: [32f+16f, 8f], [8f+8f, 4f], [4f+4f, 2f], [2f+2f, f]
+            below = f * 2 ** (lv + 1) if lv == levels - 1 else f * 2 ** lv
+            skip = f * 2 ** lv
+            self.up_modules.append(FPModule_PD(1, [below + skip, f * 2 ** (lv - 1)], bn_momentum=bn_momentum))
+        self.FC_layer = torch.nn.Sequential()
+        self.FC_layer.add_module("1", torch.nn.Sequential(torch.nn.Linear(f, f, bias=False),
+                                                          FastBatchNorm1d(f, momentum=bn_momentum),
+                                                          torch.nn.LeakyReLU(0.2)))
+        self.FC_layer.add_module("Class", torch.nn.Linear(f, num_classes, bias=False))
+        self.FC_layer.add_module("Softmax", torch.nn.LogSoftmax(-1))
+
+    def forward(self, pos, x, batch, multiscale=None, upsample=None):
+        data = Cloud(pos, add_ones(pos, x, True), batch)
+        stack_down = []
+        for i in range(len(self.down_modules) - 1):
+            data = self.down_modules[i](data, precomputed=multiscale)
+            stack_down.append(data)
+        data = self.down_modules[-1](data, precomputed=multiscale)
+        for i in range(len(self.up_modules)):
+            # no innermost module in this architecture: every level is an interpolation (has_innermost = False is
+            # what the reference's `len(data.x) == data.batch.max() + 1` evaluates to, without its device read)
+            data = self.up_modules[i]((data, stack_down.pop()), precomputed=upsample, has_innermost=False)
+        return self.FC_layer(data.x)
+
+    def strategies(self):
+        """what the reference's model hands to MultiScaleTransform (models/base_architectures/unet.py
+        `_spatial_ops_dict`): samplers and neighbour finders of every down block in order, upsample ops innermost first"""
+        samplers, finders = [], []
+        for m in self.down_modules:
+            samplers += m.sampler
+            finders += m.neighbour_finder
+        return {"sampler": samplers, "neighbour_finder": finders,
+                "upsample_op": [m.upsample_op for m in self.up_modules]}
 
 
 class MultiScaleTransform:

@@ -330,7 +330,7 @@ def _side_stream(dev: torch.device) -> torch.cuda.Stream:
 class _Prepared:
     """inverse index being built on a side stream: workspace + the event the backward waits on"""
 
-    def __init__(self, name, dev, ws_bytes, *args):
+    def __init__(self, name, dev, ws_bytes, idx, *args):
         self.ws_bytes = ws_bytes
         self.ws = _workspace(ws_bytes, dev)
         cur = torch.cuda.current_stream(dev)
@@ -338,11 +338,14 @@ class _Prepared:
         side.wait_stream(cur)  # the indices (and the fresh workspace) are produced on the current stream
         with torch.cuda.stream(side):
             with torch.cuda.device(dev):
-                _cabi.call(name, *args, self.ws.data_ptr(), ws_bytes, side.cuda_stream)
+                _cabi.call(name, idx.data_ptr(), *args, self.ws.data_ptr(), ws_bytes, side.cuda_stream)
             self.event = torch.cuda.Event()
             self.event.record(side)
         if not torch.cuda.is_current_stream_capturing():
-            self.ws.record_stream(side)  # if no backward ever joins, the allocator still waits for the side stream
+            # if no backward ever joins (a forward under grad mode whose graph is dropped), the allocator must still
+            # wait for the side stream before it recycles the workspace OR the index tensor the kernel is reading
+            self.ws.record_stream(side)
+            idx.record_stream(side)
 
     def join(self, dev):
         torch.cuda.current_stream(dev).wait_event(self.event)
@@ -394,7 +397,7 @@ def _prepare_group(idx, B, C, N, S, K):
     ws_bytes = _cabi.lib().p3d_group_bwd_ws_bytes(B, C, N, S, K)
     if not ws_bytes:
         return None
-    return _Prepared("p3d_group_bwd_prepare", idx.device, ws_bytes, idx.data_ptr(), B, C, N, S, K)
+    return _Prepared("p3d_group_bwd_prepare", idx.device, ws_bytes, idx, B, C, N, S, K)
 
 
 def _group_bwd(grad_out, idx, B, C, N, S, K, batch_stride, c_off, prepared=None):
@@ -515,7 +518,7 @@ class _ThreeInterpolate(torch.autograd.Function):
         if prepared is None and PREPARE_INVERSE_IN_FORWARD and ctx.needs_input_grad[0]:
             ws_bytes = _cabi.lib().p3d_three_interp_bwd_ws_bytes(B, C, m, n)
             if ws_bytes:
-                ctx.prepared = _Prepared("p3d_three_interp_bwd_prepare", dev, ws_bytes, idx.data_ptr(), B, C, m, n)
+                ctx.prepared = _Prepared("p3d_three_interp_bwd_prepare", dev, ws_bytes, idx, B, C, m, n)
         return out
 
     @staticmethod

@@ -79,12 +79,19 @@ class DenseFPSSampler(BaseSampler):
 
 
 class RandomSampler(BaseSampler):
-    """sampling.py:103-112 (RandLA-Net style)."""
+    """sampling.py:103-112 (RandLA-Net style): draws with replacement over the whole batch.  `sorted_indices=True`
+    returns the draw in ascending order, so that `batch[idx]` stays sorted -- which the batched searches downstream
+    require (torch_cluster's knn states the same precondition; the reference feeds it the unsorted draw)."""
 
-    def sample(self, pos, batch, **kwargs):
+    def __init__(self, ratio=None, num_to_sample=None, subsampling_param=None, sorted_indices=False):
+        super().__init__(ratio, num_to_sample, subsampling_param)
+        self._sorted = sorted_indices
+
+    def sample(self, pos, batch=None, **kwargs):
         if len(pos.shape) != 2:
             raise ValueError(" This class is for sparse data and expects the pos tensor to be of dimension 2")
-        return torch.randint(0, pos.shape[0], (self._get_num_to_sample(pos.shape[0]),), device=pos.device)
+        idx = torch.randint(0, pos.shape[0], (self._get_num_to_sample(pos.shape[0]),), device=pos.device)
+        return torch.sort(idx)[0] if self._sorted else idx
 
 
 class DenseRandomSampler(BaseSampler):
