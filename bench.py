@@ -12,8 +12,11 @@ are stock cuDNN/cuBLAS in the reference and are not part of the path.  One step 
 that chain over one batch; metric = clouds/s.  With N GPUs every rank runs its own batch
 (clouds shard, no data-path collective; weak scaling).
 
-The JSON line also carries the KPConv layer numbers (points/s, C3 layer 32->32, ~50k points,
-<=34 neighbours) under "kpconv", the roofline of the dominant kernel and the CPU baseline.
+The JSON line also carries, as extra keys: the roofline of the dominant kernel (measured on the launch that is in
+the step), the CPU baseline, the KPConv layer numbers with their own live roofline and CPU baseline ("kpconv", C3
+layer 32->32, ~50k points, <=34 neighbours), the KPConvPaper segmentation training step ("kpconv_stack", C3/C5; under
+DDP when N > 1), C4 (FPS 4096 of 120k + knn k=16, and the RandLA chain on top) sharded over the ranks, the C1 chain,
+the whole C2 network step against the published iteration time, and per-operator figures ("operators").
 """
 import argparse
 import json
@@ -62,13 +65,16 @@ def make_host_inputs(seed):
 class Chain:
     """the C2 operator chain on one GPU through the public API (torch_points3d_b200.ops)"""
 
+    REAL_INPUTS = ("pos", "x0")  # what a training pipeline gets from the host: positions and the input features
+
     def __init__(self, dev, seed):
         import torch
         from torch_points3d_b200 import synthetic
         self.torch, self.dev = torch, dev
         self.sa = synthetic.C2_SA
-        self.host = {k: torch.from_numpy(v).pin_memory() for k, v in make_host_inputs(seed).items()}
-        self.d = {k: torch.empty_like(v, device=dev) for k, v in self.host.items()}
+        self.host_all = {k: torch.from_numpy(v).pin_memory() for k, v in make_host_inputs(seed).items()}
+        self.host = self.host_all
+        self.d = {k: torch.empty_like(v, device=dev) for k, v in self.host_all.items()}
         for k in ("x0", "x1", "x2", "x3"):
             self.d[k].requires_grad_(True)
         g = torch.Generator(device=dev).manual_seed(seed)
@@ -79,22 +85,27 @@ class Chain:
                      torch.randn((B_CLOUDS, 128, 2048), device=dev, generator=g)]
         self.geo_stream = torch.cuda.Stream(device=dev)
         self.geo_stream2 = torch.cuda.Stream(device=dev)
-        self.result_host = torch.empty(B_CLOUDS * (512 + 128) + 1, dtype=torch.int64).pin_memory()
-        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
-        self.d2h_bytes = self.result_host.numel() * 8
+        # result of a step read back by the host: sampled indices of both levels + the gradient w.r.t. the input features
+        self.result_shapes = [((B_CLOUDS * (512 + 128),), torch.int64), ((B_CLOUDS, 3, N_PTS), torch.float32)]
+        self.d2h_bytes = B_CLOUDS * (512 + 128) * 8 + B_CLOUDS * 3 * N_PTS * 4
 
     def upload(self):
-        for k, v in self.host.items():
+        for k, v in self.host_all.items():
             self.d[k].data.copy_(v, non_blocking=True)
 
-    def make_staging(self):
-        """two device staging sets: the H2D copy of step i+1 runs on a copy stream while step i computes"""
+    def make_staging(self, keys=None):
+        """two device staging sets: the H2D copy of step i+1 runs on a copy stream while step i computes.
+        `keys` = which inputs come from the host every step (default: all of them)"""
         torch = self.torch
+        self.host = {k: v for k, v in self.host_all.items() if keys is None or k in keys}
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
         self.stage = [{k: torch.empty_like(v, device=self.dev) for k, v in self.host.items()} for _ in range(2)]
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.staged = [torch.cuda.Event() for _ in range(2)]
         self.consumed = [torch.cuda.Event() for _ in range(2)]
-        self.results = [self.torch.empty_like(self.result_host).pin_memory() for _ in range(2)]
+        self.results = [[torch.empty(shape, dtype=dt).pin_memory() for shape, dt in self.result_shapes] for _ in range(2)]
+        for slot in range(2):
+            self.consumed[slot].record(torch.cuda.current_stream())
 
     def h2d_async(self, slot):
         torch = self.torch
@@ -186,8 +197,8 @@ class Chain:
 
     def step(self):
         """FEATURES of the current batch (tables in self.tables) overlapped with GEOMETRY of the next batch
-        (positions in d["pos"]); the new tables replace the old ones at the end.  Returns a small result tensor:
-        the sampled indices of both levels (next batch) + one element of the last gradient (current batch)."""
+        (positions in d["pos"]); the new tables replace the old ones at the end.  Returns the step's result:
+        the sampled indices of both levels (next batch) and the gradient w.r.t. the input features (current batch)."""
         torch = self.torch
         cur = torch.cuda.current_stream()
         self.geo_stream.wait_stream(cur)
@@ -197,7 +208,7 @@ class Chain:
         cur.wait_stream(self.geo_stream)
         keys = list(self.tables)
         torch._foreach_copy_([self.tables[k] for k in keys], [new[k] for k in keys])
-        return torch.cat([new["idx1"].reshape(-1), new["idx2"].reshape(-1), gx.reshape(-1)[:1].to(torch.int64)])
+        return torch.cat([new["idx1"].reshape(-1), new["idx2"].reshape(-1)]), gx
 
     def step_serial(self):
         """the same chain without pipelining (geometry, then features, of ONE batch): used once to check that the
@@ -209,11 +220,16 @@ class Chain:
             t = self.geometry(self.d["pos"])
         cur.wait_stream(self.geo_stream)
         gx = self.features(t)
-        return torch.cat([t["idx1"].reshape(-1), t["idx2"].reshape(-1), gx.reshape(-1)[:1].to(torch.int64)]), gx
+        return torch.cat([t["idx1"].reshape(-1), t["idx2"].reshape(-1)]), gx
 
-    def algorithmic_bytes_dominant(self):
-        """group_fwd of SA2 scale 2: 4*C*N + 8*S*K + 4*C*S*K per cloud"""
+    @staticmethod
+    def algorithmic_bytes_dominant(fused=True):
+        """grouping of SA2 scale 2 (4*C*N + 8*S*K + 4*C*S*K per cloud).  The kernel in the step is the
+        fused xyz+feature gather (p3d_group_xyz_feat_f32): it also reads the positions of both levels (12*(N+S)) and
+        writes three more channels; `fused=False` is the plain 320-channel gather (p3d_group_fwd_f32)."""
         C, Np, S, K = 320, 512, 128, 128
+        if fused:
+            return B_CLOUDS * (4 * C * Np + 12 * (Np + S) + 8 * S * K + 4 * (C + 3) * S * K)
         return B_CLOUDS * (4 * C * Np + 8 * S * K + 4 * C * S * K)
 
 
@@ -249,6 +265,20 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+def _watchdog(seconds, line_holder):
+    """the secondary sections run after the headline is measured; if one of them wedges (e.g. a collective that one
+    rank never reaches), print what is measured and leave instead of hanging the whole run"""
+    def fire():
+        if line_holder.get("line") is not None and int(os.environ.get("RANK", "0")) == 0:
+            line_holder["line"]["aborted_extras"] = "watchdog after %d s" % seconds
+            print(json.dumps(line_holder["line"]), flush=True)
+        os._exit(0 if line_holder.get("line") is not None or int(os.environ.get("RANK", "0")) != 0 else 3)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -263,6 +293,7 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")  # required to capture NCCL work in CUDA graphs
         dist.init_process_group("nccl", device_id=dev)
 
     import __graft_entry__
@@ -285,10 +316,10 @@ def run_b200(args):
     chain.prime()
     serial_out, serial_gx = chain.step_serial()
     for _ in range(2):
-        piped_out = chain.step()
+        piped_out, piped_gx = chain.step()
     torch.cuda.synchronize()
-    if not torch.equal(serial_out, piped_out):  # same inputs every step -> the pipelined step must reproduce it
-        raise SystemExit("bench.py: pipelined step disagrees with the serial chain")
+    if not (torch.equal(serial_out, piped_out) and torch.equal(serial_gx, piped_gx)):
+        raise SystemExit("bench.py: pipelined step disagrees with the serial chain")  # same inputs every step
     c0 = _cabi.launch_count()
     chain.step()
     torch.cuda.synchronize()
@@ -340,83 +371,40 @@ def run_b200(args):
     ms_total = float(ms.item())
 
     # ---- end to end: every step copies ITS inputs from pinned host memory (copy stream, one step ahead of
-    # the compute stream), runs the chain and reads its result back to pinned host memory ----
-    chain.make_staging()
-    for slot in range(2):
-        chain.consumed[slot].record(torch.cuda.current_stream())
+    # the compute stream), runs the chain and reads its result back to pinned host memory.  Measured twice:
+    # (1) the inputs a training pipeline really gets from the host (positions + input features; the SA/FP
+    #     activations x1..x3 are produced on the device by the network's MLPs) -- the headline `e2e`;
+    # (2) every tensor the chain reads, synthetic activations included, from the host (`e2e_all_from_host`,
+    #     the round-1 configuration: an upper bound on input traffic no real pipeline has).
+    def e2e_measure(keys):
+        chain.make_staging(keys)
 
-    def e2e_run(nsteps):
-        chain.h2d_async(0)
-        for i in range(nsteps):
-            slot = i & 1
-            if i + 1 < nsteps:
-                chain.h2d_async(slot ^ 1)
-            chain.stage_to_inputs(slot)
-            out = one_step()
-            chain.results[slot].copy_(out, non_blocking=True)
+        def e2e_run(nsteps):
+            chain.h2d_async(0)
+            for i in range(nsteps):
+                slot = i & 1
+                if i + 1 < nsteps:
+                    chain.h2d_async(slot ^ 1)
+                chain.stage_to_inputs(slot)
+                out = one_step()
+                for dst, src in zip(chain.results[slot], out):
+                    dst.copy_(src.reshape(dst.shape), non_blocking=True)
 
-    e2e_run(max(3, args.warmup // 2))
-    barrier()
-    e0.record()
-    e2e_run(args.steps)
-    e1.record()
-    barrier()
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_ms_total = float(ms2.item())
-    clocks = sampler.summary() if sampler else None
-
-    stack, c4 = None, None
-    if not args.skip_extras:
-        try:
-            stack = bench_kpconv_stack(dev, world, rank)
-        except Exception as e:  # noqa: BLE001  (never lose the headline line to the secondary section)
-            stack = {"error": str(e)[:200]}
-        try:
-            c4 = bench_c4(dev) if world <= 8 else None
-        except Exception as e:  # noqa: BLE001
-            c4 = {"error": str(e)[:200]}
-    if rank != 0:
+        e2e_run(max(3, args.warmup // 2))
+        barrier()
+        e0.record()
+        e2e_run(args.steps)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
-            dist.destroy_process_group()
-        return
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), chain.h2d_bytes
 
-    # ---- roofline of the dominant kernel (group_fwd, SA2 scale 2: 335 MB of stores) ----
-    peaks, peaks_src = _peaks()
-    x1 = chain.d["x1"].detach()
-    ridx = ops.ball_query(0.8, 128, chain.d["pos1"], chain.d["pos2"], return_dist=False)[0]
-    outs = [torch.empty((B_CLOUDS, 320, 128, 128), device=dev) for _ in range(2)]  # 2 x 335 MB > 126 MB L2
-
-    def dominant(i):
-        _cabi.call("p3d_group_fwd_f32", x1.data_ptr(), ridx.data_ptr(), B_CLOUDS, 320, 512, 128, 128,
-                   outs[i & 1].data_ptr(), 320 * 128 * 128, 0, torch.cuda.current_stream().cuda_stream)
-
-    for i in range(5):
-        dominant(i)
-    reps = max(args.steps, 20)
-    torch.cuda.synchronize()
-    e0.record()
-    for i in range(reps):
-        dominant(i)
-    e1.record()
-    torch.cuda.synchronize()
-    dom_ms = e0.elapsed_time(e1) / reps
-    dom_bytes = chain.algorithmic_bytes_dominant()
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "group_fwd_kernel (SA2 scale 2, [16,320,512] -> [16,320,128,128])",
-                "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": _ncu_traffic(),
-                "algorithmic_bytes": dom_bytes, "avg_launch_ms": round(dom_ms, 5), "peak_source": peaks_src}
-
-    kp = bench_kpconv(dev, args) if not args.skip_extras else None
-    operators = None
-    if not args.skip_extras:
-        try:
-            operators = bench_operators(dev)
-        except Exception as e:  # noqa: BLE001
-            operators = {"error": str(e)[:200]}
-    cpu = cpu_baseline(max_seconds=12.0) if not args.skip_extras else None
+    e2e_ms_total, e2e_h2d = e2e_measure(Chain.REAL_INPUTS)
+    e2e_all_ms_total, e2e_all_h2d = e2e_measure(None)
+    chain.upload()
+    clocks = sampler.summary() if sampler else None
 
     clouds = B_CLOUDS * world * args.steps
     line = {
@@ -432,16 +420,106 @@ def run_b200(args):
                               "the same captured graph; every batch gets the whole chain, one batch completes per step",
                    "l2": "each step streams ~1.1 GB of grouped tensors (> 126 MB L2), no flush needed"},
         "e2e": {"value": round(clouds / (e2e_ms_total * 1e-3), 2), "unit": UNIT,
-                "h2d_bytes_per_step": chain.h2d_bytes, "d2h_bytes_per_step": chain.d2h_bytes,
-                "ms_per_step": round(e2e_ms_total / args.steps, 4)},
+                "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": chain.d2h_bytes,
+                "ms_per_step": round(e2e_ms_total / args.steps, 4),
+                "inputs_from_host": "pos [16,2048,3] + input features x0 [16,3,2048] (what a data loader delivers); "
+                                    "result read back: sampled indices of both levels + d(loss)/d(x0)"},
+        "e2e_all_from_host": {"value": round(clouds / (e2e_all_ms_total * 1e-3), 2), "unit": UNIT,
+                              "h2d_bytes_per_step": e2e_all_h2d, "d2h_bytes_per_step": chain.d2h_bytes,
+                              "ms_per_step": round(e2e_all_ms_total / args.steps, 4),
+                              "inputs_from_host": "pos, x0 and the synthetic SA/FP activations x1, x2, x3 (16.8 MB that a "
+                                                  "real network produces on the device)"},
         "gpu_launches": int(launches_per_step * args.steps),
         "launches_per_step": int(launches_per_step),
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "kpconv": kp, "kpconv_stack": stack, "c4": c4,
-        "operators": operators,
+        "clocks": clocks,
     }
+    holder = {"line": line if rank == 0 else None}
+    dog = _watchdog(args.extras_timeout, holder)
+
+    def section(name, fn, all_ranks=False):
+        """secondary sections never cost the headline line: errors are recorded, not raised"""
+        if args.skip_extras or (rank != 0 and not all_ranks):
+            return
+        try:
+            res = fn()
+        except Exception as e:  # noqa: BLE001
+            res = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+        if rank == 0:
+            line[name] = res
+
+    # sections every rank takes part in (collectives / sharded work) come first, in the same order on every rank
+    section("kpconv_stack", lambda: bench_kpconv_stack(dev, world, rank), all_ranks=True)
+    section("c4", lambda: bench_c4(dev, world, rank), all_ranks=True)
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        dog.cancel()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    line["roofline"] = bench_roofline(dev, chain, args)
+    section("kpconv", lambda: bench_kpconv(dev, args))
+    section("operators", lambda: bench_operators(dev))
+    section("c1", lambda: bench_c1(dev))
+    section("c2_model", lambda: bench_c2_model(dev, line["ms_per_step"]))
+    line["cpu_baseline"] = None
+    section("cpu_baseline", lambda: cpu_baseline(max_seconds=12.0))
+    dog.cancel()
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_roofline(dev, chain, args):
+    """roofline of the dominant kernel, measured live on the launch that is IN the step: the fused xyz+feature gather
+    of SA2 scale 2 (p3d_group_xyz_feat_f32, [16,320,512] + positions -> [16,323,128,128], 339 MB of stores); the plain
+    320-channel gather (p3d_group_fwd_f32) is timed beside it.  Back-to-back launches alternate between two outputs
+    (2 x 339 MB > 126 MB L2)."""
+    import torch
+    from torch_points3d_b200 import _cabi, ops
+    peaks, peaks_src = _peaks()
+    x1 = chain.d["x1"].detach()
+    pos1, pos2 = chain.d["pos1"], chain.d["pos2"]
+    ridx = ops.ball_query(0.8, 128, pos1, pos2, return_dist=False)[0]
+    outs = [torch.empty((B_CLOUDS, 323, 128, 128), device=dev) for _ in range(2)]
+    st = torch.cuda.current_stream
+
+    def fused(i):
+        _cabi.call("p3d_group_xyz_feat_f32", pos1.data_ptr(), pos2.data_ptr(), x1.data_ptr(), ridx.data_ptr(), B_CLOUDS,
+                   320, 512, 128, 128, 1.0, outs[i & 1].data_ptr(), st().cuda_stream)
+
+    def plain(i):
+        _cabi.call("p3d_group_fwd_f32", x1.data_ptr(), ridx.data_ptr(), B_CLOUDS, 320, 512, 128, 128,
+                   outs[i & 1].data_ptr(), 323 * 128 * 128, 3, st().cuda_stream)
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def avg_ms(fn):
+        for i in range(5):
+            fn(i)
+        reps = max(args.steps, 20)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(reps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms_f, ms_p = avg_ms(fused), avg_ms(plain)
+    by_f, by_p = Chain.algorithmic_bytes_dominant(True), Chain.algorithmic_bytes_dominant(False)
+    ach_f, ach_p = by_f / (ms_f * 1e-3) / 1e9, by_p / (ms_p * 1e-3) / 1e9
+    return {"bound": "hbm",
+            "kernel": "group_fwd_kernel as launched in the step: p3d_group_xyz_feat_f32, SA2 scale 2, "
+                      "[16,320,512] + pos -> [16,323,128,128]",
+            "achieved": round(ach_f, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": round(ach_f / peaks["hbm_gbs"], 4), "traffic": _ncu_traffic(),
+            "algorithmic_bytes": by_f, "avg_launch_ms": round(ms_f, 5), "peak_source": peaks_src,
+            "frac_of_nominal_8TBs": round(ach_f / 8000.0, 4),
+            "plain_gather": {"kernel": "p3d_group_fwd_f32 (320 channels, same table)", "achieved": round(ach_p, 1),
+                             "frac": round(ach_p / peaks["hbm_gbs"], 4), "algorithmic_bytes": by_p,
+                             "avg_launch_ms": round(ms_p, 5)}}
 
 
 def _ncu_traffic():
@@ -522,8 +600,12 @@ def bench_kpconv(dev, args):
         t_fb = t_fb_graph
     with torch.no_grad():
         err = float((fwd() - fwd_fp32()).abs().max() / fwd_fp32().abs().max())
-    flops = n * (2 * 15 * 34 * 32 + 2 * 15 * 32 * 32 + 12 * 15 * 34)
-    peaks, _ = _peaks()
+    # flops = n (2 K M Cin + 2 K Cin Cout + 12 K M); bytes = 12 (n + N0) + 8 n M + 4 N0 Cin + 4 K Cin Cout + 4 n Cout
+    K_, M_, Ci, Co = 15, 34, 32, 32
+    flops = n * (2 * K_ * M_ * Ci + 2 * K_ * Ci * Co + 12 * K_ * M_)
+    nbytes = 12 * (n + n) + 8 * n * M_ + 4 * n * Ci + 4 * K_ * Ci * Co + 4 * n * Co
+    peaks, peaks_src = _peaks()
+    tf, gbs = flops / (t_f * 1e-3) / 1e12, nbytes / (t_f * 1e-3) / 1e9
     res = {"workload": "C3 layer 0b: KPConv 32->32, %d points in 8 spheres, M=34, K=15, linear/sum" % n,
            "fwd_points_per_s": round(n / (t_f * 1e-3), 1), "fwd_ms": round(t_f, 4),
            "fwd_path": "tcgen05 (bf16 hi+lo operands, fp32 accumulate in TMEM)",
@@ -532,15 +614,35 @@ def bench_kpconv(dev, args):
            "fwd_bwd_points_per_s": round(n / (t_fb * 1e-3), 1), "fwd_bwd_ms": round(t_fb, 4),
            "fwd_bwd_eager_ms": round(t_fb_eager, 4),
            "fwd_bwd_timing": "CUDA graph replay" if t_fb is not t_fb_eager and t_fb != t_fb_eager else "eager launches",
-           "fwd_tflops": round(flops / (t_f * 1e-3) / 1e12, 3),
-           "neighbour_search_ms": round(t_q, 4), "unit": "points/s"}
-    prof = os.path.join(ROOT, "profiles", "kpconv_tensor_pipe.json")
-    if os.path.exists(prof):
-        try:
-            with open(prof) as f:
-                res["tensor_pipe"] = json.load(f)
-        except Exception:  # noqa: BLE001
-            pass
+           "neighbour_search_ms": round(t_q, 4), "unit": "points/s",
+           # live roofline of the forward kernel (this build, this run): both ceilings, since the operator is a gather
+           # (HBM / L2) feeding a small dense contraction (tensor pipe); the SIMT neighbour aggregation bounds it
+           "roofline": {"flops": flops, "algorithmic_bytes": nbytes, "avg_launch_ms": round(t_f, 5),
+                        "tensor": {"achieved": round(tf, 3), "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                   "frac": round(tf / peaks["bf16_tflops_sustained"], 5)},
+                        "hbm": {"achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                "frac": round(gbs / peaks["hbm_gbs"], 4)},
+                        "peak_source": peaks_src,
+                        "ncu_capture": "profiles/r2_kpconv_fwd.json (tensor-pipe / issue counters of the same kernel)"}}
+    # CPU baseline beside it (north_star: "the torch KPConv ops" on the host cores): the oracle's restatement of
+    # convolution_ops.py:19-107 (pinned to the reference's own outputs by tests/golden/kpconv_*.npz), on a bounded sample
+    try:
+        import oracle
+        oracle.set_num_threads(os.cpu_count() or 1)
+        sub = min(n, 6000)
+        nb_h = nb[:sub].cpu().numpy()
+        pos_n, x_n, W_n, kp_n = pos_h, x.detach().cpu().numpy(), W.detach().cpu().numpy(), kp.cpu().numpy()
+        oracle.kpconv_fwd(pos_n[:64], pos_n, nb_h[:64], x_n, kp_n, W_n, 0.04, "linear", "sum")
+        t0, done = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 4.0:
+            oracle.kpconv_fwd(pos_n[:sub], pos_n, nb_h, x_n, kp_n, W_n, 0.04, "linear", "sum")
+            done += sub
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": round(done / dt, 1), "unit": "points/s", "cores": oracle.num_threads(),
+                               "kind": "port", "sample": "%d query points of the same layer through oracle.kpconv_fwd "
+                               "(forward only, %.1f s)" % (done, dt)}
+    except Exception as e:  # noqa: BLE001
+        res["cpu_baseline"] = {"error": str(e)[:160]}
     return res
 
 
@@ -670,58 +772,23 @@ def bench_operators(dev):
 
 
 def bench_kpconv_stack(dev, world, rank):
-    """C3 / C5: the KPConvPaper encoder stack (conf/models/segmentation/kpconv.yaml:14-57, S3DIS-shaped spheres,
-    ~50k points per rank, max_num_neighbors clipped to 34), forward + backward + SGD step; with more than one
-    rank the model is wrapped in DistributedDataParallel (one NCCL gradient all-reduce per step, C5)."""
+    """C3 / C5: the KPConvPaper segmentation network (encoder + FPModule_PD decoder + per-point head, NLL loss,
+    SGD momentum 0.98 -- models/segmentation/kpconv.py:106-140, conf/training/kpconv.yaml:8-16) on S3DIS-shaped spheres,
+    ~50k points per rank, max_num_neighbors clipped to 34.  With more than one rank the model is wrapped in
+    DistributedDataParallel (one NCCL gradient all-reduce per step).  Numbers: the step with the pyramid built on the
+    device inside it; with a precomputed pyramid (the reference's DataLoader configuration); the precomputed step as
+    ONE CUDA graph (forward + backward + all-reduce + SGD); and the all-reduce time that does not hide behind the
+    backward pass (step with vs without gradient synchronisation)."""
     import torch
     import torch.distributed as dist
-    from torch_points3d_b200 import kpconv, synthetic
-    pos_h, batch_h = synthetic.indoor_spheres(seed=1003 + 97 * rank)
-    pos, batch = torch.from_numpy(pos_h).to(dev), torch.from_numpy(batch_h).to(dev)
-    n = pos.shape[0]
+    from torch_points3d_b200 import segmentation
     torch.manual_seed(5)
-    enc = kpconv.KPConvEncoder(5, max_nn_cap=34).to(dev)
-    head = torch.nn.Linear(enc.out_channels, 13).to(dev)
-    model = torch.nn.Sequential()
-    model.add_module("enc", enc)
-    model.add_module("head", head)
-    params = list(model.parameters())
-    nparams = sum(p.numel() for p in params if p.requires_grad)
-    ddp = None
-    if world > 1:
-        class Wrapper(torch.nn.Module):
-            def __init__(self, enc, head):
-                super().__init__()
-                self.enc, self.head = enc, head
+    tr = segmentation.KPConvSegmentationTrainer(feat_dim=4, num_classes=13, device=dev, ddp=world > 1,
+                                                seed=1003 + 97 * rank)
+    n = int(tr.pos.shape[0])
 
-            def forward(self, pos, x, batch, ms):
-                return self.head(self.enc(pos, x, batch, precomputed=ms).x)
-        # BatchNorm statistics stay per rank (the reference has no SyncBN): no buffer broadcast every forward;
-        # gradients live in the all-reduce buckets (no copy in / out), two ~25 MB buckets overlap the backward pass
-        ddp = torch.nn.parallel.DistributedDataParallel(Wrapper(enc, head), device_ids=[dev.index],
-                                                        broadcast_buffers=False, gradient_as_bucket_view=True,
-                                                        bucket_cap_mb=25)
-    opt = torch.optim.SGD([p for p in params if p.requires_grad], lr=0.01, momentum=0.98)
-    g = torch.Generator(device=dev).manual_seed(7 + rank)
-    feats = torch.cat([torch.ones(n, 1, device=dev), torch.randn(n, 4, device=dev, generator=g)], 1)
-
-    transform = kpconv.MultiScaleTransform(enc.strategies())
-    labels_cache = {}
-
-    def step(ms=None):
-        opt.zero_grad(set_to_none=True)
-        if ms is None:  # geometry of this batch on the device, then the network (what a training loop pays per batch)
-            ms = transform(pos, batch)
-        logits = ddp(pos, feats, batch, ms) if ddp is not None else head(enc(pos, feats, batch, precomputed=ms).x)
-        if logits.shape[0] not in labels_cache:
-            labels_cache[logits.shape[0]] = torch.arange(logits.shape[0], device=dev) % 13
-        loss = torch.nn.functional.cross_entropy(logits, labels_cache[logits.shape[0]])
-        loss.backward()
-        opt.step()
-        return loss
-
-    def timed(fn, reps=10):
-        for _ in range(3):
+    def timed(fn, reps=10, warm=3):
+        for _ in range(warm):
             fn()
         torch.cuda.synchronize()
         if world > 1:
@@ -729,96 +796,253 @@ def bench_kpconv_stack(dev, world, rank):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
-            out = fn()
+            fn()
         e1.record()
         torch.cuda.synchronize()
         ms_ = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
         if world > 1:
             dist.all_reduce(ms_, op=dist.ReduceOp.MAX)
-        # only a float leaves: a live loss tensor would keep this step's autograd graph (and its AccumulateGrad
-        # nodes, bound to the eager stream) alive into the graph capture below
-        val = float(out.detach().item()) if torch.is_tensor(out) and out.numel() == 1 else None
-        del out
-        return float(ms_.item()), val
+        return float(ms_.item())
 
-    ms_full, loss = timed(step)
-    # the reference's configuration: the pyramid is precomputed (DataLoader workers there, one call here), the timed
-    # step is the network alone
-    pyramid = transform(pos, batch)
-    ms_geo, _ = timed(lambda: transform(pos, batch))
-    ms_pre, _ = timed(lambda: step(pyramid))
-    res = {"workload": "C3/C5: KPConvPaper encoder stack (10 KPConv blocks, %.1f M params), ~%d points/rank in 8 spheres, "
-                       "fwd+bwd+SGD%s" % (nparams / 1e6, n, ", DDP over NCCL" if world > 1 else ""),
-           "ms_per_step": round(ms_full, 3), "points_per_s": round(world * n / (ms_full * 1e-3), 1),
+    loss0 = tr.step()
+    ms_full = timed(lambda: tr.step_async(rebuild_geometry=True))
+    ms_geo = timed(tr.build_pyramid)
+    ms_pre = timed(lambda: tr.step_async(rebuild_geometry=False))
+    loss1 = float(tr.step_async(rebuild_geometry=False))
+    npts = torch.tensor([float(n)], device=dev)
+    if world > 1:
+        dist.all_reduce(npts)
+    total_pts = float(npts.item())
+    res = {"workload": "C3/C5: KPConvPaper segmentation network (5 KPDualBlocks down, 4 FPModule_PD up, %.1f M params), "
+                       "~%d points/rank in 8 spheres, fwd+bwd+SGD%s" % (tr.num_params / 1e6, n,
+                                                                       ", DDP over NCCL" if world > 1 else ""),
+           "ms_per_step": round(ms_full, 3), "points_per_s": round(total_pts / (ms_full * 1e-3), 1),
            "geometry_ms": round(ms_geo, 3), "precomputed_geometry_ms_per_step": round(ms_pre, 3),
-           "loss": round(loss, 4), "unit": "points/s"}
-    if world == 1:
-        # with the pyramid given, every shape of the step is static: capture forward + backward + SGD in one graph
-        # (the parameters' AccumulateGrad nodes were created on the eager stream: the mismatch is intended here)
-        quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
-        if quiet is not None:
-            quiet(False)
-        try:
-            opt.zero_grad(set_to_none=False)
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(2):
-                    opt.zero_grad(set_to_none=False)
-                    lg = head(enc(pos, feats, batch, precomputed=pyramid).x)
-                    torch.nn.functional.cross_entropy(lg, labels_cache[lg.shape[0]]).backward()
-                    opt.step()
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                opt.zero_grad(set_to_none=False)
-                lg = head(enc(pos, feats, batch, precomputed=pyramid).x)
-                gloss = torch.nn.functional.cross_entropy(lg, labels_cache[lg.shape[0]])
-                gloss.backward()
-                opt.step()
-            ms_graph, _ = timed(lambda: graph.replay() or None)
-            res["precomputed_geometry_cuda_graph_ms_per_step"] = round(ms_graph, 3)
-            res["points_per_s_graph"] = round(n / ((ms_graph + ms_geo) * 1e-3), 1)
-            res["graph_loss"] = round(float(gloss.item()), 4)
-        except Exception as e:  # noqa: BLE001
-            res["cuda_graph_error"] = str(e)[:160]
+           "loss_first": round(loss0, 4), "loss_after": round(loss1, 4), "unit": "points/s"}
+    if world > 1:
+        with_sync, no_sync = segmentation.exposed_allreduce_ms(tr)
+        t = torch.tensor([with_sync, no_sync], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res["allreduce"] = {"collective": "DistributedDataParallel gradient all-reduce (NCCL ring/NVLS over NVSwitch), "
+                                          "%.1f MB fp32 in 25 MB buckets" % (tr.num_params * 4 / 1e6),
+                            "step_ms_with_sync": round(float(t[0]), 3), "step_ms_without_sync": round(float(t[1]), 3),
+                            "exposed_ms": round(float(t[0] - t[1]), 3)}
+        # no_sync steps let the ranks' parameters drift apart: put them back in step before the graph section
+        for p_ in tr.model.parameters():
+            dist.broadcast(p_.data, 0)
+    ok = torch.ones(1, device=dev)
+    try:
+        tr.capture()
+    except Exception as e:  # noqa: BLE001
+        ok.zero_()
+        res["cuda_graph_error"] = "%s: %s" % (type(e).__name__, str(e)[:200])
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # replay only if every rank captured
+    if float(ok.item()) > 0:
+        ms_graph = timed(tr.replay)
+        res["precomputed_geometry_cuda_graph_ms_per_step"] = round(ms_graph, 3)
+        res["points_per_s_graph"] = round(total_pts / ((ms_graph + ms_geo) * 1e-3), 1)
+        res["graph_loss"] = round(float(tr.graph_loss.item()), 4)
     return res
 
 
-def bench_c4(dev):
-    """C4 (BASELINE.json configs[3]): SemanticKITTI-shaped FPS 4096 of 120k + knn k=16, this rank's clouds"""
+def bench_c4(dev, world, rank):
+    """C4 (BASELINE.json configs[3]): SemanticKITTI-shaped scans, FPS 4096 of 120 000 + knn k = 16, batch of 8 scans
+    sharded by cloud over the ranks.  Timed twice: the two operators alone, and the RandLA-Net down-convolution chain
+    the config names -- sampler -> KNNNeighbourFinder(16) -> RandlaKernel (BaseConvolutionDown.forward,
+    core/base_conv/message_passing.py:44-58; modules/RandLANet/modules.py:9-67) with the chain's stock MLPs."""
     import torch
-    from torch_points3d_b200 import ops, synthetic
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
+    import torch.distributed as dist
+    from torch_points3d_b200 import message_passing as mp, ops, partial_dense as pd, spatial_ops, synthetic
     from torch_points3d_b200.sharding import cloud_range
     lo, hi = cloud_range(8, world, rank)
-    scans = torch.from_numpy(synthetic.lidar_scans(B=8)[lo:hi]).to(dev)
+    scans_h = synthetic.lidar_scans(B=8)[lo:hi]
+    scans = torch.from_numpy(scans_h).to(dev)
     b = hi - lo
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     x = scans.reshape(-1, 3)
     bx = torch.arange(b, device=dev).repeat_interleave(120000)
     by = torch.arange(b, device=dev).repeat_interleave(4096)
 
-    def step():
+    def step_ops():
         qi = ops.furthest_point_sample(scans, 4096)
         q = scans.gather(1, qi.unsqueeze(-1).expand(-1, -1, 3)).reshape(-1, 3)
         return ops.knn_table(x, q, 16, bx, by, return_dist=False)[0]
 
-    step()
+    torch.manual_seed(9)
+    conv = mp.RandlaConv(ratio=4096.0 / 120000.0, k=16, sampler=spatial_ops.FPSSampler(num_to_sample=4096 * b, random_start=False),
+                         point_pos_nn=[10, 8, 3], attention_nn=[6, 8, 6], down_conv_nn=[6, 8, 16]).to(dev).eval()
+    data = pd._Data(x=x, pos=x, batch=bx)
+
+    def step_chain():
+        with torch.no_grad():
+            return conv(data).x
+
+    def timed(fn, warm=3, reps=10):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_fps = timed(lambda: ops.furthest_point_sample(scans, 4096))
+    ms_ops = timed(step_ops)
+    ms_chain = timed(step_chain)
+    res = {"workload": "C4: FPS 4096 of 120000 + knn k=16, batch of 8 scans sharded over %d GPU(s)" % world,
+           "ms_per_batch": round(ms_ops, 3), "clouds_per_s": round(8 / (ms_ops * 1e-3), 2),
+           "fps_ms": round(ms_fps, 3), "knn_ms": round(ms_ops - ms_fps, 3),
+           "us_per_fps_round": round(ms_fps * 1e3 / 4095, 3),
+           "randla_chain_ms_per_batch": round(ms_chain, 3), "randla_chain_clouds_per_s": round(8 / (ms_chain * 1e-3), 2),
+           "timing": "3 warm-ups, 10 repetitions, CUDA events, max over ranks"}
+    if rank == 0:
+        try:
+            res["cpu_baseline"] = cpu_c4(scans_h[:1])
+        except Exception as e:  # noqa: BLE001
+            res["cpu_baseline"] = {"error": str(e)[:160]}
+    return res
+
+
+def cpu_c4(scan):
+    """host-core baseline of C4 on ONE scan: FPS through the oracle (the ATen-loop restatement of torch_cluster's fps is
+    ~6 s per scan) and knn through scipy's cKDTree (stand-in for the nanoflann kd-tree inside
+    torch_cluster / torch-points-kernels, which is not installable here), all host threads"""
+    import oracle
+    from scipy.spatial import cKDTree
+    oracle.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    idx = oracle.fps_dense(scan, 4096)
+    t_fps = time.perf_counter() - t0
+    q = np.take_along_axis(scan, idx[..., None], 1)[0]
+    t0 = time.perf_counter()
+    tree = cKDTree(scan[0])
+    tree.query(q, k=16, workers=-1)
+    t_kd = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    oracle.knn_csr(scan[0], q, 16, np.array([0, scan.shape[1]]), np.array([0, 4096]))
+    t_bf = time.perf_counter() - t0
+    total = t_fps + t_kd
+    return {"value": round(1.0 / total, 3), "unit": "clouds/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "1 of the 8 scans: oracle FPS %.3f s (one thread per cloud) + cKDTree build+query %.3f s "
+                      "(workers=-1; kd-tree stand-in for nanoflann); oracle brute-force knn %.3f s" % (t_fps, t_kd, t_bf)}
+
+
+def bench_c1(dev):
+    """C1 (BASELINE.json configs[0], the reference's own CPU-runnable case): FPS 512 of 1024 + ball_query r = 0.2 k = 32
+    + grouping of 64 feature channels, batch of 16 clouds -- the dense SA-layer chain of core/base_conv/dense.py:60-87"""
+    import torch
+    from torch_points3d_b200 import ops, synthetic
+    xyz_h = synthetic.surface_clouds(16, 1024, 1001)
+    xyz = torch.from_numpy(xyz_h).to(dev)
+    feat = torch.randn((16, 64, 1024), device=dev, generator=torch.Generator(device=dev).manual_seed(1001))
+
+    def step():
+        idx, new_xyz = ops.furthest_point_sample(xyz, 512, return_xyz=True)
+        ridx = ops.ball_query(0.2, 32, xyz, new_xyz, return_dist=False)[0]
+        return ops.group_features(feat, xyz, new_xyz, ridx)
+
+    for _ in range(3):
+        step()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        keep = step()  # noqa: F841
+    for _ in range(5):
+        graph.replay()
     torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 50
     e0.record()
-    for _ in range(2):
+    for _ in range(reps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"workload": C1_WORKLOAD, "ms_per_step": round(ms, 4), "clouds_per_s": round(16 / (ms * 1e-3), 1),
+            "unit": "clouds/s", "cpu_baseline": cpu_c1(4.0)}
+
+
+C1_WORKLOAD = "C1: PointNet++ SA-layer op chain forward: FPS 512 of 1024 + ball_query r=0.2 k=32 + grouping C=64+3, batch 16"
+
+
+def cpu_c1(max_seconds):
+    import oracle
+    from torch_points3d_b200 import synthetic
+    oracle.set_num_threads(os.cpu_count() or 1)
+    xyz = synthetic.surface_clouds(16, 1024, 1001)
+    feat = np.random.default_rng(1001).standard_normal((16, 64, 1024)).astype(np.float32)
+    pos_t = np.ascontiguousarray(xyz.transpose(0, 2, 1))
+
+    def once():
+        idx = oracle.fps_dense(xyz, 512)
+        new = np.take_along_axis(xyz, idx[..., None], 1)
+        ridx, _ = oracle.ball_query_dense(0.2, 32, xyz, new)
+        gp = oracle.group_fwd(pos_t, ridx)
+        gp -= new.transpose(0, 2, 1)[..., None]
+        oracle.group_fwd(feat, ridx)
+
+    once()
+    t0, done = time.perf_counter(), 0
+    while time.perf_counter() - t0 < max_seconds:
+        once()
+        done += 16
+    dt = time.perf_counter() - t0
+    return {"value": round(done / dt, 2), "unit": "clouds/s", "cores": oracle.num_threads(), "kind": "port",
+            "sample": "%d clouds of the C1 chain through oracle/p3d_oracle.c (%.1f s)" % (done, dt)}
+
+
+def bench_c2_model(dev, chain_ms):
+    """BASELINE.json configs[1] as the reference runs it: the whole `pointnet2_charlesmsg` network
+    (conf/models/segmentation/pointnet2.yaml:95-130; models/segmentation/pointnet2.py:90-113), forward + cross-entropy
+    on 50 classes + backward + Adam step, batch 16 x 2048 points with 3 normals.  Operators from libp3d_b200.so, MLPs /
+    BatchNorm / max-pool stock cuDNN as in the reference.  Places the operator chain against the only published
+    figure: `iteration=0.231 s` per batch of 16 (benchmark/shapenet/pointnet2_charlesmsg.md:211, hardware not stated)."""
+    import torch
+    from torch_points3d_b200 import pointnet2, synthetic
+    torch.manual_seed(12)
+    pos_h = synthetic.surface_clouds(B_CLOUDS, N_PTS, 1002)
+    pos = torch.from_numpy(pos_h).to(dev)
+    nrm = pos / (pos.norm(dim=-1, keepdim=True) + 1e-12)
+    labels = torch.randint(0, 50, (B_CLOUDS, N_PTS), device=dev)
+    model = pointnet2.PointNet2_D(feat_dim=3, num_classes=50).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = model.loss(model(pos, nrm), labels)
+        loss.backward()
+        opt.step()
+        return loss
+
+    losses = [float(step()) for _ in range(5)]
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record()
+    for _ in range(reps):
         step()
     e1.record()
     torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1) / 2], device=dev)
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
-    return {"workload": "C4: FPS 4096 of 120000 + knn k=16, batch of 8 scans sharded over %d GPU(s)" % world,
-            "ms_per_batch": round(ms, 3), "clouds_per_s": round(8 / (ms * 1e-3), 2)}
+    ms = e0.elapsed_time(e1) / reps
+    return {"workload": "C2 full model: pointnet2_charlesmsg fwd + cross-entropy + bwd + Adam, batch 16 x 2048 (eager)",
+            "ms_per_step": round(ms, 3), "clouds_per_s": round(B_CLOUDS / (ms * 1e-3), 1),
+            "loss_first": round(losses[0], 4), "loss_fifth": round(losses[-1], 4),
+            "operator_chain_ms": chain_ms, "operator_share_of_step": round(chain_ms / ms, 3),
+            "published_reference": {"iteration_s": 0.231, "clouds_per_s": round(16 / 0.231, 1), "hardware": "not stated",
+                                    "source": "benchmark/shapenet/pointnet2_charlesmsg.md:211"},
+            "speedup_vs_published_iteration": round(231.0 / ms, 1)}
 
 
 # ------------------------------------------------------------ CPU arm (oracle port) -----------
@@ -900,6 +1124,10 @@ def run_reference(args):
                              "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    try:  # the reference's own CPU-runnable case (BASELINE.json configs[0]) beside the headline
+        line["c1"] = {"workload": C1_WORKLOAD, **cpu_c1(4.0)}
+    except Exception as e:  # noqa: BLE001
+        line["c1"] = {"error": str(e)[:160]}
     print(json.dumps(line))
 
 
@@ -912,6 +1140,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph replay")
     ap.add_argument("--skip-extras", action="store_true",
                     help="profiling runs: skip the KPConv section and the CPU baseline")
+    ap.add_argument("--extras-timeout", type=int, default=420,
+                    help="seconds the secondary sections may take before the measured line is printed without them")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

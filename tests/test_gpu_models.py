@@ -103,7 +103,10 @@ def test_kpconv_paper_network_trains_and_pyramid_paths_agree():
     with torch.no_grad():
         a = model(pos, feats, batch)
         b = model(pos, feats, batch, multiscale=ms, upsample=up)
-    assert torch.equal(a, b)
+    # the encoder half is bit-identical (test_multiscale_transform_precomputed_path_equals_on_the_fly); the decoder's
+    # two routes weight with 1/d2 from different fp32 expressions (kernel d2 vs the (diff*diff).sum of
+    # interpolate.py:27-28), so (x*w)/w rounds differently in the last bit -- in the reference as well
+    assert relerr(N(a), N(b)) <= 1e-5
     model.train()
     opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9)
     losses = []
@@ -163,7 +166,14 @@ def test_reference_format_pyramid_feeds_the_blocks():
         fly = model(pos, x, batch)
         rep = model(pos, x, batch, multiscale=repaired, upsample=mb.upsample)
         raw = model(pos, x, batch, multiscale=mb.multiscale, upsample=mb.upsample)
-    assert torch.equal(fly, rep)
+    assert relerr(N(fly), N(rep)) <= 1e-5
+    # encoder only (no interpolation arithmetic in between): bit for bit
+    d_fly = kpconv.Cloud(pos, kpconv.add_ones(pos, x, True), batch)
+    d_rep = d_fly.clone()
+    with torch.no_grad():
+        for m in model.down_modules:
+            d_fly, d_rep = m(d_fly), m(d_rep, precomputed=repaired)
+    assert torch.equal(d_fly.x, d_rep.x)
     assert torch.isfinite(raw).all() and raw.shape == fly.shape
 
 

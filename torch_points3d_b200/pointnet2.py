@@ -112,3 +112,69 @@ class DenseFPModule(nn.Module):
             new_features = torch.cat([new_features, data_skip.x], dim=1)
         new_features = self.nn(new_features.unsqueeze(-1))
         return SimpleNamespace(x=new_features.squeeze(-1), pos=data_skip.pos)
+
+
+def Conv1D(in_channels, out_channels, bias=True, bn=True, activation="default"):
+    """common_modules/dense_modules.py:15-22"""
+    layers = [nn.Conv1d(in_channels, out_channels, kernel_size=1, bias=bias)]
+    if bn:
+        layers.append(nn.BatchNorm1d(out_channels))
+    if activation == "default":
+        activation = nn.LeakyReLU(negative_slope=0.01)
+    if activation:
+        layers.append(activation)
+    return nn.Sequential(*layers)
+
+
+class GlobalDenseBaseModule(nn.Module):
+    """core/base_conv/dense.py:150-185: MLP over cat(x, pos^T), max / mean over the points, `pos = None` afterwards"""
+
+    def __init__(self, nn, aggr="max", bn=True, activation=None, **kwargs):
+        super().__init__()
+        self.nn = MLP2D(nn, bn=bn, activation=activation, bias=False)
+        if aggr.lower() not in ["mean", "max"]:
+            raise Exception("The aggregation provided is unrecognized {}".format(aggr))
+        self._aggr = aggr.lower()
+
+    def forward(self, data, **kwargs):
+        x, pos = data.x, data.pos
+        x = self.nn(torch.cat([x, pos.transpose(1, 2).contiguous()], dim=1).unsqueeze(-1))
+        x = x.squeeze(-1).max(-1)[0] if self._aggr == "max" else x.squeeze(-1).mean(-1)
+        return SimpleNamespace(x=x.unsqueeze(-1), pos=None)
+
+
+class PointNet2_D(nn.Module):
+    """models/segmentation/pointnet2.py:19-113 with the `pointnet2_charlesmsg` architecture resolved
+    (conf/models/segmentation/pointnet2.yaml:95-130): two multi-scale-grouping SA levels, the global module, three
+    feature-propagation levels wired as UnetBasedModel nests them (skip connections to the level's input), and the
+    mlp_cls head (Conv1D 128 -> 128 + BN, Dropout 0.5, Conv1D 128 -> classes).  forward(pos [B,N,3], x [B,N,FEAT])
+    returns the [B*N, classes] logits of pointnet2.py:103; `loss` is its cross-entropy (:108-110)."""
+
+    def __init__(self, feat_dim=3, num_classes=50, dropout=0.5):
+        super().__init__()
+        F_ = feat_dim
+        self.down = nn.ModuleList([
+            PointNetMSGDown(npoint=512, radii=[0.1, 0.2, 0.4], nsample=[32, 64, 128],
+                            down_conv_nn=[[F_ + 3, 32, 32, 64], [F_ + 3, 64, 64, 128], [F_ + 3, 64, 96, 128]]),
+            PointNetMSGDown(npoint=128, radii=[0.4, 0.8], nsample=[64, 128],
+                            down_conv_nn=[[64 + 128 + 128 + 3, 128, 128, 256], [64 + 128 + 128 + 3, 128, 196, 256]])])
+        self.inner = GlobalDenseBaseModule([256 * 2 + 3, 256, 512, 1024])
+        self.up = nn.ModuleList([DenseFPModule([1024 + 256 * 2, 256, 256]),
+                                 DenseFPModule([256 + 128 * 2 + 64, 256, 128]),
+                                 DenseFPModule([128 + F_, 128, 128])])
+        self.FC_layer = nn.Sequential(Conv1D(128, 128, bn=True, bias=False), nn.Dropout(p=dropout),
+                                      Conv1D(128, num_classes, activation=None, bias=True, bn=False))
+        self._num_classes = num_classes
+
+    def forward(self, pos, x):
+        d0 = SimpleNamespace(pos=pos, x=None if x is None else x.transpose(1, 2).contiguous())
+        d1 = self.down[0](d0)
+        d2 = self.down[1](d1)
+        u = self.inner(d2)
+        u = self.up[0]((u, d2))
+        u = self.up[1]((u, d1))
+        u = self.up[2]((u, d0))
+        return self.FC_layer(u.x).transpose(1, 2).contiguous().view((-1, self._num_classes))
+
+    def loss(self, logits, labels):
+        return F.cross_entropy(logits, torch.flatten(labels).long())
