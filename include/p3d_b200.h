@@ -119,6 +119,21 @@ int p3d_knn_batch_f32(const float *x, const float *y, const int64_t *batch_x, co
 int p3d_knn_dense_f32(const float *x, const float *y, int B, int N, int M, int k, int64_t *idx, float *d2,
                       void *stream);
 
+/* Cell-list accelerated forms of the two batched searches (csrc/cellgrid.cu).  Same arguments and BIT-IDENTICAL
+ * results as p3d_ball_query_batch_f32 / p3d_knn_batch_f32 -- first `nsample` hits in candidate index order, resp. the k
+ * nearest ordered by (d2, index) -- but a query only meets the support points of the 27 lattice cells around it
+ * (knn: growing cubes of cells, with a plain sweep when the neighbourhood is sparse).  The support points are hashed
+ * by (cloud, cell) on the device in `ws` (p3d_cellgrid_ws_bytes(Nx) bytes, 256-byte aligned); nothing is read back.
+ * Worth it when clouds hold thousands of points (KPConv levels: neighbour_finder.py:34-37 at ~6k points per cloud;
+ * RandLA / FPModule knn: neighbour_finder.py:46-47, interpolate.py:25); nsample <= 64, k <= 32. */
+size_t p3d_cellgrid_ws_bytes(int64_t Nx);
+int p3d_ball_query_batch_grid_f32(const float *x, const float *y, const int64_t *batch_x, const int64_t *batch_y,
+                                  int64_t Nx, int64_t Ny, float radius, int nsample, int strict, int64_t shadow,
+                                  int64_t *idx, float *dist2, void *ws, size_t ws_bytes, void *stream);
+int p3d_knn_batch_grid_f32(const float *x, const float *y, const int64_t *batch_x, const int64_t *batch_y, int64_t Nx,
+                           int64_t Ny, int k, int64_t *col, float *d2, void *ws, size_t ws_bytes, void *stream);
+
+
 /* Replaces tp.three_nn(unknown[B,n,3], known[B,m,3]) -> (dist[B,n,3] = sqrt(d2), idx[B,n,3])
  *   reference call site: core/base_conv/dense.py:136
  * weight (nullable) [B,n,3]: the inverse-distance weights of core/base_conv/dense.py:137-139,
@@ -186,7 +201,7 @@ int p3d_three_interp_bwd_f32(const float *dout, const int64_t *idx, const float 
  * three MMAs per product: relative error ~1e-5 of max|out|, stated and tested at 2e-5) when
  * Cin % 32 == 0, Cout % 32 == 0, Cout <= 512, M <= 40 and a workspace of
  * p3d_kpconv_fwd_ws_bytes() is given; other shapes and P3D_PRECISION_FP32 use exact fp32 SIMT. */
-size_t p3d_kpconv_fwd_ws_bytes(int K, int Cin, int Cout);
+size_t p3d_kpconv_fwd_ws_bytes(int64_t n, int K, int Cin, int Cout);
 int p3d_kpconv_fwd_f32(const float *query, const float *support, const int64_t *neighbors, const float *feat,
                        const float *k_points, const float *k_values, int64_t n, int64_t N0, int M, int K, int Cin,
                        int Cout, float extent, int influence, int aggregation, int precision, float *out,

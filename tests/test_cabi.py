@@ -43,8 +43,9 @@ def test_library_loads_and_reports_arch(cabi):
     assert lib.p3d_fps_dense_ws_bytes(4, 1024) == 0
     assert lib.p3d_fps_dense_ws_bytes(2, 200000) == 2 * 200000 * 4
     # wf + dwf buffers, plus the bf16 hi/lo image of W^T for the tensor-core dwf GEMM (15 x 32 outputs / 32 per chunk x 4 pieces x 16 KB)
-    assert lib.p3d_kpconv_bwd_ws_bytes(10, 34, 15, 32, 32) == 2 * 10 * 15 * 32 * 4 + 15 * 4 * 16384
-    assert lib.p3d_kpconv_bwd_ws_bytes(10, 34, 15, 5, 64) == 2 * 10 * 15 * 5 * 4
+    # ... plus the partial blocks of the deterministic dW reduction (one point chunk here: K*Cin x Cout floats)
+    assert lib.p3d_kpconv_bwd_ws_bytes(10, 34, 15, 32, 32) == 2 * 10 * 15 * 32 * 4 + 15 * 4 * 16384 + 480 * 32 * 4
+    assert lib.p3d_kpconv_bwd_ws_bytes(10, 34, 15, 5, 64) == 2 * 10 * 15 * 5 * 4 + 75 * 64 * 4
 
 
 def test_sass_is_sm100a_only(cabi):
@@ -64,7 +65,9 @@ def test_argument_validation_is_reported_not_crashed(cabi):
     assert lib.p3d_three_nn_f32(None, None, 1, 4, 2, None, None, None, None) == -1
     assert lib.p3d_kpconv_fwd_f32(None, None, None, None, None, None, 4, 4, 200, 15, 8, 8, 1.0, 1, 0, 1, None, None,
                                   0, None) == -1
-    assert lib.p3d_kpconv_fwd_ws_bytes(15, 32, 64) == 1 * 2 * 2 * 32768 and lib.p3d_kpconv_fwd_ws_bytes(15, 5, 64) == 0
+    assert lib.p3d_kpconv_fwd_ws_bytes(100000, 15, 32, 64) == 1 * 2 * 2 * 32768 and lib.p3d_kpconv_fwd_ws_bytes(100000, 15, 5, 64) == 0
+    # few query points: the slabs of the contraction are split over CTAs, partial outputs live in the workspace
+    assert lib.p3d_kpconv_fwd_ws_bytes(100, 15, 512, 512) > 16 * 16 * 4 * 16384
     # empty problems are a successful no-op
     assert lib.p3d_fps_dense_f32(None, 0, 4, 2, None, 1, None, None, 0, None) == 0
     assert lib.p3d_ball_query_dense_f32(None, None, 0, 0, 0, 0.1, 4, 1, None, None, None) == 0
@@ -242,7 +245,7 @@ def test_kpconv_autograd_plumbing_with_stubbed_device_calls(monkeypatch):
     monkeypatch.setattr(ops, "_require_cuda", lambda name, *t: torch.device("cpu"))
 
     class FakeLib:
-        def p3d_kpconv_fwd_ws_bytes(self, K, Cin, Cout):
+        def p3d_kpconv_fwd_ws_bytes(self, n, K, Cin, Cout):
             return 1024 if Cin % 32 == 0 and Cout % 32 == 0 else 0
 
         def p3d_kpconv_bwd_ws_bytes(self, *a):

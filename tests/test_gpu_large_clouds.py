@@ -55,6 +55,29 @@ def test_fps_cluster_variants_bit_exact(B, n, S):
     assert np.array_equal(got, oracle.fps_dense(xyz, S))
 
 
+def test_fps_pruned_kernel_ties_and_orders():
+    """the bounding-box-pruned cluster kernel (32 769..131 072 points): exact ties (integer lattice, duplicated and
+    identical points) go to the lowest index; the result does not depend on how compact consecutive points are
+    (lattice order = compact blocks, shuffled order = every block spans the cloud, pruning never fires)"""
+    g = np.stack(np.meshgrid(np.arange(36), np.arange(36), np.arange(36), indexing="ij"), -1).reshape(1, -1, 3)
+    lattice = g.astype(np.float32) * 0.25
+    assert np.array_equal(N(ops.furthest_point_sample(T(lattice), 300)), oracle.fps_dense(lattice, 300))
+    rng = np.random.default_rng(11)
+    shuffled = lattice[:, rng.permutation(lattice.shape[1])]
+    assert np.array_equal(N(ops.furthest_point_sample(T(shuffled), 300)), oracle.fps_dense(shuffled, 300))
+    same = np.ones((2, 40000, 3), dtype=np.float32)
+    assert np.array_equal(N(ops.furthest_point_sample(T(same), 6)), oracle.fps_dense(same, 6))
+    dup = synthetic.surface_clouds(1, 50000, seed=77)
+    dup[0, 25000:] = dup[0, :25000]          # every point twice: each round is a two-way tie
+    assert np.array_equal(N(ops.furthest_point_sample(T(dup), 500)), oracle.fps_dense(dup, 500))
+    # CSR form with a random start inside a large cloud and a small cloud beside it
+    pos = np.concatenate([synthetic.surface_clouds(1, 70000, seed=78)[0], synthetic.surface_clouds(1, 900, seed=79)[0]])
+    batch = np.repeat(np.arange(2), [70000, 900])
+    ptr = oracle.batch_to_ptr(batch)
+    got = N(ops.fps(T(pos), T(batch), ratio=0.004, random_start=False))
+    assert np.array_equal(got, oracle.fps_csr(pos, ptr, oracle.fps_counts(ptr, 0.004)))
+
+
 def test_fps_c4_shape_all_rounds_bit_exact(scans):
     """B = 8 x 120 000 -> 4096 (the kernel bench_c4 times at N = 1) and B = 1 (one scan per GPU at N = 8)"""
     want = oracle.fps_dense(scans, 4096)

@@ -30,6 +30,10 @@ SIGNATURES = {
                                          c_vp, c_vp]),
     "p3d_knn_batch_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp]),
     "p3d_knn_dense_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "p3d_cellgrid_ws_bytes": (c_sz, [c_i64]),
+    "p3d_ball_query_batch_grid_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_f32, c_int, c_int, c_i64, c_vp,
+                                              c_vp, c_vp, c_sz, c_vp]),
+    "p3d_knn_batch_grid_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "p3d_three_nn_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "p3d_group_fwd_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64, c_int, c_vp]),
     "p3d_group_bwd_ws_bytes": (c_sz, [c_int, c_int, c_int, c_int, c_int]),
@@ -43,7 +47,7 @@ SIGNATURES = {
     "p3d_three_interp_bwd_prepare": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_sz, c_vp]),
     "p3d_three_interp_bwd_f32": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_sz, c_int,
                                          c_vp]),
-    "p3d_kpconv_fwd_ws_bytes": (c_sz, [c_int, c_int, c_int]),
+    "p3d_kpconv_fwd_ws_bytes": (c_sz, [c_i64, c_int, c_int, c_int]),
     "p3d_kpconv_fwd_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_int,
                                    c_f32, c_int, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
     "p3d_kpconv_bwd_ws_bytes": (c_sz, [c_i64, c_int, c_int, c_int, c_int]),

@@ -16,6 +16,7 @@
 //   * clusters: each CTA's winner record is pushed into every peer's shared memory through
 //     DSMEM, then one barrier.cluster per round.
 #include <cooperative_groups.h>
+#include <math_constants.h>
 
 #include "common.cuh"
 
@@ -174,6 +175,208 @@ fps_reg_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr, i
         // no CTA may exit while a peer can still write into its shared memory
         cg::this_cluster().sync();
     }
+}
+
+// ---- large clouds: cluster kernel with exact bounding-box pruning and a one-hop record exchange -------------------
+// One cloud per cluster of CLUSTER CTAs.  Every thread owns PPT CONSECUTIVE points of the cloud: their running
+// min-distances live in registers, their coordinates in the CTA's shared memory (slot = j * T + tid: conflict-free),
+// plus the bounding box of the block and the (value, slot) of its current farthest point.
+//   * pruning: a round's new sample can only lower a min-distance if it is closer to the point than that
+//     min-distance.  With d_box = squared distance from the sample to the block's bounding box -- computed with the
+//     same fp32 operations as sqdist3, so d_box <= d2(sample, p) holds bit-exactly for every p of the block (fp32
+//     subtraction, multiplication and addition are monotone) -- a block with d_box >= max(min-distances) is untouched
+//     by the round and keeps its cached farthest point.  After a few hundred samples almost every block is skipped;
+//     how many depends on how compact 32 consecutive points are (scan order, voxel order: very; random order: the
+//     kernel degrades to the unpruned update, results never change).
+//   * exchange: each WARP pushes its 32-byte record (key, index, coordinates) straight into every CTA of the cluster
+//     with st.async (remote shared-memory store that signals the receiver's mbarrier with complete_tx); a CTA then
+//     waits on its OWN mbarrier for CLUSTER x warps records and every warp reduces them redundantly.  One remote hop
+//     per round: no __syncthreads, no CTA-level reduction, no barrier.cluster on the critical path.
+//   Records and barriers are double-buffered by round parity: a CTA can be at most one round ahead of a peer.
+struct __align__(16) FpsRec32 {
+    unsigned key, idx;
+    float x, y, z;
+    unsigned pad[3];
+};
+
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+                 "r"(a), "r"(b), "r"(c), "r"(d), "r"(rbar)
+                 : "memory");
+}
+__device__ __forceinline__ void fps_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fps_mbar_expect(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void fps_mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FPS_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra FPS_DONE_%=;\n"
+        "bra FPS_WAIT_%=;\n"
+        "FPS_DONE_%=:\n"
+        "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <int T, int PPT, int CLUSTER, typename IdxT>
+__global__ void __launch_bounds__(T, 1)
+fps_pruned_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr, int64_t n_dense,
+                  const int64_t *__restrict__ out_ptr, int64_t s_dense, IdxT *__restrict__ out,
+                  const int64_t *__restrict__ first, float *__restrict__ new_xyz) {
+    constexpr int NW = T / 32;
+    constexpr int NREC = CLUSTER * NW;           // records a CTA receives per round
+    static_assert(NREC % 32 == 0 && NREC <= 256, "record count per round");
+    extern __shared__ float csm[];               // cx | cy | cz, T * PPT floats each (slot = j * T + tid)
+    float *cx = csm, *cy = csm + T * PPT, *cz = csm + 2 * T * PPT;
+    __shared__ FpsRec32 recs[2][NREC];
+    __shared__ __align__(8) uint64_t bars[2];
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cloud = blockIdx.x / CLUSTER;
+    const int rank = blockIdx.x % CLUSTER;
+
+    int64_t start, n, s, obase, add;
+    if (ptr != nullptr) {
+        start = ptr[cloud];
+        n = ptr[cloud + 1] - start;
+        obase = out_ptr[cloud];
+        s = out_ptr[cloud + 1] - obase;
+        add = start;
+    } else {
+        start = (int64_t)cloud * n_dense;
+        n = n_dense;
+        obase = (int64_t)cloud * s_dense;
+        s = s_dense;
+        add = 0;
+    }
+    if (s > n) s = n;
+
+    const float *__restrict__ p = xyz + 3 * start;
+    // this thread's block of consecutive points: [blk, blk + PPT)
+    const int64_t blk = ((int64_t)rank * T + tid) * PPT;
+    float md[PPT];
+    float bx0 = CUDART_INF_F, by0 = CUDART_INF_F, bz0 = CUDART_INF_F, bx1 = -CUDART_INF_F, by1 = -CUDART_INF_F,
+          bz1 = -CUDART_INF_F;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int64_t i = blk + j;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (i < n) {
+            x = p[3 * i]; y = p[3 * i + 1]; z = p[3 * i + 2];
+            md[j] = 1e10f;
+            bx0 = fminf(bx0, x); by0 = fminf(by0, y); bz0 = fminf(bz0, z);
+            bx1 = fmaxf(bx1, x); by1 = fmaxf(by1, y); bz1 = fmaxf(bz1, z);
+        } else {
+            md[j] = -1.f;  // never selected: min(-1, d) stays -1
+        }
+        cx[j * T + tid] = x; cy[j * T + tid] = y; cz[j * T + tid] = z;
+    }
+    float mybest = blk < n ? 1e10f : -1.f;   // max of md[] (exact), and the first slot that holds it
+    int myj = 0;
+
+    if (tid == 0) {
+        fps_mbar_init(&bars[0], 1);
+        fps_mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    float lx = 0.f, ly = 0.f, lz = 0.f;
+    int64_t f0 = 0;
+    if (n > 0) {
+        if (first != nullptr) {
+            f0 = first[cloud];
+            f0 = f0 < 0 ? 0 : (f0 >= n ? n - 1 : f0);
+        }
+        lx = p[3 * f0]; ly = p[3 * f0 + 1]; lz = p[3 * f0 + 2];
+    }
+    if (tid == 0 && rank == 0 && s > 0) {
+        out[obase] = (IdxT)(add + f0);
+        if (new_xyz) { new_xyz[3 * obase] = lx; new_xyz[3 * obase + 1] = ly; new_xyz[3 * obase + 2] = lz; }
+    }
+    cluster.sync();  // every CTA's barriers are initialised before the first remote store can arrive
+
+    // remote addresses of this warp's record slot and of the barriers in CTA `lane` (lanes < CLUSTER push)
+    const uint32_t my_rec0 = (uint32_t)__cvta_generic_to_shared(&recs[0][rank * NW + warp]);
+    const uint32_t my_rec1 = (uint32_t)__cvta_generic_to_shared(&recs[1][rank * NW + warp]);
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&bars[0]);
+    const uint32_t bar1 = (uint32_t)__cvta_generic_to_shared(&bars[1]);
+    uint32_t r_rec[2] = {0u, 0u}, r_bar[2] = {0u, 0u};
+    if (lane < CLUSTER) {
+        r_rec[0] = mapa_shared(my_rec0, (uint32_t)lane);
+        r_rec[1] = mapa_shared(my_rec1, (uint32_t)lane);
+        r_bar[0] = mapa_shared(bar0, (uint32_t)lane);
+        r_bar[1] = mapa_shared(bar1, (uint32_t)lane);
+    }
+
+    for (int64_t r = 1; r < s; ++r) {
+        const int buf = (int)(r & 1);
+        if (tid == 0) fps_mbar_expect(&bars[buf], NREC * (uint32_t)sizeof(FpsRec32));
+        // squared distance from the new sample to this block's bounding box, in sqdist3's operation order
+        {
+            const float ex = fmaxf(fmaxf(__fsub_rn(bx0, lx), __fsub_rn(lx, bx1)), 0.f);
+            const float ey = fmaxf(fmaxf(__fsub_rn(by0, ly), __fsub_rn(ly, by1)), 0.f);
+            const float ez = fmaxf(fmaxf(__fsub_rn(bz0, lz), __fsub_rn(lz, bz1)), 0.f);
+            const float dbox = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+            if (dbox < mybest) {
+                float best = -1.f;
+                int bj = 0;
+#pragma unroll
+                for (int j = 0; j < PPT; ++j) {
+                    const float d = sqdist3(cx[j * T + tid], cy[j * T + tid], cz[j * T + tid], lx, ly, lz);
+                    const float m = fminf(md[j], d);
+                    md[j] = m;
+                    if (m > best) { best = m; bj = j; }  // strict: the lowest index wins inside a thread
+                }
+                mybest = best;
+                myj = bj;
+            }
+        }
+        const unsigned bi = mybest >= 0.f ? (unsigned)(blk + myj) : 0xffffffffu;
+        const unsigned key = mybest >= 0.f ? __float_as_uint(mybest) : 0u;
+        unsigned wkey, widx;
+        warp_argmax(key, bi, wkey, widx);
+        const int wl = __ffs(__ballot_sync(0xffffffffu, key == wkey && bi == widx)) - 1;
+        // the winning lane's coordinates, broadcast; lanes < CLUSTER push the record to one CTA each
+        const int wslot = __shfl_sync(0xffffffffu, myj * T + tid, wl);
+        const float wx = cx[wslot], wy = cy[wslot], wz = cz[wslot];
+        if (lane < CLUSTER) {
+            st_async_v4(r_rec[buf], wkey, widx, __float_as_uint(wx), __float_as_uint(wy), r_bar[buf]);
+            st_async_v4(r_rec[buf] + 16u, __float_as_uint(wz), 0u, 0u, 0u, r_bar[buf]);
+        }
+        fps_mbar_wait(&bars[buf], (uint32_t)(((r - 1) >> 1) & 1));  // rounds 1, 2 are the first use of bars[1], bars[0]
+        // every warp reduces the NREC records: NREC / 32 per lane, then the warp argmax
+        unsigned k2 = 0u, i2 = 0xffffffffu;
+        int src = 0;
+#pragma unroll
+        for (int u = 0; u < NREC / 32; ++u) {
+            const uint2 kv = *reinterpret_cast<const uint2 *>(&recs[buf][u * 32 + lane]);
+            if (kv.x > k2 || (kv.x == k2 && kv.y < i2)) { k2 = kv.x; i2 = kv.y; src = u * 32 + lane; }
+        }
+        unsigned gkey, gidx;
+        warp_argmax(k2, i2, gkey, gidx);
+        const int gl = __ffs(__ballot_sync(0xffffffffu, k2 == gkey && i2 == gidx)) - 1;
+        src = __shfl_sync(0xffffffffu, src, gl);
+        lx = recs[buf][src].x;
+        ly = recs[buf][src].y;
+        lz = recs[buf][src].z;
+        if (tid == 0 && rank == 0) {
+            out[obase + r] = (IdxT)(add + (int64_t)gidx);
+            if (new_xyz) { float *o = new_xyz + 3 * (obase + r); o[0] = lx; o[1] = ly; o[2] = lz; }
+        }
+    }
+    cluster.sync();  // no CTA may exit while a peer's stores to it can still be in flight
 }
 
 // Single-CTA variant (clouds of up to 8192 points): besides the register copy used for the distance update, the
@@ -387,6 +590,36 @@ static int launch_reg(const float *xyz, const int64_t *ptr, int64_t n_dense, con
     return finish_launch("fps");
 }
 
+template <int T, int PPT, int CLUSTER, typename IdxT>
+static int launch_pruned(const float *xyz, const int64_t *ptr, int64_t n_dense, const int64_t *out_ptr,
+                         int64_t s_dense, IdxT *out, const int64_t *first, float *new_xyz, int clouds, cudaStream_t st) {
+    auto kern = fps_pruned_kernel<T, PPT, CLUSTER, IdxT>;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(clouds * CLUSTER));
+    cfg.blockDim = dim3(T);
+    cfg.dynamicSmemBytes = (size_t)3 * T * PPT * sizeof(float);
+    static DeviceOnce smem_done;
+    if (!smem_done.done()) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+        smem_done.mark();
+    }
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz);
+    if (e != cudaSuccess) {
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        set_error("fps launch (pruned, T=%d PPT=%d CLUSTER=%d): %s", T, PPT, CLUSTER, cudaGetErrorString(e));
+        return P3D_ERR_CUDA;
+    }
+    return finish_launch("fps_pruned");
+}
+
 template <typename IdxT>
 static int fps_dispatch(const float *xyz, const int64_t *ptr, int64_t n_dense, const int64_t *out_ptr,
                         int64_t s_dense, IdxT *out, const int64_t *first, float *new_xyz, int clouds, int64_t max_n,
@@ -407,11 +640,9 @@ static int fps_dispatch(const float *xyz, const int64_t *ptr, int64_t n_dense, c
 #undef P3D_FPS_CTA
     P3D_FPS_CASE(16384, 1024, 8, 2)
     P3D_FPS_CASE(32768, 1024, 8, 4)
-    P3D_FPS_CASE(65536, 1024, 8, 8)
-    // 65537..131072 points (measured on B200, profiles/r1_fps_tuning.md): a 16-CTA cluster needs a whole GPC, so
-    // only ~4 run at once; with more clouds than that, 8-CTA clusters of fatter threads finish the batch sooner
-    if (max_n <= 131072 && clouds > 4) return launch_reg<512, 32, 8, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
-    P3D_FPS_CASE(131072, 256, 32, 16)
+    // 32 769..131 072 points: 8-CTA clusters with bounding-box pruning and the one-hop record exchange
+    if (max_n <= 65536) return launch_pruned<512, 16, 8, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
+    if (max_n <= 131072) return launch_pruned<512, 32, 8, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
 #undef P3D_FPS_CASE
     if (ws == nullptr || ws_bytes < (size_t)total_rows * sizeof(float)) {
         set_error("fps: clouds of more than 131072 points need a workspace of %lld bytes",

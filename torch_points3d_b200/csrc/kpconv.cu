@@ -397,12 +397,14 @@ int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neigh
                   const float *k_points, const float *k_values, int64_t n, int64_t N0, int M, int K, int Cin,
                   int Cout, float extent, int influence, int aggregation, float *out, void *ws, size_t ws_bytes,
                   cudaStream_t st, float *wf_out = nullptr);
-size_t kpconv_tc_ws_bytes(int K, int Cin, int Cout);
+size_t kpconv_tc_ws_bytes(int64_t n, int K, int Cin, int Cout);
 // tensor-core / register-tiled GEMMs of the backward (kpconv_tc.cu)
 size_t gemm_tc_ws_bytes(int Kd, int N);
 int gemm_tc(const float *A, int64_t lda, const float *Bp, int64_t sbk, int64_t sbj, int64_t R, int Kd, int N, float *C,
             int64_t ldc, void *ws, size_t ws_bytes, cudaStream_t st);
-int dw_accumulate(const float *A, const float *B, int64_t n, int R, int Cn, float *dW, cudaStream_t st);
+int dw_accumulate(const float *A, const float *B, int64_t n, int R, int Cn, float *dW, cudaStream_t st, float *part = nullptr,
+                  size_t part_bytes = 0);
+size_t dw_partial_bytes(int64_t n, int R, int Cn);
 // sparse-influence backward helpers (kpconv_tc.cu)
 bool kpconv_sparse_supported(int M, int K, int Cin);
 int kpconv_wf_sparse(const float *query, const float *support, const int64_t *neighbors, const float *feat,
@@ -413,7 +415,7 @@ int kpconv_scatter_sparse(const float *query, const float *support, const int64_
                           int aggregation, float *dfeat, cudaStream_t st);
 }  // namespace p3d
 
-P3D_EXPORT size_t p3d_kpconv_fwd_ws_bytes(int K, int Cin, int Cout) { return kpconv_tc_ws_bytes(K, Cin, Cout); }
+P3D_EXPORT size_t p3d_kpconv_fwd_ws_bytes(int64_t n, int K, int Cin, int Cout) { return kpconv_tc_ws_bytes(n, K, Cin, Cout); }
 
 P3D_EXPORT int p3d_kpconv_fwd_f32(const float *query, const float *support, const int64_t *neighbors,
                                   const float *feat, const float *k_points, const float *k_values, int64_t n,
@@ -508,8 +510,10 @@ static int kpconv_bwd_impl(const float *query, const float *support, const int64
 
 P3D_EXPORT size_t p3d_kpconv_bwd_ws_bytes(int64_t n, int M, int K, int Cin, int Cout) {
     (void)M;
-    // wf + dwf  [n, K, Cin] each, then the bf16 hi/lo image of W^T for the tensor-core dwf GEMM (0 if unsupported)
-    return (size_t)2 * (size_t)n * (size_t)K * (size_t)Cin * sizeof(float) + gemm_tc_ws_bytes(Cout, K * Cin);
+    // wf + dwf  [n, K, Cin] each, then the bf16 hi/lo image of W^T for the tensor-core dwf GEMM (0 if unsupported),
+    // then the per-chunk partial blocks of the deterministic dW reduction
+    return (size_t)2 * (size_t)n * (size_t)K * (size_t)Cin * sizeof(float) + gemm_tc_ws_bytes(Cout, K * Cin) +
+           dw_partial_bytes(n, K * Cin, Cout);
 }
 
 P3D_EXPORT int p3d_kpconv_bwd_f32(const float *query, const float *support, const int64_t *neighbors,
@@ -559,9 +563,11 @@ static int kpconv_bwd_impl(const float *query, const float *support, const int64
     int64_t grid = (n + KPF_WARPS - 1) / KPF_WARPS;
     if (grid > 16 * kNumSMs) grid = 16 * kNumSMs;
     const bool sparse = kpconv_sparse_supported(M, K, Cin);
+    const size_t part_bytes = dw_partial_bytes(n, (int)KC, Cout);
+    float *dw_part = (float *)((char *)ws + (size_t)2 * n * K * Cin * sizeof(float) + gemm_tc_ws_bytes(Cout, K * Cin));
     if (dweights && wf_saved != nullptr) {
         // dW[kc][o] += sum_p wf[p][kc] * dout[p][o] straight from the forward's slab
-        const int r = dw_accumulate(wf_saved, dout, n, (int)KC, Cout, dweights, st);
+        const int r = dw_accumulate(wf_saved, dout, n, (int)KC, Cout, dweights, st, dw_part, part_bytes);
         if (r < 0) return r;
         if (r == 1)  // shape outside the register-tiled kernel
             if (int e = sgemm_splitk_atomic(wf_saved, dout, n, KC, Cout, dweights, st)) return e;
@@ -577,7 +583,7 @@ static int kpconv_bwd_impl(const float *query, const float *support, const int64
         }
         // dW[kc][o] += sum_p wf[p][kc] * dout[p][o]
         {
-        const int r = dw_accumulate(wf, dout, n, (int)KC, Cout, dweights, st);
+        const int r = dw_accumulate(wf, dout, n, (int)KC, Cout, dweights, st, dw_part, part_bytes);
         if (r < 0) return r;
         if (r == 0) goto dw_done;
         }
@@ -597,7 +603,7 @@ static int kpconv_bwd_impl(const float *query, const float *support, const int64
     if (dfeat) {
         // dwf[p][kc] = sum_o dout[p][o] * W[kc][o]: tcgen05 GEMM (bf16 hi+lo operands) when the shape allows it
         void *bimg = (char *)ws + (size_t)2 * n * K * Cin * sizeof(float);
-        const size_t bimg_bytes = ws_bytes - (size_t)2 * n * K * Cin * sizeof(float);
+        const size_t bimg_bytes = gemm_tc_ws_bytes(Cout, K * Cin);
         int r = gemm_smallk(dout, Cout, k_values, 1, Cout, n, Cout, (int)KC, dwf, KC, st);  // Cout <= 64: write-bound
         if (r == 1) r = gemm_tc(dout, Cout, k_values, 1, Cout, n, Cout, (int)KC, dwf, KC, bimg, bimg_bytes, st);
         if (r < 0) return r;

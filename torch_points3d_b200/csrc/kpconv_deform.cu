@@ -22,7 +22,9 @@ namespace p3d {
 
 int sgemm_strided(const float *A, int64_t sai, int64_t sak, const float *B, int64_t sbk, int64_t sbj, float *C,
                   int64_t ldc, int64_t Mr, int64_t Nc, int64_t Kd, cudaStream_t st);  // kpconv.cu
-int dw_accumulate(const float *A, const float *B, int64_t n, int R, int Cn, float *dW, cudaStream_t st);  // kpconv_tc.cu
+int dw_accumulate(const float *A, const float *B, int64_t n, int R, int Cn, float *dW, cudaStream_t st, float *part = nullptr,
+                  size_t part_bytes = 0);  // kpconv_tc.cu
+size_t dw_partial_bytes(int64_t n, int R, int Cn);
 int sgemm_splitk_atomic(const float *A, const float *B, int64_t n, int64_t KC, int Cout, float *dW,
                         cudaStream_t st);  // kpconv.cu
 

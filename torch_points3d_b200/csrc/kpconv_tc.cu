@@ -4,21 +4,25 @@
 //
 //   out[p, :] = sum_k wf[p, k, :] @ W[k]          wf[p, k, c] = sum_m w[p, k, m] * x[nb[p, m], c]
 //
-// A CTA owns a tile of 128 query points (the M dimension of the MMA).  The contraction over
-// (kernel point, input channel) is cut into PASSES of 8 kernel points x 32 channels = 256 K-elements:
+// A persistent CTA walks tiles of 16 query points (one per producer warp).  The contraction over (kernel point, input channel) is cut into
+// PASSES of one 32-channel slab = 16 kernel points x 32 channels = 512 K-elements.  Three roles, coupled by
+// mbarriers only (no CTA-wide barrier after start-up):
 //
-//   producers (8 warps, SIMT)  -- per point: influence weights of the 8 kernel points of this pass
-//       (lanes = neighbours, warp ballots give one bit mask of influencing neighbours per kernel
-//       point: the linear influence is ~6% dense, so only ~1 kernel point per neighbour does any
-//       work), the influencing neighbour rows are staged once in shared memory (back-to-back LDGs)
-//       and wf[8][32] is accumulated from shared memory; the result is split into bf16 hi + lo and
-//       written with two 16-byte stores per lane into the A operand tile [128 x 256] (K-major,
-//       128-byte swizzle -- the canonical UMMA layout).
-//   MMA warp (one elected thread) -- W tiles (pre-split bf16 hi/lo, pre-swizzled by
-//       kpconv_prep_w_kernel) arrive by TMA bulk copy; D[128 x 32] += A_hi*B_hi + A_lo*B_hi +
-//       A_hi*B_lo (bf16x2 split: ~2^-17 relative, fp32 accumulation in TMEM), one N = 32 column
-//       chunk of Cout at a time; tcgen05.commit hands the A tile back to the producers.
-//   epilogue (warps 0-3) -- tcgen05.ld of the [128 x Cout] accumulator, 128-byte row stores.
+//   producers (16 warps, SIMT) -- per point (its influence table is built once and serves every slab): the neighbour rows of the slab go to shared memory with 16-byte cp.async
+//       (in flight while the influence weights are computed with lanes = neighbours; one warp ballot per kernel
+//       point marks the ~6 % of (kernel point, neighbour) pairs with a nonzero linear influence); then lanes =
+//       (kernel point, half slab): every lane walks the influencing neighbours of ITS kernel point and accumulates
+//       16 channels from shared memory (4 LDS.128 + 16 FMA per pair).  The fp32 result is split into bf16 hi + lo
+//       and stored with two 16-byte stores per operand into the A tile (K-major, 128-byte swizzle: the canonical
+//       UMMA layout).  ONE A stage is enough: a warp needs the tile only at the very end of its point (the store),
+//       by which time the MMAs of the previous pass -- a fraction of a producer pass -- have long retired; the
+//       shared memory goes to 16 producer warps and a 4-deep weight ring instead.
+//   MMA warp (one elected thread) -- W pieces (pre-split bf16 hi/lo, pre-swizzled by kpconv_prep_w_kernel) stream
+//       through a ring of TMA bulk copies that runs ahead of the MMAs; D[128 x 32] += A_hi*B_hi + A_lo*B_hi +
+//       A_hi*B_lo (bf16x2 split: ~2^-17 relative, fp32 accumulation in TMEM; rows 16-127 of the M = 128 MMA are
+//       don't-care rows); tcgen05.commit hands A stages and W slots back.  Accumulators are double-buffered in TMEM.
+//   epilogue warp -- tcgen05.ld of the finished [16 x Cout] accumulator, 128-byte row stores, while the next tile
+//       is already being accumulated in the other TMEM buffer.
 //
 // No [n,M,K], [n,M,Cin], [n,K,Cin] or [K,n,Cout] intermediate exists in HBM.
 #include <cuda_bf16.h>
@@ -28,9 +32,10 @@
 
 namespace p3d {
 
-constexpr int TC_TILE = 64;           // query points per tile (rows 0-63 of the M = 128 MMA; rows 64-127 are junk)
+// (TC_TILE / TC_PWARPS / TC_THREADS describe the generic GEMM kernel below; the KPConv forward has its own F2_* set)
+constexpr int TC_TILE = 64;           // rows per tile of gemm_tc_kernel (rows 0-63 of the M = 128 MMA)
 constexpr int TC_MMA_M = 128;
-constexpr int TC_PWARPS = 16;         // producer warps
+constexpr int TC_PWARPS = 16;         // producer warps of gemm_tc_kernel
 constexpr int TC_THREADS = (TC_PWARPS + 1) * 32;
 constexpr int TC_MCAP = 40;           // neighbours per point supported by this path
 constexpr int TC_NCH = 32;            // output channels per MMA (UMMA N)
@@ -38,7 +43,7 @@ constexpr int TC_A_CHUNK = TC_TILE * 128;            // one 64-K chunk of the A 
 constexpr int TC_A_BYTES = 2 * 8 * TC_A_CHUNK;       // hi|lo x 8 chunks = 128 KB
 constexpr int TC_WCH = 2;                            // 64-K chunks per weight piece
 constexpr int TC_W_PIECE = 2 * TC_WCH * TC_NCH * 128;  // hi|lo x 2 chunks x 32 rows x 128 B = 16 KB (a quarter slab of K)
-constexpr int TC_SCRATCH_FLOATS = TC_MCAP * 32;      // per producer warp: staged neighbour rows
+constexpr int TC_SCRATCH_FLOATS = TC_MCAP * 32;      // per warp of the sparse backward kernels: staged neighbour rows
 
 // ---- tcgen05 / TMEM wrappers -------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols) {
@@ -102,26 +107,34 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 // ---- W image: bf16 hi/lo, K-major, 128-byte swizzled tiles ---------------------------------
-// piece(s, nc, q) = [hi|lo][4 chunks of 64 K][32 rows = outputs 32nc..][128 B], q = K half of the slab;
-// K index inside a slab = c * 16 + k  (c = channel inside the 32-channel slab s, k = kernel point,
-// kernel points >= K are zero rows).
+// piece(s, nc, q) = [hi|lo][2 chunks of 64 K][32 rows = outputs 32nc..][128 B], q = K quarter of the slab;
+// K index inside a slab = k * 32 + c  (k = kernel point, c = channel inside the 32-channel slab s; kernel points
+// >= K are zero rows).
 __global__ void __launch_bounds__(256)
 kpconv_prep_w_kernel(const float *__restrict__ W, int K, int Cin, int Cout, uint8_t *__restrict__ img) {
+    __shared__ __align__(16) uint8_t tile[TC_W_PIECE];  // the piece in its final layout
     const int piece = blockIdx.x;  // ((s * ncs + nc) * 4 + q)
     const int ncs = Cout / TC_NCH;
     const int qq = piece & 3, nc = (piece >> 2) % ncs, s = (piece >> 2) / ncs;
-    uint8_t *base = img + (size_t)piece * TC_W_PIECE;
-    for (int i = threadIdx.x; i < TC_WCH * TC_NCH * 64; i += 256) {
-        const int e = i & 63, r = (i >> 6) & 31, kc = i >> 11;
-        const int kidx = (qq * TC_WCH + kc) * 64 + e;
-        const int c = kidx >> 4, k = kidx & 15;
+    // lanes run over the 32 output channels of the piece (contiguous in W): every warp load is one 128-byte line
+    const int r = threadIdx.x & 31, kg = threadIdx.x >> 5;
+#pragma unroll 4
+    for (int kk = 0; kk < TC_WCH * 64 / 8; ++kk) {
+        const int kloc = kk * 8 + kg;             // K element inside the piece: 0..127
+        const int kc = kloc >> 6, e = kloc & 63;
+        const int kidx = qq * (TC_WCH * 64) + kloc;
+        const int k = kidx >> 5, c = kidx & 31;
         const float v = k < K ? __ldg(W + ((int64_t)k * Cin + s * 32 + c) * Cout + nc * TC_NCH + r) : 0.f;
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
         const int off = (kc * TC_NCH + r) * 128 + (((e >> 3) ^ (r & 7)) << 4) + ((e & 7) << 1);
-        *reinterpret_cast<__nv_bfloat16 *>(base + off) = hi;
-        *reinterpret_cast<__nv_bfloat16 *>(base + TC_WCH * TC_NCH * 128 + off) = lo;
+        *reinterpret_cast<__nv_bfloat16 *>(tile + off) = hi;
+        *reinterpret_cast<__nv_bfloat16 *>(tile + TC_WCH * TC_NCH * 128 + off) = lo;
     }
+    __syncthreads();
+    uint4 *dst = reinterpret_cast<uint4 *>(img + (size_t)piece * TC_W_PIECE);
+    const uint4 *src = reinterpret_cast<const uint4 *>(tile);
+    for (int i = threadIdx.x; i < TC_W_PIECE / 16; i += 256) dst[i] = src[i];
 }
 
 // ---- producer: wf[16 kernel points][32 channels] of one query point -----------------------
@@ -218,221 +231,382 @@ __device__ __forceinline__ void tc_weights(const TcPoint &P, const float4 *kps, 
     }
 }
 
+// ---- forward kernel ---------------------------------------------------------------------------------------------
+constexpr int F2_ROWS = 16;                              // query points per A stage: one per producer warp
+constexpr int F2_PWARPS = 16;                            // producer warps (warps 1..16)
+constexpr int F2_THREADS = (F2_PWARPS + 2) * 32;         // warp 0 = epilogue, warps 1..16 = producers, warp 17 = MMA
+constexpr int F2_A_CHUNK = F2_ROWS * 128;                // one 64-K chunk of the A tile: 16 rows x 128 B
+constexpr int F2_A_BYTES = 2 * 8 * F2_A_CHUNK;           // hi|lo x 8 chunks = 32 KB (ONE stage: see the kernel comment)
+constexpr int F2_WSLOTS = 4;                             // W ring: 16 KB pieces, three copies in flight behind the MMAs
+constexpr int F2_XPITCH = 36;                            // floats per staged neighbour row (32 + 4: bank spread)
+constexpr int F2_WT_PITCH = 40;                          // floats per kernel point in the weight table
+constexpr int F2_SCRATCH_FLOATS = TC_MCAP * F2_XPITCH + KP_K * F2_WT_PITCH;   // per producer warp: 8320 B
+
+// influence weights of one point with lanes = neighbours: the nonzero pattern of every kernel point as a warp ballot
+// (mask0: neighbours 0-31; mask1[it]: byte q = neighbours 32-39 of kernel point q + 4 * it) and the weights themselves
+// in the warp's shared-memory table wt[k][m].  Returns the masks of the kernel point THIS lane accumulates (lane >> 1).
+template <int INFL, bool CLOSEST>
+__device__ __forceinline__ void f2_weights(const TcPoint &P, const float4 *kps, int K, int M, const KpGeom &g,
+                                           float inv_extent, float *wt, int lane, unsigned &my0, unsigned &my1) {
+    int best0 = -1, best1 = -1;
+    if (CLOSEST) {  // the winning kernel point of every neighbour over ALL K kernel points (first minimum)
+        float bd0 = CUDART_INF_F, bd1 = CUDART_INF_F;
+        for (int k = 0; k < K; ++k) {
+            const float4 kp = kps[k];
+            float d0, d1;
+            tc_influence<INFL>(P.x0, P.y0, P.z0, kp, g, inv_extent, d0);
+            tc_influence<INFL>(P.x1, P.y1, P.z1, kp, g, inv_extent, d1);
+            if (d0 < bd0) { bd0 = d0; best0 = k; }
+            if (d1 < bd1) { bd1 = d1; best1 = k; }
+        }
+    }
+    const int myk = lane >> 1;
+    my0 = 0u;
+    my1 = 0u;
+#pragma unroll
+    for (int k = 0; k < KP_K; ++k) {
+        if (k == KP_K - 1 && K < KP_K) break;  // the usual 15 kernel points: slot 15 is padding
+        float d2;
+        float w = tc_influence<INFL>(P.x0, P.y0, P.z0, kps[k], g, inv_extent, d2);
+        if (CLOSEST && best0 != k) w = 0.f;
+        const bool nz = P.j0 >= 0 && k < K && w > 0.f;
+        const unsigned b = __ballot_sync(0xffffffffu, nz);
+        wt[k * F2_WT_PITCH + lane] = w;
+        if (myk == k) my0 = b;
+    }
+    if (M > 32) {
+        // neighbours 32..39: lane = (mm = lane % 8, kq = lane / 8), four steps cover the 16 kernel points
+        const int mm = lane & 7, kq = lane >> 3;
+        const float cx = __shfl_sync(0xffffffffu, P.x1, mm), cy = __shfl_sync(0xffffffffu, P.y1, mm);
+        const float cz = __shfl_sync(0xffffffffu, P.z1, mm);
+        const int jj = __shfl_sync(0xffffffffu, P.j1, mm);
+        const int bb = __shfl_sync(0xffffffffu, best1, mm);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int k = kq + 4 * it;
+            float d2;
+            float w = tc_influence<INFL>(cx, cy, cz, kps[k], g, inv_extent, d2);
+            if (CLOSEST && bb != k) w = 0.f;
+            const bool nz = jj >= 0 && k < K && w > 0.f;
+            const unsigned b = __ballot_sync(0xffffffffu, nz);  // byte q = neighbours 32..39 of kernel point q + 4*it
+            wt[k * F2_WT_PITCH + 32 + mm] = w;
+            if ((myk >> 2) == it) my1 = (b >> (8 * (myk & 3))) & 0xffu;
+        }
+    }
+}
+
+// geometry of one query point held across the lanes of a producer warp, loaded in two dependent steps that the
+// producer loop keeps two points ahead (indices) and one point ahead (coordinates) of the point it is working on
+struct TcIdx {
+    int64_t a, b;  // neighbour index of lane / 32 + lane (-1 = none)
+};
+__device__ __forceinline__ void f2_load_idx(const int64_t *__restrict__ nbp, int M, int lane, TcIdx &I) {
+    I.a = lane < M ? __ldg(nbp + lane) : -1;
+    I.b = 32 + lane < M ? __ldg(nbp + 32 + lane) : -1;
+}
+__device__ __forceinline__ void f2_load_coords(const float *__restrict__ q, const float *__restrict__ s, int64_t N0,
+                                               const TcIdx &I, TcPoint &P) {
+    const float qx = __ldg(q), qy = __ldg(q + 1), qz = __ldg(q + 2);
+    const int64_t a = I.a >= N0 ? -1 : I.a, b = I.b >= N0 ? -1 : I.b;
+    P.j0 = (int)a;
+    P.j1 = (int)b;
+    float ax = 1e6f, ay = 1e6f, az = 1e6f, bx = 1e6f, by = 1e6f, bz = 1e6f;
+    if (a >= 0) { ax = __ldg(s + 3 * a); ay = __ldg(s + 3 * a + 1); az = __ldg(s + 3 * a + 2); }
+    if (b >= 0) { bx = __ldg(s + 3 * b); by = __ldg(s + 3 * b + 1); bz = __ldg(s + 3 * b + 2); }
+    P.x0 = __fsub_rn(ax, qx); P.y0 = __fsub_rn(ay, qy); P.z0 = __fsub_rn(az, qz);
+    P.x1 = __fsub_rn(bx, qx); P.y1 = __fsub_rn(by, qy); P.z1 = __fsub_rn(bz, qz);
+}
+
+// gridDim = (tile CTAs, output-channel groups, slab groups).  blockIdx.z owns the slabs [sl0, sl1) of the contraction
+// and writes its partial sums to out + blockIdx.z * part_stride (part_stride = 0 when the slabs are not split).
 template <int INFL, bool CLOSEST, bool SAVE_WF>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(F2_THREADS, 1)
 kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, const int64_t *__restrict__ nb,
                      const float *__restrict__ x, const float *__restrict__ kp, const uint8_t *__restrict__ wimg,
                      int64_t n, int64_t N0, int M, int K, int Cin, int Cout, KpGeom g, uint32_t tmem_cols, int ncpc,
-                     float *__restrict__ out, float *__restrict__ wf_out) {
-    extern __shared__ uint8_t smem_raw[];
-    // the UMMA 128-byte swizzle atoms need 1024-byte aligned tiles (the launch adds 1 KB of slack)
-    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t *a_tile = smem;                       // [hi|lo][8 chunks][64 rows][128 B]
-    uint8_t *w_tile = smem + TC_A_BYTES;          // [hi|lo][2 chunks][32 rows][128 B]
-    float *scratch = reinterpret_cast<float *>(smem + TC_A_BYTES + TC_W_PIECE);
-    __shared__ float4 kps[KP_K];
-    __shared__ __align__(8) uint64_t bar_a_empty, bar_w_full, bar_w_empty, bar_d_full;
-    __shared__ uint32_t tmem_base_s;
+                     int spz, int64_t part_stride, float *__restrict__ out, float *__restrict__ wf_out) {
+    // All shared memory of this kernel is dynamic (no static variables), so the buffer starts at the base of the CTA's
+    // shared window and the 1024-byte alignment the UMMA 128-byte swizzle atoms need costs no slack: the kernel uses
+    // 226.5 of the 227 KB a CTA can have.
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();            // (never observed; a misaligned tile would corrupt silently)
+    uint8_t *a_tile = smem;                                  // [hi|lo][8 chunks][16 rows][128 B]
+    uint8_t *w_ring = smem + F2_A_BYTES;                     // F2_WSLOTS x [hi|lo][2 chunks][32 rows][128 B]
+    float *scratch = reinterpret_cast<float *>(smem + F2_A_BYTES + F2_WSLOTS * TC_W_PIECE);
+    uint8_t *tail = smem + F2_A_BYTES + F2_WSLOTS * TC_W_PIECE + (size_t)F2_PWARPS * F2_SCRATCH_FLOATS * sizeof(float);
+    float4 *kps = reinterpret_cast<float4 *>(tail);                          // [KP_K]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tail + KP_K * sizeof(float4));
+    uint64_t *bar_a_full = bars, *bar_a_empty = bars + 2, *bar_d_full = bars + 4, *bar_d_empty = bars + 6,
+             *bar_w_full = bars + 8, *bar_w_empty = bars + 8 + F2_WSLOTS;
+    uint32_t &tmem_base_s = *reinterpret_cast<uint32_t *>(bars + 8 + 2 * F2_WSLOTS);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int slabs = Cin / 32, ncs = Cout / TC_NCH;
-    // blockIdx.y owns the output-channel chunks [nc0, nc0 + ncl): small point sets (deep layers) are spread over
-    // the SMs by output channels, every CTA recomputing the (cheap) producer side of its tile
+    const int ncs = Cout / TC_NCH;
+    // blockIdx.y owns the output-channel chunks [nc0, nc0 + ncl); blockIdx.z the slabs [sl0, sl1): small point sets
+    // (deep layers) are spread over the SMs by output channels and by slabs of the contraction, every CTA recomputing
+    // the (cheap) producer side of its tile
     const int nc0 = blockIdx.y * ncpc;
     const int ncl = (ncs - nc0 < ncpc) ? (ncs - nc0) : ncpc;
-    const int64_t ntiles = (n + TC_TILE - 1) / TC_TILE;
+    const int sl0 = blockIdx.z * spz;
+    const int sl1 = (sl0 + spz < Cin / 32) ? (sl0 + spz) : Cin / 32;
+    const int slabs = sl1 - sl0;
+    float *__restrict__ dst_out = out + (int64_t)blockIdx.z * part_stride;
+    const int64_t ntiles = (n + F2_ROWS - 1) / F2_ROWS;
+    const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;  // persistent: tiles blockIdx.x + i * gridDim.x
     const float inv_extent = 1.0f / g.extent;
+    const uint32_t dcols = (uint32_t)(ncl * TC_NCH);         // TMEM columns of one accumulator buffer
 
     if (tid < KP_K) kps[tid] = tid < K ? make_float4(__ldg(kp + 3 * tid), __ldg(kp + 3 * tid + 1), __ldg(kp + 3 * tid + 2), 0.f)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {
-        mbar_init(&bar_a_empty, 1);
-        mbar_init(&bar_w_full, 1);
-        mbar_init(&bar_w_empty, 1);
-        mbar_init(&bar_d_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_a_full[i], F2_PWARPS);
+            mbar_init(&bar_a_empty[i], 1);
+            mbar_init(&bar_d_full[i], 1);
+            mbar_init(&bar_d_empty[i], 1);
+        }
+        for (int i = 0; i < F2_WSLOTS; ++i) {
+            mbar_init(&bar_w_full[i], 1);
+            mbar_init(&bar_w_empty[i], 1);
+        }
         fence_barrier_init();
     }
-    for (int i = tid; i < TC_PWARPS * TC_SCRATCH_FLOATS; i += TC_THREADS) scratch[i] = 0.f;  // staged rows: never NaN
-    if (warp == TC_PWARPS) tmem_alloc(&tmem_base_s, tmem_cols);
+    if (warp == F2_PWARPS + 1) tmem_alloc(&tmem_base_s, tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    uint32_t pass = 0;       // global pass counter (phase of bar_a_empty)
-    uint32_t wloads = 0;     // W pieces loaded so far (phases of bar_w_full / bar_w_empty; MMA thread only)
-    uint32_t tile_iter = 0;  // phase of bar_d_full
-    constexpr int PPW = TC_TILE / TC_PWARPS;  // points per producer warp and pass
-
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
-        const int64_t p_base = tile * TC_TILE;
-        for (int sl = 0; sl < slabs; ++sl, ++pass) {
-            if (warp < TC_PWARPS) {
-                // ---------------------------------------------------- producers ------------------
-                float *xs = scratch + (size_t)warp * TC_SCRATCH_FLOATS;
-                const uint32_t xs_addr = smem_u32(xs) + (uint32_t)lane * 4u;
-                const float *xcol = x + sl * 32 + lane;
-                TcPoint P, Pn;
-                {
-                    const int64_t p = p_base + warp * PPW;
-                    if (p < n) tc_load_point(q + 3 * p, s, nb + p * M, N0, M, lane, P);
-                }
-                if (pass > 0) mbar_wait(&bar_a_empty, (pass - 1) & 1);  // the previous pass' MMAs have read the A tile
-                for (int pi = 0; pi < PPW; ++pi) {
-                    const int row = warp * PPW + pi;
-                    const int64_t p = p_base + row;
-                    float acc[KP_K];
+    if (warp >= 1 && warp <= F2_PWARPS) {
+        // ------------------------------------------------------------ producers ----------------------------
+        // a warp owns ONE row of every tile: its point's influence table is built once and serves every slab
+        const int pw = warp - 1;
+        float *xs = scratch + (size_t)pw * F2_SCRATCH_FLOATS;     // staged neighbour rows [40][36]
+        float *wt = xs + TC_MCAP * F2_XPITCH;                      // weight table [16][40]
+        for (int i = lane; i < F2_SCRATCH_FLOATS; i += 32) xs[i] = 0.f;
+        __syncwarp();
+        const int myk = lane >> 1, myh = lane & 1;
+        const uint32_t xs_row = smem_u32(xs) + (uint32_t)((lane >> 3) * F2_XPITCH * 4 + (lane & 7) * 16);
+        const float *wrow = wt + myk * F2_WT_PITCH;
+        const float *xh = xs + myh * 16;
+        auto point_of = [&](int64_t ti) { return (blockIdx.x + ti * gridDim.x) * F2_ROWS + pw; };
+        // geometry pipeline: coordinates of the current point, indices of the next one
+        TcPoint P;
+        TcIdx I1;
+        I1.a = I1.b = -1;
+        {
+            TcIdx I0;
+            I0.a = I0.b = -1;
+            if (my_tiles > 0 && point_of(0) < n) f2_load_idx(nb + point_of(0) * M, M, lane, I0);
+            if (my_tiles > 1 && point_of(1) < n) f2_load_idx(nb + point_of(1) * M, M, lane, I1);
+            if (my_tiles > 0 && point_of(0) < n) f2_load_coords(q + 3 * point_of(0), s, N0, I0, P);
+        }
+        uint32_t pass = 0;
+        for (int64_t ti = 0; ti < my_tiles; ++ti) {
+            const int64_t p = point_of(ti);
+            TcPoint Pn;
+            TcIdx I2;
+            I2.a = I2.b = -1;
+            if (ti + 2 < my_tiles && point_of(ti + 2) < n) f2_load_idx(nb + point_of(ti + 2) * M, M, lane, I2);
+            if (ti + 1 < my_tiles && point_of(ti + 1) < n) f2_load_coords(q + 3 * point_of(ti + 1), s, N0, I1, Pn);
+            unsigned mask0 = 0u, mask1 = 0u;
+            for (int sl = sl0; sl < sl1; ++sl, ++pass) {
+                const int row = pw;
+                float acc[16];
 #pragma unroll
-                    for (int k = 0; k < KP_K; ++k) acc[k] = 0.f;
-                    if (p < n) {
-                        // all neighbour rows of this point go straight to shared memory with cp.async (no
-                        // registers held, their latency hides behind the influence weights), and the geometry
-                        // of the NEXT point is fetched right behind them
+                for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+                if (p < n) {
+                    // neighbour rows of this slab -> shared memory, 16 bytes per lane and copy: 4 rows per
+                    // instruction; their latency hides behind the influence weights (first slab) / the wait below
+                    const float *xcol = x + sl * 32 + (lane & 7) * 4;
 #pragma unroll
-                        for (int m = 0; m < TC_MCAP; ++m) {
-                            const int j = __shfl_sync(0xffffffffu, m < 32 ? P.j0 : P.j1, m & 31);
-                            if (m < M && j >= 0)
-                                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(xs_addr + m * 128u),
-                                             "l"(xcol + (int64_t)j * Cin)
-                                             : "memory");
-                        }
-                        asm volatile("cp.async.commit_group;" ::: "memory");
-                        if (pi + 1 < PPW && p + 1 < n) tc_load_point(q + 3 * (p + 1), s, nb + (p + 1) * M, N0, M, lane, Pn);
-                        float w0[KP_K], w1[4];
-                        unsigned mask0[KP_K], mask1[4];
-                        tc_weights<INFL, CLOSEST>(P, kps, K, M, g, inv_extent, w0, w1, mask0, mask1, lane);
-                        asm volatile("cp.async.wait_group 0;" ::: "memory");  // each lane reads only what it copied
-#pragma unroll
-                        for (int k = 0; k < KP_K; ++k) {
-                            if (k == KP_K - 1 && K < KP_K) break;  // the usual 15 kernel points: slot 15 is padding
-                            // ~2.3 influencing neighbours per kernel point: the first three are taken without a
-                            // branch (an absent one reads row 0 with weight 0; rows never hold NaNs, see the
-                            // zero fill at kernel start), so the loads of a point are independent and pipeline;
-                            // weights come from the owning lane's register by shuffle
-                            unsigned mk = mask0[k];
-                            const int m1 = mk ? __ffs(mk) - 1 : 0;
-                            const bool h1 = mk != 0u;
-                            mk &= mk - 1;
-                            const int m2 = mk ? __ffs(mk) - 1 : 0;
-                            const bool h2 = mk != 0u;
-                            mk &= mk - 1;
-                            const int m3 = mk ? __ffs(mk) - 1 : 0;
-                            const bool h3 = mk != 0u;
-                            mk &= mk - 1;
-                            const float w1s = __shfl_sync(0xffffffffu, w0[k], m1);
-                            const float w2s = __shfl_sync(0xffffffffu, w0[k], m2);
-                            const float w3s = __shfl_sync(0xffffffffu, w0[k], m3);
-                            // absent taps are SELECTED away (0 * stale row could be NaN if another point's
-                            // neighbour held a non-finite feature)
-                            float a = h1 ? w1s * xs[m1 * 32 + lane] : 0.f;
-                            a = h2 ? fmaf(w2s, xs[m2 * 32 + lane], a) : a;
-                            a = h3 ? fmaf(w3s, xs[m3 * 32 + lane], a) : a;
-                            while (mk) {
-                                const int m = __ffs(mk) - 1;
-                                mk &= mk - 1;
-                                a = fmaf(__shfl_sync(0xffffffffu, w0[k], m), xs[m * 32 + lane], a);
-                            }
-                            mk = (mask1[k >> 2] >> (8 * (k & 3))) & 0xffu;
-                            while (mk) {
-                                const int mm = __ffs(mk) - 1;
-                                mk &= mk - 1;
-                                a = fmaf(__shfl_sync(0xffffffffu, w1[k >> 2], mm + 8 * (k & 3)), xs[(32 + mm) * 32 + lane], a);
-                            }
-                            acc[k] = a;
-                        }
-                        if (SAVE_WF && nc0 == 0) {
-                            // training: keep the fp32 weighted features (dW = wf^T dout needs them) instead of
-                            // recomputing them in the backward pass: 15 coalesced 128-byte stores per point and slab
-                            float *wrow = wf_out + (p * K) * Cin + sl * 32 + lane;
-#pragma unroll
-                            for (int k = 0; k < KP_K; ++k)
-                                if (k < K) __stcs(wrow + (int64_t)k * Cin, acc[k]);
-                        }
-                        P = Pn;
+                    for (int i = 0; i < TC_MCAP / 4; ++i) {
+                        const int r = 4 * i + (lane >> 3);
+                        const int j = __shfl_sync(0xffffffffu, r < 32 ? P.j0 : P.j1, r & 31);
+                        if (r < M && j >= 0)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xs_row + (uint32_t)(i * 4 * F2_XPITCH * 4)),
+                                         "l"(xcol + (int64_t)j * Cin)
+                                         : "memory");
                     }
-                    // bf16 hi/lo split; K index = lane * 16 + k: 32 contiguous bytes per lane and operand
-                    uint32_t hi[8], lo[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const float a0 = acc[2 * u], a1 = acc[2 * u + 1];
-                        const float h0 = __bfloat162float(__float2bfloat16_rn(a0));
-                        const float h1 = __bfloat162float(__float2bfloat16_rn(a1));
-                        hi[u] = pack_bf16(h0, h1);
-                        lo[u] = pack_bf16(a0 - h0, a1 - h1);
-                    }
-                    uint8_t *rowp = a_tile + (lane >> 2) * TC_A_CHUNK + row * 128;
-                    const int g0 = (lane & 3) * 2, sw = row & 7;
-                    *reinterpret_cast<uint4 *>(rowp + ((g0 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4 *>(rowp + (((g0 + 1) ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                    rowp += TC_A_BYTES / 2;
-                    *reinterpret_cast<uint4 *>(rowp + ((g0 ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    *reinterpret_cast<uint4 *>(rowp + (((g0 + 1) ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    if (sl == sl0) f2_weights<INFL, CLOSEST>(P, kps, K, M, g, inv_extent, wt, lane, mask0, mask1);
                 }
+                if (pass >= 1) mbar_wait(&bar_a_empty[0], (pass - 1) & 1);  // the MMAs of the previous pass have read the tile
+                if (p < n) {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();  // rows and weights written by other lanes are visible
+                    // lane = (kernel point myk, half slab myh): walk the influencing neighbours of myk
+                    unsigned m0 = mask0, m1 = mask1;
+                    while (m0) {
+                        const int m = __ffs(m0) - 1;
+                        m0 &= m0 - 1;
+                        const float w = wrow[m];
+                        const float4 *xr = reinterpret_cast<const float4 *>(xh + m * F2_XPITCH);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const float4 xv = xr[v];
+                            acc[4 * v] = fmaf(w, xv.x, acc[4 * v]);
+                            acc[4 * v + 1] = fmaf(w, xv.y, acc[4 * v + 1]);
+                            acc[4 * v + 2] = fmaf(w, xv.z, acc[4 * v + 2]);
+                            acc[4 * v + 3] = fmaf(w, xv.w, acc[4 * v + 3]);
+                        }
+                    }
+                    while (m1) {
+                        const int m = 32 + __ffs(m1) - 1;
+                        m1 &= m1 - 1;
+                        const float w = wrow[m];
+                        const float4 *xr = reinterpret_cast<const float4 *>(xh + m * F2_XPITCH);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            const float4 xv = xr[v];
+                            acc[4 * v] = fmaf(w, xv.x, acc[4 * v]);
+                            acc[4 * v + 1] = fmaf(w, xv.y, acc[4 * v + 1]);
+                            acc[4 * v + 2] = fmaf(w, xv.z, acc[4 * v + 2]);
+                            acc[4 * v + 3] = fmaf(w, xv.w, acc[4 * v + 3]);
+                        }
+                    }
+                    __syncwarp();  // the staged rows are rewritten for the next slab / point
+                    if (SAVE_WF && nc0 == 0 && myk < K) {
+                        // training: keep the fp32 weighted features (dW = wf^T dout needs them): 64 contiguous
+                        // bytes per lane, the warp covers the K x 32 block of this point and slab
+                        float4 *dst = reinterpret_cast<float4 *>(wf_out + (p * K + myk) * Cin + sl * 32 + myh * 16);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v)
+                            __stcs(dst + v, make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]));
+                    }
+                }
+                // bf16 hi/lo split; K index = myk * 32 + myh * 16 + c = lane * 16 + c: 32 contiguous bytes per lane
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float a0 = acc[2 * u], a1 = acc[2 * u + 1];
+                    const float h0 = __bfloat162float(__float2bfloat16_rn(a0));
+                    const float h1 = __bfloat162float(__float2bfloat16_rn(a1));
+                    hi[u] = pack_bf16(h0, h1);
+                    lo[u] = pack_bf16(a0 - h0, a1 - h1);
+                }
+                uint8_t *rowp = a_tile + (lane >> 2) * F2_A_CHUNK + row * 128;
+                const int g0 = (lane & 3) * 2, sw = row & 7;
+                *reinterpret_cast<uint4 *>(rowp + ((g0 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4 *>(rowp + (((g0 + 1) ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                rowp += F2_A_BYTES / 2;
+                *reinterpret_cast<uint4 *>(rowp + ((g0 ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<uint4 *>(rowp + (((g0 + 1) ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
                 fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_a_full[0]);
             }
-            __syncthreads();  // A tile of this pass complete (the MMA warp waits here too)
-            if (warp == TC_PWARPS) {
-                // ---------------------------------------------------- MMA issuer -----------------
+            P = Pn;
+            I1 = I2;
+        }
+    } else if (warp == F2_PWARPS + 1) {
+        // ------------------------------------------------------------ MMA issuer ---------------------------
+        if (lane == 0) {
+            const uint32_t idesc = tc_idesc(TC_MMA_M, TC_NCH);
+            // shared-memory matrix descriptors differ only in their 14-bit start-address field (bytes >> 4, low word):
+            // one 32-bit add per operand instead of rebuilding the 64-bit descriptor for each of the 96 MMAs of a pass
+            const uint64_t a_desc0 = tc_smem_desc(smem_u32(a_tile)), w_desc0 = tc_smem_desc(smem_u32(w_ring));
+            const uint32_t desc_hi = (uint32_t)(a_desc0 >> 32);
+            const uint32_t a_lo0 = (uint32_t)a_desc0, w_lo0 = (uint32_t)w_desc0;
+            auto mkdesc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | lo; };
+            const uint32_t ppp = (uint32_t)(4 * ncl);                       // W pieces per pass
+            const uint32_t total_pieces = (uint32_t)(my_tiles * slabs) * ppp;
+            // piece i of this CTA's stream: pass i / ppp (slab = sl0 + pass % slabs), chunk (i % ppp) / 4, K quarter i % 4
+            auto load_piece = [&](uint32_t i) {
+                const uint32_t slot = i % F2_WSLOTS;
+                const uint32_t j = i % ppp, sl = (uint32_t)sl0 + (i / ppp) % (uint32_t)slabs;
+                const size_t piece = ((size_t)(sl * ncs + nc0 + (j >> 2)) * 4 + (j & 3));
+                mbar_arrive_expect_tx(&bar_w_full[slot], TC_W_PIECE);
+                bulk_g2s(w_ring + slot * TC_W_PIECE, wimg + piece * TC_W_PIECE, TC_W_PIECE, &bar_w_full[slot]);
+            };
+            for (uint32_t i = 0; i < F2_WSLOTS && i < total_pieces; ++i) load_piece(i);
+            uint32_t piece_i = 0, pass = 0;
+            for (int64_t ti = 0; ti < my_tiles; ++ti) {
+                const uint32_t dbuf = (uint32_t)(ti & 1);
+                if (ti >= 2) mbar_wait(&bar_d_empty[dbuf], (uint32_t)(((ti >> 1) - 1) & 1));  // epilogue drained this buffer
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t idesc = tc_idesc(TC_MMA_M, TC_NCH);
-                    const uint32_t a_addr = smem_u32(a_tile), w_addr = smem_u32(w_tile);
+                for (int sl = 0; sl < slabs; ++sl, ++pass) {
+                    mbar_wait(&bar_a_full[0], pass & 1);
+                    tc_fence_after();
                     for (int ncq = 0; ncq < ncl; ++ncq) {
-                        const int nc = nc0 + ncq;
-                        const uint32_t d = tmem_base + (uint32_t)(ncq * TC_NCH);
-                        for (int qq = 0; qq < 4; ++qq, ++wloads) {
-                            if (wloads > 0) mbar_wait(&bar_w_empty, (wloads - 1) & 1);  // W buffer is free
-                            mbar_arrive_expect_tx(&bar_w_full, TC_W_PIECE);
-                            bulk_g2s(w_tile, wimg + ((size_t)(sl * ncs + nc) * 4 + qq) * TC_W_PIECE, TC_W_PIECE,
-                                     &bar_w_full);
-                            mbar_wait(&bar_w_full, wloads & 1);
+                        const uint32_t d = tmem_base + dbuf * dcols + (uint32_t)(ncq * TC_NCH);
+                        for (int qq = 0; qq < 4; ++qq, ++piece_i) {
+                            const uint32_t slot = piece_i % F2_WSLOTS;
+                            // keep the ring full: the slot of the previous piece is free as soon as its MMAs are done;
+                            // its refill (the piece F2_WSLOTS - 1 ahead of this one) flies behind this piece's MMAs
+                            if (piece_i >= 1 && piece_i - 1 + F2_WSLOTS < total_pieces) {
+                                const uint32_t prev = piece_i - 1;
+                                mbar_wait(&bar_w_empty[prev % F2_WSLOTS], (prev / F2_WSLOTS) & 1);
+                                load_piece(prev + F2_WSLOTS);
+                            }
+                            mbar_wait(&bar_w_full[slot], (piece_i / F2_WSLOTS) & 1);
                             tc_fence_after();
+                            const uint32_t wl = w_lo0 + ((slot * TC_W_PIECE) >> 4);
+                            const uint32_t al = a_lo0 + (uint32_t)((qq * TC_WCH * F2_A_CHUNK) >> 4);
 #pragma unroll
                             for (int kc = 0; kc < TC_WCH; ++kc) {
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks) {
-                                    const uint32_t ko = (uint32_t)(ks * 32);
-                                    const uint32_t ac = a_addr + (uint32_t)((qq * TC_WCH + kc) * TC_A_CHUNK) + ko;
-                                    const uint64_t a_hi = tc_smem_desc(ac);
-                                    const uint64_t a_lo = tc_smem_desc(ac + TC_A_BYTES / 2);
-                                    const uint64_t b_hi = tc_smem_desc(w_addr + kc * (TC_NCH * 128) + ko);
-                                    const uint64_t b_lo = tc_smem_desc(w_addr + TC_W_PIECE / 2 + kc * (TC_NCH * 128) + ko);
+                                    const uint32_t ao = (uint32_t)((kc * F2_A_CHUNK + ks * 32) >> 4);
+                                    const uint32_t bo = (uint32_t)((kc * (TC_NCH * 128) + ks * 32) >> 4);
+                                    const uint64_t a_hi = mkdesc(al + ao);
+                                    const uint64_t a_lo = mkdesc(al + ao + ((F2_A_BYTES / 2) >> 4));
+                                    const uint64_t b_hi = mkdesc(wl + bo);
+                                    const uint64_t b_lo = mkdesc(wl + bo + ((TC_W_PIECE / 2) >> 4));
                                     const uint32_t first = (sl == 0 && qq == 0 && kc == 0 && ks == 0) ? 0u : 1u;
                                     tc_mma_bf16(d, a_hi, b_hi, idesc, first);
                                     tc_mma_bf16(d, a_lo, b_hi, idesc, 1u);
                                     tc_mma_bf16(d, a_hi, b_lo, idesc, 1u);
                                 }
                             }
-                            tc_commit(&bar_w_empty);
+                            tc_commit(&bar_w_empty[slot]);
                         }
                     }
-                    tc_commit(&bar_a_empty);
-                    if (sl == slabs - 1) tc_commit(&bar_d_full);
+                    tc_commit(&bar_a_empty[0]);
                 }
-                __syncwarp();
+                tc_commit(&bar_d_full[dbuf]);
             }
         }
-        // -------------------------------------------------------------- epilogue ----------------
-        if (warp < TC_TILE / 32) {
-            mbar_wait(&bar_d_full, tile_iter & 1);
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------ epilogue (warp 0: TMEM lanes 0-31) ----
+        for (int64_t ti = 0; ti < my_tiles; ++ti) {
+            const uint32_t dbuf = (uint32_t)(ti & 1);
+            mbar_wait(&bar_d_full[dbuf], (uint32_t)((ti >> 1) & 1));
             tc_fence_after();
-            const int64_t p = p_base + warp * 32 + lane;
+            const int64_t p = (blockIdx.x + ti * gridDim.x) * F2_ROWS + lane;
             for (int ncq = 0; ncq < ncl; ++ncq) {
                 float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ncq * TC_NCH), v);
-                if (p < n) {
-                    float4 *dst = reinterpret_cast<float4 *>(out + p * Cout + (nc0 + ncq) * TC_NCH);
+                tmem_ld32(tmem_base + dbuf * dcols + (uint32_t)(ncq * TC_NCH), v);
+                if (lane < F2_ROWS && p < n) {
+                    float4 *dst = reinterpret_cast<float4 *>(dst_out + p * Cout + (nc0 + ncq) * TC_NCH);
 #pragma unroll
                     for (int u = 0; u < 8; ++u) dst[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
                 }
             }
-            tc_fence_before();  // the next tile's first MMA overwrites D after the next __syncthreads
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_d_empty[dbuf]);
         }
     }
     __syncthreads();
-    if (warp == TC_PWARPS) {
+    if (warp == F2_PWARPS + 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// out[i] = ((part[0][i] + part[1][i]) + ...) in slab-group order (the split of the contraction over CTAs is
+// deterministic: partial sums are stored, not accumulated atomically)
+__global__ void __launch_bounds__(256)
+kpconv_reduce_parts_kernel(const float4 *__restrict__ part, int splits, int64_t n4, float4 *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+        float4 a = part[i];
+        for (int z = 1; z < splits; ++z) {
+            const float4 b = part[(int64_t)z * n4 + i];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        out[i] = a;
     }
 }
 
@@ -847,7 +1021,7 @@ constexpr int DW_SUB = 32;
 
 __global__ void __launch_bounds__(256)
 dw_accumulate_kernel(const float *__restrict__ A, const float *__restrict__ B, int64_t n, int R, int Cn, int64_t p_per_cta,
-                     float *__restrict__ dW) {
+                     float *__restrict__ dW, float *__restrict__ part) {
     extern __shared__ __align__(16) float dsm[];  // [2][DW_SUB][256 + 32]: double-buffered wf rows | dout rows
     constexpr int ROW = 256 + 32;
     const int tid = threadIdx.x, tr = tid >> 3, tc = tid & 7;  // row group (32), column group (8)
@@ -908,32 +1082,101 @@ dw_accumulate_kernel(const float *__restrict__ A, const float *__restrict__ B, i
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int r = r0 + tr * 8 + i, c = c0 + tc * 4 + j;
-            if (r < R && c < Cn) atomicAdd(dW + (int64_t)r * Cn + c, acc[i][j]);
+            if (r < R && c < Cn) {
+                // deterministic form: every point chunk stores its partial block, dw_reduce_kernel adds them in chunk
+                // order; without a partial buffer the blocks are reduced with fp32 atomics at L2
+                if (part) part[((int64_t)blockIdx.x * R + r) * Cn + c] = acc[i][j];
+                else atomicAdd(dW + (int64_t)r * Cn + c, acc[i][j]);
+            }
         }
 }
 
-int dw_accumulate(const float *A, const float *B, int64_t n, int R, int Cn, float *dW, cudaStream_t st) {
-    const int rb = (R + 255) / 256, cb = (Cn + 31) / 32;
-    int64_t chunks = (3 * kNumSMs + rb * cb - 1) / (rb * cb);  // 72 KB of staging per CTA: three CTAs per SM
+// dW[i] += ((part[0][i] + part[1][i]) + ...) in point-chunk order
+__global__ void __launch_bounds__(256)
+dw_reduce_kernel(const float *__restrict__ part, int chunks, int64_t total, float *__restrict__ dW) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        float a = part[i];
+        for (int c = 1; c < chunks; ++c) a += part[(int64_t)c * total + i];
+        dW[i] += a;
+    }
+}
+
+static void dw_plan(int64_t n, int R, int Cn, int &rb, int &cb, int64_t &chunks, int64_t &ppc) {
+    rb = (R + 255) / 256;
+    cb = (Cn + 31) / 32;
+    chunks = (3 * kNumSMs + rb * cb - 1) / (rb * cb);  // 72 KB of staging per CTA: three CTAs per SM
     if (chunks < 1) chunks = 1;
-    int64_t ppc = (n + chunks - 1) / chunks;
+    ppc = (n + chunks - 1) / chunks;
     ppc = (ppc + DW_SUB - 1) / DW_SUB * DW_SUB;
     if (ppc < 4 * DW_SUB) ppc = 4 * DW_SUB;
     chunks = (n + ppc - 1) / ppc;
+}
+
+// bytes of the partial buffer that makes dw_accumulate deterministic
+size_t dw_partial_bytes(int64_t n, int R, int Cn) {
+    int rb, cb;
+    int64_t chunks, ppc;
+    dw_plan(n, R, Cn, rb, cb, chunks, ppc);
+    return (size_t)chunks * (size_t)R * (size_t)Cn * sizeof(float);
+}
+
+// dW += A^T B; `part` (dw_partial_bytes, nullable) selects the deterministic two-pass reduction
+int dw_accumulate(const float *A, const float *B, int64_t n, int R, int Cn, float *dW, cudaStream_t st, float *part,
+                  size_t part_bytes) {
+    int rb, cb;
+    int64_t chunks, ppc;
+    dw_plan(n, R, Cn, rb, cb, chunks, ppc);
     if (rb > 65535 || cb > 65535) return 1;
+    if (part != nullptr && part_bytes < (size_t)chunks * R * Cn * sizeof(float)) part = nullptr;
     static DeviceOnce attr_done;
     const size_t smem = (size_t)2 * DW_SUB * (256 + 32) * sizeof(float);
     if (!attr_done.done()) {
         cudaFuncSetAttribute(dw_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done.mark();
     }
-    dw_accumulate_kernel<<<dim3((unsigned)chunks, (unsigned)rb, (unsigned)cb), 256, smem, st>>>(A, B, n, R, Cn, ppc, dW);
-    return finish_launch("kpconv_dW");
+    dw_accumulate_kernel<<<dim3((unsigned)chunks, (unsigned)rb, (unsigned)cb), 256, smem, st>>>(A, B, n, R, Cn, ppc, dW, part);
+    if (part == nullptr) return finish_launch("kpconv_dW");
+    if (int e = finish_launch("kpconv_dW")) return e;
+    const int64_t total = (int64_t)R * Cn;
+    int64_t rg = (total + 255) / 256;
+    if (rg > 4 * kNumSMs) rg = 4 * kNumSMs;
+    dw_reduce_kernel<<<(unsigned)rg, 256, 0, st>>>(part, (int)chunks, total, dW);
+    return finish_launch("kpconv_dW_reduce");
 }
 
-size_t kpconv_tc_ws_bytes(int K, int Cin, int Cout) {
+// how the forward kernel spreads a problem over the SMs: output-channel groups (grid.y) and slab groups (grid.z)
+struct FwdSplit {
+    int ygroups, ncpc, zsplit, spz;
+};
+static FwdSplit fwd_split(int64_t n, int Cin, int Cout) {
+    const int64_t ntiles = (n + F2_ROWS - 1) / F2_ROWS;
+    const int ncs = Cout / TC_NCH, slabs = Cin / 32;
+    FwdSplit f;
+    f.ygroups = (ncs + 7) / 8;  // one accumulator buffer holds at most 256 TMEM columns (two buffers)
+    f.zsplit = 1;
+    if (ntiles > 0 && ntiles * f.ygroups < kNumSMs) {
+        // fewer tiles than SMs: first cut the sequential chain of slab passes, then the output channels
+        int64_t want = kNumSMs / (ntiles * f.ygroups);
+        f.zsplit = (int)(want < slabs ? want : slabs);
+        if (f.zsplit < 1) f.zsplit = 1;
+        want = kNumSMs / (ntiles * f.zsplit);
+        if (want > ncs) want = ncs;
+        if (want > f.ygroups) f.ygroups = (int)want;
+    }
+    f.ncpc = (ncs + f.ygroups - 1) / f.ygroups;
+    f.ygroups = (ncs + f.ncpc - 1) / f.ncpc;
+    f.spz = (slabs + f.zsplit - 1) / f.zsplit;
+    f.zsplit = (slabs + f.spz - 1) / f.spz;
+    return f;
+}
+
+// workspace: the bf16 hi/lo weight image, then (slab-split problems only) the partial outputs [zsplit][n][Cout]
+size_t kpconv_tc_ws_bytes(int64_t n, int K, int Cin, int Cout) {
     if (K > KP_K || Cin % 32 != 0 || Cout % TC_NCH != 0 || Cout > 512) return 0;
-    return (size_t)(Cin / 32) * (Cout / TC_NCH) * 4 * TC_W_PIECE;
+    size_t bytes = (size_t)(Cin / 32) * (Cout / TC_NCH) * 4 * TC_W_PIECE;
+    const FwdSplit f = fwd_split(n, Cin, Cout);
+    if (f.zsplit > 1) bytes += (size_t)f.zsplit * (size_t)n * Cout * sizeof(float);
+    return bytes;
 }
 
 // returns 1 when the shape is not supported by this path (the caller then runs the fp32 SIMT kernel)
@@ -941,9 +1184,10 @@ int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neigh
                   const float *k_points, const float *k_values, int64_t n, int64_t N0, int M, int K, int Cin,
                   int Cout, float extent, int influence, int aggregation, float *out, void *ws, size_t ws_bytes,
                   cudaStream_t st, float *wf_out) {
-    const size_t need = kpconv_tc_ws_bytes(K, Cin, Cout);
+    const size_t need = kpconv_tc_ws_bytes(n, K, Cin, Cout);
     if (need == 0 || M > TC_MCAP || ws == nullptr || ws_bytes < need) return 1;
     if ((((uintptr_t)out) & 15) != 0 || (((uintptr_t)ws) & 15) != 0) return 1;  // float4 row stores, TMA source
+    if ((((uintptr_t)feat) & 15) != 0 || (wf_out && (((uintptr_t)wf_out) & 15) != 0)) return 1;  // 16-byte row copies
     KpGeom g;
     g.extent = extent;
     const float sig = extent * 0.3f;
@@ -953,9 +1197,10 @@ int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neigh
     const int tiles_w = (Cin / 32) * (Cout / TC_NCH) * 4;
     kpconv_prep_w_kernel<<<tiles_w, 256, 0, st>>>(k_values, K, Cin, Cout, (uint8_t *)ws);
     if (int e = finish_launch("kpconv_prep_w")) return e;
-    const size_t smem = TC_A_BYTES + TC_W_PIECE + (size_t)TC_PWARPS * TC_SCRATCH_FLOATS * sizeof(float) + 1024;
+    const size_t smem = F2_A_BYTES + F2_WSLOTS * TC_W_PIECE + (size_t)F2_PWARPS * F2_SCRATCH_FLOATS * sizeof(float) +
+                        KP_K * sizeof(float4) + (8 + 2 * F2_WSLOTS) * sizeof(uint64_t) + 16;
     using Kern = void (*)(const float *, const float *, const int64_t *, const float *, const float *, const uint8_t *,
-                          int64_t, int64_t, int, int, int, int, KpGeom, uint32_t, int, float *, float *);
+                          int64_t, int64_t, int, int, int, int, KpGeom, uint32_t, int, int, int64_t, float *, float *);
     static const Kern kerns[2][3][2] = {
         {{kpconv_fwd_tc_kernel<P3D_INFLUENCE_CONSTANT, false, false>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_CONSTANT, true, false>},
          {kpconv_fwd_tc_kernel<P3D_INFLUENCE_LINEAR, false, false>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_LINEAR, true, false>},
@@ -968,24 +1213,26 @@ int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neigh
         for (int w = 0; w < 2; ++w)
             for (int a = 0; a < 3; ++a)
                 for (int b = 0; b < 2; ++b)
-                    cudaFuncSetAttribute(kerns[w][a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024));
+                    cudaFuncSetAttribute(kerns[w][a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // (+ static <= 227 KB)
         attr_done.mark();
     }
-    const int64_t ntiles = (n + TC_TILE - 1) / TC_TILE;
-    const int ncs = Cout / TC_NCH;
-    int ygroups = 1;
-    if (ntiles < kNumSMs) {
-        ygroups = (int)((kNumSMs + ntiles - 1) / ntiles);
-        if (ygroups > ncs) ygroups = ncs;
-    }
-    const int ncpc = (ncs + ygroups - 1) / ygroups;
-    ygroups = (ncs + ncpc - 1) / ncpc;
+    const int64_t ntiles = (n + F2_ROWS - 1) / F2_ROWS;
+    const FwdSplit f = fwd_split(n, Cin, Cout);
     uint32_t cols = 32;
-    while ((int)cols < ncpc * TC_NCH) cols <<= 1;
-    const dim3 grid((unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs), (unsigned)ygroups);
-    kerns[wf_out != nullptr ? 1 : 0][influence][aggregation]<<<grid, TC_THREADS, smem, st>>>(query, support, neighbors, feat, k_points,
-                                                                  (const uint8_t *)ws, n, N0, M, K, Cin, Cout, g, cols,
-                                                                  ncpc, out, wf_out);
+    while ((int)cols < 2 * f.ncpc * TC_NCH) cols <<= 1;
+    float *parts = f.zsplit > 1 ? (float *)((char *)ws + (size_t)tiles_w * TC_W_PIECE) : out;
+    const int64_t part_stride = f.zsplit > 1 ? n * (int64_t)Cout : 0;
+    const dim3 grid((unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs), (unsigned)f.ygroups, (unsigned)f.zsplit);
+    kerns[wf_out != nullptr ? 1 : 0][influence][aggregation]<<<grid, F2_THREADS, smem, st>>>(
+        query, support, neighbors, feat, k_points, (const uint8_t *)ws, n, N0, M, K, Cin, Cout, g, cols, f.ncpc, f.spz,
+        part_stride, parts, wf_out);
+    if (f.zsplit > 1) {
+        if (int e = finish_launch("kpconv_fwd_tc")) return e;
+        const int64_t n4 = n * (int64_t)Cout / 4;
+        int64_t rg = (n4 + 255) / 256;
+        if (rg > 4 * kNumSMs) rg = 4 * kNumSMs;
+        kpconv_reduce_parts_kernel<<<(unsigned)rg, 256, 0, st>>>((const float4 *)parts, f.zsplit, n4, (float4 *)out);
+    }
     return finish_launch("kpconv_fwd_tc");
 }
 

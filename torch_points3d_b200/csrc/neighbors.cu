@@ -17,54 +17,12 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "neighbors_common.cuh"
 
 namespace p3d {
 
 constexpr int NB_TILE = 2048;  // candidate points per shared-memory tile (24 KB)
 constexpr int NB_WARPS = 8;
-
-struct RangeCache {
-    int64_t c[2], x0[2], x1[2];
-};
-
-// candidate range [x0, x1) of the cloud that owns query q (executed by a whole warp)
-template <bool DENSE>
-__device__ __forceinline__ void query_range(int64_t q, const int64_t *__restrict__ batch_x,
-                                            const int64_t *__restrict__ batch_y, int64_t Nx, int64_t n_dense,
-                                            int64_t s_dense, const RangeCache &rc, int lane, int64_t &x0,
-                                            int64_t &x1) {
-    if (DENSE) {
-        const int64_t b = q / s_dense;
-        x0 = b * n_dense;
-        x1 = x0 + n_dense;
-    } else if (batch_x == nullptr || batch_y == nullptr) {
-        x0 = 0;
-        x1 = Nx;
-    } else {
-        const int64_t c = batch_y[q];
-        if (c == rc.c[0]) { x0 = rc.x0[0]; x1 = rc.x1[0]; }
-        else if (c == rc.c[1]) { x0 = rc.x0[1]; x1 = rc.x1[1]; }
-        else {
-            x0 = warp_lower_bound(batch_x, Nx, c, lane);
-            x1 = warp_lower_bound(batch_x, Nx, c + 1, lane);
-        }
-    }
-}
-
-template <bool DENSE>
-__device__ __forceinline__ void cta_ranges(int64_t q0, int64_t q1, const int64_t *__restrict__ batch_x,
-                                           const int64_t *__restrict__ batch_y, int64_t Nx, RangeCache &rc,
-                                           int warp, int lane) {
-    if (!DENSE && batch_x != nullptr && batch_y != nullptr) {
-        if (warp < 2) {
-            const int64_t c = batch_y[warp == 0 ? q0 : q1 - 1];
-            const int64_t a = warp_lower_bound(batch_x, Nx, c, lane);
-            const int64_t b = warp_lower_bound(batch_x, Nx, c + 1, lane);
-            if (lane == 0) { rc.c[warp] = c; rc.x0[warp] = a; rc.x1[warp] = b; }
-        }
-    }
-    __syncthreads();
-}
 
 __device__ __forceinline__ void load_tile(const float *__restrict__ x, int64_t tb, int tn, float *sx, float *sy,
                                           float *sz, int tid, int nthreads) {

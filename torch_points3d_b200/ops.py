@@ -164,8 +164,7 @@ def ball_query(radius: float, nsample: int, x: torch.Tensor, y: torch.Tensor, mo
         n = y.shape[0]
         idx = torch.empty((n, nsample), dtype=torch.int64, device=dev)
         dist2 = torch.empty((n, nsample), dtype=torch.float32, device=dev) if return_dist else None
-        _call(dev, "p3d_ball_query_batch_f32", x.data_ptr(), y.data_ptr(), batch_x.data_ptr(), batch_y.data_ptr(),
-              x.shape[0], n, float(radius), int(nsample), 0, x.shape[0], idx.data_ptr(), _ptr(dist2))
+        _ball_query_batch(dev, x, y, batch_x, batch_y, float(radius), int(nsample), 0, x.shape[0], idx, dist2)
         return idx, dist2
     if mode == "dense":
         if batch_x is not None or batch_y is not None:
@@ -182,6 +181,29 @@ def ball_query(radius: float, nsample: int, x: torch.Tensor, y: torch.Tensor, mo
               idx.data_ptr(), _ptr(dist2))
         return idx, dist2
     raise Exception("unrecognized mode {}".format(mode))
+
+
+# Batched searches switch to the cell-list kernels (csrc/cellgrid.cu: same results bit for bit) once the support set is
+# large enough for the table build (4 small launches) to pay: below this many support points the plain sweep is used.
+GRID_SEARCH_MIN_POINTS = 4096
+GRID_BALL_MAX_NSAMPLE = 64
+GRID_KNN_MAX_K = 32
+
+
+def _grid_ws(dev, nx):
+    nbytes = _cabi.lib().p3d_cellgrid_ws_bytes(nx)
+    return torch.empty(nbytes, dtype=torch.uint8, device=dev), nbytes  # caching-allocator blocks are 512-byte aligned
+
+
+def _ball_query_batch(dev, x, y, batch_x, batch_y, radius, nsample, strict, shadow, idx, dist2):
+    nx = x.shape[0]
+    if nx >= GRID_SEARCH_MIN_POINTS and nsample <= GRID_BALL_MAX_NSAMPLE and radius > 0:
+        ws, nbytes = _grid_ws(dev, nx)
+        _call(dev, "p3d_ball_query_batch_grid_f32", x.data_ptr(), y.data_ptr(), _ptr(batch_x), _ptr(batch_y), nx,
+              y.shape[0], radius, nsample, strict, shadow, idx.data_ptr(), _ptr(dist2), ws.data_ptr(), nbytes)
+    else:
+        _call(dev, "p3d_ball_query_batch_f32", x.data_ptr(), y.data_ptr(), _ptr(batch_x), _ptr(batch_y), nx,
+              y.shape[0], radius, nsample, strict, shadow, idx.data_ptr(), _ptr(dist2))
 
 
 def ball_query_multi(radii, nsamples, x: torch.Tensor, y: torch.Tensor, strict: bool = True):
@@ -224,9 +246,8 @@ def radius(x: torch.Tensor, y: torch.Tensor, r: float, batch_x: Optional[torch.T
     n = y.shape[0]
     shadow = -1
     idx = torch.empty((n, max_num_neighbors), dtype=torch.int64, device=dev)
-    _call(dev, "p3d_ball_query_batch_f32", x.data_ptr(), y.data_ptr(), _ptr(None if batch_x is None else _i64(batch_x)),
-          _ptr(None if batch_y is None else _i64(batch_y)), x.shape[0], n, float(r), int(max_num_neighbors), 1, shadow,
-          idx.data_ptr(), None)
+    _ball_query_batch(dev, x, y, None if batch_x is None else _i64(batch_x), None if batch_y is None else _i64(batch_y),
+                      float(r), int(max_num_neighbors), 1, shadow, idx, None)
     keep = idx >= 0
     row = torch.arange(n, device=dev).view(-1, 1).expand_as(idx)[keep]
     return torch.stack([row, idx[keep]], dim=0)
@@ -251,8 +272,13 @@ def knn_table(x: torch.Tensor, y: torch.Tensor, k: int, batch_x: Optional[torch.
     by = None if batch_y is None else _i64(batch_y)
     col = torch.empty((y.shape[0], k), dtype=torch.int64, device=dev)
     d2 = torch.empty((y.shape[0], k), dtype=torch.float32, device=dev) if return_dist else None
-    _call(dev, "p3d_knn_batch_f32", x.data_ptr(), y.data_ptr(), _ptr(bx), _ptr(by), x.shape[0], y.shape[0], int(k),
-          col.data_ptr(), _ptr(d2))
+    if x.shape[0] >= GRID_SEARCH_MIN_POINTS and k <= GRID_KNN_MAX_K:
+        ws, nbytes = _grid_ws(dev, x.shape[0])
+        _call(dev, "p3d_knn_batch_grid_f32", x.data_ptr(), y.data_ptr(), _ptr(bx), _ptr(by), x.shape[0], y.shape[0],
+              int(k), col.data_ptr(), _ptr(d2), ws.data_ptr(), nbytes)
+    else:
+        _call(dev, "p3d_knn_batch_f32", x.data_ptr(), y.data_ptr(), _ptr(bx), _ptr(by), x.shape[0], y.shape[0], int(k),
+              col.data_ptr(), _ptr(d2))
     return col, d2
 
 
@@ -570,7 +596,7 @@ class _KPConv(torch.autograd.Function):
         N0, Cin = feat.shape
         K, _, Cout = k_values.shape
         out = torch.empty((n, Cout), dtype=torch.float32, device=dev)
-        ws_bytes = _cabi.lib().p3d_kpconv_fwd_ws_bytes(K, Cin, Cout) if precision else 0
+        ws_bytes = _cabi.lib().p3d_kpconv_fwd_ws_bytes(n, K, Cin, Cout) if precision else 0
         ws = _workspace(ws_bytes, dev)
         wf = None
         if save_wf and ws_bytes and M <= 40 and n > 0 and ctx.needs_input_grad[5]:
