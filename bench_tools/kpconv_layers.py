@@ -77,7 +77,7 @@ def main():
               (L["level"], L["cin"], L["cout"], n, N0, L["M"], t[0], t[1], t[2], t[3], err), flush=True)
         if L["strided"]:
             s_pos, s_batch, grid = q_pos, q_batch, grid * 2
-    ops.KPCONV_SPLIT_MAX_POINTS = 4096
+    ops.KPCONV_SPLIT_MAX_POINTS = 0
 
 
 if __name__ == "__main__":

@@ -513,13 +513,29 @@ def test_kpconv_split_path_small_point_sets(n, N0, M, cin, cout, influence, agg)
     W = (rng.standard_normal((15, cin, cout)) * 0.1).astype(np.float32)
     dout = rng.standard_normal((n, cout)).astype(np.float32)
     tx, tW = T(x).requires_grad_(True), T(W).requires_grad_(True)
-    assert n <= ops.KPCONV_SPLIT_MAX_POINTS and W.size >= ops.KPCONV_SPLIT_MIN_WEIGHTS
-    out = ops.KPConv_ops(T(qry), T(sup), T(nb), tx, T(Kp), tW, 0.06, influence, agg)
-    assert out.grad_fn.name().startswith("_KPConvSplit")
-    assert relerr(N(out), oracle.kpconv_fwd(qry, sup, nb, x, Kp, W, 0.06, influence, agg)) <= RTOL
-    out.backward(T(dout))
+    ref = oracle.kpconv_fwd(qry, sup, nb, x, Kp, W, 0.06, influence, agg)
     dx, dW = oracle.kpconv_bwd(qry, sup, nb, x, Kp, W, dout, 0.06, influence, agg)
+    # default path: the fused kernel, slabs of the contraction / output channels spread over the SMs
+    assert ops.KPCONV_SPLIT_MAX_POINTS == 0
+    out = ops.KPConv_ops(T(qry), T(sup), T(nb), tx, T(Kp), tW, 0.06, influence, agg)
+    assert out.grad_fn.name().startswith("_KPConv") and not out.grad_fn.name().startswith("_KPConvSplit")
+    assert relerr(N(out), ref) <= (RTOL_TENSOR if cin % 32 == 0 and cout % 32 == 0 and M <= 40 else RTOL)
+    out.backward(T(dout))
     assert relerr(N(tx.grad), dx) <= RTOL and relerr(N(tW.grad), dW) <= RTOL
+    again = ops.KPConv_ops(T(qry), T(sup), T(nb), tx, T(Kp), tW, 0.06, influence, agg)
+    assert torch.equal(out, again)          # split contractions add their partial sums in a fixed order
+    # opt-in: aggregation kernel + library GEMM (exact fp32)
+    ops.KPCONV_SPLIT_MAX_POINTS = 4096
+    try:
+        tx.grad = tW.grad = None
+        assert W.size >= ops.KPCONV_SPLIT_MIN_WEIGHTS
+        out = ops.KPConv_ops(T(qry), T(sup), T(nb), tx, T(Kp), tW, 0.06, influence, agg)
+        assert out.grad_fn.name().startswith("_KPConvSplit")
+        assert relerr(N(out), ref) <= RTOL
+        out.backward(T(dout))
+        assert relerr(N(tx.grad), dx) <= RTOL and relerr(N(tW.grad), dW) <= RTOL
+    finally:
+        ops.KPCONV_SPLIT_MAX_POINTS = 0
 
 
 @pytest.mark.parametrize("K,cin,cout,n", [(16, 32, 32, 3000), (16, 64, 64, 900), (16, 128, 128, 400), (7, 32, 64, 1500),

@@ -29,7 +29,7 @@ constexpr int CG_CAP = 256;            // hit buffer entries per warp (ball quer
 constexpr int CG_MAX_K = 64;           // largest nsample served by the cell-list ball query
 constexpr int CG_SMALL_CLOUD = 384;    // clouds up to this size are swept directly
 constexpr int CG_COORD_MASK = 16383;   // cell coordinates live on a periodic lattice of 2^14 cells per axis
-constexpr int CG_KNN_RMAX = 3;         // knn: rings of cells tried before the plain sweep
+constexpr int CG_KNN_RMAX = 8;         // knn: rings of cells tried before the plain sweep (17^3 cells: still far cheaper)
 constexpr uint64_t CG_EMPTY = 0ull;    // keys carry bit 63, so an all-zero table is an empty table
 
 struct __align__(16) CgSlot {
@@ -448,12 +448,23 @@ cg_knn_kernel(const float *__restrict__ x, const float *__restrict__ y, const in
             // plain sweep of the whole cloud in index order (small clouds, sparse neighbourhoods, fewer than k points)
             t = CUDART_INF_F; d_l = CUDART_INF_F;
             ti = 0x7fffffff; i_l = 0x7fffffff;
-            for (int64_t i0 = x0; i0 < x1; i0 += 32) {
-                const int64_t i = i0 + lane;
-                const bool ok = i < x1;
-                const int64_t ii = ok ? i : x0;
-                const float d = sqdist3(__ldg(x + 3 * ii), __ldg(x + 3 * ii + 1), __ldg(x + 3 * ii + 2), qx, qy, qz);
-                cg_knn_offer(d, (int)ii, ok, k, lane, d_l, i_l, t, ti);
+            for (int64_t i0 = x0; i0 < x1; i0 += 128) {  // 4 x 32 candidates per trip, their loads in flight together
+                float cxv[4], cyv[4], czv[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int64_t i = i0 + 32 * v + lane;
+                    const int64_t ii = i < x1 ? i : x0;
+                    cxv[v] = __ldg(x + 3 * ii);
+                    cyv[v] = __ldg(x + 3 * ii + 1);
+                    czv[v] = __ldg(x + 3 * ii + 2);
+                }
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int64_t i = i0 + 32 * v + lane;
+                    if (i0 + 32 * v >= x1) break;  // warp-uniform
+                    const float d = sqdist3(cxv[v], cyv[v], czv[v], qx, qy, qz);
+                    cg_knn_offer(d, (int)(i < x1 ? i : x0), i < x1, k, lane, d_l, i_l, t, ti);
+                }
             }
         }
         if (lane < k) {

@@ -43,7 +43,6 @@ constexpr int TC_A_CHUNK = TC_TILE * 128;            // one 64-K chunk of the A 
 constexpr int TC_A_BYTES = 2 * 8 * TC_A_CHUNK;       // hi|lo x 8 chunks = 128 KB
 constexpr int TC_WCH = 2;                            // 64-K chunks per weight piece
 constexpr int TC_W_PIECE = 2 * TC_WCH * TC_NCH * 128;  // hi|lo x 2 chunks x 32 rows x 128 B = 16 KB (a quarter slab of K)
-constexpr int TC_SCRATCH_FLOATS = TC_MCAP * 32;      // per warp of the sparse backward kernels: staged neighbour rows
 
 // ---- tcgen05 / TMEM wrappers -------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols) {
@@ -107,34 +106,43 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 // ---- W image: bf16 hi/lo, K-major, 128-byte swizzled tiles ---------------------------------
-// piece(s, nc, q) = [hi|lo][2 chunks of 64 K][32 rows = outputs 32nc..][128 B], q = K quarter of the slab;
-// K index inside a slab = k * 32 + c  (k = kernel point, c = channel inside the 32-channel slab s; kernel points
-// >= K are zero rows).
+// The output channels are cut into GROUPS of F2_NG = min(Cout, 128) columns (one UMMA N).  piece(s, g, kc) =
+// [hi | lo] x [N_g rows = outputs of group g][128 B] for the 64 K-elements kc of slab s, always F2_PIECE(NG) bytes
+// apart (a narrower last group leaves the tail of its piece unused).  K index inside a slab = k * 32 + c (k = kernel
+// point, c = channel inside the 32-channel slab s; kernel points >= K are zero rows), so chunk kc holds kernel points
+// 2 kc and 2 kc + 1.
+__host__ __device__ constexpr int f2_piece_bytes(int ng) { return 2 * ng * 128; }
+
 __global__ void __launch_bounds__(256)
-kpconv_prep_w_kernel(const float *__restrict__ W, int K, int Cin, int Cout, uint8_t *__restrict__ img) {
-    __shared__ __align__(16) uint8_t tile[TC_W_PIECE];  // the piece in its final layout
-    const int piece = blockIdx.x;  // ((s * ncs + nc) * 4 + q)
-    const int ncs = Cout / TC_NCH;
-    const int qq = piece & 3, nc = (piece >> 2) % ncs, s = (piece >> 2) / ncs;
-    // lanes run over the 32 output channels of the piece (contiguous in W): every warp load is one 128-byte line
-    const int r = threadIdx.x & 31, kg = threadIdx.x >> 5;
+kpconv_prep_w_kernel(const float *__restrict__ W, int K, int Cin, int Cout, int NG, uint8_t *__restrict__ img) {
+    extern __shared__ __align__(16) uint8_t tile[];  // the piece in its final layout (f2_piece_bytes(NG))
+    const int groups = (Cout + NG - 1) / NG;
+    const int piece = blockIdx.x;  // (s * groups + g) * 8 + kc
+    const int kc = piece & 7, g = (piece >> 3) % groups, s = (piece >> 3) / groups;
+    const int ng = (Cout - g * NG < NG) ? (Cout - g * NG) : NG;
+    // lanes run over output channels (contiguous in W): every warp load is one 128-byte line
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    for (int r0 = 0; r0 < ng; r0 += 32) {
+        const int r = r0 + lane;
 #pragma unroll 4
-    for (int kk = 0; kk < TC_WCH * 64 / 8; ++kk) {
-        const int kloc = kk * 8 + kg;             // K element inside the piece: 0..127
-        const int kc = kloc >> 6, e = kloc & 63;
-        const int kidx = qq * (TC_WCH * 64) + kloc;
-        const int k = kidx >> 5, c = kidx & 31;
-        const float v = k < K ? __ldg(W + ((int64_t)k * Cin + s * 32 + c) * Cout + nc * TC_NCH + r) : 0.f;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-        const int off = (kc * TC_NCH + r) * 128 + (((e >> 3) ^ (r & 7)) << 4) + ((e & 7) << 1);
-        *reinterpret_cast<__nv_bfloat16 *>(tile + off) = hi;
-        *reinterpret_cast<__nv_bfloat16 *>(tile + TC_WCH * TC_NCH * 128 + off) = lo;
+        for (int ee = 0; ee < 8; ++ee) {
+            const int e = ee * 8 + wq;               // K element inside the chunk: 0..63
+            const int kidx = kc * 64 + e;
+            const int k = kidx >> 5, c = kidx & 31;
+            const float v = (k < K && r < ng) ? __ldg(W + ((int64_t)k * Cin + s * 32 + c) * Cout + g * NG + r) : 0.f;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+            if (r < ng) {
+                const int off = r * 128 + (((e >> 3) ^ (r & 7)) << 4) + ((e & 7) << 1);
+                *reinterpret_cast<__nv_bfloat16 *>(tile + off) = hi;
+                *reinterpret_cast<__nv_bfloat16 *>(tile + ng * 128 + off) = lo;
+            }
+        }
     }
     __syncthreads();
-    uint4 *dst = reinterpret_cast<uint4 *>(img + (size_t)piece * TC_W_PIECE);
+    uint4 *dst = reinterpret_cast<uint4 *>(img + (size_t)piece * f2_piece_bytes(NG));
     const uint4 *src = reinterpret_cast<const uint4 *>(tile);
-    for (int i = threadIdx.x; i < TC_W_PIECE / 16; i += 256) dst[i] = src[i];
+    for (int i = threadIdx.x; i < f2_piece_bytes(ng) / 16; i += 256) dst[i] = src[i];
 }
 
 // ---- producer: wf[16 kernel points][32 channels] of one query point -----------------------
@@ -232,12 +240,12 @@ __device__ __forceinline__ void tc_weights(const TcPoint &P, const float4 *kps, 
 }
 
 // ---- forward kernel ---------------------------------------------------------------------------------------------
-constexpr int F2_ROWS = 16;                              // query points per A stage: one per producer warp
 constexpr int F2_PWARPS = 16;                            // producer warps (warps 1..16)
 constexpr int F2_THREADS = (F2_PWARPS + 2) * 32;         // warp 0 = epilogue, warps 1..16 = producers, warp 17 = MMA
-constexpr int F2_A_CHUNK = F2_ROWS * 128;                // one 64-K chunk of the A tile: 16 rows x 128 B
-constexpr int F2_A_BYTES = 2 * 8 * F2_A_CHUNK;           // hi|lo x 8 chunks = 32 KB (ONE stage: see the kernel comment)
-constexpr int F2_WSLOTS = 4;                             // W ring: 16 KB pieces, three copies in flight behind the MMAs
+// A tile: [hi|lo][8 chunks of 64 K][rows][128 B] with rows = 16 * ppw query points (ONE stage: see the kernel comment);
+// the weight ring takes the rest of a fixed 96 KB block: ppw = 1 -> 32 KB tile + 64 KB ring, ppw = 2 -> 64 KB + 32 KB
+constexpr int F2_AW_BYTES = 98304;
+constexpr int F2_MAXSLOTS = 8;                           // W ring slots = ring bytes / piece bytes, at most 8
 constexpr int F2_XPITCH = 36;                            // floats per staged neighbour row (32 + 4: bank spread)
 constexpr int F2_WT_PITCH = 40;                          // floats per kernel point in the weight table
 constexpr int F2_SCRATCH_FLOATS = TC_MCAP * F2_XPITCH + KP_K * F2_WT_PITCH;   // per producer warp: 8320 B
@@ -304,17 +312,24 @@ __device__ __forceinline__ void f2_load_idx(const int64_t *__restrict__ nbp, int
     I.a = lane < M ? __ldg(nbp + lane) : -1;
     I.b = 32 + lane < M ? __ldg(nbp + 32 + lane) : -1;
 }
+// raw loads only: the result (P = neighbour coordinates, Q = query point) is centred by f2_centre when the point's
+// turn comes, one tile later, so no instruction waits on these loads here
+struct TcQuery {
+    float x, y, z;
+};
 __device__ __forceinline__ void f2_load_coords(const float *__restrict__ q, const float *__restrict__ s, int64_t N0,
-                                               const TcIdx &I, TcPoint &P) {
-    const float qx = __ldg(q), qy = __ldg(q + 1), qz = __ldg(q + 2);
+                                               const TcIdx &I, TcPoint &P, TcQuery &Q) {
+    Q.x = __ldg(q); Q.y = __ldg(q + 1); Q.z = __ldg(q + 2);
     const int64_t a = I.a >= N0 ? -1 : I.a, b = I.b >= N0 ? -1 : I.b;
     P.j0 = (int)a;
     P.j1 = (int)b;
-    float ax = 1e6f, ay = 1e6f, az = 1e6f, bx = 1e6f, by = 1e6f, bz = 1e6f;
-    if (a >= 0) { ax = __ldg(s + 3 * a); ay = __ldg(s + 3 * a + 1); az = __ldg(s + 3 * a + 2); }
-    if (b >= 0) { bx = __ldg(s + 3 * b); by = __ldg(s + 3 * b + 1); bz = __ldg(s + 3 * b + 2); }
-    P.x0 = __fsub_rn(ax, qx); P.y0 = __fsub_rn(ay, qy); P.z0 = __fsub_rn(az, qz);
-    P.x1 = __fsub_rn(bx, qx); P.y1 = __fsub_rn(by, qy); P.z1 = __fsub_rn(bz, qz);
+    P.x0 = P.y0 = P.z0 = P.x1 = P.y1 = P.z1 = 1e6f;
+    if (a >= 0) { P.x0 = __ldg(s + 3 * a); P.y0 = __ldg(s + 3 * a + 1); P.z0 = __ldg(s + 3 * a + 2); }
+    if (b >= 0) { P.x1 = __ldg(s + 3 * b); P.y1 = __ldg(s + 3 * b + 1); P.z1 = __ldg(s + 3 * b + 2); }
+}
+__device__ __forceinline__ void f2_centre(TcPoint &P, const TcQuery &Q) {
+    P.x0 = __fsub_rn(P.x0, Q.x); P.y0 = __fsub_rn(P.y0, Q.y); P.z0 = __fsub_rn(P.z0, Q.z);
+    P.x1 = __fsub_rn(P.x1, Q.x); P.y1 = __fsub_rn(P.y1, Q.y); P.z1 = __fsub_rn(P.z1, Q.z);
 }
 
 // gridDim = (tile CTAs, output-channel groups, slab groups).  blockIdx.z owns the slabs [sl0, sl1) of the contraction
@@ -323,38 +338,46 @@ template <int INFL, bool CLOSEST, bool SAVE_WF>
 __global__ void __launch_bounds__(F2_THREADS, 1)
 kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, const int64_t *__restrict__ nb,
                      const float *__restrict__ x, const float *__restrict__ kp, const uint8_t *__restrict__ wimg,
-                     int64_t n, int64_t N0, int M, int K, int Cin, int Cout, KpGeom g, uint32_t tmem_cols, int ncpc,
-                     int spz, int64_t part_stride, float *__restrict__ out, float *__restrict__ wf_out) {
+                     int64_t n, int64_t N0, int M, int K, int Cin, int Cout, KpGeom g, uint32_t tmem_cols, int NG, int gpc,
+                     int spz, int ppw, int64_t part_stride, float *__restrict__ out, float *__restrict__ wf_out) {
     // All shared memory of this kernel is dynamic (no static variables), so the buffer starts at the base of the CTA's
     // shared window and the 1024-byte alignment the UMMA 128-byte swizzle atoms need costs no slack: the kernel uses
     // 226.5 of the 227 KB a CTA can have.
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();            // (never observed; a misaligned tile would corrupt silently)
-    uint8_t *a_tile = smem;                                  // [hi|lo][8 chunks][16 rows][128 B]
-    uint8_t *w_ring = smem + F2_A_BYTES;                     // F2_WSLOTS x [hi|lo][2 chunks][32 rows][128 B]
-    float *scratch = reinterpret_cast<float *>(smem + F2_A_BYTES + F2_WSLOTS * TC_W_PIECE);
-    uint8_t *tail = smem + F2_A_BYTES + F2_WSLOTS * TC_W_PIECE + (size_t)F2_PWARPS * F2_SCRATCH_FLOATS * sizeof(float);
+    const int a_rows = F2_PWARPS * ppw;                      // query points per tile
+    const uint32_t a_chunk = (uint32_t)a_rows * 128u;        // one 64-K chunk of the A tile
+    const uint32_t a_bytes = 16u * a_chunk;                  // hi|lo x 8 chunks
+    uint8_t *a_tile = smem;                                  // [hi|lo][8 chunks][a_rows][128 B]
+    uint8_t *w_ring = smem + a_bytes;                        // slots x [hi | lo][N rows][128 B]
+    float *scratch = reinterpret_cast<float *>(smem + F2_AW_BYTES);
+    uint8_t *tail = smem + F2_AW_BYTES + (size_t)F2_PWARPS * F2_SCRATCH_FLOATS * sizeof(float);
     float4 *kps = reinterpret_cast<float4 *>(tail);                          // [KP_K]
     uint64_t *bars = reinterpret_cast<uint64_t *>(tail + KP_K * sizeof(float4));
     uint64_t *bar_a_full = bars, *bar_a_empty = bars + 2, *bar_d_full = bars + 4, *bar_d_empty = bars + 6,
-             *bar_w_full = bars + 8, *bar_w_empty = bars + 8 + F2_WSLOTS;
-    uint32_t &tmem_base_s = *reinterpret_cast<uint32_t *>(bars + 8 + 2 * F2_WSLOTS);
+             *bar_w_full = bars + 8, *bar_w_empty = bars + 8 + F2_MAXSLOTS;
+    uint32_t &tmem_base_s = *reinterpret_cast<uint32_t *>(bars + 8 + 2 * F2_MAXSLOTS);
+    const uint32_t piece_bytes = (uint32_t)f2_piece_bytes(NG);
+    const uint32_t wslots = min((uint32_t)F2_MAXSLOTS, (F2_AW_BYTES - a_bytes) / piece_bytes);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ncs = Cout / TC_NCH;
-    // blockIdx.y owns the output-channel chunks [nc0, nc0 + ncl); blockIdx.z the slabs [sl0, sl1): small point sets
+    const int groups = (Cout + NG - 1) / NG;
+    // blockIdx.y owns the output-channel groups [g0, g0 + gl); blockIdx.z the slabs [sl0, sl1): small point sets
     // (deep layers) are spread over the SMs by output channels and by slabs of the contraction, every CTA recomputing
     // the (cheap) producer side of its tile
-    const int nc0 = blockIdx.y * ncpc;
-    const int ncl = (ncs - nc0 < ncpc) ? (ncs - nc0) : ncpc;
+    const int g0 = blockIdx.y * gpc;
+    const int gl = (groups - g0 < gpc) ? (groups - g0) : gpc;
+    const int col0 = g0 * NG;                                                      // first output channel of this CTA
+    const int ncols = (Cout - col0 < gl * NG) ? (Cout - col0) : gl * NG;           // its output channels
+    const int nc0 = g0;  // (the CTA with g0 == 0 stores wf)
     const int sl0 = blockIdx.z * spz;
     const int sl1 = (sl0 + spz < Cin / 32) ? (sl0 + spz) : Cin / 32;
     const int slabs = sl1 - sl0;
     float *__restrict__ dst_out = out + (int64_t)blockIdx.z * part_stride;
-    const int64_t ntiles = (n + F2_ROWS - 1) / F2_ROWS;
+    const int64_t ntiles = (n + a_rows - 1) / a_rows;
     const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;  // persistent: tiles blockIdx.x + i * gridDim.x
     const float inv_extent = 1.0f / g.extent;
-    const uint32_t dcols = (uint32_t)(ncl * TC_NCH);         // TMEM columns of one accumulator buffer
+    const uint32_t dcols = (uint32_t)(gl * NG);              // TMEM columns of one accumulator buffer
 
     if (tid < KP_K) kps[tid] = tid < K ? make_float4(__ldg(kp + 3 * tid), __ldg(kp + 3 * tid + 1), __ldg(kp + 3 * tid + 2), 0.f)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -365,7 +388,7 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
             mbar_init(&bar_d_full[i], 1);
             mbar_init(&bar_d_empty[i], 1);
         }
-        for (int i = 0; i < F2_WSLOTS; ++i) {
+        for (int i = 0; i < F2_MAXSLOTS; ++i) {
             mbar_init(&bar_w_full[i], 1);
             mbar_init(&bar_w_empty[i], 1);
         }
@@ -389,29 +412,40 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
         const uint32_t xs_row = smem_u32(xs) + (uint32_t)((lane >> 3) * F2_XPITCH * 4 + (lane & 7) * 16);
         const float *wrow = wt + myk * F2_WT_PITCH;
         const float *xh = xs + myh * 16;
-        auto point_of = [&](int64_t ti) { return (blockIdx.x + ti * gridDim.x) * F2_ROWS + pw; };
+        // the points of this warp in processing order: unit u = (tile u / ppw, row pw * ppw + u % ppw)
+        const int units = (int)my_tiles * ppw;
+        const int psh = ppw - 1;  // ppw is 1 or 2: u / ppw = u >> psh, u % ppw = u & psh (no integer division in the loop)
+        auto point_of = [&](int u) {
+            return ((int64_t)blockIdx.x + (int64_t)(u >> psh) * gridDim.x) * a_rows + pw * ppw + (u & psh);
+        };
         // geometry pipeline: coordinates of the current point, indices of the next one
         TcPoint P;
+        TcQuery Q;
+        Q.x = Q.y = Q.z = 0.f;
         TcIdx I1;
         I1.a = I1.b = -1;
         {
             TcIdx I0;
             I0.a = I0.b = -1;
-            if (my_tiles > 0 && point_of(0) < n) f2_load_idx(nb + point_of(0) * M, M, lane, I0);
-            if (my_tiles > 1 && point_of(1) < n) f2_load_idx(nb + point_of(1) * M, M, lane, I1);
-            if (my_tiles > 0 && point_of(0) < n) f2_load_coords(q + 3 * point_of(0), s, N0, I0, P);
+            if (units > 0 && point_of(0) < n) f2_load_idx(nb + point_of(0) * M, M, lane, I0);
+            if (units > 1 && point_of(1) < n) f2_load_idx(nb + point_of(1) * M, M, lane, I1);
+            if (units > 0 && point_of(0) < n) f2_load_coords(q + 3 * point_of(0), s, N0, I0, P, Q);
         }
         uint32_t pass = 0;
-        for (int64_t ti = 0; ti < my_tiles; ++ti) {
-            const int64_t p = point_of(ti);
+        for (int u = 0; u < units; ++u) {
+            const int64_t p = point_of(u);
+            const int pi = u & psh;
             TcPoint Pn;
+            TcQuery Qn;
+            Qn.x = Qn.y = Qn.z = 0.f;
             TcIdx I2;
             I2.a = I2.b = -1;
-            if (ti + 2 < my_tiles && point_of(ti + 2) < n) f2_load_idx(nb + point_of(ti + 2) * M, M, lane, I2);
-            if (ti + 1 < my_tiles && point_of(ti + 1) < n) f2_load_coords(q + 3 * point_of(ti + 1), s, N0, I1, Pn);
+            if (u + 2 < units && point_of(u + 2) < n) f2_load_idx(nb + point_of(u + 2) * M, M, lane, I2);
+            if (u + 1 < units && point_of(u + 1) < n) f2_load_coords(q + 3 * point_of(u + 1), s, N0, I1, Pn, Qn);
+            if (p < n) f2_centre(P, Q);
             unsigned mask0 = 0u, mask1 = 0u;
-            for (int sl = sl0; sl < sl1; ++sl, ++pass) {
-                const int row = pw;
+            for (int sl = sl0; sl < sl1; ++sl) {   // (ppw == 2 is only launched with one slab per CTA)
+                const int row = pw * ppw + pi;
                 float acc[16];
 #pragma unroll
                 for (int c = 0; c < 16; ++c) acc[c] = 0.f;
@@ -431,7 +465,7 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                     asm volatile("cp.async.commit_group;" ::: "memory");
                     if (sl == sl0) f2_weights<INFL, CLOSEST>(P, kps, K, M, g, inv_extent, wt, lane, mask0, mask1);
                 }
-                if (pass >= 1) mbar_wait(&bar_a_empty[0], (pass - 1) & 1);  // the MMAs of the previous pass have read the tile
+                if (pi == 0 && pass >= 1) mbar_wait(&bar_a_empty[0], (pass - 1) & 1);  // the MMAs of the previous pass have read the tile
                 if (p < n) {
                     asm volatile("cp.async.wait_group 0;" ::: "memory");
                     __syncwarp();  // rows and weights written by other lanes are visible
@@ -485,41 +519,49 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                     hi[u] = pack_bf16(h0, h1);
                     lo[u] = pack_bf16(a0 - h0, a1 - h1);
                 }
-                uint8_t *rowp = a_tile + (lane >> 2) * F2_A_CHUNK + row * 128;
+                uint8_t *rowp = a_tile + (lane >> 2) * a_chunk + row * 128;
                 const int g0 = (lane & 3) * 2, sw = row & 7;
                 *reinterpret_cast<uint4 *>(rowp + ((g0 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<uint4 *>(rowp + (((g0 + 1) ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                rowp += F2_A_BYTES / 2;
+                rowp += a_bytes / 2;
                 *reinterpret_cast<uint4 *>(rowp + ((g0 ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 *reinterpret_cast<uint4 *>(rowp + (((g0 + 1) ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-                fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_a_full[0]);
+                if (pi == ppw - 1) {  // the last row of this warp for the pass
+                    fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_a_full[0]);
+                    ++pass;
+                }
             }
             P = Pn;
+            Q = Qn;
             I1 = I2;
         }
     } else if (warp == F2_PWARPS + 1) {
         // ------------------------------------------------------------ MMA issuer ---------------------------
         if (lane == 0) {
-            const uint32_t idesc = tc_idesc(TC_MMA_M, TC_NCH);
+            // every MMA re-reads its whole A operand (M = 128 rows, 16 or 32 of them real) from shared memory: the
+            // count of MMAs per point is what bounds this warp, hence wide N (up to 128 output channels per
+            // instruction) and, for single-slab layers, 32-point tiles
             // shared-memory matrix descriptors differ only in their 14-bit start-address field (bytes >> 4, low word):
-            // one 32-bit add per operand instead of rebuilding the 64-bit descriptor for each of the 96 MMAs of a pass
+            // one 32-bit add per operand instead of rebuilding the 64-bit descriptor for each MMA
             const uint64_t a_desc0 = tc_smem_desc(smem_u32(a_tile)), w_desc0 = tc_smem_desc(smem_u32(w_ring));
             const uint32_t desc_hi = (uint32_t)(a_desc0 >> 32);
             const uint32_t a_lo0 = (uint32_t)a_desc0, w_lo0 = (uint32_t)w_desc0;
             auto mkdesc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | lo; };
-            const uint32_t ppp = (uint32_t)(4 * ncl);                       // W pieces per pass
+            const uint32_t ppp = (uint32_t)(8 * gl);                        // W pieces per pass: groups x 64-K chunks
             const uint32_t total_pieces = (uint32_t)(my_tiles * slabs) * ppp;
-            // piece i of this CTA's stream: pass i / ppp (slab = sl0 + pass % slabs), chunk (i % ppp) / 4, K quarter i % 4
+            // piece i of this CTA's stream: pass i / ppp (slab = sl0 + pass % slabs), group (i % ppp) / 8, chunk i % 8
             auto load_piece = [&](uint32_t i) {
-                const uint32_t slot = i % F2_WSLOTS;
+                const uint32_t slot = i % wslots;
                 const uint32_t j = i % ppp, sl = (uint32_t)sl0 + (i / ppp) % (uint32_t)slabs;
-                const size_t piece = ((size_t)(sl * ncs + nc0 + (j >> 2)) * 4 + (j & 3));
-                mbar_arrive_expect_tx(&bar_w_full[slot], TC_W_PIECE);
-                bulk_g2s(w_ring + slot * TC_W_PIECE, wimg + piece * TC_W_PIECE, TC_W_PIECE, &bar_w_full[slot]);
+                const uint32_t gg = (uint32_t)g0 + (j >> 3);
+                const uint32_t ng = (uint32_t)((Cout - (int)gg * NG < NG) ? (Cout - (int)gg * NG) : NG);
+                const size_t piece = ((size_t)(sl * groups + gg) * 8 + (j & 7));
+                mbar_arrive_expect_tx(&bar_w_full[slot], 2 * ng * 128);
+                bulk_g2s(w_ring + slot * piece_bytes, wimg + piece * piece_bytes, 2 * ng * 128, &bar_w_full[slot]);
             };
-            for (uint32_t i = 0; i < F2_WSLOTS && i < total_pieces; ++i) load_piece(i);
+            for (uint32_t i = 0; i < wslots && i < total_pieces; ++i) load_piece(i);
             uint32_t piece_i = 0, pass = 0;
             for (int64_t ti = 0; ti < my_tiles; ++ti) {
                 const uint32_t dbuf = (uint32_t)(ti & 1);
@@ -528,38 +570,38 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                 for (int sl = 0; sl < slabs; ++sl, ++pass) {
                     mbar_wait(&bar_a_full[0], pass & 1);
                     tc_fence_after();
-                    for (int ncq = 0; ncq < ncl; ++ncq) {
-                        const uint32_t d = tmem_base + dbuf * dcols + (uint32_t)(ncq * TC_NCH);
-                        for (int qq = 0; qq < 4; ++qq, ++piece_i) {
-                            const uint32_t slot = piece_i % F2_WSLOTS;
-                            // keep the ring full: the slot of the previous piece is free as soon as its MMAs are done;
-                            // its refill (the piece F2_WSLOTS - 1 ahead of this one) flies behind this piece's MMAs
-                            if (piece_i >= 1 && piece_i - 1 + F2_WSLOTS < total_pieces) {
-                                const uint32_t prev = piece_i - 1;
-                                mbar_wait(&bar_w_empty[prev % F2_WSLOTS], (prev / F2_WSLOTS) & 1);
-                                load_piece(prev + F2_WSLOTS);
-                            }
-                            mbar_wait(&bar_w_full[slot], (piece_i / F2_WSLOTS) & 1);
+                    for (int gq = 0; gq < gl; ++gq) {
+                        const int ng = (Cout - (g0 + gq) * NG < NG) ? (Cout - (g0 + gq) * NG) : NG;
+                        const uint32_t idesc = tc_idesc(TC_MMA_M, ng);
+                        const uint32_t d = tmem_base + dbuf * dcols + (uint32_t)(gq * NG);
+                        for (int kc = 0; kc < 8; ++kc, ++piece_i) {
+                            const uint32_t slot = piece_i % wslots;
+                            mbar_wait(&bar_w_full[slot], (piece_i / wslots) & 1);
                             tc_fence_after();
-                            const uint32_t wl = w_lo0 + ((slot * TC_W_PIECE) >> 4);
-                            const uint32_t al = a_lo0 + (uint32_t)((qq * TC_WCH * F2_A_CHUNK) >> 4);
+                            const uint32_t wl = w_lo0 + ((slot * piece_bytes) >> 4);
+                            const uint32_t al = a_lo0 + ((kc * a_chunk) >> 4);
+                            const uint32_t lo_off = (uint32_t)((ng * 128) >> 4);
 #pragma unroll
-                            for (int kc = 0; kc < TC_WCH; ++kc) {
-#pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) {
-                                    const uint32_t ao = (uint32_t)((kc * F2_A_CHUNK + ks * 32) >> 4);
-                                    const uint32_t bo = (uint32_t)((kc * (TC_NCH * 128) + ks * 32) >> 4);
-                                    const uint64_t a_hi = mkdesc(al + ao);
-                                    const uint64_t a_lo = mkdesc(al + ao + ((F2_A_BYTES / 2) >> 4));
-                                    const uint64_t b_hi = mkdesc(wl + bo);
-                                    const uint64_t b_lo = mkdesc(wl + bo + ((TC_W_PIECE / 2) >> 4));
-                                    const uint32_t first = (sl == 0 && qq == 0 && kc == 0 && ks == 0) ? 0u : 1u;
-                                    tc_mma_bf16(d, a_hi, b_hi, idesc, first);
-                                    tc_mma_bf16(d, a_lo, b_hi, idesc, 1u);
-                                    tc_mma_bf16(d, a_hi, b_lo, idesc, 1u);
-                                }
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint32_t ko = (uint32_t)((ks * 32) >> 4);
+                                const uint64_t a_hi = mkdesc(al + ko);
+                                const uint64_t a_lo = mkdesc(al + ko + ((a_bytes / 2) >> 4));
+                                const uint64_t b_hi = mkdesc(wl + ko);
+                                const uint64_t b_lo = mkdesc(wl + ko + lo_off);
+                                const uint32_t first = (sl == 0 && kc == 0 && ks == 0) ? 0u : 1u;
+                                tc_mma_bf16(d, a_hi, b_hi, idesc, first);
+                                tc_mma_bf16(d, a_lo, b_hi, idesc, 1u);
+                                tc_mma_bf16(d, a_hi, b_lo, idesc, 1u);
                             }
                             tc_commit(&bar_w_empty[slot]);
+                            // keep the ring full: the slot of the PREVIOUS piece is free once its MMAs have retired --
+                            // which they do while this piece's MMAs, just issued, keep the tensor pipe busy -- and
+                            // takes the piece wslots - 1 ahead of the next one
+                            if (piece_i >= 1 && piece_i - 1 + wslots < total_pieces) {
+                                const uint32_t prev = piece_i - 1;
+                                mbar_wait(&bar_w_empty[prev % wslots], (prev / wslots) & 1);
+                                load_piece(prev + wslots);
+                            }
                         }
                     }
                     tc_commit(&bar_a_empty[0]);
@@ -574,12 +616,12 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
             const uint32_t dbuf = (uint32_t)(ti & 1);
             mbar_wait(&bar_d_full[dbuf], (uint32_t)((ti >> 1) & 1));
             tc_fence_after();
-            const int64_t p = (blockIdx.x + ti * gridDim.x) * F2_ROWS + lane;
-            for (int ncq = 0; ncq < ncl; ++ncq) {
+            const int64_t p = (blockIdx.x + ti * gridDim.x) * a_rows + lane;
+            for (int cq = 0; cq < ncols / 32; ++cq) {
                 float v[32];
-                tmem_ld32(tmem_base + dbuf * dcols + (uint32_t)(ncq * TC_NCH), v);
-                if (lane < F2_ROWS && p < n) {
-                    float4 *dst = reinterpret_cast<float4 *>(dst_out + p * Cout + (nc0 + ncq) * TC_NCH);
+                tmem_ld32(tmem_base + dbuf * dcols + (uint32_t)(cq * 32), v);
+                if (lane < a_rows && p < n) {
+                    float4 *dst = reinterpret_cast<float4 *>(dst_out + p * Cout + col0 + cq * 32);
 #pragma unroll
                     for (int u = 0; u < 8; ++u) dst[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
                 }
@@ -1144,15 +1186,26 @@ int dw_accumulate(const float *A, const float *B, int64_t n, int R, int Cn, floa
     return finish_launch("kpconv_dW_reduce");
 }
 
-// how the forward kernel spreads a problem over the SMs: output-channel groups (grid.y) and slab groups (grid.z)
+// how the forward kernel spreads a problem over the SMs: output-channel groups of NG columns (grid.y takes gpc groups
+// each) and slab groups (grid.z takes spz slabs each)
 struct FwdSplit {
-    int ygroups, ncpc, zsplit, spz;
+    int NG, groups, ygroups, gpc, zsplit, spz, ppw;
 };
 static FwdSplit fwd_split(int64_t n, int Cin, int Cout) {
-    const int64_t ntiles = (n + F2_ROWS - 1) / F2_ROWS;
-    const int ncs = Cout / TC_NCH, slabs = Cin / 32;
+    const int slabs = Cin / 32;
     FwdSplit f;
-    f.ygroups = (ncs + 7) / 8;  // one accumulator buffer holds at most 256 TMEM columns (two buffers)
+    f.NG = Cout < 128 ? Cout : 128;
+    f.groups = (Cout + f.NG - 1) / f.NG;
+    // single-slab layers with narrow outputs (the big first levels): 32-point tiles, two points per producer warp --
+    // half the MMAs per point; the tile then takes 64 of the 96 KB block, which leaves room for >= 2 weight pieces
+    // only when a piece is <= 16 KB
+    f.ppw = (slabs == 1 && f.NG <= 64) ? 2 : 1;
+    const int rows = F2_PWARPS * f.ppw;
+    const int64_t ntiles = (n + rows - 1) / rows;
+    // two accumulator buffers of gpc * NG columns must fit the 512 TMEM columns
+    int max_gpc = 256 / f.NG;
+    if (max_gpc < 1) max_gpc = 1;
+    f.ygroups = (f.groups + max_gpc - 1) / max_gpc;
     f.zsplit = 1;
     if (ntiles > 0 && ntiles * f.ygroups < kNumSMs) {
         // fewer tiles than SMs: first cut the sequential chain of slab passes, then the output channels
@@ -1160,20 +1213,25 @@ static FwdSplit fwd_split(int64_t n, int Cin, int Cout) {
         f.zsplit = (int)(want < slabs ? want : slabs);
         if (f.zsplit < 1) f.zsplit = 1;
         want = kNumSMs / (ntiles * f.zsplit);
-        if (want > ncs) want = ncs;
+        if (want > f.groups) want = f.groups;
         if (want > f.ygroups) f.ygroups = (int)want;
     }
-    f.ncpc = (ncs + f.ygroups - 1) / f.ygroups;
-    f.ygroups = (ncs + f.ncpc - 1) / f.ncpc;
+    f.gpc = (f.groups + f.ygroups - 1) / f.ygroups;
+    f.ygroups = (f.groups + f.gpc - 1) / f.gpc;
     f.spz = (slabs + f.zsplit - 1) / f.zsplit;
     f.zsplit = (slabs + f.spz - 1) / f.spz;
     return f;
 }
 
+static size_t fwd_image_bytes(int Cin, int Cout) {
+    const int NG = Cout < 128 ? Cout : 128;
+    return (size_t)(Cin / 32) * ((Cout + NG - 1) / NG) * 8 * f2_piece_bytes(NG);
+}
+
 // workspace: the bf16 hi/lo weight image, then (slab-split problems only) the partial outputs [zsplit][n][Cout]
 size_t kpconv_tc_ws_bytes(int64_t n, int K, int Cin, int Cout) {
     if (K > KP_K || Cin % 32 != 0 || Cout % TC_NCH != 0 || Cout > 512) return 0;
-    size_t bytes = (size_t)(Cin / 32) * (Cout / TC_NCH) * 4 * TC_W_PIECE;
+    size_t bytes = fwd_image_bytes(Cin, Cout);
     const FwdSplit f = fwd_split(n, Cin, Cout);
     if (f.zsplit > 1) bytes += (size_t)f.zsplit * (size_t)n * Cout * sizeof(float);
     return bytes;
@@ -1194,13 +1252,20 @@ int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neigh
     g.gauss_den = 2.0f * sig * sig + 1e-9f;
     g.influence = influence;
     g.aggregation = aggregation;
-    const int tiles_w = (Cin / 32) * (Cout / TC_NCH) * 4;
-    kpconv_prep_w_kernel<<<tiles_w, 256, 0, st>>>(k_values, K, Cin, Cout, (uint8_t *)ws);
+    const FwdSplit f = fwd_split(n, Cin, Cout);
+    const int pieces_w = (Cin / 32) * f.groups * 8;
+    static DeviceOnce prep_done;
+    if (!prep_done.done()) {
+        cudaFuncSetAttribute(kpconv_prep_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f2_piece_bytes(128));
+        prep_done.mark();
+    }
+    kpconv_prep_w_kernel<<<pieces_w, 256, f2_piece_bytes(f.NG), st>>>(k_values, K, Cin, Cout, f.NG, (uint8_t *)ws);
     if (int e = finish_launch("kpconv_prep_w")) return e;
-    const size_t smem = F2_A_BYTES + F2_WSLOTS * TC_W_PIECE + (size_t)F2_PWARPS * F2_SCRATCH_FLOATS * sizeof(float) +
-                        KP_K * sizeof(float4) + (8 + 2 * F2_WSLOTS) * sizeof(uint64_t) + 16;
+    const size_t smem = F2_AW_BYTES + (size_t)F2_PWARPS * F2_SCRATCH_FLOATS * sizeof(float) + KP_K * sizeof(float4) +
+                        (8 + 2 * F2_MAXSLOTS) * sizeof(uint64_t) + 16;
     using Kern = void (*)(const float *, const float *, const int64_t *, const float *, const float *, const uint8_t *,
-                          int64_t, int64_t, int, int, int, int, KpGeom, uint32_t, int, int, int64_t, float *, float *);
+                          int64_t, int64_t, int, int, int, int, KpGeom, uint32_t, int, int, int, int, int64_t, float *,
+                          float *);
     static const Kern kerns[2][3][2] = {
         {{kpconv_fwd_tc_kernel<P3D_INFLUENCE_CONSTANT, false, false>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_CONSTANT, true, false>},
          {kpconv_fwd_tc_kernel<P3D_INFLUENCE_LINEAR, false, false>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_LINEAR, true, false>},
@@ -1216,16 +1281,15 @@ int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neigh
                     cudaFuncSetAttribute(kerns[w][a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // (+ static <= 227 KB)
         attr_done.mark();
     }
-    const int64_t ntiles = (n + F2_ROWS - 1) / F2_ROWS;
-    const FwdSplit f = fwd_split(n, Cin, Cout);
+    const int64_t ntiles = (n + F2_PWARPS * f.ppw - 1) / (F2_PWARPS * f.ppw);
     uint32_t cols = 32;
-    while ((int)cols < 2 * f.ncpc * TC_NCH) cols <<= 1;
-    float *parts = f.zsplit > 1 ? (float *)((char *)ws + (size_t)tiles_w * TC_W_PIECE) : out;
+    while ((int)cols < 2 * f.gpc * f.NG) cols <<= 1;
+    float *parts = f.zsplit > 1 ? (float *)((char *)ws + fwd_image_bytes(Cin, Cout)) : out;
     const int64_t part_stride = f.zsplit > 1 ? n * (int64_t)Cout : 0;
     const dim3 grid((unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs), (unsigned)f.ygroups, (unsigned)f.zsplit);
     kerns[wf_out != nullptr ? 1 : 0][influence][aggregation]<<<grid, F2_THREADS, smem, st>>>(
-        query, support, neighbors, feat, k_points, (const uint8_t *)ws, n, N0, M, K, Cin, Cout, g, cols, f.ncpc, f.spz,
-        part_stride, parts, wf_out);
+        query, support, neighbors, feat, k_points, (const uint8_t *)ws, n, N0, M, K, Cin, Cout, g, cols, f.NG, f.gpc, f.spz,
+        f.ppw, part_stride, parts, wf_out);
     if (f.zsplit > 1) {
         if (int e = finish_launch("kpconv_fwd_tc")) return e;
         const int64_t n4 = n * (int64_t)Cout / 4;

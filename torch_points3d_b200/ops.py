@@ -184,8 +184,11 @@ def ball_query(radius: float, nsample: int, x: torch.Tensor, y: torch.Tensor, mo
 
 
 # Batched searches switch to the cell-list kernels (csrc/cellgrid.cu: same results bit for bit) once the support set is
-# large enough for the table build (4 small launches) to pay: below this many support points the plain sweep is used.
-GRID_SEARCH_MIN_POINTS = 4096
+# large enough for the table build (a memset + 3 small launches, ~20 us) to pay: below this many support points the plain
+# sweep is used.  Measured on B200 (profiles/r2_search_times.md): 50 k points in 8 clouds 87 vs 310 us, 15 k points in 8
+# clouds 48 vs 39 us -- the sweep's cost grows with points PER CLOUD, which the host does not know without a device
+# read, so the switch is on the total; lower it for batches of few large clouds.
+GRID_SEARCH_MIN_POINTS = 24576
 GRID_BALL_MAX_NSAMPLE = 64
 GRID_KNN_MAX_K = 32
 
@@ -675,8 +678,10 @@ class _KPConvSplit(torch.autograd.Function):
         return None, None, None, dfeat, None, dW, None, None, None
 
 
-# query-point count below which KPConv_ops runs as aggregation kernel + library GEMM (see _KPConvSplit)
-KPCONV_SPLIT_MAX_POINTS = 4096
+# Opt-in (default off): query-point count below which KPConv_ops runs as aggregation kernel + library GEMM (see
+# _KPConvSplit).  The fused tcgen05 kernel spreads small point sets over the SMs by output channels and by slabs of the
+# contraction and is the faster forward at every level of the KPConvPaper encoder (profiles/r2_kpconv_layers.md).
+KPCONV_SPLIT_MAX_POINTS = 0
 KPCONV_SPLIT_MIN_WEIGHTS = 15 * 64 * 64
 
 
