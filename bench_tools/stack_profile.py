@@ -1,28 +1,21 @@
-"""Three eager training steps of the KPConv encoder stack with a precomputed pyramid (for an ncu launch list):
-    ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file out.csv python bench_tools/stack_profile.py"""
+"""Eager training steps of the KPConvPaper segmentation network (C3 / C5 shape) for an ncu launch list:
+    ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file out.csv python bench_tools/stack_profile.py
+With the argument `geometry` the pyramid is rebuilt inside every step (the searches show up in the list)."""
 import os
 import sys
 
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from torch_points3d_b200 import kpconv, synthetic  # noqa: E402
+from torch_points3d_b200 import segmentation  # noqa: E402
 
 dev = torch.device("cuda", 0)
-pos_h, batch_h = synthetic.indoor_spheres(seed=1003)
-pos, batch = torch.from_numpy(pos_h).to(dev), torch.from_numpy(batch_h).to(dev)
 torch.manual_seed(5)
-enc = kpconv.KPConvEncoder(5, max_nn_cap=34).to(dev)
-head = torch.nn.Linear(enc.out_channels, 13).to(dev)
-opt = torch.optim.SGD(list(enc.parameters()) + list(head.parameters()), lr=0.01, momentum=0.98)
-feats = torch.cat([torch.ones(pos.shape[0], 1, device=dev), torch.randn(pos.shape[0], 4, device=dev)], 1)
-ms = kpconv.MultiScaleTransform(enc.strategies())(pos, batch)
-print("points per level:", [m.pos.shape[0] for m in ms])
+tr = segmentation.KPConvSegmentationTrainer(feat_dim=4, num_classes=13, device=dev)
+rebuild = len(sys.argv) > 1 and sys.argv[1] == "geometry"
+tr.build_pyramid()
+print("points per level:", [m.pos.shape[0] for m in tr.pyramid[0]])
 for it in range(3):
-    opt.zero_grad(set_to_none=True)
-    logits = head(enc(pos, feats, batch, precomputed=ms).x)
-    loss = torch.nn.functional.cross_entropy(logits, torch.arange(logits.shape[0], device=dev) % 13)
-    loss.backward()
-    opt.step()
+    loss = tr.step(rebuild_geometry=rebuild)
 torch.cuda.synchronize()
-print("loss", float(loss))
+print("loss", loss)

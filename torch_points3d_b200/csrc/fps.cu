@@ -188,10 +188,12 @@ fps_reg_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr, i
 //     by the round and keeps its cached farthest point.  After a few hundred samples almost every block is skipped;
 //     how many depends on how compact 32 consecutive points are (scan order, voxel order: very; random order: the
 //     kernel degrades to the unpruned update, results never change).
-//   * exchange: each WARP pushes its 32-byte record (key, index, coordinates) straight into every CTA of the cluster
-//     with st.async (remote shared-memory store that signals the receiver's mbarrier with complete_tx); a CTA then
-//     waits on its OWN mbarrier for CLUSTER x warps records and every warp reduces them redundantly.  One remote hop
-//     per round: no __syncthreads, no CTA-level reduction, no barrier.cluster on the critical path.
+//   * exchange: the CTA's winner (warp argmax -> one record per warp in shared memory -> __syncthreads -> warp 0 reduces
+//     them) is pushed as ONE 32-byte record (key, index, coordinates) into every CTA of the cluster with st.async (a
+//     remote shared-memory store that signals the receiver's mbarrier with complete_tx); a CTA then waits on its OWN
+//     mbarrier for the CLUSTER records and every warp reduces them redundantly.  One remote hop per round and no
+//     barrier.cluster on the critical path.  (Pushing every WARP's record to every CTA instead -- no __syncthreads, no
+//     CTA-level reduction -- was measured slower: 256 transaction updates per round serialise on each CTA's mbarrier.)
 //   Records and barriers are double-buffered by round parity: a CTA can be at most one round ahead of a peer.
 struct __align__(16) FpsRec32 {
     unsigned key, idx;
@@ -236,11 +238,11 @@ fps_pruned_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr
                   const int64_t *__restrict__ out_ptr, int64_t s_dense, IdxT *__restrict__ out,
                   const int64_t *__restrict__ first, float *__restrict__ new_xyz) {
     constexpr int NW = T / 32;
-    constexpr int NREC = CLUSTER * NW;           // records a CTA receives per round
-    static_assert(NREC % 32 == 0 && NREC <= 256, "record count per round");
+    static_assert(CLUSTER <= 32 && NW <= 32, "one record per lane");
     extern __shared__ float csm[];               // cx | cy | cz, T * PPT floats each (slot = j * T + tid)
     float *cx = csm, *cy = csm + T * PPT, *cz = csm + 2 * T * PPT;
-    __shared__ FpsRec32 recs[2][NREC];
+    __shared__ FpsRec32 recs[2][CLUSTER];        // the CTA winners of a round, one per cluster rank
+    __shared__ uint4 wrec[2][NW];                // this CTA's warp winners: key, index, slot
     __shared__ __align__(8) uint64_t bars[2];
 
     cg::cluster_group cluster = cg::this_cluster();
@@ -307,9 +309,9 @@ fps_pruned_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr
     }
     cluster.sync();  // every CTA's barriers are initialised before the first remote store can arrive
 
-    // remote addresses of this warp's record slot and of the barriers in CTA `lane` (lanes < CLUSTER push)
-    const uint32_t my_rec0 = (uint32_t)__cvta_generic_to_shared(&recs[0][rank * NW + warp]);
-    const uint32_t my_rec1 = (uint32_t)__cvta_generic_to_shared(&recs[1][rank * NW + warp]);
+    // remote addresses of this CTA's record slot and of the barriers in CTA `lane` (warp 0, lanes < CLUSTER push)
+    const uint32_t my_rec0 = (uint32_t)__cvta_generic_to_shared(&recs[0][rank]);
+    const uint32_t my_rec1 = (uint32_t)__cvta_generic_to_shared(&recs[1][rank]);
     const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&bars[0]);
     const uint32_t bar1 = (uint32_t)__cvta_generic_to_shared(&bars[1]);
     uint32_t r_rec[2] = {0u, 0u}, r_bar[2] = {0u, 0u};
@@ -322,7 +324,7 @@ fps_pruned_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr
 
     for (int64_t r = 1; r < s; ++r) {
         const int buf = (int)(r & 1);
-        if (tid == 0) fps_mbar_expect(&bars[buf], NREC * (uint32_t)sizeof(FpsRec32));
+        if (tid == 0) fps_mbar_expect(&bars[buf], CLUSTER * (uint32_t)sizeof(FpsRec32));
         // squared distance from the new sample to this block's bounding box, in sqdist3's operation order
         {
             const float ex = fmaxf(fmaxf(__fsub_rn(bx0, lx), __fsub_rn(lx, bx1)), 0.f);
@@ -347,27 +349,33 @@ fps_pruned_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr
         const unsigned key = mybest >= 0.f ? __float_as_uint(mybest) : 0u;
         unsigned wkey, widx;
         warp_argmax(key, bi, wkey, widx);
-        const int wl = __ffs(__ballot_sync(0xffffffffu, key == wkey && bi == widx)) - 1;
-        // the winning lane's coordinates, broadcast; lanes < CLUSTER push the record to one CTA each
-        const int wslot = __shfl_sync(0xffffffffu, myj * T + tid, wl);
-        const float wx = cx[wslot], wy = cy[wslot], wz = cz[wslot];
-        if (lane < CLUSTER) {
-            st_async_v4(r_rec[buf], wkey, widx, __float_as_uint(wx), __float_as_uint(wy), r_bar[buf]);
-            st_async_v4(r_rec[buf] + 16u, __float_as_uint(wz), 0u, 0u, 0u, r_bar[buf]);
+        if (key == wkey && bi == widx) wrec[buf][warp] = make_uint4(wkey, widx, (unsigned)(myj * T + tid), 0u);
+        __syncthreads();
+        if (warp == 0) {
+            // CTA winner, pushed to every CTA of the cluster (this one included) by lanes < CLUSTER
+            uint4 w = make_uint4(0u, 0xffffffffu, 0u, 0u);
+            if (lane < NW) w = wrec[buf][lane];
+            unsigned ckey, cidx;
+            warp_argmax(w.x, w.y, ckey, cidx);
+            const int cl = __ffs(__ballot_sync(0xffffffffu, w.x == ckey && w.y == cidx)) - 1;
+            const unsigned cslot = __shfl_sync(0xffffffffu, w.z, cl);
+            const float wx = cx[cslot], wy = cy[cslot], wz = cz[cslot];
+            if (lane < CLUSTER) {
+                st_async_v4(r_rec[buf], ckey, cidx, __float_as_uint(wx), __float_as_uint(wy), r_bar[buf]);
+                st_async_v4(r_rec[buf] + 16u, __float_as_uint(wz), 0u, 0u, 0u, r_bar[buf]);
+            }
         }
         fps_mbar_wait(&bars[buf], (uint32_t)(((r - 1) >> 1) & 1));  // rounds 1, 2 are the first use of bars[1], bars[0]
-        // every warp reduces the NREC records: NREC / 32 per lane, then the warp argmax
+        // every warp reduces the CLUSTER records
         unsigned k2 = 0u, i2 = 0xffffffffu;
-        int src = 0;
-#pragma unroll
-        for (int u = 0; u < NREC / 32; ++u) {
-            const uint2 kv = *reinterpret_cast<const uint2 *>(&recs[buf][u * 32 + lane]);
-            if (kv.x > k2 || (kv.x == k2 && kv.y < i2)) { k2 = kv.x; i2 = kv.y; src = u * 32 + lane; }
+        if (lane < CLUSTER) {
+            const uint2 kv = *reinterpret_cast<const uint2 *>(&recs[buf][lane]);
+            k2 = kv.x;
+            i2 = kv.y;
         }
         unsigned gkey, gidx;
         warp_argmax(k2, i2, gkey, gidx);
-        const int gl = __ffs(__ballot_sync(0xffffffffu, k2 == gkey && i2 == gidx)) - 1;
-        src = __shfl_sync(0xffffffffu, src, gl);
+        const int src = __ffs(__ballot_sync(0xffffffffu, k2 == gkey && i2 == gidx)) - 1;
         lx = recs[buf][src].x;
         ly = recs[buf][src].y;
         lz = recs[buf][src].z;

@@ -179,7 +179,7 @@ __device__ __forceinline__ float tc_influence(float cx, float cy, float cz, cons
     d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
     if (INFL == P3D_INFLUENCE_LINEAR) {
         float r;
-        asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(d2));
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d2));
         return fmaxf(fmaf(-r, inv_extent, 1.0f), 0.f);
     }
     if (INFL == P3D_INFLUENCE_CONSTANT) return 1.0f;
@@ -242,8 +242,9 @@ __device__ __forceinline__ void tc_weights(const TcPoint &P, const float4 *kps, 
 // ---- forward kernel ---------------------------------------------------------------------------------------------
 constexpr int F2_PWARPS = 16;                            // producer warps (warps 1..16)
 constexpr int F2_THREADS = (F2_PWARPS + 2) * 32;         // warp 0 = epilogue, warps 1..16 = producers, warp 17 = MMA
-// A tile: [hi|lo][8 chunks of 64 K][rows][128 B] with rows = 16 * ppw query points (ONE stage: see the kernel comment);
-// the weight ring takes the rest of a fixed 96 KB block: ppw = 1 -> 32 KB tile + 64 KB ring, ppw = 2 -> 64 KB + 32 KB
+// A tile: [hi|lo][8 chunks of 64 K][stages x 16 * ppw rows][128 B] = 32 KB x stages x ppw (with two stages the
+// producers fill one while the tensor core reads the other); the weight ring takes the rest of a fixed 96 KB block.
+// fwd_split() picks (stages, ppw) in {(1,1), (2,1), (1,2)} per layer shape
 constexpr int F2_AW_BYTES = 98304;
 constexpr int F2_MAXSLOTS = 8;                           // W ring slots = ring bytes / piece bytes, at most 8
 constexpr int F2_XPITCH = 36;                            // floats per staged neighbour row (32 + 4: bank spread)
@@ -339,16 +340,18 @@ __global__ void __launch_bounds__(F2_THREADS, 1)
 kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, const int64_t *__restrict__ nb,
                      const float *__restrict__ x, const float *__restrict__ kp, const uint8_t *__restrict__ wimg,
                      int64_t n, int64_t N0, int M, int K, int Cin, int Cout, KpGeom g, uint32_t tmem_cols, int NG, int gpc,
-                     int spz, int ppw, int64_t part_stride, float *__restrict__ out, float *__restrict__ wf_out) {
+                     int spz, int ppw, int stages, int64_t part_stride, float *__restrict__ out, float *__restrict__ wf_out) {
     // All shared memory of this kernel is dynamic (no static variables), so the buffer starts at the base of the CTA's
     // shared window and the 1024-byte alignment the UMMA 128-byte swizzle atoms need costs no slack: the kernel uses
     // 226.5 of the 227 KB a CTA can have.
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();            // (never observed; a misaligned tile would corrupt silently)
     const int a_rows = F2_PWARPS * ppw;                      // query points per tile
-    const uint32_t a_chunk = (uint32_t)a_rows * 128u;        // one 64-K chunk of the A tile
+    const uint32_t a_stage = (uint32_t)a_rows * 128u;        // one stage of a chunk
+    const uint32_t a_chunk = (uint32_t)stages * a_stage;     // one 64-K chunk of the A tile (all stages)
+    const int ssh = stages - 1;   // stages is 1 or 2: pass % stages = pass & ssh, pass / stages = pass >> ssh
     const uint32_t a_bytes = 16u * a_chunk;                  // hi|lo x 8 chunks
-    uint8_t *a_tile = smem;                                  // [hi|lo][8 chunks][a_rows][128 B]
+    uint8_t *a_tile = smem;                                  // [hi|lo][8 chunks][stages x a_rows][128 B]
     uint8_t *w_ring = smem + a_bytes;                        // slots x [hi | lo][N rows][128 B]
     float *scratch = reinterpret_cast<float *>(smem + F2_AW_BYTES);
     uint8_t *tail = smem + F2_AW_BYTES + (size_t)F2_PWARPS * F2_SCRATCH_FLOATS * sizeof(float);
@@ -445,7 +448,8 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
             if (p < n) f2_centre(P, Q);
             unsigned mask0 = 0u, mask1 = 0u;
             for (int sl = sl0; sl < sl1; ++sl) {   // (ppw == 2 is only launched with one slab per CTA)
-                const int row = pw * ppw + pi;
+                const int stage = (int)(pass & (uint32_t)ssh);
+                const int row = stage * a_rows + pw * ppw + pi;
                 float acc[16];
 #pragma unroll
                 for (int c = 0; c < 16; ++c) acc[c] = 0.f;
@@ -465,7 +469,8 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                     asm volatile("cp.async.commit_group;" ::: "memory");
                     if (sl == sl0) f2_weights<INFL, CLOSEST>(P, kps, K, M, g, inv_extent, wt, lane, mask0, mask1);
                 }
-                if (pi == 0 && pass >= 1) mbar_wait(&bar_a_empty[0], (pass - 1) & 1);  // the MMAs of the previous pass have read the tile
+                // the MMAs that read this stage two passes ago are done
+                if (pi == 0 && pass >= (uint32_t)stages) mbar_wait(&bar_a_empty[stage], ((pass >> ssh) - 1) & 1);
                 if (p < n) {
                     asm volatile("cp.async.wait_group 0;" ::: "memory");
                     __syncwarp();  // rows and weights written by other lanes are visible
@@ -529,7 +534,7 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                 if (pi == ppw - 1) {  // the last row of this warp for the pass
                     fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_a_full[0]);
+                    if (lane == 0) mbar_arrive(&bar_a_full[stage]);
                     ++pass;
                 }
             }
@@ -549,38 +554,48 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
             const uint32_t desc_hi = (uint32_t)(a_desc0 >> 32);
             const uint32_t a_lo0 = (uint32_t)a_desc0, w_lo0 = (uint32_t)w_desc0;
             auto mkdesc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | lo; };
-            const uint32_t ppp = (uint32_t)(8 * gl);                        // W pieces per pass: groups x 64-K chunks
-            const uint32_t total_pieces = (uint32_t)(my_tiles * slabs) * ppp;
-            // piece i of this CTA's stream: pass i / ppp (slab = sl0 + pass % slabs), group (i % ppp) / 8, chunk i % 8
-            auto load_piece = [&](uint32_t i) {
-                const uint32_t slot = i % wslots;
-                const uint32_t j = i % ppp, sl = (uint32_t)sl0 + (i / ppp) % (uint32_t)slabs;
-                const uint32_t gg = (uint32_t)g0 + (j >> 3);
+            // W pieces stream through the ring in the order the MMAs use them: pass by pass (slab = sl0 + pass % slabs),
+            // group by group, 64-K chunk by chunk.  All ring / stream positions are kept as running counters: this
+            // thread's instruction stream is the pacing item of the CTA, an integer division per piece is not affordable
+            uint32_t loads_left = (uint32_t)(my_tiles * slabs) * (uint32_t)(8 * gl);
+            uint32_t ld_slot = 0, ld_round = 0, ld_sl = 0, ld_g = 0, ld_kc = 0;
+            auto issue_load = [&]() {
+                const uint32_t gg = (uint32_t)g0 + ld_g;
                 const uint32_t ng = (uint32_t)((Cout - (int)gg * NG < NG) ? (Cout - (int)gg * NG) : NG);
-                const size_t piece = ((size_t)(sl * groups + gg) * 8 + (j & 7));
-                mbar_arrive_expect_tx(&bar_w_full[slot], 2 * ng * 128);
-                bulk_g2s(w_ring + slot * piece_bytes, wimg + piece * piece_bytes, 2 * ng * 128, &bar_w_full[slot]);
+                const size_t piece = ((size_t)(((uint32_t)sl0 + ld_sl) * groups + gg) * 8 + ld_kc);
+                mbar_arrive_expect_tx(&bar_w_full[ld_slot], 2 * ng * 128);
+                bulk_g2s(w_ring + ld_slot * piece_bytes, wimg + piece * piece_bytes, 2 * ng * 128, &bar_w_full[ld_slot]);
+                if (++ld_kc == 8) {
+                    ld_kc = 0;
+                    if (++ld_g == (uint32_t)gl) {
+                        ld_g = 0;
+                        if (++ld_sl == (uint32_t)slabs) ld_sl = 0;
+                    }
+                }
+                if (++ld_slot == wslots) { ld_slot = 0; ++ld_round; }
+                --loads_left;
             };
-            for (uint32_t i = 0; i < wslots && i < total_pieces; ++i) load_piece(i);
-            uint32_t piece_i = 0, pass = 0;
+            for (uint32_t i = 0; i < wslots && loads_left; ++i) issue_load();
+            uint32_t c_slot = 0, c_round = 0, pass = 0;
+            bool first_piece = true;
             for (int64_t ti = 0; ti < my_tiles; ++ti) {
                 const uint32_t dbuf = (uint32_t)(ti & 1);
                 if (ti >= 2) mbar_wait(&bar_d_empty[dbuf], (uint32_t)(((ti >> 1) - 1) & 1));  // epilogue drained this buffer
                 tc_fence_after();
                 for (int sl = 0; sl < slabs; ++sl, ++pass) {
-                    mbar_wait(&bar_a_full[0], pass & 1);
+                    const uint32_t stage = pass & (uint32_t)ssh;
+                    mbar_wait(&bar_a_full[stage], (pass >> ssh) & 1);
                     tc_fence_after();
                     for (int gq = 0; gq < gl; ++gq) {
                         const int ng = (Cout - (g0 + gq) * NG < NG) ? (Cout - (g0 + gq) * NG) : NG;
                         const uint32_t idesc = tc_idesc(TC_MMA_M, ng);
                         const uint32_t d = tmem_base + dbuf * dcols + (uint32_t)(gq * NG);
-                        for (int kc = 0; kc < 8; ++kc, ++piece_i) {
-                            const uint32_t slot = piece_i % wslots;
-                            mbar_wait(&bar_w_full[slot], (piece_i / wslots) & 1);
+                        const uint32_t lo_off = (uint32_t)((ng * 128) >> 4);
+                        for (int kc = 0; kc < 8; ++kc) {
+                            mbar_wait(&bar_w_full[c_slot], c_round & 1);
                             tc_fence_after();
-                            const uint32_t wl = w_lo0 + ((slot * piece_bytes) >> 4);
-                            const uint32_t al = a_lo0 + ((kc * a_chunk) >> 4);
-                            const uint32_t lo_off = (uint32_t)((ng * 128) >> 4);
+                            const uint32_t wl = w_lo0 + ((c_slot * piece_bytes) >> 4);
+                            const uint32_t al = a_lo0 + ((kc * a_chunk + stage * a_stage) >> 4);
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
                                 const uint32_t ko = (uint32_t)((ks * 32) >> 4);
@@ -593,18 +608,19 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                                 tc_mma_bf16(d, a_lo, b_hi, idesc, 1u);
                                 tc_mma_bf16(d, a_hi, b_lo, idesc, 1u);
                             }
-                            tc_commit(&bar_w_empty[slot]);
-                            // keep the ring full: the slot of the PREVIOUS piece is free once its MMAs have retired --
-                            // which they do while this piece's MMAs, just issued, keep the tensor pipe busy -- and
-                            // takes the piece wslots - 1 ahead of the next one
-                            if (piece_i >= 1 && piece_i - 1 + wslots < total_pieces) {
-                                const uint32_t prev = piece_i - 1;
-                                mbar_wait(&bar_w_empty[prev % wslots], (prev / wslots) & 1);
-                                load_piece(prev + wslots);
+                            tc_commit(&bar_w_empty[c_slot]);
+                            if (++c_slot == wslots) { c_slot = 0; ++c_round; }
+                            // keep the ring full: the slot of the PREVIOUS piece (== the stream's next slot: loads run
+                            // exactly one ring ahead) is free once its MMAs have retired -- which they do while this
+                            // piece's MMAs, just issued, keep the tensor pipe busy
+                            if (!first_piece && loads_left) {
+                                mbar_wait(&bar_w_empty[ld_slot], (ld_round - 1) & 1);
+                                issue_load();
                             }
+                            first_piece = false;
                         }
                     }
-                    tc_commit(&bar_a_empty[0]);
+                    tc_commit(&bar_a_empty[stage]);
                 }
                 tc_commit(&bar_d_full[dbuf]);
             }
@@ -1189,17 +1205,24 @@ int dw_accumulate(const float *A, const float *B, int64_t n, int R, int Cn, floa
 // how the forward kernel spreads a problem over the SMs: output-channel groups of NG columns (grid.y takes gpc groups
 // each) and slab groups (grid.z takes spz slabs each)
 struct FwdSplit {
-    int NG, groups, ygroups, gpc, zsplit, spz, ppw;
+    int NG, groups, ygroups, gpc, zsplit, spz, ppw, stages;
 };
+constexpr int F2_NG_MAX = 128;   // output channels per accumulator group (one MMA's N)
 static FwdSplit fwd_split(int64_t n, int Cin, int Cout) {
     const int slabs = Cin / 32;
     FwdSplit f;
-    f.NG = Cout < 128 ? Cout : 128;
+    f.NG = Cout < F2_NG_MAX ? Cout : F2_NG_MAX;
     f.groups = (Cout + f.NG - 1) / f.NG;
-    // single-slab layers with narrow outputs (the big first levels): 32-point tiles, two points per producer warp --
-    // half the MMAs per point; the tile then takes 64 of the 96 KB block, which leaves room for >= 2 weight pieces
-    // only when a piece is <= 16 KB
+    // The A tile holds stages x 16 * ppw rows and takes 32 KB x stages x ppw of the 96 KB block, the weight ring the
+    // rest; a weight piece is NG / 4 KB.  Measured on the KPConvPaper encoder shapes (profiles/r2_kpconv_layers.md):
+    //  - single-slab layers with narrow outputs (the big first levels): 32-point tiles, two points per producer warp
+    //    -- half the MMAs per point (119 vs 145 us at level 0);
+    //  - other layers with NG <= 64: two 16-point stages, so the producers fill one while the tensor core reads the
+    //    other (105 vs 109 us at 64 -> 64);
+    //  - NG = 128: one 16-point stage and a 64 KB ring -- two 32 KB weight pieces in flight matter more than the
+    //    second stage (85 vs 110 us at 128 -> 128).
     f.ppw = (slabs == 1 && f.NG <= 64) ? 2 : 1;
+    f.stages = (f.ppw == 1 && f.NG <= 64) ? 2 : 1;
     const int rows = F2_PWARPS * f.ppw;
     const int64_t ntiles = (n + rows - 1) / rows;
     // two accumulator buffers of gpc * NG columns must fit the 512 TMEM columns
@@ -1224,7 +1247,7 @@ static FwdSplit fwd_split(int64_t n, int Cin, int Cout) {
 }
 
 static size_t fwd_image_bytes(int Cin, int Cout) {
-    const int NG = Cout < 128 ? Cout : 128;
+    const int NG = Cout < F2_NG_MAX ? Cout : F2_NG_MAX;
     return (size_t)(Cin / 32) * ((Cout + NG - 1) / NG) * 8 * f2_piece_bytes(NG);
 }
 
@@ -1264,7 +1287,7 @@ int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neigh
     const size_t smem = F2_AW_BYTES + (size_t)F2_PWARPS * F2_SCRATCH_FLOATS * sizeof(float) + KP_K * sizeof(float4) +
                         (8 + 2 * F2_MAXSLOTS) * sizeof(uint64_t) + 16;
     using Kern = void (*)(const float *, const float *, const int64_t *, const float *, const float *, const uint8_t *,
-                          int64_t, int64_t, int, int, int, int, KpGeom, uint32_t, int, int, int, int, int64_t, float *,
+                          int64_t, int64_t, int, int, int, int, KpGeom, uint32_t, int, int, int, int, int, int64_t, float *,
                           float *);
     static const Kern kerns[2][3][2] = {
         {{kpconv_fwd_tc_kernel<P3D_INFLUENCE_CONSTANT, false, false>, kpconv_fwd_tc_kernel<P3D_INFLUENCE_CONSTANT, true, false>},
@@ -1289,7 +1312,7 @@ int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neigh
     const dim3 grid((unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs), (unsigned)f.ygroups, (unsigned)f.zsplit);
     kerns[wf_out != nullptr ? 1 : 0][influence][aggregation]<<<grid, F2_THREADS, smem, st>>>(
         query, support, neighbors, feat, k_points, (const uint8_t *)ws, n, N0, M, K, Cin, Cout, g, cols, f.NG, f.gpc, f.spz,
-        f.ppw, part_stride, parts, wf_out);
+        f.ppw, f.stages, part_stride, parts, wf_out);
     if (f.zsplit > 1) {
         if (int e = finish_launch("kpconv_fwd_tc")) return e;
         const int64_t n4 = n * (int64_t)Cout / 4;
