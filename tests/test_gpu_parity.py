@@ -391,7 +391,8 @@ def test_group_features_fused_rows_crossing_vector_boundaries(S, K, C):
 
 
 # -------------------------------------------------------------------- interpolation ---------
-@pytest.mark.parametrize("B,C,m,n", [(16, 256, 128, 512), (16, 128, 512, 2048), (2, 5, 7, 9), (1, 33, 40000, 100)])
+@pytest.mark.parametrize("B,C,m,n", [(16, 256, 128, 512), (16, 128, 512, 2048), (2, 5, 7, 9), (1, 33, 40000, 100),
+                                     (3, 100, 77, 1001), (150, 64, 16, 40), (5, 40, 512, 300)])
 def test_three_interpolate_bit_exact_and_backward(B, C, m, n):
     rng = np.random.default_rng(61)
     feat = rng.standard_normal((B, C, m)).astype(np.float32)
@@ -718,3 +719,4 @@ def test_pointnet_msg_down_layer_c1_chain():
     assert out.x.shape == (16, 32, 512) and out.pos.shape == (16, 512, 3)
     out.x.sum().backward()
     assert all(p.grad is not None for p in layer.parameters())
+

@@ -342,7 +342,7 @@ constexpr int SB_KPT = 4;         // source points per thread (one z-block cover
 constexpr int SB_CC = 4;          // channel rows per CTA
 constexpr int SB_EC_GROUP = 2048; // slots per chunk (grouping)
 constexpr int SB_EC_INTERP = 3072;  // slots per chunk (three_interpolate: 1024 points x 3 taps)
-constexpr int SB_MAX_STAGES = 4;
+constexpr int SB_STAGES = 2;      // compile-time: the stage of a chunk is (chunk - first) & 1, no integer division
 
 constexpr int INV_MAX_EC = 3072;  // SB_EC_INTERP
 constexpr int INV_STEPS = INV_MAX_EC / (INV_WARPS * 32);  // 32-slot steps per warp: 12
@@ -523,9 +523,9 @@ __global__ void __launch_bounds__(SB_THREADS, 2)
 bwd_sorted_kernel(const float *__restrict__ dout, const float *__restrict__ weight, const uint16_t *__restrict__ order,
                   const int *__restrict__ seg, const uint32_t *__restrict__ runs, const int *__restrict__ nruns, int C,
                   int N, int64_t E, int EC, int nchunks, int splits, int cps, float *__restrict__ dst_base,
-                  int64_t split_stride, int64_t dout_batch_stride, int c_off, int SB_STAGES, int use_tma) {
+                  int64_t split_stride, int64_t dout_batch_stride, int c_off, int use_tma) {
     extern __shared__ __align__(128) float stage[];
-    __shared__ __align__(8) uint64_t full[SB_MAX_STAGES];
+    __shared__ __align__(8) uint64_t full[SB_STAGES];
     const int Wd = INTERP ? EC / 3 : EC;             // gradient values per channel row and chunk
     const int buf_floats = SB_CC * Wd + (INTERP ? EC : 0) + EC / 2 + (INTERP ? 0 : EC / 2);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -652,16 +652,22 @@ bwd_sorted_kernel(const float *__restrict__ dout, const float *__restrict__ weig
 #pragma unroll
                     for (int c = 0; c < SB_CC; ++c) v[c] += cur[c * Wd + st + i];
                 }
-#pragma unroll
-                for (int d = 16; d >= 1; d >>= 1) {
-#pragma unroll
-                    for (int c = 0; c < SB_CC; ++c) v[c] += __shfl_xor_sync(0xffffffffu, v[c], d);
-                }
-                if (lane < SB_CC) {
-                    float mine = v[0];
-#pragma unroll
-                    for (int c = 1; c < SB_CC; ++c) mine = lane == c ? v[c] : mine;
-                    cur[lane * Wd + st] = mine;
+                // 4 values x 32 lanes -> 4 sums with 6 shuffles instead of 20: the upper half-warp takes over rows 2,3
+                // (step 16), then the odd quarter the second row of each pair (step 8); fixed order -> deterministic
+                static_assert(SB_CC == 4, "the butterfly below folds exactly 4 rows");
+                {
+                    const bool up = lane & 16;
+                    const float s0 = up ? v[0] : v[2], s1 = up ? v[1] : v[3];   // what this lane gives away
+                    const float k0 = up ? v[2] : v[0], k1 = up ? v[3] : v[1];   // what it keeps: rows (0,1) or (2,3)
+                    const float p0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+                    const float p1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+                    const bool odd = lane & 8;
+                    float m = (odd ? p1 : p0) + __shfl_xor_sync(0xffffffffu, odd ? p0 : p1, 8);
+                    m += __shfl_xor_sync(0xffffffffu, m, 4);
+                    m += __shfl_xor_sync(0xffffffffu, m, 2);
+                    m += __shfl_xor_sync(0xffffffffu, m, 1);
+                    // lanes 0..7 hold row 0, 8..15 row 1, 16..23 row 2, 24..31 row 3
+                    if ((lane & 7) == 0) cur[(lane >> 3) * Wd + st] = m;
                 }
             }
             __syncthreads();
@@ -901,7 +907,7 @@ static int launch_bwd_sorted(const float *dout, const float *weight, const int64
         if (mode == BWD_PREPARE) return P3D_OK;
     }
     const int Wd = INTERP ? EC / 3 : EC;
-    const int SB_STAGES = 2, use_tma = 1;
+    const int use_tma = 1;
     const size_t smem =
         (size_t)SB_STAGES * (SB_CC * Wd + (INTERP ? EC : 0) + EC / 2 + (INTERP ? 0 : EC / 2)) * sizeof(float);
     const int splits = L.splits;
@@ -911,7 +917,7 @@ static int launch_bwd_sorted(const float *dout, const float *weight, const int64
     const int64_t total = (int64_t)B * C * N;
     bwd_sorted_kernel<INTERP><<<grid, SB_THREADS, smem, st>>>(dout, weight, order, seg, runs, nruns, C, N, E, EC,
                                                              nchunks, splits, cps, splits > 1 ? part : dfeat, total,
-                                                             dout_batch_stride, c_off, SB_STAGES, use_tma);
+                                                             dout_batch_stride, c_off, use_tma);
     if (int e = finish_launch(INTERP ? "three_interp_bwd_sorted" : "group_bwd_sorted")) return e;
     if (splits > 1) {
         int64_t gr = (total + 255) / 256;
