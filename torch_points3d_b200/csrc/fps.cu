@@ -218,12 +218,26 @@ __device__ __forceinline__ void fps_mbar_expect(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes)
                  : "memory");
 }
+// The default (.acquire.cta) form, as cluster-transaction barriers are waited on elsewhere (TMA multicast): the
+// records land in THIS CTA's shared memory and their bytes are counted on THIS CTA's barrier, so a completed phase
+// means they are here.  The .acquire.cluster form compiles to an L1 invalidate (CCTL.IVALL) after every successful
+// wait, in every warp, every round (2 % of the round).
+//
+// What a round costs (clock64 instrumentation, one 120 000-point cloud, 8 CTAs): ~2000 cycles, of which the remote hop
+// is ~150 (a run with every CTA exchanging with itself only is 8 % faster); the rest is the CTA-local chain -- the
+// slowest warp's block update, then the barrier, warp 0's reduction and the second reduction of every warp.  Variants
+// measured and NOT kept (no change within 2 %): 1024 threads x 16 points, tagged 16-byte records polled in shared
+// memory instead of st.async + mbarrier, skipping the warp arg-max of untouched warps, batched coordinate loads.
+// Freezing the min-distances (no update at all) gives 0.54 us per round: half of a round is the block updates of
+// whichever warps the new sample touches.  Transposing the blocks (lane j = point j of 32 blocks, a touched block
+// updated by the whole warp with a REDUX for its new maximum) was bit-exact but slower (1.26 us; 3.2 us on shuffled
+// clouds): the per-block REDUX -> ballot -> select chains of one warp do not overlap.
 __device__ __forceinline__ void fps_mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "FPS_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra FPS_DONE_%=;\n"
         "bra FPS_WAIT_%=;\n"
         "FPS_DONE_%=:\n"
@@ -345,19 +359,22 @@ fps_pruned_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr
                 myj = bj;
             }
         }
-        const unsigned bi = mybest >= 0.f ? (unsigned)(blk + myj) : 0xffffffffu;
-        const unsigned key = mybest >= 0.f ? __float_as_uint(mybest) : 0u;
-        unsigned wkey, widx;
-        warp_argmax(key, bi, wkey, widx);
-        if (key == wkey && bi == widx) wrec[buf][warp] = make_uint4(wkey, widx, (unsigned)(myj * T + tid), 0u);
+        // Point indices grow with the lane (blocks of consecutive points), with the warp and with the cluster rank, so
+        // at all three levels "largest key, lowest index on ties" is "largest key, lowest lane on ties": one REDUX and
+        // a ballot instead of two dependent REDUX -- the round is a latency chain, every link counts.
+        // Keys: fp32 bit patterns of non-negative distances order like unsigned integers, + 1 so that 0 = "no point".
+        const unsigned key = mybest >= 0.f ? __float_as_uint(mybest) + 1u : 0u;
+        const unsigned wkey = __reduce_max_sync(0xffffffffu, key);
+        const int wl = __ffs(__ballot_sync(0xffffffffu, key == wkey)) - 1;
+        if (lane == wl) wrec[buf][warp] = make_uint4(wkey, (unsigned)(blk + myj), (unsigned)(myj * T + tid), 0u);
         __syncthreads();
         if (warp == 0) {
             // CTA winner, pushed to every CTA of the cluster (this one included) by lanes < CLUSTER
             uint4 w = make_uint4(0u, 0xffffffffu, 0u, 0u);
             if (lane < NW) w = wrec[buf][lane];
-            unsigned ckey, cidx;
-            warp_argmax(w.x, w.y, ckey, cidx);
-            const int cl = __ffs(__ballot_sync(0xffffffffu, w.x == ckey && w.y == cidx)) - 1;
+            const unsigned ckey = __reduce_max_sync(0xffffffffu, w.x);
+            const int cl = __ffs(__ballot_sync(0xffffffffu, w.x == ckey)) - 1;
+            const unsigned cidx = __shfl_sync(0xffffffffu, w.y, cl);
             const unsigned cslot = __shfl_sync(0xffffffffu, w.z, cl);
             const float wx = cx[cslot], wy = cy[cslot], wz = cz[cslot];
             if (lane < CLUSTER) {
@@ -373,9 +390,9 @@ fps_pruned_kernel(const float *__restrict__ xyz, const int64_t *__restrict__ ptr
             k2 = kv.x;
             i2 = kv.y;
         }
-        unsigned gkey, gidx;
-        warp_argmax(k2, i2, gkey, gidx);
-        const int src = __ffs(__ballot_sync(0xffffffffu, k2 == gkey && i2 == gidx)) - 1;
+        const unsigned gkey = __reduce_max_sync(0xffffffffu, k2);
+        const int src = __ffs(__ballot_sync(0xffffffffu, k2 == gkey)) - 1;
+        const unsigned gidx = __shfl_sync(0xffffffffu, i2, src);
         lx = recs[buf][src].x;
         ly = recs[buf][src].y;
         lz = recs[buf][src].z;
