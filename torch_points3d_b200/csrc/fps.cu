@@ -15,6 +15,8 @@
 //     second barrier (records are double-buffered by round parity);
 //   * clusters: each CTA's winner record is pushed into every peer's shared memory through
 //     DSMEM, then one barrier.cluster per round.
+#include <atomic>
+
 #include <cooperative_groups.h>
 #include <math_constants.h>
 
@@ -615,27 +617,56 @@ static int launch_reg(const float *xyz, const int64_t *ptr, int64_t n_dense, con
     return finish_launch("fps");
 }
 
+// launch configuration of a pruned variant (function attributes are set once per device)
 template <int T, int PPT, int CLUSTER, typename IdxT>
-static int launch_pruned(const float *xyz, const int64_t *ptr, int64_t n_dense, const int64_t *out_ptr,
-                         int64_t s_dense, IdxT *out, const int64_t *first, float *new_xyz, int clouds, cudaStream_t st) {
+static void pruned_config(int clouds, cudaStream_t st, cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr) {
     auto kern = fps_pruned_kernel<T, PPT, CLUSTER, IdxT>;
-    cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(clouds * CLUSTER));
     cfg.blockDim = dim3(T);
     cfg.dynamicSmemBytes = (size_t)3 * T * PPT * sizeof(float);
-    static DeviceOnce smem_done;
-    if (!smem_done.done()) {
+    static DeviceOnce attr_done;
+    if (!attr_done.done()) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
-        smem_done.mark();
+        if (CLUSTER > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        attr_done.mark();
     }
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CLUSTER;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+}
+
+// how many clusters of this variant the device runs at once (0 when the cluster size cannot be placed); per device
+template <int T, int PPT, int CLUSTER, typename IdxT>
+static int pruned_active_clusters() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    const int c = cache[dev].load(std::memory_order_relaxed);
+    if (c != 0) return c > 0 ? c : 0;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    pruned_config<T, PPT, CLUSTER, IdxT>(1, nullptr, cfg, attr);
+    int num = 0;
+    if (cudaOccupancyMaxActiveClusters(&num, fps_pruned_kernel<T, PPT, CLUSTER, IdxT>, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        num = 0;
+    }
+    cache[dev].store(num > 0 ? num : -1, std::memory_order_relaxed);
+    return num;
+}
+
+template <int T, int PPT, int CLUSTER, typename IdxT>
+static int launch_pruned(const float *xyz, const int64_t *ptr, int64_t n_dense, const int64_t *out_ptr,
+                         int64_t s_dense, IdxT *out, const int64_t *first, float *new_xyz, int clouds, cudaStream_t st) {
+    auto kern = fps_pruned_kernel<T, PPT, CLUSTER, IdxT>;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    pruned_config<T, PPT, CLUSTER, IdxT>(clouds, st, cfg, attr);
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz);
     if (e != cudaSuccess) {
         g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -666,8 +697,27 @@ static int fps_dispatch(const float *xyz, const int64_t *ptr, int64_t n_dense, c
     P3D_FPS_CASE(16384, 1024, 8, 2)
     P3D_FPS_CASE(32768, 1024, 8, 4)
     // 32 769..131 072 points: 8-CTA clusters with bounding-box pruning and the one-hop record exchange
-    if (max_n <= 65536) return launch_pruned<512, 16, 8, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
-    if (max_n <= 131072) return launch_pruned<512, 32, 8, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
+    // A round is a latency chain whose longest link is the block update (PPT points by one lane): a 16-CTA cluster
+    // halves the block (0.82 vs 1.02 us per round at 120 000 points), but a 16-CTA cluster needs 16 free SMs of ONE
+    // GPC -- the device places only a handful at once (cudaOccupancyMaxActiveClusters), so it is used when that
+    // takes fewer waves: few clouds per launch (one LiDAR scan per GPU), not the batch of 8.
+    if (max_n <= 131072) {
+        const bool small = max_n <= 65536;
+        const int a8 = small ? pruned_active_clusters<512, 16, 8, IdxT>() : pruned_active_clusters<512, 32, 8, IdxT>();
+        const int a16 = small ? pruned_active_clusters<512, 8, 16, IdxT>() : pruned_active_clusters<512, 16, 16, IdxT>();
+        bool wide = false;
+        if (a16 > 0) {
+            const double t16 = 0.8 * ((clouds + a16 - 1) / a16);
+            const double t8 = a8 > 0 ? 1.0 * ((clouds + a8 - 1) / a8) : 1e30;
+            wide = t16 < t8;
+        }
+        if (small) {
+            if (wide) return launch_pruned<512, 8, 16, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
+            return launch_pruned<512, 16, 8, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
+        }
+        if (wide) return launch_pruned<512, 16, 16, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
+        return launch_pruned<512, 32, 8, IdxT>(xyz, ptr, n_dense, out_ptr, s_dense, out, first, new_xyz, clouds, st);
+    }
 #undef P3D_FPS_CASE
     if (ws == nullptr || ws_bytes < (size_t)total_rows * sizeof(float)) {
         set_error("fps: clouds of more than 131072 points need a workspace of %lld bytes",
