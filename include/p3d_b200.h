@@ -272,6 +272,9 @@ int p3d_kpconv_bwd_wf_f32(const float *query, const float *support, const int64_
  * (N0 for the shadow row) for the backward pass. */
 int p3d_neighbor_max_f32(const float *x, const int64_t *neighbors, int64_t n, int64_t N0, int M, int C,
                          float *out, int64_t *arg, void *stream);
+/* its backward: dx[N0,C] (overwritten) = sum over the query points whose arg[p,c] names the row, of dout[p,c] */
+int p3d_neighbor_max_bwd_f32(const float *dout, const int64_t *arg, int64_t n, int64_t N0, int C, float *dx,
+                             void *stream);
 
 /* ------------------------------------------------------ GridSampling3D ------
  * Replaces the position side of GridSampling3D._process (core/data_transform/grid_transform.py:110-126):

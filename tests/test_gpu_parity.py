@@ -720,3 +720,46 @@ def test_pointnet_msg_down_layer_c1_chain():
     out.x.sum().backward()
     assert all(p.grad is not None for p in layer.parameters())
 
+
+
+def test_compat_tp_namespace_on_the_rsconv_call_sites():
+    """`import torch_points3d_b200.compat.tp as tp` serves the reference's call sites unchanged: the RSConv feature
+    preparation (modules/RSConv/dense.py:144-163: two `tp.grouping_operation` calls on transposed positions and on
+    features, concatenated with the centred positions) and the DENSE sampler / finder / FP calls
+    (sampling.py:100, neighbour_finder.py:164, core/base_conv/dense.py:136-140), against the oracle."""
+    import torch_points3d_b200.compat.tp as tp
+
+    B, n, S, K, C = 3, 600, 64, 24, 10
+    xyz = synthetic.surface_clouds(B, n, seed=91)
+    feat = np.random.default_rng(91).standard_normal((B, C, n)).astype(np.float32)
+    pos, x = T(xyz), T(feat).requires_grad_(True)
+    idx = tp.furthest_point_sample(pos, S)
+    oidx = oracle.fps_dense(xyz, S)
+    assert np.array_equal(N(idx), oidx)
+    new_pos = pos.gather(1, idx.unsqueeze(-1).repeat(1, 1, 3))
+    radius_idx = tp.ball_query(0.25, K, pos, new_pos, mode="dense")[0]
+    onew = np.take_along_axis(xyz, oidx[..., None], 1)
+    oball = oracle.ball_query_dense(0.25, K, xyz, onew)[0]
+    assert np.array_equal(N(radius_idx), oball)
+    # RSConv._prepare_features, line for line
+    new_pos_trans = pos.transpose(1, 2).contiguous()
+    grouped_pos_absolute = tp.grouping_operation(new_pos_trans, radius_idx)
+    centroids = new_pos.transpose(1, 2).unsqueeze(-1)
+    grouped_pos_normalized = grouped_pos_absolute - centroids
+    grouped_features = tp.grouping_operation(x, radius_idx)
+    new_features = torch.cat([grouped_pos_absolute, grouped_pos_normalized, grouped_features], dim=1)
+    want_abs = oracle.group_fwd(np.ascontiguousarray(xyz.transpose(0, 2, 1)), oball)
+    want = np.concatenate([want_abs, want_abs - onew.transpose(0, 2, 1)[..., None], oracle.group_fwd(feat, oball)], 1)
+    assert np.array_equal(N(new_features), want)
+    g = torch.randn_like(new_features)
+    new_features.backward(g)
+    assert relerr(N(x.grad), oracle.group_bwd(N(g)[:, 6:], oball, n)) <= RTOL
+    # DenseFPModule.conv's two calls
+    dist, i3 = tp.three_nn(pos, new_pos)
+    odist, oi3 = oracle.three_nn(xyz, onew)
+    assert np.array_equal(N(i3), oi3)
+    recip = 1.0 / (dist + 1e-8)
+    weight = recip / torch.sum(recip, dim=2, keepdim=True)
+    coarse = np.random.default_rng(92).standard_normal((B, C, S)).astype(np.float32)
+    got = tp.three_interpolate(T(coarse), i3, weight)
+    assert np.array_equal(N(got), oracle.three_interpolate_fwd(coarse, oi3, N(weight)))

@@ -65,6 +65,7 @@ SIGNATURES = {
     "p3d_kpconv_deform_bwd_f32": (c_int, [c_vp] * 13 + [c_i64, c_i64, c_int, c_int, c_int, c_int, c_f32, c_int] +
                                   [c_vp] * 4 + [c_vp, c_sz, c_vp]),
     "p3d_neighbor_max_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
+    "p3d_neighbor_max_bwd_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp]),
     "p3d_edge_message_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp]),
     "p3d_edge_message_bwd_f32": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp]),
     "p3d_edge_encoding_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),

@@ -938,6 +938,18 @@ static int pick_cc(int C, int N, bool &staged) {
     return cc;
 }
 
+// backward of the neighbour max-pool: the gradient of out[p,c] goes to the winning row arg[p,c] (the shadow row N0
+// receives nothing).  Several query points can have picked the same support row: fp32 reductions at L2, like the
+// dfeat scatter of the KPConv backward.
+__global__ void __launch_bounds__(GR_THREADS)
+neighbor_max_bwd_kernel(const float *__restrict__ dout, const int64_t *__restrict__ arg, int64_t total, int C,
+                        int64_t N0, float *__restrict__ dx) {
+    for (int64_t i = (int64_t)blockIdx.x * GR_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * GR_THREADS) {
+        const int64_t row = __ldg(arg + i);
+        if (row >= 0 && row < N0) atomicAdd(dx + row * C + (i % C), __ldg(dout + i));
+    }
+}
+
 }  // namespace p3d
 
 using namespace p3d;
@@ -1185,4 +1197,21 @@ P3D_EXPORT int p3d_neighbor_max_f32(const float *x, const int64_t *neighbors, in
     const int64_t grid = (n + GR_THREADS / 32 - 1) / (GR_THREADS / 32);
     neighbor_max_kernel<<<(unsigned)grid, GR_THREADS, 0, (cudaStream_t)stream>>>(x, neighbors, n, N0, M, C, out, arg);
     return finish_launch("neighbor_max");
+}
+
+P3D_EXPORT int p3d_neighbor_max_bwd_f32(const float *dout, const int64_t *arg, int64_t n, int64_t N0, int C, float *dx,
+                                        void *stream) {
+    P3D_REQUIRE(n >= 0 && N0 >= 0 && C >= 0, "neighbor_max_bwd: bad dimension");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N0 > 0 && C > 0) {
+        P3D_REQUIRE(dx, "neighbor_max_bwd: null pointer");
+        cudaMemsetAsync(dx, 0, (size_t)N0 * C * sizeof(float), st);
+    }
+    if (n == 0 || C == 0 || N0 == 0) return P3D_OK;
+    P3D_REQUIRE(dout && arg, "neighbor_max_bwd: null pointer");
+    const int64_t total = n * C;
+    int64_t grid = (total + GR_THREADS - 1) / GR_THREADS;
+    if (grid > 8 * kNumSMs) grid = 8 * kNumSMs;
+    neighbor_max_bwd_kernel<<<(unsigned)grid, GR_THREADS, 0, st>>>(dout, arg, total, C, N0, dx);
+    return finish_launch("neighbor_max_bwd");
 }

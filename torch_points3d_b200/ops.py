@@ -831,9 +831,11 @@ class _NeighborMax(torch.autograd.Function):
     def backward(ctx, grad_out):
         (arg,) = ctx.saved_tensors
         n, C = grad_out.shape
-        dx = torch.zeros((ctx.N0 + 1, C), dtype=grad_out.dtype, device=grad_out.device)
-        dx.scatter_add_(0, arg, grad_out.contiguous())
-        return dx[:-1], None
+        grad_out = _f32(grad_out)
+        dx = torch.empty((ctx.N0, C), dtype=torch.float32, device=grad_out.device)
+        _call(grad_out.device, "p3d_neighbor_max_bwd_f32", grad_out.data_ptr(), arg.data_ptr(), n, ctx.N0, C,
+              dx.data_ptr())
+        return dx, None
 
 
 def neighbor_max(x: torch.Tensor, neighbors: torch.Tensor) -> torch.Tensor:
