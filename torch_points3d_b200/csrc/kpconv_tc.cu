@@ -60,6 +60,18 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
+// true in exactly one lane of a fully converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 // D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
 __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -371,7 +383,6 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
     const int g0 = blockIdx.y * gpc;
     const int gl = (groups - g0 < gpc) ? (groups - g0) : gpc;
     const int col0 = g0 * NG;                                                      // first output channel of this CTA
-    const int ncols = (Cout - col0 < gl * NG) ? (Cout - col0) : gl * NG;           // its output channels
     const int nc0 = g0;  // (the CTA with g0 == 0 stores wf)
     const int sl0 = blockIdx.z * spz;
     const int sl1 = (sl0 + spz < Cin / 32) ? (sl0 + spz) : Cin / 32;
@@ -380,7 +391,10 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
     const int64_t ntiles = (n + a_rows - 1) / a_rows;
     const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;  // persistent: tiles blockIdx.x + i * gridDim.x
     const float inv_extent = 1.0f / g.extent;
-    const uint32_t dcols = (uint32_t)(gl * NG);              // TMEM columns of one accumulator buffer
+    // TMEM columns of one accumulator buffer: every output-channel group takes 2 * NG columns -- [A_hi B_hi + A_lo B_hi |
+    // A_hi B_lo]: the hi and lo rows of a weight piece are contiguous, so ONE MMA with N = 2 * ng multiplies A_hi by
+    // both (two issues per product instead of three; the epilogue adds the two halves)
+    const uint32_t dcols = (uint32_t)(gl * 2 * NG);
 
     if (tid < KP_K) kps[tid] = tid < K ? make_float4(__ldg(kp + 3 * tid), __ldg(kp + 3 * tid + 1), __ldg(kp + 3 * tid + 2), 0.f)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -544,7 +558,10 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
         }
     } else if (warp == F2_PWARPS + 1) {
         // ------------------------------------------------------------ MMA issuer ---------------------------
-        if (lane == 0) {
+        // The whole warp runs the issue loop (so its counters, ring positions and descriptors are warp-uniform values
+        // the compiler can keep in uniform registers); one elected lane executes the instructions with side effects.
+        const bool leader = elect_one();
+        {
             // every MMA re-reads its whole A operand (M = 128 rows, 16 or 32 of them real) from shared memory: the
             // count of MMAs per point is what bounds this warp, hence wide N (up to 128 output channels per
             // instruction) and, for single-slab layers, 32-point tiles
@@ -563,8 +580,10 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                 const uint32_t gg = (uint32_t)g0 + ld_g;
                 const uint32_t ng = (uint32_t)((Cout - (int)gg * NG < NG) ? (Cout - (int)gg * NG) : NG);
                 const size_t piece = ((size_t)(((uint32_t)sl0 + ld_sl) * groups + gg) * 8 + ld_kc);
-                mbar_arrive_expect_tx(&bar_w_full[ld_slot], 2 * ng * 128);
-                bulk_g2s(w_ring + ld_slot * piece_bytes, wimg + piece * piece_bytes, 2 * ng * 128, &bar_w_full[ld_slot]);
+                if (leader) {
+                    mbar_arrive_expect_tx(&bar_w_full[ld_slot], 2 * ng * 128);
+                    bulk_g2s(w_ring + ld_slot * piece_bytes, wimg + piece * piece_bytes, 2 * ng * 128, &bar_w_full[ld_slot]);
+                }
                 if (++ld_kc == 8) {
                     ld_kc = 0;
                     if (++ld_g == (uint32_t)gl) {
@@ -588,9 +607,8 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                     tc_fence_after();
                     for (int gq = 0; gq < gl; ++gq) {
                         const int ng = (Cout - (g0 + gq) * NG < NG) ? (Cout - (g0 + gq) * NG) : NG;
-                        const uint32_t idesc = tc_idesc(TC_MMA_M, ng);
-                        const uint32_t d = tmem_base + dbuf * dcols + (uint32_t)(gq * NG);
-                        const uint32_t lo_off = (uint32_t)((ng * 128) >> 4);
+                        const uint32_t idesc = tc_idesc(TC_MMA_M, ng), idesc_wide = tc_idesc(TC_MMA_M, 2 * ng);
+                        const uint32_t d = tmem_base + dbuf * dcols + (uint32_t)(gq * 2 * NG);
                         for (int kc = 0; kc < 8; ++kc) {
                             mbar_wait(&bar_w_full[c_slot], c_round & 1);
                             tc_fence_after();
@@ -601,14 +619,14 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                                 const uint32_t ko = (uint32_t)((ks * 32) >> 4);
                                 const uint64_t a_hi = mkdesc(al + ko);
                                 const uint64_t a_lo = mkdesc(al + ko + ((a_bytes / 2) >> 4));
-                                const uint64_t b_hi = mkdesc(wl + ko);
-                                const uint64_t b_lo = mkdesc(wl + ko + lo_off);
+                                const uint64_t b_hi = mkdesc(wl + ko);   // hi rows, followed by the lo rows
                                 const uint32_t first = (sl == 0 && kc == 0 && ks == 0) ? 0u : 1u;
-                                tc_mma_bf16(d, a_hi, b_hi, idesc, first);
-                                tc_mma_bf16(d, a_lo, b_hi, idesc, 1u);
-                                tc_mma_bf16(d, a_hi, b_lo, idesc, 1u);
+                                if (leader) {
+                                    tc_mma_bf16(d, a_hi, b_hi, idesc_wide, first);  // [A_hi B_hi | A_hi B_lo]
+                                    tc_mma_bf16(d, a_lo, b_hi, idesc, 1u);          // + A_lo B_hi into the first half
+                                }
                             }
-                            tc_commit(&bar_w_empty[c_slot]);
+                            if (leader) tc_commit(&bar_w_empty[c_slot]);
                             if (++c_slot == wslots) { c_slot = 0; ++c_round; }
                             // keep the ring full: the slot of the PREVIOUS piece (== the stream's next slot: loads run
                             // exactly one ring ahead) is free once its MMAs have retired -- which they do while this
@@ -620,9 +638,9 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                             first_piece = false;
                         }
                     }
-                    tc_commit(&bar_a_empty[stage]);
+                    if (leader) tc_commit(&bar_a_empty[stage]);
                 }
-                tc_commit(&bar_d_full[dbuf]);
+                if (leader) tc_commit(&bar_d_full[dbuf]);
             }
         }
         __syncwarp();
@@ -633,13 +651,20 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
             mbar_wait(&bar_d_full[dbuf], (uint32_t)((ti >> 1) & 1));
             tc_fence_after();
             const int64_t p = (blockIdx.x + ti * gridDim.x) * a_rows + lane;
-            for (int cq = 0; cq < ncols / 32; ++cq) {
-                float v[32];
-                tmem_ld32(tmem_base + dbuf * dcols + (uint32_t)(cq * 32), v);
-                if (lane < a_rows && p < n) {
-                    float4 *dst = reinterpret_cast<float4 *>(dst_out + p * Cout + col0 + cq * 32);
+            for (int gq = 0; gq < gl; ++gq) {
+                const int ng = (Cout - (g0 + gq) * NG < NG) ? (Cout - (g0 + gq) * NG) : NG;
+                const uint32_t dg = tmem_base + dbuf * dcols + (uint32_t)(gq * 2 * NG);
+                for (int cq = 0; cq < ng / 32; ++cq) {
+                    float v[32], v2[32];
+                    tmem_ld32(dg + (uint32_t)(cq * 32), v);
+                    tmem_ld32(dg + (uint32_t)(ng + cq * 32), v2);
+                    if (lane < a_rows && p < n) {
+                        float4 *dst = reinterpret_cast<float4 *>(dst_out + p * Cout + col0 + gq * NG + cq * 32);
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) dst[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                        for (int u = 0; u < 8; ++u)
+                            dst[u] = make_float4(v[4 * u] + v2[4 * u], v[4 * u + 1] + v2[4 * u + 1],
+                                                 v[4 * u + 2] + v2[4 * u + 2], v[4 * u + 3] + v2[4 * u + 3]);
+                    }
                 }
             }
             tc_fence_before();
@@ -1251,7 +1276,8 @@ static FwdSplit fwd_split(int64_t n, int Cin, int Cout) {
     // The A tile holds stages x 16 * ppw rows and takes 32 KB x stages x ppw of the 96 KB block, the weight ring the
     // rest; a weight piece is NG / 4 KB.  Measured on the KPConvPaper encoder shapes (profiles/r2_kpconv_layers.md):
     //  - single-slab layers with narrow outputs (the big first levels): 32-point tiles, two points per producer warp
-    //    -- half the MMAs per point (119 vs 145 us at level 0);
+    //    -- half the MMAs per point (119 vs 145 us at level 0; 101 vs 108 us after the MMA issue stream was made
+    //    cheaper: wide-N hi|lo products, warp-uniform issue loop);
     //  - other layers with NG <= 64: two 16-point stages, so the producers fill one while the tensor core reads the
     //    other (105 vs 109 us at 64 -> 64);
     //  - NG = 128: one 16-point stage and a 64 KB ring -- two 32 KB weight pieces in flight matter more than the
@@ -1260,8 +1286,8 @@ static FwdSplit fwd_split(int64_t n, int Cin, int Cout) {
     f.stages = (f.ppw == 1 && f.NG <= 64) ? 2 : 1;
     const int rows = F2_PWARPS * f.ppw;
     const int64_t ntiles = (n + rows - 1) / rows;
-    // two accumulator buffers of gpc * NG columns must fit the 512 TMEM columns
-    int max_gpc = 256 / f.NG;
+    // two accumulator buffers of gpc * 2 * NG columns must fit the 512 TMEM columns
+    int max_gpc = 256 / (2 * f.NG);   // (hi | lo halves: 2 * NG columns per group)
     if (max_gpc < 1) max_gpc = 1;
     f.ygroups = (f.groups + max_gpc - 1) / max_gpc;
     f.zsplit = 1;
@@ -1341,7 +1367,7 @@ int kpconv_fwd_tc(const float *query, const float *support, const int64_t *neigh
     }
     const int64_t ntiles = (n + F2_PWARPS * f.ppw - 1) / (F2_PWARPS * f.ppw);
     uint32_t cols = 32;
-    while ((int)cols < 2 * f.gpc * f.NG) cols <<= 1;
+    while ((int)cols < 2 * f.gpc * 2 * f.NG) cols <<= 1;
     float *parts = f.zsplit > 1 ? (float *)((char *)ws + fwd_image_bytes(Cin, Cout)) : out;
     const int64_t part_stride = f.zsplit > 1 ? n * (int64_t)Cout : 0;
     const dim3 grid((unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs), (unsigned)f.ygroups, (unsigned)f.zsplit);
