@@ -449,6 +449,12 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
             if (units > 0 && point_of(0) < n) f2_load_coords(q + 3 * point_of(0), s, N0, I0, P, Q);
         }
         uint32_t pass = 0;
+        // 32-point tiles (ppw == 2): the first point's operand row is held in registers while the second point is
+        // gathered, weighted and aggregated, and both rows are stored after ONE late wait for the tile -- a whole
+        // point's work runs under the MMAs of the previous pass
+        uint32_t held_hi[8], held_lo[8];
+#pragma unroll
+        for (int u8 = 0; u8 < 8; ++u8) held_hi[u8] = held_lo[u8] = 0u;
         for (int u = 0; u < units; ++u) {
             const int64_t p = point_of(u);
             const int pi = u & psh;
@@ -483,8 +489,6 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                     asm volatile("cp.async.commit_group;" ::: "memory");
                     if (sl == sl0) f2_weights<INFL, CLOSEST>(P, kps, K, M, g, inv_extent, wt, lane, mask0, mask1);
                 }
-                // the MMAs that read this stage two passes ago are done
-                if (pi == 0 && pass >= (uint32_t)stages) mbar_wait(&bar_a_empty[stage], ((pass >> ssh) - 1) & 1);
                 if (p < n) {
                     asm volatile("cp.async.wait_group 0;" ::: "memory");
                     __syncwarp();  // rows and weights written by other lanes are visible
@@ -538,13 +542,31 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                     hi[u] = pack_bf16(h0, h1);
                     lo[u] = pack_bf16(a0 - h0, a1 - h1);
                 }
-                uint8_t *rowp = a_tile + (lane >> 2) * a_chunk + row * 128;
-                const int g0 = (lane & 3) * 2, sw = row & 7;
-                *reinterpret_cast<uint4 *>(rowp + ((g0 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4 *>(rowp + (((g0 + 1) ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                rowp += a_bytes / 2;
-                *reinterpret_cast<uint4 *>(rowp + ((g0 ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                *reinterpret_cast<uint4 *>(rowp + (((g0 + 1) ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                if (ppw == 2 && pi == 0) {
+#pragma unroll
+                    for (int u8 = 0; u8 < 8; ++u8) { held_hi[u8] = hi[u8]; held_lo[u8] = lo[u8]; }
+                } else {
+                    // the MMAs that read this stage `stages` passes ago must be done before a row is overwritten: waited
+                    // for as late as possible -- the gather, the weights and the aggregation ran under them
+                    if (pass >= (uint32_t)stages) mbar_wait(&bar_a_empty[stage], ((pass >> ssh) - 1) & 1);
+                    const int g0 = (lane & 3) * 2;
+                    if (ppw == 2) {
+                        const int row0 = row - 1, sw0 = row0 & 7;
+                        uint8_t *rp = a_tile + (lane >> 2) * a_chunk + row0 * 128;
+                        *reinterpret_cast<uint4 *>(rp + ((g0 ^ sw0) << 4)) = make_uint4(held_hi[0], held_hi[1], held_hi[2], held_hi[3]);
+                        *reinterpret_cast<uint4 *>(rp + (((g0 + 1) ^ sw0) << 4)) = make_uint4(held_hi[4], held_hi[5], held_hi[6], held_hi[7]);
+                        rp += a_bytes / 2;
+                        *reinterpret_cast<uint4 *>(rp + ((g0 ^ sw0) << 4)) = make_uint4(held_lo[0], held_lo[1], held_lo[2], held_lo[3]);
+                        *reinterpret_cast<uint4 *>(rp + (((g0 + 1) ^ sw0) << 4)) = make_uint4(held_lo[4], held_lo[5], held_lo[6], held_lo[7]);
+                    }
+                    uint8_t *rowp = a_tile + (lane >> 2) * a_chunk + row * 128;
+                    const int sw = row & 7;
+                    *reinterpret_cast<uint4 *>(rowp + ((g0 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4 *>(rowp + (((g0 + 1) ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    rowp += a_bytes / 2;
+                    *reinterpret_cast<uint4 *>(rowp + ((g0 ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4 *>(rowp + (((g0 + 1) ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                }
                 if (pi == ppw - 1) {  // the last row of this warp for the pass
                     fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
                     __syncwarp();
