@@ -40,6 +40,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
+// same wait for warps that are NOT on the critical path (an epilogue waiting for a finished tile, an MMA issuer waiting
+// for the producers): the suspend-time hint lets the hardware park the warp for up to `ns` nanoseconds per attempt
+// instead of returning after the default short interval, so the polling loop stops competing for issue slots with
+// the warps doing the work
+__device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity, uint32_t ns) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAITP_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra LAB_DONEP_%=;\n"
+        "bra LAB_WAITP_%=;\n"
+        "LAB_DONEP_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(ns)
+        : "memory");
+}
+
 // global -> shared bulk copy through the TMA unit; bytes % 16 == 0, both addresses 16-byte aligned;
 // completion is signalled as `bytes` of transaction count on `bar`
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {

@@ -625,7 +625,7 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
                 tc_fence_after();
                 for (int sl = 0; sl < slabs; ++sl, ++pass) {
                     const uint32_t stage = pass & (uint32_t)ssh;
-                    mbar_wait(&bar_a_full[stage], (pass >> ssh) & 1);
+                    mbar_wait_parked(&bar_a_full[stage], (pass >> ssh) & 1, 2000);
                     tc_fence_after();
                     for (int gq = 0; gq < gl; ++gq) {
                         const int ng = (Cout - (g0 + gq) * NG < NG) ? (Cout - (g0 + gq) * NG) : NG;
@@ -670,7 +670,7 @@ kpconv_fwd_tc_kernel(const float *__restrict__ q, const float *__restrict__ s, c
         // ------------------------------------------------------------ epilogue (warp 0: TMEM lanes 0-31) ----
         for (int64_t ti = 0; ti < my_tiles; ++ti) {
             const uint32_t dbuf = (uint32_t)(ti & 1);
-            mbar_wait(&bar_d_full[dbuf], (uint32_t)((ti >> 1) & 1));
+            mbar_wait_parked(&bar_d_full[dbuf], (uint32_t)((ti >> 1) & 1), 4000);
             tc_fence_after();
             const int64_t p = (blockIdx.x + ti * gridDim.x) * a_rows + lane;
             for (int gq = 0; gq < gl; ++gq) {
