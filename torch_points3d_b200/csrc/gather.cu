@@ -338,7 +338,9 @@ neighbor_max_vec_kernel(const float *__restrict__ x, const int64_t *__restrict__
 constexpr int INV_WARPS = 8;
 constexpr int INV_MAX_N = 4096;   // per-warp histograms: N * 8 * 4 B of shared memory
 constexpr int SB_THREADS = 512;
-constexpr int SB_KPT = 4;         // source points per thread (one z-block covers 2048 points)
+constexpr int SB_KPT = 4;         // source points per thread at most (one z-block covers 2048 points); the kernel is
+                                  // instantiated for 1, 2 and 4 so that small tables do not pay registers for absent slots
+__host__ inline int sb_kpt(int N) { return N <= 512 ? 1 : (N <= 1024 ? 2 : SB_KPT); }
 constexpr int SB_CC = 4;          // channel rows per CTA
 constexpr int SB_EC_GROUP = 2048; // slots per chunk (grouping)
 constexpr int SB_EC_INTERP = 3072;  // slots per chunk (three_interpolate: 1024 points x 3 taps)
@@ -518,7 +520,7 @@ invert_kernel(const int64_t *__restrict__ keys, int64_t E, int N, int EC, int nc
 // gridDim.z = key blocks x splits: split s sums chunks [s*cps, (s+1)*cps) into its own partial
 // gradient (reduced in split order by reduce_partials_kernel), which gives small-C problems
 // (C = 3 at the first SA level) enough CTAs without atomics.
-template <bool INTERP>
+template <bool INTERP, int KPT>
 __global__ void __launch_bounds__(SB_THREADS, 2)
 bwd_sorted_kernel(const float *__restrict__ dout, const float *__restrict__ weight, const uint16_t *__restrict__ order,
                   const int *__restrict__ seg, const uint32_t *__restrict__ runs, const int *__restrict__ nruns, int C,
@@ -531,11 +533,11 @@ bwd_sorted_kernel(const float *__restrict__ dout, const float *__restrict__ weig
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
     const int c0 = blockIdx.x * SB_CC;
-    const int cc = (C - c0 < SB_CC) ? (C - c0) : SB_CC;
     const int split = blockIdx.z % splits;
-    const int jbase = (blockIdx.z / splits) * (SB_KPT * SB_THREADS);
+    const int jbase = (blockIdx.z / splits) * (KPT * SB_THREADS);
     const int ch_lo = split * cps;
     const int ch_hi = (ch_lo + cps < nchunks) ? (ch_lo + cps) : nchunks;
+    const int cc = (C - c0 < SB_CC) ? (C - c0) : SB_CC;
     const int64_t Ed = INTERP ? E / 3 : E;  // length of a gradient row
     const float *__restrict__ gb = dout + (int64_t)b * dout_batch_stride + (int64_t)(c_off + c0) * Ed;
     const float *__restrict__ wb = INTERP ? weight + (int64_t)b * E : nullptr;
@@ -543,9 +545,9 @@ bwd_sorted_kernel(const float *__restrict__ dout, const float *__restrict__ weig
     const bool tma = use_tma && ((Ed & 3) == 0) && ((((uintptr_t)gb) & 15) == 0) && ((Wd & 3) == 0) &&
                      (!INTERP || (((E & 3) == 0) && ((((uintptr_t)wb) & 15) == 0)));
 
-    float acc[SB_KPT][SB_CC];
+    float acc[KPT][SB_CC];
 #pragma unroll
-    for (int k = 0; k < SB_KPT; ++k)
+    for (int k = 0; k < KPT; ++k)
 #pragma unroll
         for (int c = 0; c < SB_CC; ++c) acc[k][c] = 0.f;
 
@@ -595,15 +597,15 @@ bwd_sorted_kernel(const float *__restrict__ dout, const float *__restrict__ weig
             for (int i = tid; i < EC / 8; i += SB_THREADS) odst[EC / 8 + i] = __ldg(rsrc + i);
         }
     };
-    int s0[SB_KPT], s1[SB_KPT], nr = 0;
+    int s0[KPT], s1[KPT], nr = 0;
     // key slots of this thread that exist at all (N = 512 -> 1): the others cost no instructions
-    const int kpt = (N - jbase + SB_THREADS - 1) / SB_THREADS < SB_KPT ? (N - jbase + SB_THREADS - 1) / SB_THREADS : SB_KPT;
+    const int kpt = (N - jbase + SB_THREADS - 1) / SB_THREADS < KPT ? (N - jbase + SB_THREADS - 1) / SB_THREADS : KPT;
 #pragma unroll
-    for (int k = 0; k < SB_KPT; ++k) s0[k] = s1[k] = 0;
+    for (int k = 0; k < KPT; ++k) s0[k] = s1[k] = 0;
     auto bounds = [&](int chunk) {
         const int *__restrict__ sb = seg + ((int64_t)b * nchunks + chunk) * (N + 1);
 #pragma unroll
-        for (int k = 0; k < SB_KPT; ++k) {
+        for (int k = 0; k < KPT; ++k) {
             if (k >= kpt) break;
             const int j = jbase + k * SB_THREADS + tid;
             s0[k] = j < N ? __ldg(sb + j) : 0;
@@ -623,9 +625,9 @@ bwd_sorted_kernel(const float *__restrict__ dout, const float *__restrict__ weig
     for (int chunk = ch_lo; chunk < ch_hi; ++chunk) {
         const int it = chunk - ch_lo;
         float *cur = stage + (size_t)(it % SB_STAGES) * buf_floats;
-        int a0[SB_KPT], a1[SB_KPT];
+        int a0[KPT], a1[KPT];
 #pragma unroll
-        for (int k = 0; k < SB_KPT; ++k) { a0[k] = s0[k]; a1[k] = s1[k]; }
+        for (int k = 0; k < KPT; ++k) { a0[k] = s0[k]; a1[k] = s1[k]; }
         const int nr_cur = nr;
         if (tma) {
             if (tid == 0 && chunk + SB_STAGES - 1 < ch_hi) issue(chunk + SB_STAGES - 1);
@@ -673,11 +675,40 @@ bwd_sorted_kernel(const float *__restrict__ dout, const float *__restrict__ weig
             __syncthreads();
         }
 #pragma unroll
-        for (int k = 0; k < SB_KPT; ++k) {
+        for (int k = 0; k < KPT; ++k) {
             if (k >= kpt) break;
             const int te = a1[k];
+            int t = a0[k];
+            if (!INTERP) {
+                // two list entries per step: their index and value loads are independent (the walk is a chain of
+                // shared-memory latencies otherwise); the additions keep the slot order
 #pragma unroll 1
-            for (int t = a0[k]; t < te; ++t) {  // slot order: deterministic
+                if (KPT == 1) {
+#pragma unroll 1
+                    for (; t + 4 <= te; t += 4) {
+                        const int e0 = ob[t], e1 = ob[t + 1], e2 = ob[t + 2], e3 = ob[t + 3];
+                        float v0[SB_CC], v1[SB_CC], v2[SB_CC], v3[SB_CC];
+#pragma unroll
+                        for (int c = 0; c < SB_CC; ++c) {
+                            v0[c] = cur[c * Wd + e0]; v1[c] = cur[c * Wd + e1];
+                            v2[c] = cur[c * Wd + e2]; v3[c] = cur[c * Wd + e3];
+                        }
+#pragma unroll
+                        for (int c = 0; c < SB_CC; ++c) acc[k][c] = (((acc[k][c] + v0[c]) + v1[c]) + v2[c]) + v3[c];
+                    }
+                }
+#pragma unroll 1
+                for (; KPT < 4 && t + 2 <= te; t += 2) {   // (the 4-slot instantiation has no registers to spare)
+                    const int e0 = ob[t], e1 = ob[t + 1];
+                    float v0[SB_CC], v1[SB_CC];
+#pragma unroll
+                    for (int c = 0; c < SB_CC; ++c) { v0[c] = cur[c * Wd + e0]; v1[c] = cur[c * Wd + e1]; }
+#pragma unroll
+                    for (int c = 0; c < SB_CC; ++c) acc[k][c] = (acc[k][c] + v0[c]) + v1[c];
+                }
+            }
+#pragma unroll 1
+            for (; t < te; ++t) {  // slot order: deterministic
                 const int ea = ob[t];
                 if (INTERP) {
                     const float wa = wst[ea];
@@ -694,7 +725,7 @@ bwd_sorted_kernel(const float *__restrict__ dout, const float *__restrict__ weig
     }
     float *__restrict__ dst = dst_base + (int64_t)split * split_stride;
 #pragma unroll
-    for (int k = 0; k < SB_KPT; ++k) {
+    for (int k = 0; k < KPT; ++k) {
         const int j = jbase + k * SB_THREADS + tid;
         if (j < N) {
 #pragma unroll
@@ -849,7 +880,7 @@ static int launch_bwd_direct(const float *dout, const int64_t *keys, int B, int 
 }
 
 static int pick_splits(int B, int C, int N, int nchunks) {
-    const int64_t ctas = (int64_t)((C + SB_CC - 1) / SB_CC) * B * ((N + SB_KPT * SB_THREADS - 1) / (SB_KPT * SB_THREADS));
+    const int64_t ctas = (int64_t)((C + SB_CC - 1) / SB_CC) * B * ((N + sb_kpt(N) * SB_THREADS - 1) / (sb_kpt(N) * SB_THREADS));
     int splits = 1;
     if (ctas < 2 * kNumSMs) splits = (int)((2 * kNumSMs + ctas - 1) / ctas);
     if (splits > nchunks) splits = nchunks;
@@ -895,8 +926,9 @@ static int launch_bwd_sorted(const float *dout, const float *weight, const int64
     static DeviceOnce attr_done;
     if (!attr_done.done()) {
         cudaFuncSetAttribute(invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(bwd_sorted_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(bwd_sorted_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(bwd_sorted_kernel<INTERP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(bwd_sorted_kernel<INTERP, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(bwd_sorted_kernel<INTERP, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_done.mark();
     }
     if (mode != BWD_PREPARED) {
@@ -912,10 +944,12 @@ static int launch_bwd_sorted(const float *dout, const float *weight, const int64
         (size_t)SB_STAGES * (SB_CC * Wd + (INTERP ? EC : 0) + EC / 2 + (INTERP ? 0 : EC / 2)) * sizeof(float);
     const int splits = L.splits;
     const int cps = (nchunks + splits - 1) / splits;
-    const int zblocks = (N + SB_KPT * SB_THREADS - 1) / (SB_KPT * SB_THREADS);
+    const int kpt = sb_kpt(N);
+    const int zblocks = (N + kpt * SB_THREADS - 1) / (kpt * SB_THREADS);
     dim3 grid((unsigned)((C + SB_CC - 1) / SB_CC), (unsigned)B, (unsigned)(zblocks * splits));
     const int64_t total = (int64_t)B * C * N;
-    bwd_sorted_kernel<INTERP><<<grid, SB_THREADS, smem, st>>>(dout, weight, order, seg, runs, nruns, C, N, E, EC,
+    auto kern = kpt == 1 ? bwd_sorted_kernel<INTERP, 1> : (kpt == 2 ? bwd_sorted_kernel<INTERP, 2> : bwd_sorted_kernel<INTERP, 4>);
+    kern<<<grid, SB_THREADS, smem, st>>>(dout, weight, order, seg, runs, nruns, C, N, E, EC,
                                                              nchunks, splits, cps, splits > 1 ? part : dfeat, total,
                                                              dout_batch_stride, c_off, use_tma);
     if (int e = finish_launch(INTERP ? "three_interp_bwd_sorted" : "group_bwd_sorted")) return e;
