@@ -198,7 +198,7 @@ int p3d_three_interp_bwd_f32(const float *dout, const int64_t *idx, const float 
  * intermediate is written to HBM.
  * precision = P3D_PRECISION_TENSOR runs the (kernel point x Cin) -> Cout contraction on tcgen05
  * tensor cores (TMA-fed pre-split weights, fp32 accumulation in TMEM; operands are bf16 hi+lo pairs,
- * three MMAs per product: relative error ~1e-5 of max|out|, stated and tested at 2e-5) when
+ * three partial products (hi.hi, lo.hi, hi.lo) per product: relative error ~1e-5 of max|out|, stated and tested at 2e-5) when
  * Cin % 32 == 0, Cout % 32 == 0, Cout <= 512, M <= 40 and a workspace of
  * p3d_kpconv_fwd_ws_bytes() is given; other shapes and P3D_PRECISION_FP32 use exact fp32 SIMT. */
 size_t p3d_kpconv_fwd_ws_bytes(int64_t n, int K, int Cin, int Cout);

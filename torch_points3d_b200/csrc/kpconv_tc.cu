@@ -4,25 +4,29 @@
 //
 //   out[p, :] = sum_k wf[p, k, :] @ W[k]          wf[p, k, c] = sum_m w[p, k, m] * x[nb[p, m], c]
 //
-// A persistent CTA walks tiles of 16 query points (one per producer warp).  The contraction over (kernel point, input channel) is cut into
-// PASSES of one 32-channel slab = 16 kernel points x 32 channels = 512 K-elements.  Three roles, coupled by
-// mbarriers only (no CTA-wide barrier after start-up):
+// A persistent CTA walks tiles of 16 or 32 query points (one or two per producer warp).  The contraction over (kernel
+// point, input channel) is cut into PASSES of one 32-channel slab = 16 kernel points x 32 channels = 512 K-elements.
+// Three roles, coupled by mbarriers only (no CTA-wide barrier after start-up):
 //
-//   producers (16 warps, SIMT) -- per point (its influence table is built once and serves every slab): the neighbour rows of the slab go to shared memory with 16-byte cp.async
-//       (in flight while the influence weights are computed with lanes = neighbours; one warp ballot per kernel
-//       point marks the ~6 % of (kernel point, neighbour) pairs with a nonzero linear influence); then lanes =
-//       (kernel point, half slab): every lane walks the influencing neighbours of ITS kernel point and accumulates
-//       16 channels from shared memory (4 LDS.128 + 16 FMA per pair).  The fp32 result is split into bf16 hi + lo
-//       and stored with two 16-byte stores per operand into the A tile (K-major, 128-byte swizzle: the canonical
-//       UMMA layout).  ONE A stage is enough: a warp needs the tile only at the very end of its point (the store),
-//       by which time the MMAs of the previous pass -- a fraction of a producer pass -- have long retired; the
-//       shared memory goes to 16 producer warps and a 4-deep weight ring instead.
-//   MMA warp (one elected thread) -- W pieces (pre-split bf16 hi/lo, pre-swizzled by kpconv_prep_w_kernel) stream
-//       through a ring of TMA bulk copies that runs ahead of the MMAs; D[128 x 32] += A_hi*B_hi + A_lo*B_hi +
-//       A_hi*B_lo (bf16x2 split: ~2^-17 relative, fp32 accumulation in TMEM; rows 16-127 of the M = 128 MMA are
-//       don't-care rows); tcgen05.commit hands A stages and W slots back.  Accumulators are double-buffered in TMEM.
-//   epilogue warp -- tcgen05.ld of the finished [16 x Cout] accumulator, 128-byte row stores, while the next tile
-//       is already being accumulated in the other TMEM buffer.
+//   producers (16 warps, SIMT) -- per point (its influence table is built once and serves every slab): the neighbour
+//       rows of the slab go to shared memory with 16-byte cp.async (in flight while the influence weights are computed
+//       with lanes = neighbours; one warp ballot per kernel point marks the ~6 % of (kernel point, neighbour) pairs
+//       with a nonzero linear influence); then lanes = (kernel point, half slab): every lane walks the influencing
+//       neighbours of ITS kernel point and accumulates 16 channels from shared memory (4 LDS.128 + 16 FMA per pair).
+//       The fp32 result is split into bf16 hi + lo and stored with two 16-byte stores per operand into the A tile
+//       (K-major, 128-byte swizzle: the canonical UMMA layout).  A warp needs the tile only at the very end of its
+//       point (the store): it waits for the previous pass's MMAs there and nowhere earlier; with 32-point tiles the
+//       first point's row waits in registers until the second point is done.  Shared memory goes to the gather scratch
+//       of 16 producer warps and a 2..8-slot weight ring; layers whose ring allows it get a second A stage (fwd_split).
+//   MMA warp -- W pieces (pre-split bf16 hi/lo rows, contiguous, pre-swizzled by kpconv_prep_w_kernel) stream through a
+//       ring of TMA bulk copies that runs ahead of the MMAs.  Per 16-K step TWO instructions: A_hi x [B_hi | B_lo]
+//       (N = 2 ng: the two partial products land in separate accumulator columns) and A_lo x B_hi (bf16x2 split:
+//       ~2^-17 relative, fp32 accumulation in TMEM; rows beyond the tile of the M = 128 MMA are don't-care rows).
+//       The whole warp runs the issue loop so that its counters and descriptors are uniform registers; one elected
+//       lane executes the tcgen05 / TMA / commit instructions.  tcgen05.commit hands A stages and W slots back.
+//       Accumulators are double-buffered in TMEM.
+//   epilogue warp -- tcgen05.ld of both halves of the finished accumulator, their sum, 128-byte row stores, while
+//       the next tile is already being accumulated in the other TMEM buffer.
 //
 // No [n,M,K], [n,M,Cin], [n,K,Cin] or [K,n,Cout] intermediate exists in HBM.
 #include <cuda_bf16.h>
