@@ -816,7 +816,13 @@ def bench_kpconv_stack(dev, world, rank):
     res = {"workload": "C3/C5: KPConvPaper segmentation network (5 KPDualBlocks down, 4 FPModule_PD up, %.1f M params), "
                        "~%d points/rank in 8 spheres, fwd+bwd+SGD%s" % (tr.num_params / 1e6, n,
                                                                        ", DDP over NCCL" if world > 1 else ""),
-           "ms_per_step": round(ms_full, 3), "points_per_s": round(total_pts / (ms_full * 1e-3), 1),
+           # headline of this section: the training step in the reference's configuration -- the multi-scale pyramid comes
+           # precomputed (the reference builds it in DataLoader workers: MultiScaleTransform); replaced below by the
+           # CUDA-graph replay of the same step when the capture succeeds on every rank
+           "ms_per_step": round(ms_pre, 3), "points_per_s": round(total_pts / (ms_pre * 1e-3), 1),
+           "execution": "eager launches, precomputed pyramid",
+           "eager_ms_per_step": round(ms_pre, 3),
+           "eager_ms_per_step_with_on_device_geometry": round(ms_full, 3),
            "geometry_ms": round(ms_geo, 3), "precomputed_geometry_ms_per_step": round(ms_pre, 3),
            "loss_first": round(loss0, 4), "loss_after": round(loss1, 4), "unit": "points/s"}
     if world > 1:
@@ -841,7 +847,11 @@ def bench_kpconv_stack(dev, world, rank):
     if float(ok.item()) > 0:
         ms_graph = timed(tr.replay)
         res["precomputed_geometry_cuda_graph_ms_per_step"] = round(ms_graph, 3)
-        res["points_per_s_graph"] = round(total_pts / ((ms_graph + ms_geo) * 1e-3), 1)
+        res["points_per_s_graph"] = round(total_pts / ((ms_graph + ms_geo) * 1e-3), 1)  # (pyramid build included)
+        res["ms_per_step"] = round(ms_graph, 3)
+        res["points_per_s"] = round(total_pts / (ms_graph * 1e-3), 1)
+        res["execution"] = ("one CUDA graph per step: forward + NLL loss + backward%s + SGD; precomputed pyramid"
+                            % (" + DDP bucketed all-reduce (NCCL)" if world > 1 else ""))
         res["graph_loss"] = round(float(tr.graph_loss.item()), 4)
     return res
 
