@@ -267,6 +267,17 @@ int p3d_kpconv_bwd_wf_f32(const float *query, const float *support, const int64_
                           int64_t N0, int M, int K, int Cin, int Cout, float extent, int influence, int aggregation,
                           float *dfeat, float *dweights, void *ws, size_t ws_bytes, void *stream);
 
+/* ---- tall GEMM of the KPConv blocks -----------------------------------------------------------------------------
+ * C[R,N] (row stride ldc) = A[R,Kd] (row stride lda) . B, B(k,j) = B[k*sbk + j*sbj], fp32 in and out, on the tcgen05
+ * tensor cores (bf16 hi+lo operands, the three significant partial products, fp32 accumulation in TMEM: error
+ * <= 2e-5 of max|C|).  R = points of a level, Kd / N = channel counts.  It is the product behind the unary layers of
+ * the KPConv blocks (modules/KPConv/blocks.py:176-194: y = x . W^T -> sbk = 1, sbj = Cin; dx = dy . W -> sbk = Cin,
+ * sbj = 1) and behind the KPConv backward's dwf = dout . W^T.  N must be a multiple of 16 (else P3D_ERR_INVALID);
+ * ws: p3d_rowgemm_ws_bytes(Kd, N) bytes, 16-byte aligned. */
+size_t p3d_rowgemm_ws_bytes(int Kd, int N);
+int p3d_rowgemm_f32(const float *A, int64_t lda, const float *B, int64_t sbk, int64_t sbj, int64_t R, int Kd, int N,
+                    float *C, int64_t ldc, void *ws, size_t ws_bytes, void *stream);
+
 /* Strided-shortcut neighbour max-pool (modules/KPConv/blocks.py:206-210):
  * out[p,c] = max_m x'[neighbors[p,m], c], x' = cat(x, zeros); arg (nullable) = winning row
  * (N0 for the shadow row) for the backward pass. */

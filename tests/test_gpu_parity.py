@@ -763,3 +763,35 @@ def test_compat_tp_namespace_on_the_rsconv_call_sites():
     coarse = np.random.default_rng(92).standard_normal((B, C, S)).astype(np.float32)
     got = tp.three_interpolate(T(coarse), i3, weight)
     assert np.array_equal(N(got), oracle.three_interpolate_fwd(coarse, oi3, N(weight)))
+
+
+# ---------------------------------------------------------------- tall tcgen05 GEMM / unary layers ---------
+@pytest.mark.parametrize("n,Cin,Cout", [(50000, 64, 128), (15000, 128, 32), (777, 4, 32), (500, 1536, 512),
+                                        (300, 512, 1024), (100, 64, 13), (5000, 100, 96), (2000, 40, 48), (1, 256, 256),
+                                        (129, 16, 16), (4000, 480, 7680 // 16), (0, 32, 32)])
+def test_linear_forward_backward(n, Cin, Cout):
+    """ops.linear / ops.Linear (the unary layers of the KPConv blocks, blocks.py:176-194) against float64 matmuls:
+    tcgen05 row GEMM for output widths that are multiples of 16 (forward: K-contiguous weights, input gradient:
+    column-contiguous weights; partial last row tile, reductions that are not multiples of 64, several column groups),
+    library fallback otherwise.  Tolerance 2e-5 of the largest magnitude."""
+    rng = np.random.default_rng(n + Cin)
+    x = rng.standard_normal((n, Cin)).astype(np.float32)
+    w = (rng.standard_normal((Cout, Cin)) / np.sqrt(Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    dy = rng.standard_normal((n, Cout)).astype(np.float32)
+    lin = ops.Linear(Cin, Cout, bias=True).to(DEV)
+    with torch.no_grad():
+        lin.weight.copy_(T(w))
+        lin.bias.copy_(T(b))
+    assert set(lin.state_dict()) == {"weight", "bias"}
+    tx = T(x).requires_grad_(True)
+    y = lin(tx)
+    assert y.shape == (n, Cout)
+    y.backward(T(dy))
+    x64, w64, dy64 = x.astype(np.float64), w.astype(np.float64), dy.astype(np.float64)
+    if n:
+        assert relerr(N(y), x64 @ w64.T + b) <= 2e-5
+        assert relerr(N(tx.grad), dy64 @ w64) <= 2e-5
+        assert relerr(N(lin.weight.grad), dy64.T @ x64) <= 2e-5
+    else:
+        assert float(lin.weight.grad.abs().sum()) == 0.0

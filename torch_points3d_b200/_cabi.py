@@ -47,6 +47,8 @@ SIGNATURES = {
     "p3d_three_interp_bwd_prepare": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_sz, c_vp]),
     "p3d_three_interp_bwd_f32": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_sz, c_int,
                                          c_vp]),
+    "p3d_rowgemm_ws_bytes": (c_sz, [c_int, c_int]),
+    "p3d_rowgemm_f32": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_sz, c_vp]),
     "p3d_kpconv_fwd_ws_bytes": (c_sz, [c_i64, c_int, c_int, c_int]),
     "p3d_kpconv_fwd_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_int,
                                    c_f32, c_int, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),

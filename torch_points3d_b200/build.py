@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libp3d_b200.so")
-SOURCES = ["cabi.cu", "fps.cu", "neighbors.cu", "cellgrid.cu", "gather.cu", "kpconv.cu", "kpconv_tc.cu", "kpconv_deform.cu", "grid.cu", "edges.cu"]
+SOURCES = ["cabi.cu", "fps.cu", "neighbors.cu", "cellgrid.cu", "gather.cu", "kpconv.cu", "kpconv_tc.cu", "kpconv_deform.cu", "rowgemm_tc.cu", "grid.cu", "edges.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",

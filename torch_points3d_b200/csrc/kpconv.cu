@@ -405,6 +405,15 @@ int gemm_tc(const float *A, int64_t lda, const float *Bp, int64_t sbk, int64_t s
 int dw_accumulate(const float *A, const float *B, int64_t n, int R, int Cn, float *dW, cudaStream_t st, float *part = nullptr,
                   size_t part_bytes = 0);
 size_t dw_partial_bytes(int64_t n, int R, int Cn);
+// rowgemm_tc.cu: tall tcgen05 GEMM (128-row tiles, wide hi|lo MMAs); returns 1 when the shape is not supported
+size_t rowgemm_tc_ws_bytes(int Kd, int N);
+int rowgemm_tc(const float *A, int64_t lda, const float *Bp, int64_t sbk, int64_t sbj, int64_t R, int Kd, int N, float *C,
+               int64_t ldc, void *ws, size_t ws_bytes, cudaStream_t st);
+// bytes of the weight image of the backward's dwf GEMM (the larger of the two tensor-core kernels' needs)
+static size_t dwf_image_bytes(int Cout, int KC) {
+    const size_t a = gemm_tc_ws_bytes(Cout, KC), b = rowgemm_tc_ws_bytes(Cout, KC);
+    return ((a > b ? a : b) + 255) / 256 * 256;
+}
 // sparse-influence backward helpers (kpconv_tc.cu)
 bool kpconv_sparse_supported(int M, int K, int Cin);
 int kpconv_wf_sparse(const float *query, const float *support, const int64_t *neighbors, const float *feat,
@@ -512,7 +521,7 @@ P3D_EXPORT size_t p3d_kpconv_bwd_ws_bytes(int64_t n, int M, int K, int Cin, int 
     (void)M;
     // wf + dwf  [n, K, Cin] each, then the bf16 hi/lo image of W^T for the tensor-core dwf GEMM (0 if unsupported),
     // then the per-chunk partial blocks of the deterministic dW reduction
-    return (size_t)2 * (size_t)n * (size_t)K * (size_t)Cin * sizeof(float) + gemm_tc_ws_bytes(Cout, K * Cin) +
+    return (size_t)2 * (size_t)n * (size_t)K * (size_t)Cin * sizeof(float) + dwf_image_bytes(Cout, K * Cin) +
            dw_partial_bytes(n, K * Cin, Cout);
 }
 
@@ -564,7 +573,7 @@ static int kpconv_bwd_impl(const float *query, const float *support, const int64
     if (grid > 16 * kNumSMs) grid = 16 * kNumSMs;
     const bool sparse = kpconv_sparse_supported(M, K, Cin);
     const size_t part_bytes = dw_partial_bytes(n, (int)KC, Cout);
-    float *dw_part = (float *)((char *)ws + (size_t)2 * n * K * Cin * sizeof(float) + gemm_tc_ws_bytes(Cout, K * Cin));
+    float *dw_part = (float *)((char *)ws + (size_t)2 * n * K * Cin * sizeof(float) + dwf_image_bytes(Cout, K * Cin));
     if (dweights && wf_saved != nullptr) {
         // dW[kc][o] += sum_p wf[p][kc] * dout[p][o] straight from the forward's slab
         const int r = dw_accumulate(wf_saved, dout, n, (int)KC, Cout, dweights, st, dw_part, part_bytes);
@@ -603,8 +612,11 @@ static int kpconv_bwd_impl(const float *query, const float *support, const int64
     if (dfeat) {
         // dwf[p][kc] = sum_o dout[p][o] * W[kc][o]: tcgen05 GEMM (bf16 hi+lo operands) when the shape allows it
         void *bimg = (char *)ws + (size_t)2 * n * K * Cin * sizeof(float);
-        const size_t bimg_bytes = gemm_tc_ws_bytes(Cout, K * Cin);
-        int r = gemm_smallk(dout, Cout, k_values, 1, Cout, n, Cout, (int)KC, dwf, KC, st);  // Cout <= 64: write-bound
+        const size_t bimg_bytes = dwf_image_bytes(Cout, K * Cin);
+        // the tall row GEMM takes every shape with K * Cin % 16 == 0 (measured against the two older kernels on the
+        // encoder shapes: 61 vs 72 us at 32 -> 32 / 50 k points, 33 vs 70 us at 128 -> 128, 31 vs 90 us at 512 -> 512)
+        int r = rowgemm_tc(dout, Cout, k_values, 1, Cout, n, Cout, (int)KC, dwf, KC, bimg, bimg_bytes, st);
+        if (r == 1) r = gemm_smallk(dout, Cout, k_values, 1, Cout, n, Cout, (int)KC, dwf, KC, st);  // Cout <= 64, fp32
         if (r == 1) r = gemm_tc(dout, Cout, k_values, 1, Cout, n, Cout, (int)KC, dwf, KC, bimg, bimg_bytes, st);
         if (r < 0) return r;
         if (r == 1) {

@@ -588,6 +588,71 @@ def knn_interpolate(x, pos_x, pos_y, batch_x=None, batch_y=None, k: int = 3, num
 
 
 # -------------------------------------------------------------------- KPConv ---------------
+# ------------------------------------------------------------ unary layers of the KPConv blocks ------------
+def _rowgemm(A: torch.Tensor, B: torch.Tensor, sbk: int, sbj: int, Kd: int, N: int) -> torch.Tensor:
+    """C[R, N] = A[R, Kd] . B with B(k, j) = B.flatten()[k * sbk + j * sbj] on the tcgen05 row GEMM (csrc/rowgemm_tc.cu)"""
+    dev = A.device
+    R = A.shape[0]
+    C = torch.empty((R, N), dtype=torch.float32, device=dev)
+    ws_bytes = _cabi.lib().p3d_rowgemm_ws_bytes(Kd, N)
+    ws = _workspace(ws_bytes, dev)
+    _call(dev, "p3d_rowgemm_f32", A.data_ptr(), A.stride(0), B.data_ptr(), sbk, sbj, R, Kd, N, C.data_ptr(), N, _ptr(ws),
+          ws_bytes)
+    return C
+
+
+def rowgemm_supported(Kd: int, N: int) -> bool:
+    return N % 16 == 0 and N >= 16 and Kd >= 1
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight):
+        _require_cuda("linear", x, weight)
+        x, weight = _f32(x), _f32(weight)
+        Cout, Cin = weight.shape
+        if x.shape[1] != Cin:
+            raise ValueError("linear: x is [n, %d] but weight is %s" % (x.shape[1], tuple(weight.shape)))
+        ctx.save_for_backward(x, weight)
+        if x.shape[0] == 0 or not rowgemm_supported(Cin, Cout):
+            return x @ weight.t()
+        return _rowgemm(x, weight, 1, Cin, Cin, Cout)          # B(k, j) = W[j][k]
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = _f32(dy)
+        Cout, Cin = weight.shape
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            if x.shape[0] == 0 or not rowgemm_supported(Cout, Cin):
+                dx = dy @ weight
+            else:
+                dx = _rowgemm(dy, weight, Cin, 1, Cout, Cin)   # B(k, j) = W[k][j]
+        if ctx.needs_input_grad[1]:
+            dw = dy.t() @ x                                    # [Cout, Cin]: a short, wide reduction over the points
+        return dx, dw
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = x @ weight.T (+ bias) on a [n, Cin] point-feature table: the unary layers of the KPConv blocks
+    (modules/KPConv/blocks.py:176-194) and the decoder MLPs (base_modules.py:35-45).  Forward and input gradient run
+    on the tcgen05 row GEMM (output widths that are multiples of 16); the weight gradient -- a reduction over the
+    points with a tiny output -- stays a library call."""
+    y = _Linear.apply(x, weight)
+    return y if bias is None else y + bias
+
+
+class Linear(torch.nn.Linear):
+    """torch.nn.Linear with the same parameters and state_dict keys; [n, Cin] fp32 CUDA tables go through `linear`,
+    anything else through the stock implementation"""
+
+    def forward(self, x):
+        if x.dim() == 2 and x.is_cuda and x.dtype == torch.float32 and self.weight.dtype == torch.float32:
+            return linear(x, self.weight, self.bias)
+        return super().forward(x)
+
+
 class _KPConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, query, support, neighbors, feat, k_points, k_values, extent, influence, aggregation,
