@@ -43,9 +43,12 @@ def test_library_loads_and_reports_arch(cabi):
     assert lib.p3d_fps_dense_ws_bytes(4, 1024) == 0
     assert lib.p3d_fps_dense_ws_bytes(2, 200000) == 2 * 200000 * 4
     # wf + dwf buffers, plus the bf16 hi/lo image of W^T for the tensor-core dwf GEMM (15 x 32 outputs / 32 per chunk x 4 pieces x 16 KB)
-    # ... plus the partial blocks of the deterministic dW reduction (one point chunk here: K*Cin x Cout floats)
-    assert lib.p3d_kpconv_bwd_ws_bytes(10, 34, 15, 32, 32) == 2 * 10 * 15 * 32 * 4 + 15 * 4 * 16384 + 480 * 32 * 4
-    assert lib.p3d_kpconv_bwd_ws_bytes(10, 34, 15, 5, 64) == 2 * 10 * 15 * 5 * 4 + 75 * 64 * 4
+    # ... plus the workspace of the weight gradient on the tcgen05 row GEMM: the bf16 hi/lo image of dout (one 64-point
+    # chunk x 32 columns = 8 KB) and one partial K*Cin x Cout block (the reduction over 10 points is not split)
+    assert lib.p3d_kpconv_bwd_ws_bytes(10, 34, 15, 32, 32) == 2 * 10 * 15 * 32 * 4 + 15 * 4 * 16384 + (8192 + 480 * 32 * 4)
+    # Cin = 5: no tensor-core dwf image (K * Cin = 75 is not a multiple of 16); the weight gradient's workspace is sized
+    # for the row GEMM (Cout = 64 is): a 16 KB image of dout + one 75 x 64 partial block
+    assert lib.p3d_kpconv_bwd_ws_bytes(10, 34, 15, 5, 64) == 2 * 10 * 15 * 5 * 4 + (2 * 64 * 128 + 75 * 64 * 4)
 
 
 def test_sass_is_sm100a_only(cabi):

@@ -409,6 +409,26 @@ size_t dw_partial_bytes(int64_t n, int R, int Cn);
 size_t rowgemm_tc_ws_bytes(int Kd, int N);
 int rowgemm_tc(const float *A, int64_t lda, const float *Bp, int64_t sbk, int64_t sbj, int64_t R, int Kd, int N, float *C,
                int64_t ldc, void *ws, size_t ws_bytes, cudaStream_t st);
+// dW[R x N] += X^T . B on the same kernel (transposed operand, reduction cut over CTAs, deterministic partial sums)
+size_t rowgemm_dw_ws_bytes(int64_t n, int R, int N);
+int rowgemm_dw(const float *X, const float *Bp, int64_t n, int R, int N, float *dW, void *ws, size_t ws_bytes,
+               cudaStream_t st);
+// workspace of the weight gradient: the tensor-core kernel's image + partials, or the SIMT kernel's partial blocks
+static size_t dw_ws_bytes(int64_t n, int KC, int Cout) {
+    const size_t a = dw_partial_bytes(n, KC, Cout), b = rowgemm_dw_ws_bytes(n, KC, Cout);
+    return a > b ? a : b;
+}
+// dW += wf^T . dout: tcgen05 row GEMM when the shape allows it (Cout % 16 == 0), else the register-tiled fp32 kernel;
+// returns 1 when neither takes the shape
+static int dw_product(const float *wf, const float *dout, int64_t n, int KC, int Cout, float *dW, cudaStream_t st,
+                      void *ws, size_t ws_bytes) {
+    // few points (deep levels: 114-464 points against a 7680 x 512 gradient) leave the tensor-core kernel with two or
+    // three 64-point chunks per CTA and a weight image to build first: the fp32 kernel wins there (measured: 108 vs
+    // 126 us at 256 -> 256 / 114 points; 176 vs 214 us the other way at 128 -> 128 / 2580 points)
+    int r = n >= 1024 ? rowgemm_dw(wf, dout, n, KC, Cout, dW, ws, ws_bytes, st) : 1;
+    if (r == 1) r = dw_accumulate(wf, dout, n, KC, Cout, dW, st, (float *)ws, ws_bytes);
+    return r;
+}
 // bytes of the weight image of the backward's dwf GEMM (the larger of the two tensor-core kernels' needs)
 static size_t dwf_image_bytes(int Cout, int KC) {
     const size_t a = gemm_tc_ws_bytes(Cout, KC), b = rowgemm_tc_ws_bytes(Cout, KC);
@@ -522,7 +542,7 @@ P3D_EXPORT size_t p3d_kpconv_bwd_ws_bytes(int64_t n, int M, int K, int Cin, int 
     // wf + dwf  [n, K, Cin] each, then the bf16 hi/lo image of W^T for the tensor-core dwf GEMM (0 if unsupported),
     // then the per-chunk partial blocks of the deterministic dW reduction
     return (size_t)2 * (size_t)n * (size_t)K * (size_t)Cin * sizeof(float) + dwf_image_bytes(Cout, K * Cin) +
-           dw_partial_bytes(n, K * Cin, Cout);
+           dw_ws_bytes(n, K * Cin, Cout);
 }
 
 P3D_EXPORT int p3d_kpconv_bwd_f32(const float *query, const float *support, const int64_t *neighbors,
@@ -572,11 +592,11 @@ static int kpconv_bwd_impl(const float *query, const float *support, const int64
     int64_t grid = (n + KPF_WARPS - 1) / KPF_WARPS;
     if (grid > 16 * kNumSMs) grid = 16 * kNumSMs;
     const bool sparse = kpconv_sparse_supported(M, K, Cin);
-    const size_t part_bytes = dw_partial_bytes(n, (int)KC, Cout);
+    const size_t part_bytes = dw_ws_bytes(n, (int)KC, Cout);
     float *dw_part = (float *)((char *)ws + (size_t)2 * n * K * Cin * sizeof(float) + dwf_image_bytes(Cout, K * Cin));
     if (dweights && wf_saved != nullptr) {
         // dW[kc][o] += sum_p wf[p][kc] * dout[p][o] straight from the forward's slab
-        const int r = dw_accumulate(wf_saved, dout, n, (int)KC, Cout, dweights, st, dw_part, part_bytes);
+        const int r = dw_product(wf_saved, dout, n, (int)KC, Cout, dweights, st, dw_part, part_bytes);
         if (r < 0) return r;
         if (r == 1)  // shape outside the register-tiled kernel
             if (int e = sgemm_splitk_atomic(wf_saved, dout, n, KC, Cout, dweights, st)) return e;
@@ -592,7 +612,7 @@ static int kpconv_bwd_impl(const float *query, const float *support, const int64
         }
         // dW[kc][o] += sum_p wf[p][kc] * dout[p][o]
         {
-        const int r = dw_accumulate(wf, dout, n, (int)KC, Cout, dweights, st, dw_part, part_bytes);
+        const int r = dw_product(wf, dout, n, (int)KC, Cout, dweights, st, dw_part, part_bytes);
         if (r < 0) return r;
         if (r == 0) goto dw_done;
         }

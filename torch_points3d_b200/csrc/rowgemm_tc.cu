@@ -62,9 +62,15 @@ rowgemm_prep_b_kernel(const float *__restrict__ Bp, int64_t sbk, int64_t sbj, in
     for (int i = threadIdx.x; i < rg_piece_bytes(ng) / 16; i += 256) dst[i] = src[i];
 }
 
+// TRANS_A = false: A(r, k) = A[r * lda + k] (rows contiguous along the reduction).
+// TRANS_A = true : A(r, k) = A[k * lda + r] (the reduction index is the slow one: C = X^T . B with X = A as stored) -- the
+//     KPConv weight gradient dW[K * Cin, Cout] = wf^T . dout, a reduction over ALL points with a small output: the
+//     reduction is also cut over CTAs (gridDim.z ranges of cps chunks, partial outputs part_stride apart, added in
+//     range order by rowgemm_add_parts_kernel: deterministic).
+template <bool TRANS_A>
 __global__ void __launch_bounds__(RG_THREADS, 1)
-rowgemm_tc_kernel(const float *__restrict__ A, int64_t lda, const uint8_t *__restrict__ bimg, int64_t R, int Kd, int N,
-                  int NG, uint32_t tmem_cols, float *__restrict__ C, int64_t ldc) {
+rowgemm_tc_kernel(const float *__restrict__ A, int64_t lda, const uint8_t *__restrict__ bimg, int64_t R, int64_t Kd, int N,
+                  int NG, uint32_t tmem_cols, float *__restrict__ C, int64_t ldc, int cps, int64_t part_stride) {
     extern __shared__ __align__(1024) uint8_t rg_smem[];
     if ((smem_u32(rg_smem) & 1023u) != 0u) __trap();
     const uint32_t piece_bytes = (uint32_t)rg_piece_bytes(NG);
@@ -77,7 +83,10 @@ rowgemm_tc_kernel(const float *__restrict__ A, int64_t lda, const uint8_t *__res
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = blockIdx.y;
     const int ng = (N - g * NG < NG) ? (N - g * NG) : NG;
-    const int nk = (Kd + 63) / 64;
+    const int nk_all = (int)((Kd + 63) / 64);
+    const int c_lo = blockIdx.z * cps;                                   // this CTA's chunks of the reduction
+    const int nk = (c_lo + cps < nk_all ? c_lo + cps : nk_all) - c_lo;   // (>= 1 by construction of the grid)
+    C += (int64_t)blockIdx.z * part_stride;
     const int64_t ntiles = (R + RG_ROWS - 1) / RG_ROWS;
     const int64_t my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     if (tid == 0) {
@@ -103,7 +112,53 @@ rowgemm_tc_kernel(const float *__restrict__ A, int64_t lda, const uint8_t *__res
             const int64_t r_base = (blockIdx.x + ti * gridDim.x) * RG_ROWS + pw * 16;
             for (int c = 0; c < nk; ++c, ++it) {
                 const uint32_t stage = it % RG_A_STAGES;
-                const int k0 = c * 64 + q * 4;
+                if (TRANS_A) {
+                    // warp pw = reduction elements 8 pw .. 8 pw + 7 of the chunk (one 16-byte unit of every operand
+                    // row), lane = rows 4 lane .. 4 lane + 3: each load is one 512-byte line of a point's row
+                    const int64_t r0 = (blockIdx.x + ti * gridDim.x) * RG_ROWS + lane * 4;
+                    const int64_t kb = (int64_t)(c_lo + c) * 64 + pw * 8;
+                    float4 v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (kb + i < Kd) {
+                            const float *src = A + (kb + i) * lda + r0;
+                            if (vec && r0 + 4 <= R) {
+                                v[i] = __ldg(reinterpret_cast<const float4 *>(src));
+                            } else {
+                                if (r0 < R) v[i].x = __ldg(src);
+                                if (r0 + 1 < R) v[i].y = __ldg(src + 1);
+                                if (r0 + 2 < R) v[i].z = __ldg(src + 2);
+                                if (r0 + 3 < R) v[i].w = __ldg(src + 3);
+                            }
+                        }
+                    }
+                    if (it >= RG_A_STAGES) mbar_wait(&a_empty[stage], ((it / RG_A_STAGES) - 1) & 1);
+                    uint8_t *st = a_ring + stage * RG_A_STAGE;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int row = lane * 4 + j;
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float a0 = j == 0 ? v[2 * u].x : (j == 1 ? v[2 * u].y : (j == 2 ? v[2 * u].z : v[2 * u].w));
+                            const float a1 = j == 0 ? v[2 * u + 1].x
+                                                    : (j == 1 ? v[2 * u + 1].y : (j == 2 ? v[2 * u + 1].z : v[2 * u + 1].w));
+                            const float h0 = __bfloat162float(__float2bfloat16_rn(a0));
+                            const float h1 = __bfloat162float(__float2bfloat16_rn(a1));
+                            hi[u] = pack_bf16(h0, h1);
+                            lo[u] = pack_bf16(a0 - h0, a1 - h1);
+                        }
+                        const int off = row * 128 + ((pw ^ (row & 7)) << 4);
+                        *reinterpret_cast<uint4 *>(st + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4 *>(st + RG_ROWS * 128 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_full[stage]);
+                    continue;
+                }
+                const int64_t k0 = (int64_t)(c_lo + c) * 64 + q * 4;
                 float4 v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -148,7 +203,7 @@ rowgemm_tc_kernel(const float *__restrict__ A, int64_t lda, const uint8_t *__res
         const uint32_t desc_hi = (uint32_t)(a_desc0 >> 32);
         const uint32_t a_lo0 = (uint32_t)a_desc0, b_lo0 = (uint32_t)b_desc0;
         auto mkdesc = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | lo; };
-        const uint8_t *gimg = bimg + (size_t)g * nk * piece_bytes;
+        const uint8_t *gimg = bimg + ((size_t)g * nk_all + c_lo) * piece_bytes;
         uint32_t loads_left = (uint32_t)(my_tiles * nk), ld_slot = 0, ld_round = 0, ld_c = 0;
         auto issue_load = [&]() {
             if (leader) {
@@ -242,6 +297,21 @@ rowgemm_tc_kernel(const float *__restrict__ A, int64_t lda, const uint8_t *__res
 
 static int rg_ng(int N) { return N < RG_NG_MAX ? N : RG_NG_MAX; }
 
+static size_t rg_smem_bytes(int NG) {
+    return (size_t)RG_A_STAGES * RG_A_STAGE + (size_t)RG_B_STAGES * rg_piece_bytes(NG) +
+           (2 * RG_A_STAGES + 2 * RG_B_STAGES + 4) * sizeof(uint64_t) + 16;
+}
+
+static void rg_set_attributes() {
+    static DeviceOnce attr_done;
+    if (!attr_done.done()) {
+        cudaFuncSetAttribute(rowgemm_prep_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rg_piece_bytes(RG_NG_MAX));
+        cudaFuncSetAttribute(rowgemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rg_smem_bytes(RG_NG_MAX));
+        cudaFuncSetAttribute(rowgemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rg_smem_bytes(RG_NG_MAX));
+        attr_done.mark();
+    }
+}
+
 // bytes of the B image; 0 when the shape is outside the kernel (N must be a multiple of 16: the MMA's N granularity)
 size_t rowgemm_tc_ws_bytes(int Kd, int N) {
     if (Kd < 1 || N < 16 || (N & 15) != 0) return 0;
@@ -256,16 +326,7 @@ int rowgemm_tc(const float *A, int64_t lda, const float *Bp, int64_t sbk, int64_
     if (need == 0 || ws == nullptr || ws_bytes < need || (((uintptr_t)ws) & 15) != 0 || R < 1) return 1;
     const int NG = rg_ng(N), groups = (N + NG - 1) / NG, nk = (Kd + 63) / 64;
     if (groups > 65535) return 1;
-    const size_t smem = (size_t)RG_A_STAGES * RG_A_STAGE + (size_t)RG_B_STAGES * rg_piece_bytes(NG) +
-                        (2 * RG_A_STAGES + 2 * RG_B_STAGES + 4) * sizeof(uint64_t) + 16;
-    static DeviceOnce attr_done;
-    if (!attr_done.done()) {
-        cudaFuncSetAttribute(rowgemm_prep_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rg_piece_bytes(RG_NG_MAX));
-        cudaFuncSetAttribute(rowgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)((size_t)RG_A_STAGES * RG_A_STAGE + (size_t)RG_B_STAGES * rg_piece_bytes(RG_NG_MAX) +
-                                   (2 * RG_A_STAGES + 2 * RG_B_STAGES + 4) * sizeof(uint64_t) + 16));
-        attr_done.mark();
-    }
+    rg_set_attributes();
     rowgemm_prep_b_kernel<<<groups * nk, 256, rg_piece_bytes(NG), st>>>(Bp, sbk, sbj, Kd, N, NG, nk, (uint8_t *)ws);
     if (int e = finish_launch("rowgemm_prep_b")) return e;
     const int64_t ntiles = (R + RG_ROWS - 1) / RG_ROWS;
@@ -274,9 +335,85 @@ int rowgemm_tc(const float *A, int64_t lda, const float *Bp, int64_t sbk, int64_
     if (gx > ntiles) gx = ntiles;
     uint32_t cols = 32;
     while ((int)cols < 4 * NG) cols <<= 1;  // two buffers of 2 * NG columns
-    rowgemm_tc_kernel<<<dim3((unsigned)gx, (unsigned)groups), RG_THREADS, smem, st>>>(A, lda, (const uint8_t *)ws, R, Kd, N, NG,
-                                                                                   cols, C, ldc);
+    rowgemm_tc_kernel<false><<<dim3((unsigned)gx, (unsigned)groups), RG_THREADS, rg_smem_bytes(NG), st>>>(
+        A, lda, (const uint8_t *)ws, R, Kd, N, NG, cols, C, ldc, nk, 0);
     return finish_launch("rowgemm_tc");
+}
+
+// ---- dW[R x N] += X^T . B over n points: X = [n x R] (the weighted features), B = [n x N] (the output gradient) -------
+// dst[i] += part[0][i] + part[1][i] + ... : eight thread groups add contiguous ranges of the partials in order, the
+// range sums are added in range order (fixed order: deterministic)
+__global__ void __launch_bounds__(256)
+rowgemm_add_parts_kernel(const float *__restrict__ part, int splits, int64_t total, float *__restrict__ dst) {
+    __shared__ float sums[8][32];
+    const int lane = threadIdx.x & 31, gq = threadIdx.x >> 5;
+    const int per = (splits + 7) / 8;
+    const int z0 = gq * per, z1 = (z0 + per < splits) ? z0 + per : splits;
+    for (int64_t base = (int64_t)blockIdx.x * 32; base < total; base += (int64_t)gridDim.x * 32) {
+        const int64_t i = base + lane;
+        float a = 0.f;
+        if (i < total)
+            for (int z = z0; z < z1; ++z) a += __ldg(part + (int64_t)z * total + i);
+        sums[gq][lane] = a;
+        __syncthreads();
+        if (gq == 0 && i < total) {
+            float t = sums[0][lane];
+#pragma unroll
+            for (int u = 1; u < 8; ++u) t += sums[u][lane];
+            dst[i] += t;
+        }
+        __syncthreads();
+    }
+}
+
+struct RgDwPlan {
+    int NG, groups, nk, tiles, splits, cps;
+    size_t image, total;
+};
+
+static RgDwPlan rg_dw_plan(int64_t n, int R, int N) {
+    RgDwPlan p;
+    p.NG = rg_ng(N);
+    p.groups = (N + p.NG - 1) / p.NG;
+    p.nk = (int)((n + 63) / 64);
+    p.tiles = (R + RG_ROWS - 1) / RG_ROWS;
+    int want = kNumSMs / (p.tiles * p.groups);
+    if (want < 1) want = 1;
+    if (want > p.nk) want = p.nk;
+    p.cps = (p.nk + want - 1) / want;
+    p.splits = (p.nk + p.cps - 1) / p.cps;
+    p.image = ((size_t)p.groups * p.nk * rg_piece_bytes(p.NG) + 255) / 256 * 256;
+    p.total = p.image + (size_t)p.splits * R * N * sizeof(float);
+    return p;
+}
+
+size_t rowgemm_dw_ws_bytes(int64_t n, int R, int N) {
+    if (n < 1 || R < 1 || N < 16 || (N & 15) != 0 || n > (int64_t)1 << 30) return 0;
+    return rg_dw_plan(n, R, N).total;
+}
+
+// returns 1 when the shape is not supported
+int rowgemm_dw(const float *X, const float *Bp, int64_t n, int R, int N, float *dW, void *ws, size_t ws_bytes,
+               cudaStream_t st) {
+    const size_t need = rowgemm_dw_ws_bytes(n, R, N);
+    if (need == 0 || ws == nullptr || ws_bytes < need || (((uintptr_t)ws) & 15) != 0) return 1;
+    const RgDwPlan p = rg_dw_plan(n, R, N);
+    if (p.groups > 65535 || p.splits > 65535) return 1;
+    rg_set_attributes();
+    float *part = (float *)((char *)ws + p.image);
+    // image of B(k = point, j = column) = Bp[k * N + j]
+    rowgemm_prep_b_kernel<<<p.groups * p.nk, 256, rg_piece_bytes(p.NG), st>>>(Bp, N, 1, (int)n, N, p.NG, p.nk, (uint8_t *)ws);
+    if (int e = finish_launch("rowgemm_prep_b")) return e;
+    uint32_t cols = 32;
+    while ((int)cols < 4 * p.NG) cols <<= 1;
+    rowgemm_tc_kernel<true><<<dim3((unsigned)p.tiles, (unsigned)p.groups, (unsigned)p.splits), RG_THREADS, rg_smem_bytes(p.NG), st>>>(
+        X, R, (const uint8_t *)ws, R, n, N, p.NG, cols, part, N, p.cps, (int64_t)R * N);
+    if (int e = finish_launch("rowgemm_dw")) return e;
+    const int64_t total = (int64_t)R * N;
+    int64_t gr = (total + 31) / 32;
+    if (gr > 8 * kNumSMs) gr = 8 * kNumSMs;
+    rowgemm_add_parts_kernel<<<(unsigned)gr, 256, 0, st>>>(part, p.splits, total, dW);
+    return finish_launch("rowgemm_add_parts");
 }
 
 }  // namespace p3d
