@@ -234,6 +234,7 @@ def test_sass_uses_the_blackwell_units_the_design_names(cabi):
     assert has("kpconv_fwd_tc_kernel", "UTCHMMA") and has("kpconv_fwd_tc_kernel", "LDTM")      # tcgen05.mma / tcgen05.ld
     assert has("kpconv_fwd_tc_kernel", "UBLKCP") and has("kpconv_fwd_tc_kernel", "UTCBAR")     # TMA weights, tcgen05.commit
     assert has("gemm_tc_kernel", "UTCHMMA")
+    assert has("rowgemm_tc_kernel", "UTCHMMA") and has("rowgemm_tc_kernel", "UBLKCP") and has("rowgemm_tc_kernel", "LDTM")
     assert has("bwd_sorted_kernel", "UBLKCP") and has("bwd_sorted_kernel", "SYNCS.PHASECHK")   # TMA ring + mbarrier wait
     assert has("fps_cta_kernel", "REDUX") and has("fps_reg_kernel", "UCGABAR")                 # warp redux, cluster barrier
     assert has("kpconv_fwd_tc_kernel", "LDGSTS")                                               # cp.async row staging
