@@ -277,6 +277,13 @@ int p3d_kpconv_bwd_wf_f32(const float *query, const float *support, const int64_
 size_t p3d_rowgemm_ws_bytes(int Kd, int N);
 int p3d_rowgemm_f32(const float *A, int64_t lda, const float *B, int64_t sbk, int64_t sbj, int64_t R, int Kd, int N,
                     float *C, int64_t ldc, void *ws, size_t ws_bytes, void *stream);
+/* dW[R,N] += X^T . B over the n rows of X[n,R] and B[n,N] (the weight gradient of such a layer: X = dy, B = x gives
+ * dW[Cout,Cin]; the KPConv weight gradient: X = weighted features, B = dout).  Same arithmetic; the reduction is cut
+ * over CTAs and the partial outputs are added in a fixed order (deterministic).  dW is accumulated into (zero it
+ * first for a plain product).  N must be a multiple of 16; ws: p3d_rowgemm_dw_ws_bytes(n, R, N). */
+size_t p3d_rowgemm_dw_ws_bytes(int64_t n, int R, int N);
+int p3d_rowgemm_dw_f32(const float *X, const float *B, int64_t n, int R, int N, float *dW, void *ws, size_t ws_bytes,
+                       void *stream);
 
 /* Strided-shortcut neighbour max-pool (modules/KPConv/blocks.py:206-210):
  * out[p,c] = max_m x'[neighbors[p,m], c], x' = cat(x, zeros); arg (nullable) = winning row

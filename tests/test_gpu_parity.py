@@ -769,7 +769,7 @@ def test_compat_tp_namespace_on_the_rsconv_call_sites():
 @pytest.mark.parametrize("n,Cin,Cout", [(50000, 64, 128), (15000, 128, 32), (777, 4, 32), (500, 1536, 512),
                                         (300, 512, 1024), (100, 64, 13), (5000, 100, 96), (2000, 40, 48), (1, 256, 256),
                                         (129, 16, 16), (4000, 480, 7680 // 16), (0, 32, 32)])
-def test_linear_forward_backward(n, Cin, Cout):
+def test_linear_forward_backward(n, Cin, Cout, monkeypatch):
     """ops.linear / ops.Linear (the unary layers of the KPConv blocks, blocks.py:176-194) against float64 matmuls:
     tcgen05 row GEMM for output widths that are multiples of 16 (forward: K-contiguous weights, input gradient:
     column-contiguous weights; partial last row tile, reductions that are not multiples of 64, several column groups),
@@ -779,6 +779,7 @@ def test_linear_forward_backward(n, Cin, Cout):
     w = (rng.standard_normal((Cout, Cin)) / np.sqrt(Cin)).astype(np.float32)
     b = rng.standard_normal(Cout).astype(np.float32)
     dy = rng.standard_normal((n, Cout)).astype(np.float32)
+    monkeypatch.setattr(ops, "LINEAR_MIN_ROWS", 1)   # every size through the tensor-core kernels
     lin = ops.Linear(Cin, Cout, bias=True).to(DEV)
     with torch.no_grad():
         lin.weight.copy_(T(w))
@@ -793,5 +794,9 @@ def test_linear_forward_backward(n, Cin, Cout):
         assert relerr(N(y), x64 @ w64.T + b) <= 2e-5
         assert relerr(N(tx.grad), dy64 @ w64) <= 2e-5
         assert relerr(N(lin.weight.grad), dy64.T @ x64) <= 2e-5
+        g1 = lin.weight.grad.clone()
+        lin.weight.grad = None
+        lin(T(x)).backward(T(dy))
+        assert torch.equal(g1, lin.weight.grad)          # the split reduction is deterministic
     else:
         assert float(lin.weight.grad.abs().sum()) == 0.0

@@ -49,6 +49,8 @@ SIGNATURES = {
                                          c_vp]),
     "p3d_rowgemm_ws_bytes": (c_sz, [c_int, c_int]),
     "p3d_rowgemm_f32": (c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_vp, c_sz, c_vp]),
+    "p3d_rowgemm_dw_ws_bytes": (c_sz, [c_i64, c_int, c_int]),
+    "p3d_rowgemm_dw_f32": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),
     "p3d_kpconv_fwd_ws_bytes": (c_sz, [c_i64, c_int, c_int, c_int]),
     "p3d_kpconv_fwd_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_int, c_int,
                                    c_f32, c_int, c_int, c_int, c_vp, c_vp, c_sz, c_vp]),

@@ -441,3 +441,24 @@ P3D_EXPORT int p3d_rowgemm_f32(const float *A, int64_t lda, const float *B, int6
     }
     return r;
 }
+
+P3D_EXPORT size_t p3d_rowgemm_dw_ws_bytes(int64_t n, int R, int N) { return rowgemm_dw_ws_bytes(n, R, N); }
+
+P3D_EXPORT int p3d_rowgemm_dw_f32(const float *X, const float *B, int64_t n, int R, int N, float *dW, void *ws,
+                                  size_t ws_bytes, void *stream) {
+    P3D_REQUIRE(n >= 0 && R >= 1 && N >= 1, "rowgemm_dw: bad dimension");
+    if (n == 0) return P3D_OK;
+    P3D_REQUIRE(X && B && dW, "rowgemm_dw: null pointer");
+    const size_t need = rowgemm_dw_ws_bytes(n, R, N);
+    P3D_REQUIRE(need > 0, "rowgemm_dw: the output width must be a multiple of 16 (got %d)", N);
+    if (ws == nullptr || ws_bytes < need) {
+        set_error("rowgemm_dw: workspace of %zu bytes required (p3d_rowgemm_dw_ws_bytes)", need);
+        return P3D_ERR_WORKSPACE;
+    }
+    const int r = rowgemm_dw(X, B, n, R, N, dW, ws, ws_bytes, (cudaStream_t)stream);
+    if (r == 1) {
+        set_error("rowgemm_dw: shape not supported (n=%lld R=%d N=%d)", (long long)n, R, N);
+        return P3D_ERR_INVALID;
+    }
+    return r;
+}

@@ -293,7 +293,7 @@ class ResnetBBlock(torch.nn.Module):
         self.kp_conv = SimpleBlock(down_conv_nn=kp_size, grid_size=grid_size, prev_grid_size=prev_grid_size,
                                    sigma=sigma, max_num_neighbors=max_num_neighbors, activation=act,
                                    bn_momentum=bn_momentum, bn=bn, deformable=deformable, add_one=add_one, **kwargs)
-        Lin, BN = torch.nn.Linear, bn
+        Lin, BN = ops.Linear, bn
         if has_bottleneck:
             if bn:
                 self.unary_1 = torch.nn.Sequential(Lin(num_inputs, d_2, bias=False), BN(d_2, momentum=bn_momentum), act)
@@ -443,7 +443,7 @@ class KPConvPaper(torch.nn.Module):
             skip = f * 2 ** lv
             self.up_modules.append(FPModule_PD(1, [below + skip, f * 2 ** (lv - 1)], bn_momentum=bn_momentum))
         self.FC_layer = torch.nn.Sequential()
-        self.FC_layer.add_module("1", torch.nn.Sequential(torch.nn.Linear(f, f, bias=False),
+        self.FC_layer.add_module("1", torch.nn.Sequential(ops.Linear(f, f, bias=False),
                                                           FastBatchNorm1d(f, momentum=bn_momentum),
                                                           torch.nn.LeakyReLU(0.2)))
         self.FC_layer.add_module("Class", torch.nn.Linear(f, num_classes, bias=False))

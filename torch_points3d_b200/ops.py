@@ -605,6 +605,12 @@ def rowgemm_supported(Kd: int, N: int) -> bool:
     return N % 16 == 0 and N >= 16 and Kd >= 1
 
 
+# Tables with fewer rows than this keep the library GEMMs in ops.linear: with 128-row tiles a level of a few thousand
+# points gives each SM one or two tiles and the kernel's fill / drain is the whole run (bench_tools/linear_times.py:
+# 2580 x 256 -> 64 forward 16.6 us against 8.5 us; 50 614 x 64 -> 128 forward + backward 82 us against 183 us)
+LINEAR_MIN_ROWS = 8192
+
+
 class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight):
@@ -614,7 +620,7 @@ class _Linear(torch.autograd.Function):
         if x.shape[1] != Cin:
             raise ValueError("linear: x is [n, %d] but weight is %s" % (x.shape[1], tuple(weight.shape)))
         ctx.save_for_backward(x, weight)
-        if x.shape[0] == 0 or not rowgemm_supported(Cin, Cout):
+        if x.shape[0] < LINEAR_MIN_ROWS or not rowgemm_supported(Cin, Cout):
             return x @ weight.t()
         return _rowgemm(x, weight, 1, Cin, Cin, Cout)          # B(k, j) = W[j][k]
 
@@ -625,20 +631,30 @@ class _Linear(torch.autograd.Function):
         Cout, Cin = weight.shape
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            if x.shape[0] == 0 or not rowgemm_supported(Cout, Cin):
+            if x.shape[0] < LINEAR_MIN_ROWS or not rowgemm_supported(Cout, Cin):
                 dx = dy @ weight
             else:
                 dx = _rowgemm(dy, weight, Cin, 1, Cout, Cin)   # B(k, j) = W[k][j]
         if ctx.needs_input_grad[1]:
-            dw = dy.t() @ x                                    # [Cout, Cin]: a short, wide reduction over the points
+            n = x.shape[0]
+            if n >= LINEAR_MIN_ROWS and Cin % 16 == 0:
+                # dW[Cout, Cin] = dy^T . x: reduction over the points cut over CTAs, deterministic partial sums
+                dw = torch.zeros((Cout, Cin), dtype=torch.float32, device=dy.device)
+                ws_bytes = _cabi.lib().p3d_rowgemm_dw_ws_bytes(n, Cout, Cin)
+                ws = _workspace(ws_bytes, dy.device)
+                _call(dy.device, "p3d_rowgemm_dw_f32", dy.data_ptr(), x.data_ptr(), n, Cout, Cin, dw.data_ptr(), _ptr(ws),
+                      ws_bytes)
+            else:
+                dw = dy.t() @ x
         return dx, dw
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y = x @ weight.T (+ bias) on a [n, Cin] point-feature table: the unary layers of the KPConv blocks
-    (modules/KPConv/blocks.py:176-194) and the decoder MLPs (base_modules.py:35-45).  Forward and input gradient run
-    on the tcgen05 row GEMM (output widths that are multiples of 16); the weight gradient -- a reduction over the
-    points with a tiny output -- stays a library call."""
+    (modules/KPConv/blocks.py:176-194) and the decoder MLPs (base_modules.py:35-45).  For tables of at least
+    LINEAR_MIN_ROWS rows the forward, the input gradient and the weight gradient (a reduction over all points with a
+    tiny output: the library runs it as a split-K launch of a few dozen CTAs) run on the tcgen05 row GEMM
+    (csrc/rowgemm_tc.cu; widths that are multiples of 16); smaller tables and other widths use the library."""
     y = _Linear.apply(x, weight)
     return y if bias is None else y + bias
 

@@ -37,7 +37,7 @@ def MLP(channels, activation=None, bn_momentum=0.1, bias=True):
     """base_modules.py:35-45"""
     activation = activation if activation is not None else torch.nn.LeakyReLU(0.2)
     return torch.nn.Sequential(*[
-        torch.nn.Sequential(torch.nn.Linear(channels[i - 1], channels[i], bias=bias),
+        torch.nn.Sequential(ops.Linear(channels[i - 1], channels[i], bias=bias),
                             FastBatchNorm1d(channels[i], momentum=bn_momentum), activation)
         for i in range(1, len(channels))])
 
