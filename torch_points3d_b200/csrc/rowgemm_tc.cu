@@ -45,16 +45,29 @@ rowgemm_prep_b_kernel(const float *__restrict__ Bp, int64_t sbk, int64_t sbj, in
     extern __shared__ __align__(16) uint8_t rg_tile[];
     const int piece = blockIdx.x, c = piece % nk, g = piece / nk;
     const int ng = (N - g * NG < NG) ? (N - g * NG) : NG;
-    // threads run over the reduction index first when it is the contiguous one (sbk == 1), else over the columns
-    for (int i = threadIdx.x; i < ng * 64; i += 256) {
-        const int r = sbk == 1 ? i >> 6 : i % ng, e = sbk == 1 ? i & 63 : i / ng;
-        const int k = c * 64 + e;
-        const float v = k < Kd ? __ldg(Bp + (int64_t)k * sbk + (int64_t)(g * NG + r) * sbj) : 0.f;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-        const int off = r * 128 + (((e >> 3) ^ (r & 7)) << 4) + ((e & 7) << 1);
-        *reinterpret_cast<__nv_bfloat16 *>(rg_tile + off) = hi;
-        *reinterpret_cast<__nv_bfloat16 *>(rg_tile + ng * 128 + off) = lo;
+    // One work item = one 16-byte operand unit: 8 consecutive reduction elements of one row, written with ONE 16-byte
+    // store per half (the XOR swizzle spreads the 8 rows of a quarter-warp over the 8 units of a 128-byte line:
+    // conflict-free).  Items run over the units of a row first when the reduction index is the contiguous one
+    // (sbk == 1: a warp reads 4 rows x 256 contiguous bytes), else over the rows (sbj == 1: a warp reads 32
+    // consecutive columns of 8 reduction elements).
+    for (int item = threadIdx.x; item < ng * 8; item += 256) {
+        const int r = sbk == 1 ? item >> 3 : item % ng, u = sbk == 1 ? item & 7 : item / ng;
+        const int k0 = c * 64 + u * 8;
+        const float *src = Bp + (int64_t)k0 * sbk + (int64_t)(g * NG + r) * sbj;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = k0 + i < Kd ? __ldg(src + (int64_t)i * sbk) : 0.f;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float h0 = __bfloat162float(__float2bfloat16_rn(v[2 * q]));
+            const float h1 = __bfloat162float(__float2bfloat16_rn(v[2 * q + 1]));
+            hi[q] = pack_bf16(h0, h1);
+            lo[q] = pack_bf16(v[2 * q] - h0, v[2 * q + 1] - h1);
+        }
+        const int off = r * 128 + ((u ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4 *>(rg_tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4 *>(rg_tile + ng * 128 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
     __syncthreads();
     uint4 *dst = reinterpret_cast<uint4 *>(img + (size_t)piece * rg_piece_bytes(NG));
