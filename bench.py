@@ -294,11 +294,6 @@ def run_b200(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")  # required to capture NCCL work in CUDA graphs
-        # The only collective on the path is DDP's gradient all-reduce of the C5 section (56 MB per step), which runs
-        # UNDER the backward pass: with NCCL's default channel count its kernels take enough SMs to slow that pass by
-        # 6 % (graph step 6.31 ms on 2 GPUs); 6 channels still hide the transfer and cost 2 % (6.02 ms; 2 channels no
-        # longer hide it: 6.45 ms).  A value set by the caller wins.
-        os.environ.setdefault("NCCL_MAX_NCHANNELS", "6")
         dist.init_process_group("nccl", device_id=dev)
 
     import __graft_entry__

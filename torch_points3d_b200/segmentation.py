@@ -20,8 +20,8 @@ from . import kpconv, synthetic
 # DistributedDataParallel bucket size (MB).  The all-reduce of the LAST bucket (the first layers' gradients) cannot
 # hide behind the backward pass; with 56 MB of gradients the default 25 MB leaves a large tail exposed.
 DDP_BUCKET_MB = 8
-# (Launchers should also cap NCCL's channel count -- `NCCL_MAX_NCHANNELS=6`, as bench.py does -- so that the all-reduce
-# kernels running under the backward pass leave it its SMs: 6.31 -> 6.02 ms per graph-captured step on 2 GPUs.)
+# (Measured on 2 GPUs, graph-captured step: 25 MB buckets 6.38 ms, 8 MB buckets 6.31-6.34 ms; capping NCCL at 6
+# channels gave 6.02 ms on one box and 6.34 ms on another -- inside the box-to-box spread, so no default is set.)
 
 class KPConvSegmentationTrainer:
     def __init__(self, feat_dim=4, num_classes=13, device=None, in_feat=64, levels=5, ddp=False, seed=1003,
