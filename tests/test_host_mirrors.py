@@ -190,3 +190,22 @@ def test_randla_chain_call_order_and_shapes(monkeypatch):
     lit._conv.forward = fake_kernel
     lit(pd._Data(x=torch.rand(n, 3), pos=pos, batch=batch))
     assert got["pos"][1] is pos                                                      # the reference's literal order
+
+
+def test_linear_module_is_a_drop_in_for_nn_linear_off_the_device_path():
+    """ops.Linear keeps torch.nn.Linear's parameters, keys and CPU behaviour (blocks.py:176-194 construct it as
+    `Lin(in, out, bias=False)`); only [n, C] fp32 CUDA tables take the library's kernels."""
+    import torch
+    from torch_points3d_b200 import ops
+
+    torch.manual_seed(0)
+    ref = torch.nn.Linear(12, 7, bias=True)
+    lin = ops.Linear(12, 7, bias=True)
+    lin.load_state_dict(ref.state_dict())
+    assert set(lin.state_dict()) == set(ref.state_dict()) == {"weight", "bias"}
+    x = torch.randn(5, 12)
+    assert torch.equal(lin(x), ref(x))                      # CPU tensors: the stock implementation
+    x3 = torch.randn(2, 5, 12)
+    assert torch.equal(lin(x3), ref(x3))                    # not a [n, C] table: the stock implementation
+    assert ops.rowgemm_supported(64, 128) and not ops.rowgemm_supported(64, 13)
+    assert ops.LINEAR_MIN_ROWS >= 1024
