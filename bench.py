@@ -1034,7 +1034,7 @@ def bench_c2_model(dev, chain_ms):
         loss = model.loss(model(pos, nrm), labels)
         loss.backward()
         opt.step()
-        return loss
+        return loss.detach()
 
     losses = [float(step()) for _ in range(5)]
     torch.cuda.synchronize()

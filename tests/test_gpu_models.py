@@ -115,7 +115,7 @@ def test_kpconv_paper_network_trains_and_pyramid_paths_agree():
         loss = torch.nn.functional.nll_loss(model(pos, feats, batch, multiscale=ms, upsample=up), labels)
         loss.backward()
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
     missing = [k for k, p in model.named_parameters() if p.requires_grad and p.grad is None]
     assert not missing, missing
