@@ -89,22 +89,19 @@ class BasePartialDenseConvolutionDown(torch.nn.Module):
         raise NotImplementedError
 
     def forward(self, data, **kwargs):
-        batch_obj = _Data()
-        x, pos, batch = data.x, data.pos, data.batch
-        idx_sampler = self.sampler(pos=pos, x=x, batch=batch)
-        idx_neighbour = self.neighbour_finder(pos, pos, batch_x=batch, batch_y=batch)
-        shadow_x = torch.full((1,) + tuple(x.shape[1:]), self.shadow_features_fill, dtype=x.dtype, device=x.device)
-        shadow_points = torch.full((1,) + tuple(pos.shape[1:]), self.shadow_points_fill_, dtype=pos.dtype,
-                                   device=x.device)
-        x = torch.cat([x, shadow_x], dim=0)
-        pos = torch.cat([pos, shadow_points], dim=0)
-        x_neighbour = x[idx_neighbour]
-        pos_centered_neighbour = pos[idx_neighbour] - pos[:-1].unsqueeze(1)  # centred on the query; no shadow row
-        batch_obj.x = self.conv(x, pos, x_neighbour, pos_centered_neighbour, idx_neighbour, idx_sampler)
-        batch_obj.pos = pos[idx_sampler]
-        batch_obj.batch = batch[idx_sampler]
-        copy_from_to(data, batch_obj)
-        return batch_obj
+        feats, points, cloud_of = data.x, data.pos, data.batch
+        n = points.shape[0]
+        idx_sampler = self.sampler(pos=points, x=feats, batch=cloud_of)
+        idx_neighbour = self.neighbour_finder(points, points, batch_x=cloud_of, batch_y=cloud_of)  # [n, M], shadow = n
+        # one shadow row behind the table, so that the shadow index gathers the fill values
+        feats = torch.cat([feats, feats.new_full((1,) + tuple(feats.shape[1:]), self.shadow_features_fill)], dim=0)
+        points = torch.cat([points, torch.full((1,) + tuple(points.shape[1:]), self.shadow_points_fill_,
+                                               dtype=points.dtype, device=feats.device)], dim=0)
+        centred = points[idx_neighbour] - points[:n].unsqueeze(1)  # neighbour positions relative to their query
+        out = _Data(x=self.conv(feats, points, feats[idx_neighbour], centred, idx_neighbour, idx_sampler),
+                    pos=points[idx_sampler], batch=cloud_of[idx_sampler])
+        copy_from_to(data, out)
+        return out
 
 
 def _global_pool(x, batch, num_clouds, aggr):
@@ -126,18 +123,15 @@ class GlobalPartialDenseBaseModule(torch.nn.Module):
         self.aggr = aggr
 
     def forward(self, data, **kwargs):
-        batch_obj = _Data()
-        x, pos, batch = data.x, data.pos, data.batch
-        x = self.nn(torch.cat([x, pos], dim=1))
+        cloud_of = data.batch
         num_clouds = kwargs.get("num_clouds")
         if num_clouds is None:
-            num_clouds = int(batch[-1].item()) + 1  # sizes the output (global_max_pool does the same read)
-        x = _global_pool(x, batch, num_clouds, self.aggr)
-        batch_obj.x = x
-        batch_obj.pos = pos.new_zeros((x.size(0), 3))
-        batch_obj.batch = torch.arange(x.size(0), device=x.device)
-        copy_from_to(data, batch_obj)
-        return batch_obj
+            num_clouds = int(cloud_of[-1].item()) + 1  # sizes the output (global_max_pool does the same read)
+        pooled = _global_pool(self.nn(torch.cat([data.x, data.pos], dim=1)), cloud_of, num_clouds, self.aggr)
+        out = _Data(x=pooled, pos=data.pos.new_zeros((pooled.shape[0], 3)),
+                    batch=torch.arange(pooled.shape[0], device=pooled.device))
+        copy_from_to(data, out)
+        return out
 
 
 class FPModule_PD(torch.nn.Module):
@@ -154,25 +148,21 @@ class FPModule_PD(torch.nn.Module):
         self.nn = MLP(up_conv_nn, bn_momentum=bn_momentum, bias=False)
 
     def forward(self, data, precomputed=None, has_innermost=None, **kwargs):
-        data, data_skip = data
-        batch_out = data_skip.clone()
-        x_skip = data_skip.x
+        coarse, skip = data
+        out = skip.clone()
         if has_innermost is None:
-            has_innermost = len(data.x) == int(data.batch.max().item()) + 1
+            has_innermost = len(coarse.x) == int(coarse.batch.max().item()) + 1
+        table = None
         if precomputed and not has_innermost:
-            if not hasattr(data, "up_idx"):
-                setattr(batch_out, "up_idx", 0)
-            else:
-                setattr(batch_out, "up_idx", data.up_idx)
-            pre_data = precomputed[batch_out.up_idx]
-            batch_out.up_idx = batch_out.up_idx + 1
+            # position in the list of precomputed upsampling tables: carried from module to module on the data
+            out.up_idx = coarse.up_idx if hasattr(coarse, "up_idx") else 0
+            table = precomputed[out.up_idx]
+            out.up_idx = out.up_idx + 1
+        if has_innermost:  # one pooled row per cloud: every point takes the row of its cloud
+            x = coarse.x.gather(0, skip.batch.unsqueeze(-1).repeat((1, coarse.x.shape[-1])))
         else:
-            pre_data = None
-        if has_innermost:
-            x = torch.gather(data.x, 0, data_skip.batch.unsqueeze(-1).repeat((1, data.x.shape[-1])))
-        else:
-            x = self.upsample_op(data, data_skip, precomputed=pre_data)
-        if x_skip is not None:
-            x = torch.cat([x, x_skip], dim=1)
-        batch_out.x = self.nn(x) if hasattr(self, "nn") else x
-        return batch_out
+            x = self.upsample_op(coarse, skip, precomputed=table)
+        if skip.x is not None:
+            x = torch.cat([x, skip.x], dim=1)
+        out.x = self.nn(x) if hasattr(self, "nn") else x
+        return out

@@ -16,43 +16,51 @@ from . import ops
 
 DENSE, PARTIAL_DENSE, MESSAGE_PASSING = "dense", "partial_dense", "message_passing"  # utils/enums.py:10-14
 
+_SPARSE_MSG = " This class is for sparse data and expects the pos tensor to be of dimension 2"
+_DENSE_MSG = " This class is for dense data and expects the pos tensor to be of dimension 2"  # (sic, sampling.py:98)
+
 
 def _is_list(v) -> bool:
     return isinstance(v, (list, tuple))
 
 
+def _expect_rank(pos, rank, message):
+    if pos.dim() != rank:
+        raise ValueError(message)
+
+
 # ----------------------------------------------------------------- samplers (sampling.py) ---
 class BaseSampler(ABC):
-    """sampling.py:13-49: exactly one of ratio / num_to_sample / subsampling_param."""
+    """sampling.py:13-49.  The sample count comes from exactly one source: `num_to_sample` (exclusive with the other
+    two), else `ratio`, else `subsampling_param`; the attribute that was given is the only one that exists afterwards
+    (callers test for it with hasattr, like the reference)."""
 
     def __init__(self, ratio=None, num_to_sample=None, subsampling_param=None):
-        if num_to_sample is not None:
-            if (ratio is not None) or (subsampling_param is not None):
-                raise ValueError("Can only specify ratio or num_to_sample or subsampling_param, not several !")
-            self._num_to_sample = num_to_sample
-        elif ratio is not None:
-            self._ratio = ratio
-        elif subsampling_param is not None:
-            self._subsampling_param = subsampling_param
-        else:
-            raise Exception('At least ["ratio, num_to_sample, subsampling_param"] should be defined')
+        given = {"_num_to_sample": num_to_sample, "_ratio": ratio, "_subsampling_param": subsampling_param}
+        if num_to_sample is not None and not (ratio is None and subsampling_param is None):
+            raise ValueError("Can only specify ratio or num_to_sample or subsampling_param, not several !")
+        for name, value in given.items():  # precedence: num_to_sample, ratio, subsampling_param
+            if value is not None:
+                setattr(self, name, value)
+                return
+        raise Exception('At least ["ratio, num_to_sample, subsampling_param"] should be defined')
 
     def __call__(self, pos, x=None, batch=None):
         return self.sample(pos, batch=batch, x=x)
 
     def _get_num_to_sample(self, batch_size) -> int:
-        if hasattr(self, "_num_to_sample"):
-            return self._num_to_sample
-        return math.floor(batch_size * self._ratio)
+        """the fixed count, or floor(ratio * size)"""
+        fixed = getattr(self, "_num_to_sample", None)
+        return fixed if fixed is not None else math.floor(batch_size * self._ratio)
 
     def _get_ratio_to_sample(self, batch_size) -> float:
-        if hasattr(self, "_ratio"):
-            return self._ratio
-        return self._num_to_sample / float(batch_size)
+        """the given ratio, or count / size"""
+        ratio = getattr(self, "_ratio", None)
+        return ratio if ratio is not None else self._num_to_sample / float(batch_size)
 
     @abstractmethod
     def sample(self, pos, x=None, batch=None):
-        pass
+        """indices of the sampled points"""
 
 
 class FPSSampler(BaseSampler):
@@ -64,17 +72,16 @@ class FPSSampler(BaseSampler):
         self._random_start = random_start
 
     def sample(self, pos, batch, **kwargs):
-        if len(pos.shape) != 2:
-            raise ValueError(" This class is for sparse data and expects the pos tensor to be of dimension 2")
-        return ops.fps(pos, batch, ratio=self._get_ratio_to_sample(pos.shape[0]), random_start=self._random_start)
+        _expect_rank(pos, 2, _SPARSE_MSG)
+        share = self._get_ratio_to_sample(pos.shape[0])
+        return ops.fps(pos, batch, ratio=share, random_start=self._random_start)
 
 
 class DenseFPSSampler(BaseSampler):
     """sampling.py:84-100 -> tp.furthest_point_sample; pos [B,N,3] -> idx [B,num_sample]."""
 
     def sample(self, pos, **kwargs):
-        if len(pos.shape) != 3:
-            raise ValueError(" This class is for dense data and expects the pos tensor to be of dimension 2")
+        _expect_rank(pos, 3, _DENSE_MSG)
         return ops.furthest_point_sample(pos, self._get_num_to_sample(pos.shape[1]))
 
 
@@ -88,19 +95,19 @@ class RandomSampler(BaseSampler):
         self._sorted = sorted_indices
 
     def sample(self, pos, batch=None, **kwargs):
-        if len(pos.shape) != 2:
-            raise ValueError(" This class is for sparse data and expects the pos tensor to be of dimension 2")
-        idx = torch.randint(0, pos.shape[0], (self._get_num_to_sample(pos.shape[0]),), device=pos.device)
-        return torch.sort(idx)[0] if self._sorted else idx
+        _expect_rank(pos, 2, _SPARSE_MSG)
+        total = pos.shape[0]
+        draw = torch.randint(0, total, (self._get_num_to_sample(total),), device=pos.device)
+        return draw.sort().values if self._sorted else draw
 
 
 class DenseRandomSampler(BaseSampler):
-    """sampling.py:115-127."""
+    """sampling.py:115-127: one draw shared by every cloud of the batch."""
 
     def sample(self, pos, **kwargs):
-        if len(pos.shape) != 3:
-            raise ValueError(" This class is for dense data and expects the pos tensor to be of dimension 2")
-        return torch.randint(0, pos.shape[1], (self._get_num_to_sample(pos.shape[1]),), device=pos.device)
+        _expect_rank(pos, 3, _DENSE_MSG)
+        per_cloud = pos.shape[1]
+        return torch.randint(0, per_cloud, (self._get_num_to_sample(per_cloud),), device=pos.device)
 
 
 # --------------------------------------------------- neighbour finders (neighbour_finder.py) ---
@@ -110,10 +117,10 @@ class BaseNeighbourFinder(ABC):
 
     @abstractmethod
     def find_neighbours(self, x, y, batch_x, batch_y):
-        pass
+        """neighbours of every y among x"""
 
     def __repr__(self):
-        return str(self.__class__.__name__) + " " + str(self.__dict__)
+        return "%s %s" % (type(self).__name__, self.__dict__)
 
 
 class RadiusNeighbourFinder(BaseNeighbourFinder):
@@ -121,15 +128,16 @@ class RadiusNeighbourFinder(BaseNeighbourFinder):
     ball_query(mode=conv_type) exactly as the reference's always-true `elif` does (:34)."""
 
     def __init__(self, radius: float, max_num_neighbors: int = 64, conv_type=MESSAGE_PASSING):
-        self._radius = radius
-        self._max_num_neighbors = max_num_neighbors
+        self._radius, self._max_num_neighbors = radius, max_num_neighbors
         self._conv_type = conv_type.lower()
 
     def find_neighbours(self, x, y, batch_x=None, batch_y=None):
+        r, cap = self._radius, self._max_num_neighbors
         if self._conv_type == MESSAGE_PASSING:
-            return ops.radius(x, y, self._radius, batch_x, batch_y, max_num_neighbors=self._max_num_neighbors)
-        return ops.ball_query(self._radius, self._max_num_neighbors, x, y, mode=self._conv_type, batch_x=batch_x,
-                              batch_y=batch_y, return_dist=False)[0]
+            return ops.radius(x, y, r, batch_x, batch_y, max_num_neighbors=cap)
+        table, _ = ops.ball_query(r, cap, x, y, mode=self._conv_type, batch_x=batch_x, batch_y=batch_y,
+                                  return_dist=False)
+        return table
 
 
 class KNNNeighbourFinder(BaseNeighbourFinder):
@@ -143,19 +151,20 @@ class KNNNeighbourFinder(BaseNeighbourFinder):
 
 
 class DilatedKNNNeighbourFinder(BaseNeighbourFinder):
-    """neighbour_finder.py:50-68: k*dilation nearest, then k of them drawn at random."""
+    """neighbour_finder.py:50-68: the k * dilation nearest per query, of which k are drawn at random (with
+    replacement, one independent draw per query)."""
 
     def __init__(self, k, dilation):
-        self.k = k
-        self.dilation = dilation
+        self.k, self.dilation = k, dilation
         self.initialFinder = KNNNeighbourFinder(k * dilation)
 
     def find_neighbours(self, x, y, batch_x, batch_y):
         row, col = self.initialFinder.find_neighbours(x, y, batch_x, batch_y)
-        index = torch.randint(self.k * self.dilation, (len(y), self.k), device=row.device, dtype=torch.long)
-        arange = torch.arange(len(y), dtype=torch.long, device=row.device) * (self.k * self.dilation)
-        index = (index + arange.view(-1, 1)).view(-1)
-        return row[index], col[index]
+        wide, n = self.k * self.dilation, len(y)
+        pick = torch.randint(wide, (n, self.k), device=row.device, dtype=torch.long)
+        pick += wide * torch.arange(n, dtype=torch.long, device=row.device).unsqueeze(1)  # offset of query i's block
+        pick = pick.reshape(-1)
+        return row[pick], col[pick]
 
 
 class BaseMSNeighbourFinder(ABC):
@@ -164,38 +173,34 @@ class BaseMSNeighbourFinder(ABC):
 
     @abstractmethod
     def find_neighbours(self, x, y, batch_x=None, batch_y=None, scale_idx=0):
-        pass
+        """neighbours at one of the scales"""
 
     @property
     @abstractmethod
     def num_scales(self):
-        pass
+        """number of (radius, max_num_neighbors) pairs"""
 
 
 class MultiscaleRadiusNeighbourFinder(BaseMSNeighbourFinder):
-    """neighbour_finder.py:89-153: list/scalar broadcasting of radius and max_num_neighbors."""
+    """neighbour_finder.py:89-153: a scalar on one side is repeated to the length of the list on the other side;
+    two lists must have the same length; two scalars make one scale."""
 
     def __init__(self, radius: Union[float, List[float]], max_num_neighbors: Union[int, List[int]] = 64):
-        if not _is_list(max_num_neighbors) and _is_list(radius):
-            self._radius = list(radius)
-            self._max_num_neighbors = [max_num_neighbors for _ in self._radius]
-        elif not _is_list(radius) and _is_list(max_num_neighbors):
-            self._max_num_neighbors = list(max_num_neighbors)
-            self._radius = [radius for _ in self._max_num_neighbors]
-        elif _is_list(max_num_neighbors):
-            if len(max_num_neighbors) != len(radius):
-                raise ValueError("Both lists max_num_neighbors and radius should be of the same length")
-            self._max_num_neighbors = list(max_num_neighbors)
-            self._radius = list(radius)
-        else:
-            self._max_num_neighbors = [max_num_neighbors]
-            self._radius = [radius]
+        many_r, many_k = _is_list(radius), _is_list(max_num_neighbors)
+        if many_r and many_k and len(radius) != len(max_num_neighbors):
+            raise ValueError("Both lists max_num_neighbors and radius should be of the same length")
+        scales = len(radius) if many_r else (len(max_num_neighbors) if many_k else 1)
+        self._radius = list(radius) if many_r else [radius] * scales
+        self._max_num_neighbors = list(max_num_neighbors) if many_k else [max_num_neighbors] * scales
 
-    def find_neighbours(self, x, y, batch_x=None, batch_y=None, scale_idx=0):
+    def _scale(self, scale_idx):
         if scale_idx >= self.num_scales:
             raise ValueError("Scale %i is out of bounds %i" % (scale_idx, self.num_scales))
-        return ops.radius(x, y, self._radius[scale_idx], batch_x, batch_y,
-                          max_num_neighbors=self._max_num_neighbors[scale_idx])
+        return self._radius[scale_idx], self._max_num_neighbors[scale_idx]
+
+    def find_neighbours(self, x, y, batch_x=None, batch_y=None, scale_idx=0):
+        r, cap = self._scale(scale_idx)
+        return ops.radius(x, y, r, batch_x, batch_y, max_num_neighbors=cap)
 
     @property
     def num_scales(self):
@@ -209,10 +214,9 @@ class DenseRadiusNeighbourFinder(MultiscaleRadiusNeighbourFinder):
     """neighbour_finder.py:156-178 -> tp.ball_query(r, K, x, y)[0], idx [B,S,K] int64."""
 
     def find_neighbours(self, x, y, scale_idx=0):
-        if scale_idx >= self.num_scales:
-            raise ValueError("Scale %i is out of bounds %i" % (scale_idx, self.num_scales))
-        return ops.ball_query(self._radius[scale_idx], self._max_num_neighbors[scale_idx], x, y,
-                              return_dist=False)[0]
+        r, cap = self._scale(scale_idx)
+        table, _ = ops.ball_query(r, cap, x, y, return_dist=False)
+        return table
 
     def __call__(self, x, y, scale_idx=0, **kwargs):
         return self.find_neighbours(x, y, scale_idx)
@@ -230,30 +234,28 @@ class KNNInterpolate:
     def _batch(data):
         b = getattr(data, "batch", None)
         if b is None:
-            b = torch.zeros((data.pos.shape[0],), dtype=torch.long, device=data.pos.device)
+            b = data.pos.new_zeros((data.pos.shape[0],), dtype=torch.long)
         return b
 
     def precompute(self, query, support):
-        pos_x, pos_y = query.pos, support.pos
-        batch_y, batch_x = self._batch(support), self._batch(query)
+        """the k query points nearest to every support point with their 1 / d^2 weights and the per-support-point sum
+        of the weights (interpolate.py:11-33), to be applied by __call__(..., precomputed=...)"""
+        src, dst = query.pos, support.pos
         with torch.no_grad():
-            y_idx, x_idx = ops.knn_edges(pos_x, pos_y, self.k, batch_x=batch_x, batch_y=batch_y)
-            diff = pos_x[x_idx] - pos_y[y_idx]
-            squared_distance = (diff * diff).sum(dim=-1, keepdim=True)
-            weights = 1.0 / torch.clamp(squared_distance, min=1e-16)
-        normalisation = torch.zeros((pos_y.size(0), 1), dtype=weights.dtype, device=weights.device)
-        normalisation.index_add_(0, y_idx, weights)
-        return SimpleNamespace(num_nodes=pos_y.shape[0], x_idx=x_idx, y_idx=y_idx, weights=weights,
+            y_idx, x_idx = ops.knn_edges(src, dst, self.k, batch_x=self._batch(query), batch_y=self._batch(support))
+            d2 = (src[x_idx] - dst[y_idx]).square().sum(dim=-1, keepdim=True)
+            weights = 1.0 / d2.clamp(min=1e-16)
+        normalisation = weights.new_zeros((dst.shape[0], 1)).index_add_(0, y_idx, weights)
+        return SimpleNamespace(num_nodes=dst.shape[0], x_idx=x_idx, y_idx=y_idx, weights=weights,
                                normalisation=normalisation)
 
     def __call__(self, query, support, precomputed=None):
-        if precomputed:
-            num_points = support.pos.size(0)
-            if num_points != precomputed.num_nodes:
-                raise ValueError("Precomputed indices do not match with the data given to the transform")
-            x = query.x
-            y = torch.zeros((num_points, x.shape[1]), dtype=x.dtype, device=x.device)
-            y.index_add_(0, precomputed.y_idx, x[precomputed.x_idx] * precomputed.weights)
-            return y / precomputed.normalisation
-        return ops.knn_interpolate(query.x, query.pos, support.pos, self._batch(query), self._batch(support),
-                                   k=self.k)
+        if not precomputed:
+            return ops.knn_interpolate(query.x, query.pos, support.pos, self._batch(query), self._batch(support),
+                                       k=self.k)
+        n = support.pos.shape[0]
+        if n != precomputed.num_nodes:
+            raise ValueError("Precomputed indices do not match with the data given to the transform")
+        feats = query.x
+        weighted = feats[precomputed.x_idx] * precomputed.weights
+        return feats.new_zeros((n, feats.shape[1])).index_add_(0, precomputed.y_idx, weighted) / precomputed.normalisation
