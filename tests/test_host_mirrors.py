@@ -209,3 +209,114 @@ def test_linear_module_is_a_drop_in_for_nn_linear_off_the_device_path():
     assert torch.equal(lin(x3), ref(x3))                    # not a [n, C] table: the stock implementation
     assert ops.rowgemm_supported(64, 128) and not ops.rowgemm_supported(64, 13)
     assert ops.LINEAR_MIN_ROWS >= 1024
+
+
+def test_sampler_constructor_precedence_is_the_reference_rule():
+    """sampling.py:18-31: num_to_sample excludes the other two; else ratio wins over subsampling_param; only the
+    attribute that was chosen exists afterwards (pointnet2.py tests for `_num_to_sample` with hasattr)"""
+    s = spatial_ops.DenseFPSSampler(ratio=0.25, subsampling_param=7)
+    assert s._ratio == 0.25 and not hasattr(s, "_subsampling_param") and not hasattr(s, "_num_to_sample")
+    assert s._get_num_to_sample(10) == 2                                 # floor(10 * 0.25)
+    s = spatial_ops.DenseFPSSampler(subsampling_param=7)
+    assert s._subsampling_param == 7 and not hasattr(s, "_ratio")
+    s = spatial_ops.DenseFPSSampler(num_to_sample=0)                     # 0 is a value, not "absent"
+    assert s._get_num_to_sample(10) == 0
+    for bad in ({"num_to_sample": 3, "ratio": 0.5}, {"num_to_sample": 3, "subsampling_param": 1}):
+        with pytest.raises(ValueError, match="not several"):
+            spatial_ops.DenseFPSSampler(**bad)
+    with pytest.raises(Exception, match="should be defined"):
+        spatial_ops.DenseFPSSampler()
+    with pytest.raises(ValueError, match="dense data"):
+        spatial_ops.DenseRandomSampler(num_to_sample=2).sample(torch.rand(8, 3))
+    with pytest.raises(ValueError, match="sparse data"):
+        spatial_ops.RandomSampler(num_to_sample=2).sample(torch.rand(2, 8, 3))
+    draw = spatial_ops.RandomSampler(ratio=0.5, sorted_indices=True).sample(torch.rand(40, 3))
+    assert draw.shape == (20,) and bool((draw[1:] >= draw[:-1]).all()) and int(draw.max()) < 40
+    assert spatial_ops.DenseRandomSampler(num_to_sample=5).sample(torch.rand(2, 9, 3)).shape == (5,)
+
+
+def test_multiscale_finder_broadcasting_and_repr():
+    """neighbour_finder.py:110-135: scalar against list on either side, equal-length lists, two scalars"""
+    M = spatial_ops.MultiscaleRadiusNeighbourFinder
+    assert (M((0.1, 0.2, 0.4), 16)._radius, M((0.1, 0.2, 0.4), 16)._max_num_neighbors) == ([0.1, 0.2, 0.4], [16] * 3)
+    assert (M(0.5, (4, 8))._radius, M(0.5, (4, 8))._max_num_neighbors) == ([0.5, 0.5], [4, 8])
+    assert (M([0.1, 0.2], [4, 8])._radius, M([0.1, 0.2], [4, 8])._max_num_neighbors) == ([0.1, 0.2], [4, 8])
+    one = M(0.3)
+    assert one.num_scales == 1 and one._radius == [0.3] and one._max_num_neighbors == [64]
+    with pytest.raises(ValueError, match="same length"):
+        M([0.1, 0.2, 0.3], [4, 8])
+    with pytest.raises(ValueError, match="out of bounds"):
+        M([0.1, 0.2], 8).find_neighbours(None, None, scale_idx=2)
+    assert repr(spatial_ops.KNNNeighbourFinder(3)) == "KNNNeighbourFinder {'k': 3}"
+
+
+def test_dilated_knn_draws_inside_each_query_block():
+    """neighbour_finder.py:50-68: query i draws k of ITS k * dilation candidates (block i of the sorted edge list)"""
+    k, dilation, n = 3, 4, 5
+    finder = spatial_ops.DilatedKNNNeighbourFinder(k, dilation)
+    wide = k * dilation
+
+    class Stub:
+        def find_neighbours(self, x, y, batch_x, batch_y):
+            row = torch.arange(n).repeat_interleave(wide)               # query index, sorted
+            col = torch.arange(n * wide) + 1000                         # candidate id = 1000 + position
+            return row, col
+
+    finder.initialFinder = Stub()
+    row, col = finder.find_neighbours(torch.rand(50, 3), torch.rand(n, 3), None, None)
+    assert row.tolist() == np.repeat(np.arange(n), k).tolist()
+    pos_in_list = col - 1000
+    assert bool((pos_in_list // wide == row).all())                      # every pick comes from its own block
+
+
+def test_knn_interpolate_applies_a_precomputed_table():
+    """interpolate.py:36-57: y[s] = sum_e w_e x[x_idx_e] / sum_e w_e over the edges e of support point s; a table made
+    for another support size is refused"""
+    from types import SimpleNamespace
+    g = torch.Generator().manual_seed(3)
+    nq, ns, k, C = 7, 11, 3, 4
+    x = torch.randn((nq, C), generator=g)
+    y_idx = torch.arange(ns).repeat_interleave(k)
+    x_idx = torch.randint(0, nq, (ns * k,), generator=g)
+    w = torch.rand((ns * k, 1), generator=g) + 0.1
+    norm = torch.zeros((ns, 1)).index_add_(0, y_idx, w)
+    table = SimpleNamespace(num_nodes=ns, x_idx=x_idx, y_idx=y_idx, weights=w, normalisation=norm)
+    query, support = SimpleNamespace(x=x, pos=torch.rand(nq, 3)), SimpleNamespace(x=None, pos=torch.rand(ns, 3))
+    got = spatial_ops.KNNInterpolate(k)(query, support, precomputed=table)
+    want = torch.stack([(x[x_idx[s * k:(s + 1) * k]] * w[s * k:(s + 1) * k]).sum(0) / w[s * k:(s + 1) * k].sum()
+                        for s in range(ns)])
+    assert torch.allclose(got, want, atol=1e-6)
+    with pytest.raises(ValueError, match="do not match"):
+        spatial_ops.KNNInterpolate(k)(query, SimpleNamespace(x=None, pos=torch.rand(ns + 1, 3)), precomputed=table)
+
+
+def test_fp_module_pd_innermost_and_table_counter():
+    """partial_dense.py:113-146: a coarse level of one row per cloud is broadcast by the skip level's batch vector; the
+    position in the list of precomputed tables travels on the data (`up_idx`), starting at 0"""
+    torch.manual_seed(0)
+    fp = pd.FPModule_PD(1, [6 + 2, 5])
+    fp.eval()
+    skip = pd._Data(x=torch.randn(9, 2), pos=torch.rand(9, 3), batch=torch.tensor([0, 0, 0, 0, 1, 1, 1, 2, 2]))
+    pooled = pd._Data(x=torch.randn(3, 6), pos=torch.zeros(3, 3), batch=torch.arange(3))
+    out = fp((pooled, skip), has_innermost=True)
+    want = fp.nn(torch.cat([pooled.x[skip.batch], skip.x], dim=1))
+    assert torch.equal(out.x, want) and out.pos is skip.pos and not hasattr(out, "up_idx")
+    assert torch.equal(fp((pooled, skip)).x, want)                       # decided from the data: 3 rows, 3 clouds
+
+    calls = []
+
+    class Up:
+        def __call__(self, data, data_skip, precomputed=None):
+            calls.append(precomputed)
+            return torch.zeros(data_skip.pos.shape[0], 6)
+
+    fp.upsample_op = Up()
+    coarse = pd._Data(x=torch.randn(4, 6), pos=torch.rand(4, 3), batch=torch.tensor([0, 0, 1, 2]))
+    tables = ["t0", "t1"]
+    first = fp((coarse, skip), precomputed=tables, has_innermost=False)
+    assert calls == ["t0"] and first.up_idx == 1
+    coarse.up_idx = first.up_idx
+    second = fp((coarse, skip), precomputed=tables, has_innermost=False)
+    assert calls == ["t0", "t1"] and second.up_idx == 2
+    fp((coarse, skip), has_innermost=False)                              # no tables: the search runs on the fly
+    assert calls[-1] is None
