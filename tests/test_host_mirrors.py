@@ -320,3 +320,40 @@ def test_fp_module_pd_innermost_and_table_counter():
     assert calls == ["t0", "t1"] and second.up_idx == 2
     fp((coarse, skip), has_innermost=False)                              # no tables: the search runs on the fly
     assert calls[-1] is None
+
+
+def test_mlp_and_fast_batch_norm_against_the_reference_classes():
+    """tests/golden/base_modules.npz holds outputs of the REFERENCE's own MLP / FastBatchNorm1d
+    (core/common_modules/base_modules.py:35-45,128-153, run by tests/golden/make_golden_modules.py): same state_dict
+    keys in the same order, a reference state_dict loads strictly, and two training steps, the running statistics,
+    the input gradient and the eval output agree to 1e-6 (fp32, same arithmetic up to the [N,C] vs [1,C,N] layout)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "base_modules.npz"))
+    mlp = pd.MLP([7, 12, 5], bn_momentum=0.2, bias=False)
+    assert list(mlp.state_dict().keys()) == [str(k) for k in g["mlp_keys"]]
+    mlp.load_state_dict({str(k): torch.from_numpy(g["mlp_init/" + str(k)]) for k in g["mlp_keys"]}, strict=True)
+    x = torch.from_numpy(g["mlp_x"]).requires_grad_(True)
+    mlp.train()
+    y1 = mlp(x)
+    y2 = mlp(x * 1.5 + 0.25)
+    (gx,) = torch.autograd.grad(y2, x, torch.from_numpy(g["mlp_gy"]))
+    assert np.allclose(y1.detach().numpy(), g["mlp_y1"], atol=1e-6)
+    assert np.allclose(y2.detach().numpy(), g["mlp_y2"], atol=1e-6)
+    assert np.allclose(gx.numpy(), g["mlp_gx"], atol=1e-6)
+    for k, v in mlp.state_dict().items():
+        assert np.allclose(v.numpy(), g["mlp_after/" + k], atol=1e-6), k
+    mlp.eval()
+    assert np.allclose(mlp(x).detach().numpy(), g["mlp_eval"], atol=1e-6)
+
+    bn = pd.FastBatchNorm1d(6, momentum=0.05)
+    assert list(bn.state_dict().keys()) == [str(k) for k in g["bn_keys"]]
+    with torch.no_grad():
+        bn.batch_norm.weight.copy_(torch.from_numpy(g["bn_weight"]))
+        bn.batch_norm.bias.copy_(torch.from_numpy(g["bn_bias"]))
+    bn.train()
+    assert np.allclose(bn(torch.from_numpy(g["bn_x"])).detach().numpy(), g["bn_y"], atol=1e-6)   # dense [B, N, C]
+    assert np.allclose(bn.batch_norm.running_mean.numpy(), g["bn_running_mean"], atol=1e-7)
+    assert np.allclose(bn.batch_norm.running_var.numpy(), g["bn_running_var"], atol=1e-7)
+    with pytest.raises(ValueError) as err:
+        bn(torch.zeros(2, 2, 2, 2))
+    assert str(err.value) == str(g["bn_error"])
