@@ -17,13 +17,15 @@ from .spatial_ops import DenseFPSSampler, DenseRadiusNeighbourFinder
 
 
 def MLP2D(channels, bias=False, bn=True, activation=None):
-    """dense_modules.py:25-29"""
+    """dense_modules.py:5-29: one (1x1 Conv2d, BatchNorm2d, activation) group per layer, nested like the reference's
+    Seq-of-Seq so that the parameter names are the reference's (`0.0.weight`, `0.1.running_mean`, `1.0.weight` ...)"""
     layers = []
     for i in range(len(channels) - 1):
-        layers.append(nn.Conv2d(channels[i], channels[i + 1], kernel_size=(1, 1), stride=(1, 1), bias=bias))
+        group = [nn.Conv2d(channels[i], channels[i + 1], kernel_size=(1, 1), stride=(1, 1), bias=bias)]
         if bn:
-            layers.append(nn.BatchNorm2d(channels[i + 1]))
-        layers.append(activation if activation is not None else nn.LeakyReLU(negative_slope=0.01))
+            group.append(nn.BatchNorm2d(channels[i + 1]))
+        group.append(activation if activation is not None else nn.LeakyReLU(negative_slope=0.01))
+        layers.append(nn.Sequential(*group))
     return nn.Sequential(*layers)
 
 
