@@ -149,4 +149,17 @@ def run_cases(ns, data_cls):
     seeded_parameters(dual2, 306)
     dual2.eval()
     _record(out, "dual_strided", dual2, dual2(data_cls(pos=pos, x=r_out.x.detach(), batch=batch)))
+
+    # deformable blocks (kernels.py:107-256): offset convolution -> offsets (* point_influence) [-> modulations
+    # 2 * sigmoid] -> deformable aggregation -> the regularisers kept on the layer
+    for tag, modulated, loss_mode in (("deform", False, "fitting"), ("deform_modulated", True, "fitting"),
+                                      ("deform_permissive", False, "permissive")):
+        blk = ns.SimpleBlock(down_conv_nn=[5, 8], grid_size=g0, prev_grid_size=g0, sigma=1.0, max_num_neighbors=12,
+                             deformable=True, modulated=modulated, loss_mode=loss_mode)
+        seeded_parameters(blk, 310)
+        blk.eval()
+        _record(out, tag, blk, blk(data_cls(pos=pos, x=x, batch=batch)))
+        out[tag + "/search_radius"] = np.array(float(blk.neighbour_finder._radius))
+        for name, value in blk.kp_conv.get_internal_losses().items():
+            out[tag + "/" + name] = np.array(float(value), dtype=np.float64)
     return out
