@@ -79,10 +79,6 @@ class RandlaKernel(torch.nn.Module):
         return self.global_nn(ops.segment_sum(msg, dst, pos_dst.shape[0]))
 
 
-class _Out:
-    pass
-
-
 class SAModule(torch.nn.Module):
     """modules/pointnet2/message_passing.py:9-37 over BaseMSConvolutionDown.forward
     (core/base_conv/message_passing.py:60-93): FPS -> one radius edge list per scale -> shared PointConv -> concat."""
@@ -100,15 +96,13 @@ class SAModule(torch.nn.Module):
     def forward(self, data, **kwargs):
         x, pos, batch = data.x, data.pos, data.batch
         idx = self.sampler(pos, batch)
-        out = _Out()
-        out.idx = idx
-        ms_x = []
+        centres, centre_batch = pos[idx], batch[idx]
+        per_scale = []
         for scale_idx in range(self.neighbour_finder.num_scales):
-            row, col = self.neighbour_finder(pos, pos[idx], batch_x=batch, batch_y=batch[idx], scale_idx=scale_idx)
-            edge_index = torch.stack([col, row], dim=0)
-            ms_x.append(self.conv(x, (pos, pos[idx]), edge_index, batch))
-        out.x = torch.cat(ms_x, -1)
-        out.pos, out.batch = pos[idx], batch[idx]
+            row, col = self.neighbour_finder(pos, centres, batch_x=batch, batch_y=centre_batch, scale_idx=scale_idx)
+            per_scale.append(self.conv(x, (pos, centres), torch.stack([col, row], dim=0), batch))
+        out = _Data(idx=idx, x=torch.cat(per_scale, -1), pos=centres, batch=centre_batch)
+        copy_from_to(data, out)  # labels and any other attribute travel with the level (message_passing.py:90)
         return out
 
 
@@ -265,7 +259,9 @@ class FPModule(torch.nn.Module):
     def __init__(self, up_k, up_conv_nn, *args, **kwargs):
         super().__init__()
         self.k = up_k
-        self._skip = kwargs.get("skip", True)
+        # the reference's FPModule builds its base class without its keywords (`super().__init__(None)`, :165), so a
+        # `skip=False` passed to it never arrives: the skip features are always concatenated
+        self._skip = True
         bn_momentum = kwargs.get("bn_momentum", 0.1)
         self.nn = MLP(up_conv_nn, bn_momentum=bn_momentum, bias=False)
 
