@@ -77,8 +77,7 @@ def test_point_conv_and_randla_modules():
     pos_h, batch_h = synthetic.indoor_spheres(num_spheres=3, raw_points=3000, radius=0.5, seed=9)
     pos, batch = T(pos_h), T(batch_h)
     x = torch.randn(pos.shape[0], 6, device=DEV, requires_grad=True)
-    data = mp._Out()
-    data.x, data.pos, data.batch = x, pos, batch
+    data = mp._Data(x=x, pos=pos, batch=batch)
     sa = mp.SAModule(ratio=0.25, radius=[0.1, 0.2], radius_num_point=[16, 32], down_conv_nn=[6 + 3, 32, 64],
                      random_start=False).to(DEV).eval()
     out = sa(data)
