@@ -66,7 +66,7 @@ def group_data(data, cluster=None, unique_pos_indices=None, mode="last", skip_ke
     if mode == "last" and unique_pos_indices is None:
         raise ValueError("In last mode the unique_pos_indices argument needs to be specified")
     if mode == "mean" and voxels is None:
-        raise ValueError("group_data(mode='mean') needs the VoxelClusters returned by ops.grid_cluster")
+        voxels = ops.voxels_from_cluster(cluster, unique_pos_indices)
 
     num_nodes = data.num_nodes
     for key, item in list(data):
@@ -75,7 +75,7 @@ def group_data(data, cluster=None, unique_pos_indices=None, mode="last", skip_ke
         if key in skip_keys:
             continue
         if torch.is_tensor(item) and item.size(0) == num_nodes:
-            if mode == "last" or key == "batch" or key == "origin_id":
+            if mode == "last" or key == "batch" or key == SaveOriginalPosId.KEY:
                 data[key] = item[unique_pos_indices]
             elif mode == "mean":
                 is_item_bool = item.dtype == torch.bool
@@ -124,3 +124,23 @@ class GridSampling3D:
     def __repr__(self):
         return "{}(grid_size={}, quantize_coords={}, mode={})".format(
             self.__class__.__name__, self._grid_size, self._quantize_coords, self._mode)
+
+
+class SaveOriginalPosId:
+    """grid_transform.py:144-167: adds the index of every point so that it can be traced through the samplers"""
+
+    KEY = "origin_id"
+
+    def _process(self, data):
+        if hasattr(data, self.KEY):
+            return data
+        setattr(data, self.KEY, torch.arange(0, data.pos.shape[0], device=data.pos.device))
+        return data
+
+    def __call__(self, data):
+        if isinstance(data, list):
+            return [self._process(d) for d in data]
+        return self._process(data)
+
+    def __repr__(self):
+        return self.__class__.__name__

@@ -963,6 +963,18 @@ def grid_cluster(pos: torch.Tensor, size: float, batch: Optional[torch.Tensor] =
                          None if ob is None else ob[:n].to(batch.dtype), None if co is None else co[:n])
 
 
+def voxels_from_cluster(cluster: torch.Tensor, unique_pos_indices: Optional[torch.Tensor] = None) -> VoxelClusters:
+    """the segment list of consecutive cluster ids that did not come from `grid_cluster` (group_data called with a
+    caller's own `cluster`, grid_transform.py:33): points sorted by (cluster, point index), first slot per cluster"""
+    cluster = _i64(cluster)
+    n = int(cluster.max().item()) + 1 if cluster.numel() else 0
+    order = torch.sort(cluster, stable=True).indices.to(torch.int32)
+    seg = torch.zeros(n + 1, dtype=torch.int32, device=cluster.device)
+    if n:
+        seg[1:] = torch.bincount(cluster, minlength=n).cumsum(0).to(torch.int32)
+    return VoxelClusters(cluster, unique_pos_indices, order, seg, n, None, None, None)
+
+
 def segment_mean(x: torch.Tensor, vc: VoxelClusters) -> torch.Tensor:
     """`scatter_mean(x, cluster, dim=0)` (grid_transform.py:76) over the voxels of `vc`; sums run in ascending
     point index in fp32, which is what the sequential CPU scatter_add of the reference produces."""
