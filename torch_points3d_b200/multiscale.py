@@ -42,6 +42,26 @@ class MultiScaleData(_Data):
         out.__dict__.update(self.__dict__)
         return out
 
+    def apply(self, func, *keys):
+        """datasets/multiscale_data.py:21-35: `func` on every tensor attribute (or on `keys`) and on every tensor of
+        every level of both lists"""
+        for key in (keys or list(self.keys)):
+            item = getattr(self, key, None)
+            if torch.is_tensor(item):
+                setattr(self, key, func(item))
+        for levels in (getattr(self, "multiscale", None) or [], getattr(self, "upsample", None) or []):
+            for level in levels:
+                for key, item in list(level.__dict__.items()):
+                    if torch.is_tensor(item):
+                        setattr(level, key, func(item))
+        return self
+
+    def to(self, device, *keys, **kwargs):
+        return self.apply(lambda t: t.to(device, **kwargs), *keys)
+
+    def contiguous(self, *keys):
+        return self.apply(lambda t: t.contiguous(), *keys)
+
 
 def _num_nodes(data):
     n = getattr(data, "num_nodes", None)
