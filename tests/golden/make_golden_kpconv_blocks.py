@@ -53,7 +53,8 @@ class Bag:
         return Bag(**self.__dict__)
 
 
-def main():
+def load_reference():
+    """the reference's modules/KPConv/blocks.py module object, loaded by file path over the stand-ins above"""
     def unused(*a, **kw):
         raise AssertionError("not on the tested paths")
 
@@ -91,7 +92,11 @@ def main():
     kp = "torch_points3d.modules.KPConv."
     for f in ("plyutils", "kernel_utils", "losses", "convolution_ops", "kernels"):
         _load(kp + f, os.path.join(REF, "modules/KPConv", f + ".py"))
-    ref = _load(kp + "blocks", os.path.join(REF, "modules/KPConv/blocks.py"))
+    return _load(kp + "blocks", os.path.join(REF, "modules/KPConv/blocks.py"))
+
+
+def main():
+    ref = load_reference()
     np.random.seed(0)  # load_kernels draws a random rotation; the kernel points are overwritten by seeded values anyway
     ns = types.SimpleNamespace(SimpleBlock=ref.SimpleBlock, ResnetBBlock=ref.ResnetBBlock, KPDualBlock=ref.KPDualBlock)
     out = cases.run_cases(ns, Bag)
