@@ -48,6 +48,35 @@ def wrap(obj):
     return obj
 
 
+def reference_resolver():
+    """utils/model_building_utils/model_definition_resolver.py by file path, over the omegaconf stand-ins"""
+    loader._module("omegaconf")
+    loader._module("omegaconf.dictconfig", DictConfig=DictConfig)
+    loader._module("omegaconf.listconfig", ListConfig=ListConfig)
+    return loader._load("ref_resolver", os.path.join(REF, "utils/model_building_utils/model_definition_resolver.py"))
+
+
+def reference_fetch():
+    """`_fetch_arguments_from_list` of models/base_architectures/unet.py:456-476 (identical in UnetBasedModel and
+    UnwrappedUnetBasedModel), compiled from the file's text together with SPECIAL_NAMES"""
+    path = os.path.join(REF, "models/base_architectures/unet.py")
+    tree = ast.parse(open(path).read(), filename=path)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "UnwrappedUnetBasedModel")
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "_fetch_arguments_from_list")
+    special = next(n for n in tree.body if isinstance(n, ast.Assign) and n.targets[0].id == "SPECIAL_NAMES")
+    scope = {"is_list": lambda e: isinstance(e, list)}
+    exec(compile(ast.Module(body=[special, fn], type_ignores=[]), path, "exec"), scope)
+    return scope["_fetch_arguments_from_list"]
+
+
+def load_entry(yaml_path, name, substitutions):
+    text = open(yaml_path).read()
+    for old, new in substitutions.items():
+        text = text.replace(old, new)
+    tree = yaml.safe_load(text)
+    return wrap(tree["models"][name] if "models" in tree else tree[name])
+
+
 def describe_block(block):
     kp = block.kp_conv if type(block).__name__ == "SimpleBlock" else block.kp_conv.kp_conv
     simple = block if type(block).__name__ == "SimpleBlock" else block.kp_conv
@@ -66,22 +95,10 @@ def main():
     blocks = loader.load_reference()
     loader._load("torch_points3d.core.base_conv.base_conv", os.path.join(REF, "core/base_conv/base_conv.py"))
     pdm = loader._load("torch_points3d.core.base_conv.partial_dense", os.path.join(REF, "core/base_conv/partial_dense.py"))
-    loader._module("omegaconf")
-    loader._module("omegaconf.dictconfig", DictConfig=DictConfig)
-    loader._module("omegaconf.listconfig", ListConfig=ListConfig)
-    resolver = loader._load("ref_resolver", os.path.join(REF, "utils/model_building_utils/model_definition_resolver.py"))
-    path = os.path.join(REF, "models/base_architectures/unet.py")
-    tree = ast.parse(open(path).read(), filename=path)
-    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "UnwrappedUnetBasedModel")
-    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "_fetch_arguments_from_list")
-    special = next(n for n in tree.body if isinstance(n, ast.Assign) and n.targets[0].id == "SPECIAL_NAMES")
-    scope = {"is_list": lambda e: isinstance(e, list)}
-    exec(compile(ast.Module(body=[special, fn], type_ignores=[]), path, "exec"), scope)
-    fetch = scope["_fetch_arguments_from_list"]
+    resolver, fetch = reference_resolver(), reference_fetch()
 
-    text = open("/root/reference/conf/models/segmentation/kpconv.yaml").read()
-    text = text.replace("${data.first_subsampling}", repr(FIRST_SUBSAMPLING)).replace("${data.use_category}", "False")
-    entry = wrap(yaml.safe_load(text)["models"]["KPConvPaper"] if "models" in yaml.safe_load(text) else yaml.safe_load(text)["KPConvPaper"])
+    entry = load_entry("/root/reference/conf/models/segmentation/kpconv.yaml", "KPConvPaper",
+                       {"${data.first_subsampling}": repr(FIRST_SUBSAMPLING), "${data.use_category}": "False"})
     dataset = type("Dataset", (), {"feature_dimension": FEAT, "num_classes": NUM_CLASSES})()
     resolver.resolve_model(entry, dataset, "segmentation")
 
