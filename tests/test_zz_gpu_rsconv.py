@@ -1,0 +1,71 @@
+"""GPU test of the dense RSConv down modules (torch_points3d_b200/rsconv.py): their feature preparation on
+libp3d_b200.so against the CPU oracle, bit for bit, and one training step through each module.  The arithmetic of the
+modules themselves is pinned on the CPU against the reference's own classes (tests/test_reference_rsconv.py)."""
+from types import SimpleNamespace as NS
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from torch_points3d_b200 import _cabi, rsconv, synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def test_rsconv_feature_preparation_and_step():
+    import __graft_entry__
+    __graft_entry__.build()
+    before = _cabi.launch_count()
+    B, n, S, C = 4, 1024, 128, 6
+    radii, nsample = [0.15, 0.3], [16, 32]
+    xyz = synthetic.surface_clouds(B, n, seed=77)
+    feat = np.random.default_rng(77).standard_normal((B, C, n)).astype(np.float32)
+    pos, x = T(xyz), T(feat)
+    oidx = oracle.fps_dense(xyz, S)
+    new_xyz = np.take_along_axis(xyz, oidx[..., None], 1)
+    centre = new_xyz.transpose(0, 2, 1)[..., None]
+    xyz_t = np.ascontiguousarray(xyz.transpose(0, 2, 1))
+
+    orig = rsconv.RSConvOriginalMSGDown(npoint=S, radii=radii, nsample=nsample, down_conv_nn=[[10, 16, 32], [C + 3, 32]],
+                                        channel_raising_nn=[32, 64]).to(DEV)
+    shared = rsconv.RSConvSharedMSGDown(npoint=S, radii=radii, nsample=nsample, down_conv_nn=[[10, 16, 32], [C + 3, 32]],
+                                        channel_raising_nn=[32, 64]).to(DEV)
+    assert np.array_equal(N(orig.sampler(pos)), oidx)
+    for s, (r, k) in enumerate(zip(radii, nsample)):
+        table = orig.neighbour_finder(pos, T(new_xyz), scale_idx=s)
+        otable = oracle.ball_query_dense(r, k, xyz, new_xyz)[0]
+        assert np.array_equal(N(table), otable)
+        rel = oracle.group_fwd(xyz_t, otable) - centre
+        gf = oracle.group_fwd(feat, otable)
+        # RSConvOriginalMSGDown: centred coordinates twice (the reference centres in place), fused and op by op
+        want = np.concatenate([rel, rel, gf], axis=1)
+        for fused in (True, False):
+            orig.fused_grouping = fused
+            got = orig._prepare_features(pos, T(new_xyz), x, table)
+            assert got.shape == (B, 3 + 3 + C, S, k) and np.array_equal(N(got), want), (s, fused)
+        # RSConvSharedMSGDown / RSConvMSGDown: absolute and centred coordinates
+        got, cen = shared._prepare_features(x, pos, T(new_xyz), table)
+        assert np.array_equal(N(got), np.concatenate([oracle.group_fwd(xyz_t, otable), rel, gf], axis=1))
+        assert np.array_equal(N(cen), centre)
+    orig.fused_grouping = True
+    msg = rsconv.RSConvMSGDown(npoint=S, radii=radii, nsample=nsample, down_conv_nn=[10, 16, C + 3],
+                               channel_raising_nn=[C + 3, 48]).to(DEV)
+    for module, width in ((orig, 64), (shared, 64), (msg, 48)):
+        xin = x.clone().requires_grad_(True)
+        out = module(NS(pos=pos, x=xin))
+        assert out.x.shape == (B, width * len(radii), S) and torch.isfinite(out.x).all()
+        assert np.array_equal(N(out.pos), new_xyz)
+        out.x.square().mean().backward()
+        assert xin.grad is not None and float(xin.grad.abs().sum()) > 0
+        assert all(p.grad is not None for p in module.parameters())
+    assert _cabi.launch_count() > before, "no kernel of libp3d_b200.so was launched"
