@@ -56,7 +56,8 @@ class Bag:
 class MessagePassing(torch.nn.Module):
     def __init__(self, aggr="add", flow="source_to_target", node_dim=0):
         super().__init__()
-        assert aggr == "add" and flow == "source_to_target"
+        assert aggr in ("add", "max") and flow == "source_to_target"
+        self.aggr = aggr
 
     def propagate(self, edge_index, size=None, **kwargs):
         j, i = edge_index[0], edge_index[1]
@@ -77,16 +78,22 @@ class MessagePassing(torch.nn.Module):
             args[name] = value[j] if dim == 0 else value[i]
         msg = self.message(**args)
         num_targets = size[1] if size[1] is not None else size[0]
-        summed = torch.zeros((num_targets, msg.shape[1]), dtype=msg.dtype).index_add_(0, i, msg)
-        return self.update(summed)
+        if self.aggr == "max":   # torch_scatter's max: 0 for a target without edges
+            pooled = torch.zeros((num_targets, msg.shape[1]), dtype=msg.dtype)
+            for t in torch.unique(i).tolist():
+                pooled[t] = msg[i == t].max(dim=0).values
+        else:
+            pooled = torch.zeros((num_targets, msg.shape[1]), dtype=msg.dtype).index_add_(0, i, msg)
+        return self.update(pooled)
 
 
-def main():
+def load_reference_base(radius=None):
+    """stand-ins + the reference's base classes of the MESSAGE_PASSING format, loaded by file path"""
     def unused(*a, **kw):
         raise AssertionError("not on the tested paths")
 
     _module("torch_geometric")
-    _module("torch_geometric.nn", fps=unused, knn=cases.knn, radius=unused, voxel_grid=unused, knn_interpolate=unused,
+    _module("torch_geometric.nn", fps=unused, knn=cases.knn, radius=radius if radius is not None else unused, voxel_grid=unused, knn_interpolate=unused,
             global_max_pool=unused, global_mean_pool=unused, MessagePassing=MessagePassing)
     _module("torch_geometric.nn.pool")
     _module("torch_geometric.nn.pool.consecutive", consecutive_cluster=unused)
@@ -108,6 +115,10 @@ def main():
         so.__dict__.update({k: v for k, v in vars(mod).items() if not k.startswith("_")})
     _load("torch_points3d.core.base_conv.base_conv", os.path.join(REF, "core/base_conv/base_conv.py"))
     _load("torch_points3d.core.base_conv.message_passing", os.path.join(REF, "core/base_conv/message_passing.py"))
+
+
+def main():
+    load_reference_base()
     ref = _load("ref_randla_modules", os.path.join(REF, "modules/RandLANet/modules.py"))
     ns = types.SimpleNamespace(RandlaKernel=ref.RandlaKernel, RandlaConv=ref.RandlaConv, RandLANetRes=ref.RandLANetRes)
     out = cases.run_cases(ns, Bag)

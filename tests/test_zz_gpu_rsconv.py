@@ -9,6 +9,7 @@ import torch
 
 import oracle
 from torch_points3d_b200 import _cabi, rsconv, synthetic
+from torch_points3d_b200.partial_dense import _Data
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -68,4 +69,36 @@ def test_rsconv_feature_preparation_and_step():
         out.x.square().mean().backward()
         assert xin.grad is not None and float(xin.grad.abs().sum()) > 0
         assert all(p.grad is not None for p in module.parameters())
+    assert _cabi.launch_count() > before, "no kernel of libp3d_b200.so was launched"
+
+
+def test_rsconv_message_passing_down_module():
+    """RSConvDown (FPS -> radius edge list -> relation-shape convolution with a per-target max) on the device against
+    the plain torch formulation of modules/RSConv/message_passing.py:29-52 on the same sampled points and edges."""
+    import __graft_entry__
+    __graft_entry__.build()
+    before = _cabi.launch_count()
+    torch.manual_seed(0)
+    pos_h, batch_h = synthetic.indoor_spheres(num_spheres=3, raw_points=3000, radius=0.5, seed=9)
+    pos, batch = T(pos_h), T(batch_h)
+    C = 6
+    x = torch.randn(pos.shape[0], C, device=DEV, requires_grad=True)
+    down = rsconv.RSConvDown(ratio=0.25, radius=0.2, local_nn=[10, 16, C], down_conv_nn=[C, 32, 48]).to(DEV).eval()
+    out = down(_Data(x=x, pos=pos, batch=batch))
+    T_ = out.idx.shape[0]
+    assert out.x.shape == (T_, 48) and torch.isfinite(out.x).all()
+    assert torch.equal(out.pos, pos[out.idx]) and torch.equal(out.batch, batch[out.idx])
+    src, dst = out.edge_index[0], out.edge_index[1]
+    assert bool((dst[1:] >= dst[:-1]).all()) and bool((batch[src] == batch[out.idx][dst]).all())
+    pos_i, pos_j = pos[out.idx][dst], pos[src]
+    vij = pos_i - pos_j
+    assert float(vij.norm(dim=1).max()) < 0.2
+    hij = torch.cat([vij.norm(dim=1, keepdim=True), vij, pos_i, pos_j], dim=1)
+    msg = down._conv.local_nn(hij) * x[src]
+    pooled = torch.zeros(T_, C, device=DEV).scatter_reduce(0, dst.unsqueeze(1).expand(-1, C), msg, "amax",
+                                                          include_self=False)
+    want = down._conv.global_nn(torch.relu(pooled))
+    assert torch.allclose(out.x, want, rtol=1e-4, atol=1e-5)
+    out.x.square().mean().backward()
+    assert float(x.grad.abs().sum()) > 0 and all(p.grad is not None for p in down.parameters())
     assert _cabi.launch_count() > before, "no kernel of libp3d_b200.so was launched"

@@ -4,6 +4,8 @@
   OriginalRSConv, RSConvOriginalMSGDown    torch_points3d/modules/RSConv/dense.py:202-397   (the `RSConv_MSN` benchmark model)
   RSConvMapper, SharedRSConv               torch_points3d/modules/RSConv/dense.py:18-104
   RSConvSharedMSGDown, RSConvMSGDown       torch_points3d/modules/RSConv/dense.py:107-199, 400-482
+  Convolution, RSConvDown                  torch_points3d/modules/RSConv/message_passing.py:10-60  (MESSAGE_PASSING format,
+                                           the `RSConv_2LD` / `RSConv_4LD` models; edge gathers and per-target max of csrc/edges.cu)
 
 Same constructor arguments, tensor layouts (pos [B,N,3], x [B,C,N]) and parameter names; the chain around `conv`
 (sampler -> centres -> one neighbour table per scale -> concatenation of the scales) is PointNetMSGDown's
@@ -21,8 +23,10 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from .message_passing import BaseConvolutionDown
+from .partial_dense import MLP
 from .pointnet2 import MLP2D, PointNetMSGDown
-from .spatial_ops import DenseFPSSampler, DenseRadiusNeighbourFinder
+from .spatial_ops import DenseFPSSampler, DenseRadiusNeighbourFinder, FPSSampler, RadiusNeighbourFinder
 
 
 def _relation(distance_of, centre, first, second):
@@ -221,3 +225,40 @@ class RSConvMSGDown(RSConvSharedMSGDown):
     parameters appear twice in the state_dict, as in the reference)"""
 
     PER_SCALE_MAPPER = True
+
+
+class Convolution(nn.Module):
+    """modules/RSConv/message_passing.py:10-52 (torch_geometric MessagePassing, aggr="max"): the relation vector
+    h_ij = [|v_ij|, v_ij, pos_i, pos_j] with v_ij = pos_i - pos_j goes through `local_nn`, weighs the source features
+    x_j (the source positions when there are no features), the per-target max goes through the activation and the
+    optional channel-raising `global_nn`.  Targets without edges get 0, as from torch_scatter."""
+
+    _RELATION_ORDER = [9, 6, 7, 8, 0, 1, 2, 3, 4, 5]  # ops.edge_encoding yields [pos_i, pos_j, v_ij, |v_ij|]
+
+    def __init__(self, local_nn, activation=None, global_nn=None, aggr="max", **kwargs):
+        super().__init__()
+        if aggr != "max":
+            raise ValueError("only the per-target max of the reference's RSConv layer is built (aggr=%r)" % (aggr,))
+        self.local_nn = MLP(local_nn)
+        self.activation = activation if activation is not None else nn.ReLU()
+        self.global_nn = MLP(global_nn) if global_nn is not None else None
+
+    def forward(self, x, pos, edge_index):
+        pos_src, pos_dst = (pos, pos) if torch.is_tensor(pos) else pos
+        src, dst = edge_index[0], edge_index[1]
+        relation = ops.edge_encoding(pos_src, pos_dst, src, dst)[:, self._RELATION_ORDER]
+        x_j = pos_src[src] if x is None else x[src]
+        out = self.activation(ops.segment_max(self.local_nn(relation) * x_j, dst, pos_dst.shape[0]))
+        return self.global_nn(out) if self.global_nn is not None else out
+
+
+class RSConvDown(BaseConvolutionDown):
+    """modules/RSConv/message_passing.py:55-60: FPSSampler(ratio) -> RadiusNeighbourFinder(radius) -> Convolution.
+    See BaseConvolutionDown for the order of the position pair."""
+
+    def __init__(self, ratio=None, radius=None, local_nn=None, down_conv_nn=None, *args, **kwargs):
+        super().__init__(FPSSampler(ratio), RadiusNeighbourFinder(radius), *args, **kwargs)
+        self._conv = Convolution(local_nn=local_nn, global_nn=down_conv_nn)
+
+    def conv(self, x, pos, edge_index, batch):
+        return self._conv(x, pos, edge_index)
