@@ -29,15 +29,27 @@ import make_golden_kpconv_blocks as loader  # noqa: E402
 FEAT, NUM_CLASSES, FIRST_SUBSAMPLING = 4, 13, 0.04
 
 
+def _supported(value):
+    """omegaconf refuses values that are not primitives or containers (UnsupportedValueType, a ValueError): this is
+    what leaves strings such as `max` alone when the resolver's eval turns them into a builtin"""
+    if not isinstance(value, (type(None), bool, int, float, str, dict, list)):
+        raise ValueError("Value '%s' is not a supported primitive type" % type(value).__name__)
+    return value
+
+
 class DictConfig(dict):
     __getattr__ = dict.get
 
     def __setattr__(self, k, v):
         self[k] = v
 
+    def __setitem__(self, k, v):
+        dict.__setitem__(self, k, _supported(v))
+
 
 class ListConfig(list):
-    pass
+    def __setitem__(self, k, v):
+        list.__setitem__(self, k, _supported(v))
 
 
 def wrap(obj):
