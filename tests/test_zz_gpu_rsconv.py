@@ -92,7 +92,7 @@ def test_rsconv_message_passing_down_module():
     assert bool((dst[1:] >= dst[:-1]).all()) and bool((batch[src] == batch[out.idx][dst]).all())
     pos_i, pos_j = pos[out.idx][dst], pos[src]
     vij = pos_i - pos_j
-    assert float(vij.norm(dim=1).max()) < 0.2
+    assert float(vij.norm(dim=1).max()) <= 0.2 * (1 + 1e-5)
     hij = torch.cat([vij.norm(dim=1, keepdim=True), vij, pos_i, pos_j], dim=1)
     msg = down._conv.local_nn(hij) * x[src]
     pooled = torch.zeros(T_, C, device=DEV).scatter_reduce(0, dst.unsqueeze(1).expand(-1, C), msg, "amax",
