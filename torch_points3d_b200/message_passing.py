@@ -115,7 +115,13 @@ class BaseConvolutionDown(torch.nn.Module):
     With the pair swapped torch_geometric looks support indices up in the QUERY set: an out-of-range read as soon as
     the sampler keeps fewer points than it was given (RandlaConv with ratio < 1), a silent mix-up when it keeps all
     of them.  This mirror passes (source positions, target positions) = (pos, pos[idx]); `reference_pos_order=True`
-    reproduces the literal argument order for the ratio-1 case."""
+    reproduces the literal argument order for the ratio-1 case.
+
+    Sampler call: the reference writes `self.sampler(pos, batch)` (:47), and BaseSampler.__call__ is
+    `(pos, x=None, batch=None)` (core/spatial_ops/sampling.py:33), so the batch vector lands in the `x` slot and an
+    FPSSampler there samples the whole batch as ONE cloud (RandomSampler ignores `batch` either way).  This chain
+    passes `batch=batch`: every cloud is sampled on its own and the sampled batch vector stays sorted, which the
+    neighbour search needs.  SAModule below keeps the reference's literal call."""
 
     def __init__(self, sampler, neighbour_finder, *args, reference_pos_order=False, **kwargs):
         super().__init__()
