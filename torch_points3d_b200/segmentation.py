@@ -20,6 +20,7 @@ from . import kpconv, synthetic
 # DistributedDataParallel bucket size (MB).  The all-reduce of the LAST bucket (the first layers' gradients) cannot
 # hide behind the backward pass; with 56 MB of gradients the default 25 MB leaves a large tail exposed.
 DDP_BUCKET_MB = 8
+IGNORE_LABEL = -1  # datasets/segmentation/__init__.py:1; rows with this label do not count in the loss (kpconv.py:150)
 # (Measured on 2 GPUs, graph-captured step: 25 MB buckets 6.38 ms, 8 MB buckets 6.31-6.34 ms; capping NCCL at 6
 # channels gave 6.02 ms on one box and 6.34 ms on another -- inside the box-to-box spread, so no default is set.)
 
@@ -65,7 +66,7 @@ class KPConvSegmentationTrainer:
         self.opt.zero_grad(set_to_none=set_to_none)
         ms, up = pyramid
         logp = self.net(self.pos, self.feats, self.batch, multiscale=ms, upsample=up)
-        loss = torch.nn.functional.nll_loss(logp, self.labels)
+        loss = torch.nn.functional.nll_loss(logp, self.labels, ignore_index=IGNORE_LABEL)
         loss.backward()
         self.opt.step()
         return loss
