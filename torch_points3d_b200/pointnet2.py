@@ -179,4 +179,4 @@ class PointNet2_D(nn.Module):
         return self.FC_layer(u.x).transpose(1, 2).contiguous().view((-1, self._num_classes))
 
     def loss(self, logits, labels):
-        return F.cross_entropy(logits, torch.flatten(labels).long())
+        return F.cross_entropy(logits, torch.flatten(labels).long(), ignore_index=-1)  # IGNORE_LABEL, pointnet2.py:108-110
