@@ -44,7 +44,11 @@ class GridSampling3D:
         self._grid_size = size
 
     def __call__(self, data):
-        data.pos, data.batch = grid_means(data.pos, data.batch, self._grid_size)
+        batch = getattr(data, "batch", None)
+        if batch is None:                      # one sample on its own (MultiScaleTransform in a DataLoader worker)
+            data.pos = grid_means(data.pos, torch.zeros(data.pos.shape[0], dtype=torch.long), self._grid_size)[0]
+        else:
+            data.pos, data.batch = grid_means(data.pos, batch, self._grid_size)
         data.x = None
         return data
 

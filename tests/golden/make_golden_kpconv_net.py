@@ -29,24 +29,31 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import kpconv_net_cases as cases  # noqa: E402
 import make_golden_kpconv_arch as arch  # noqa: E402
 import make_golden_kpconv_blocks as loader  # noqa: E402
+import make_golden_multiscale as pyg  # noqa: E402  (torch_geometric Data / Batch restated)
 import mp_chain_cases  # noqa: E402
+import multiscale_cases  # noqa: E402
 
 
-class Data(loader.Bag):
+class Data(pyg.Data):
     def to(self, device):
         return self
 
-    def clone(self):
-        return Data(**self.__dict__)
+
+class Batch(pyg.Batch, Data):
+    pass
 
 
 def main():
     blocks = loader.load_reference()
     sys.modules["torch_geometric.data"].Data = Data
-    sys.modules["torch_geometric.data"].Batch = Data
+    sys.modules["torch_geometric.data"].Batch = Batch
+    sys.modules["torch_geometric"].is_debug_enabled = lambda: False
     loader._load("torch_points3d.core.base_conv.base_conv", os.path.join(REF, "core/base_conv/base_conv.py"))
     pdm = loader._load("torch_points3d.core.base_conv.partial_dense", os.path.join(REF, "core/base_conv/partial_dense.py"))
-    sys.modules["torch_points3d.core.spatial_ops.interpolate"].knn_interpolate = mp_chain_cases.knn_interpolate
+    interp = sys.modules["torch_points3d.core.spatial_ops.interpolate"]
+    interp.knn_interpolate, interp.knn, interp.scatter_add = mp_chain_cases.knn_interpolate, multiscale_cases.knn, pyg.scatter_add
+    interp.Data = Data
+    msd = loader._load("torch_points3d.datasets.multiscale_data", os.path.join(REF, "datasets/multiscale_data.py"))
     base = sys.modules["torch_points3d.core.common_modules.base_modules"]
     kernels = sys.modules["torch_points3d.modules.KPConv.kernels"]
     resolver, fetch = arch.reference_resolver(), arch.reference_fetch()
@@ -83,7 +90,7 @@ def main():
     cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "KPConvPaper")
     wanted = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in ("set_input", "forward", "compute_loss")]
     scope = {"torch": torch, "F": F, "Any": Any, "add_ones": kernels.add_ones, "Identity": base.Identity,
-             "MultiScaleBatch": type("MultiScaleBatch", (), {}), "IGNORE_LABEL": -1}
+             "MultiScaleBatch": msd.MultiScaleBatch, "IGNORE_LABEL": -1}
     exec(compile(ast.Module(body=wanted, type_ignores=[]), path, "exec"), scope)
     for name in ("set_input", "forward", "compute_loss"):
         setattr(Net, name, scope[name])
@@ -98,6 +105,38 @@ def main():
             log_probs = net.forward()
         cases.record(out, tag, log_probs, net.loss)
     out["train/head_running_mean"] = net.FC_layer[0][1].batch_norm.running_mean.numpy().copy()
+
+    # ---- the same network fed with a pyramid made the reference's way: MultiScaleTransform per sample
+    # (core/data_transform/transforms.py:579-651, compiled from the file's text) with the samplers / neighbour finders
+    # / upsample operators the network's own modules hold (collected like unet.py:315-331), collated by
+    # MultiScaleBatch.from_data_list; set_input hands the lists to the blocks through `precomputed=`
+    import functools
+    tpath = os.path.join(REF, "core/data_transform/transforms.py")
+    ttree = ast.parse(open(tpath).read(), filename=tpath)
+    tnode = next(n for n in ttree.body if isinstance(n, ast.ClassDef) and n.name == "MultiScaleTransform")
+    tscope = {"partial": functools.partial, "Data": Data, "MultiScaleData": msd.MultiScaleData, "torch": torch}
+    exec(compile(ast.Module(body=[tnode], type_ignores=[]), tpath, "exec"), tscope)
+    strategies = {"sampler": [], "neighbour_finder": [], "upsample_op": []}
+    for m in net.down_modules:
+        strategies["sampler"] += m.sampler
+        strategies["neighbour_finder"] += m.neighbour_finder
+    for m in net.up_modules:
+        strategies["upsample_op"].append(m.upsample_op)
+    transform = tscope["MultiScaleTransform"](strategies)
+    for tag, training in (("eval_precomputed", False), ("train_precomputed", True)):
+        samples = []
+        for b in range(int(batch.max()) + 1):
+            sel = batch == b
+            samples.append(transform(Data(pos=pos[sel].clone(), x=x[sel].clone(), y=y[sel].clone())))
+        mb = msd.MultiScaleBatch.from_data_list(samples)
+        mb.to = lambda device, mb=mb: mb
+        out["pyramid/levels"] = np.array([int(l.pos.shape[0]) for l in mb.multiscale])
+        out["pyramid/last_table"] = mb.multiscale[-1].idx_neighboors.numpy().copy()
+        net.train(training)
+        with torch.no_grad():
+            net.set_input(mb, "cpu")
+            log_probs = net.forward()
+        cases.record(out, tag, log_probs, net.loss)
     np.savez_compressed(os.path.join(HERE, "kpconv_net.npz"), **out)
     for k, v in out.items():
         print(k, v.shape if v.ndim else v)

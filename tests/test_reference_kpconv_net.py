@@ -22,7 +22,7 @@ import kpconv_net_cases as cases  # noqa: E402
 import mp_chain_cases  # noqa: E402
 
 import oracle  # noqa: E402
-from torch_points3d_b200 import kpconv, ops  # noqa: E402
+from torch_points3d_b200 import kpconv, multiscale, ops  # noqa: E402
 
 
 def test_kpconv_paper_forward_and_loss_equal_the_reference(monkeypatch):
@@ -58,10 +58,29 @@ def test_kpconv_paper_forward_and_loss_equal_the_reference(monkeypatch):
             loss = torch.nn.functional.nll_loss(log_probs, y, ignore_index=-1)      # kpconv.py:150, IGNORE_LABEL
         cases.record(got, tag, log_probs, loss)
     got["train/head_running_mean"] = model.FC_layer[0][1].batch_norm.running_mean.numpy().copy()
+    # ---- the network fed with a pyramid made the reference's way: one MultiScaleTransform per sample with the
+    # network's own samplers / finders / upsample operators, collated by MultiScaleBatch.from_data_list (the
+    # reference side ran its own MultiScaleTransform + multiscale_data.py + the blocks' `precomputed=` branches)
+    transform = multiscale.MultiScaleTransform(model.strategies())
+    for tag, training in (("eval_precomputed", False), ("train_precomputed", True)):
+        samples = [transform(multiscale.MultiScaleData(pos=pos[batch == b], x=x[batch == b], y=y[batch == b]))
+                   for b in range(int(batch.max()) + 1)]
+        mb = multiscale.MultiScaleBatch.from_data_list(samples)
+        assert torch.equal(mb.pos, pos) and torch.equal(mb.batch, batch)
+        got["pyramid/levels"] = np.array([int(l.pos.shape[0]) for l in mb.multiscale])
+        got["pyramid/last_table"] = mb.multiscale[-1].idx_neighboors.numpy().copy()
+        model.train(training)
+        with torch.no_grad():
+            log_probs = model(mb.pos, mb.x, mb.batch, multiscale=mb.multiscale, upsample=mb.upsample)
+            loss = torch.nn.functional.nll_loss(log_probs, mb.y, ignore_index=-1)
+        cases.record(got, tag, log_probs, loss)
+    assert sorted(got) == sorted(k for k in want.files if k != "state_dict_keys")
     for key, value in got.items():
         ref = want[key]
         assert value.shape == ref.shape, key
-        if key.endswith("/pred"):
+        if key.startswith("pyramid/"):
+            assert np.array_equal(value, ref), key                                  # level sizes, the collated table
+        elif key.endswith("/pred"):
             assert float((value == ref).mean()) >= 0.995, (key, float((value == ref).mean()))   # near-ties may flip
         else:
             scale = max(float(np.abs(ref).max()), 1e-30)
