@@ -357,3 +357,31 @@ def test_mlp_and_fast_batch_norm_against_the_reference_classes():
     with pytest.raises(ValueError) as err:
         bn(torch.zeros(2, 2, 2, 2))
     assert str(err.value) == str(g["bn_error"])
+
+
+def test_compat_cluster_serves_the_reference_import_lines(monkeypatch):
+    """`from torch_geometric.nn import (knn_interpolate, fps, radius, global_max_pool, global_mean_pool, knn)`
+    (core/base_conv/message_passing.py:10-17, partial_dense.py:10-17) and `PointConv`
+    (modules/pointnet2/message_passing.py:1) resolve against compat.cluster; the pools are the per-cloud reductions."""
+    from torch_points3d_b200 import ops
+    from torch_points3d_b200.compat import cluster
+    from torch_points3d_b200.compat.cluster import (PointConv, fps, global_max_pool, global_mean_pool, knn,  # noqa: F401
+                                                   knn_interpolate, radius)
+    assert PointConv is mp.PointConv and knn is ops.knn_edges and set(cluster.__all__) <= set(dir(cluster)) | {"PointConv"}
+
+    def segment_max(msg, dst, T):
+        out = torch.zeros((T, msg.shape[1]))
+        for t in torch.unique(dst).tolist():
+            out[t] = msg[dst == t].max(dim=0).values
+        return out
+
+    monkeypatch.setattr(ops, "segment_max", segment_max)
+    monkeypatch.setattr(ops, "segment_sum", lambda msg, dst, T: torch.zeros((T, msg.shape[1])).index_add_(0, dst, msg))
+    x = torch.randn(9, 4)
+    batch = torch.tensor([0, 0, 0, 1, 1, 3, 3, 3, 3])           # cloud 2 is empty
+    want_max = torch.stack([x[batch == b].max(0).values if (batch == b).any() else torch.zeros(4) for b in range(4)])
+    want_mean = torch.stack([x[batch == b].mean(0) if (batch == b).any() else torch.zeros(4) for b in range(4)])
+    assert torch.equal(global_max_pool(x, batch), want_max)
+    assert torch.allclose(global_mean_pool(x, batch, size=4), want_mean, atol=1e-6)
+    with pytest.raises(AttributeError):
+        cluster.voxel_grid
