@@ -44,3 +44,27 @@ def test_kpconv_losses_known_answers():
     assert kpconv.fitting_loss(sq_distances, 1).item() == 0.5
     loss = kpconv.repulsion_loss(square.unsqueeze(0), 1).item()
     np.testing.assert_almost_equal(loss, 4 * np.sum(np.asarray([0.25, 0.25, 0.0074])), decimal=3)
+
+
+def test_kernel_points_are_the_reference_disposition():
+    """tests/golden/kernel_points.npz (make_golden_kernel_points.py): the table the reference's own read_ply returns
+    for kernels/dispositions/k_015_center.ply, and one output of its load_kernels(0.06, 15, 1, 3, "center").  The shipped
+    table is that table; a loaded kernel is the table scaled by the radius, rotated and jittered by ~1 % of the radius --
+    compared through what a rotation keeps (distance of every point to the centre point and to its neighbours)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "kernel_points.npz"))
+    table = kpconv.load_kernels(1.0, random_rotation=False)
+    assert table.shape == (15, 3) and np.array_equal(table, g["disposition"].astype(np.float32))
+    r = float(g["radius"])
+
+    def invariants(k):
+        d = np.linalg.norm(k[:, None, :] - k[None, :, :], axis=-1)
+        return d / r                                           # row i = distances of point i to all points, in order
+
+    ref = invariants(g["loaded"].astype(np.float64))
+    unrotated = invariants(kpconv.load_kernels(r, random_rotation=False).astype(np.float64))
+    ours = invariants(kpconv.load_kernels(r, rng=np.random.default_rng(5)).astype(np.float64))
+    assert np.abs(ref - unrotated).max() < 0.08 and np.abs(ours - unrotated).max() < 0.08   # 1 % jitter, two points
+    assert np.abs(ours - unrotated).max() > 1e-4               # the jitter is there
+    assert np.linalg.norm(g["loaded"][0]) / r < 0.05           # the centre point stays at the centre
+    assert list(g["loaded_shape"]) == [1, 15, 3]               # the reference returns [num_kernels, K, 3]
