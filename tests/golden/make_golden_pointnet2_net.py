@@ -42,6 +42,22 @@ def _functions(tree, class_name, names):
     return [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in names]
 
 
+BUILDERS = ("_init_from_compact_format", "_fetch_arguments_from_list", "_fetch_arguments_up_and_down", "_get_factory",
+            "_save_sampling_and_search")
+
+
+def reference_unet_scope(identity_cls):
+    """BaseFactory, UnetSkipConnectionBlock and UnetBasedModel's builder methods, compiled from unet.py's text"""
+    path = os.path.join(REF, "models/base_architectures/unet.py")
+    tree = ast.parse(open(path).read(), filename=path)
+    keep = [n for n in tree.body if (isinstance(n, ast.Assign) and n.targets[0].id == "SPECIAL_NAMES")
+            or (isinstance(n, ast.ClassDef) and n.name in ("BaseFactory", "UnetSkipConnectionBlock"))]
+    scope = {"nn": torch.nn, "is_list": lambda e: isinstance(e, list), "Identity": identity_cls,
+             "log": logging.getLogger("ref")}
+    exec(compile(ast.Module(body=keep + _functions(tree, "UnetBasedModel", BUILDERS), type_ignores=[]), path, "exec"), scope)
+    return scope
+
+
 def main():
     modules_lib = dense_loader.load_reference(dense_chain_cases.Kernels())
     base = sys.modules["torch_points3d.core.common_modules.base_modules"]
@@ -52,15 +68,7 @@ def main():
     dataset = type("Dataset", (), {"feature_dimension": cases.FEAT, "num_classes": cases.NUM_CLASSES})()
     resolver.resolve_model(entry, dataset, "segmentation")
 
-    path = os.path.join(REF, "models/base_architectures/unet.py")
-    tree = ast.parse(open(path).read(), filename=path)
-    keep = [n for n in tree.body if (isinstance(n, ast.Assign) and n.targets[0].id == "SPECIAL_NAMES")
-            or (isinstance(n, ast.ClassDef) and n.name in ("BaseFactory", "UnetSkipConnectionBlock"))]
-    builders = ("_init_from_compact_format", "_fetch_arguments_from_list", "_fetch_arguments_up_and_down",
-                "_get_factory", "_save_sampling_and_search")
-    scope = {"nn": torch.nn, "is_list": lambda e: isinstance(e, list), "Identity": base.Identity,
-             "log": logging.getLogger("ref"), "BaseFactory": None}
-    exec(compile(ast.Module(body=keep + _functions(tree, "UnetBasedModel", builders), type_ignores=[]), path, "exec"), scope)
+    builders, scope = BUILDERS, reference_unet_scope(base.Identity)
     path2 = os.path.join(REF, "models/segmentation/pointnet2.py")
     tree2 = ast.parse(open(path2).read(), filename=path2)
     scope2 = {"torch": torch, "F": F, "Data": Data, "IGNORE_LABEL": -1}
