@@ -4,6 +4,8 @@
   OriginalRSConv, RSConvOriginalMSGDown    torch_points3d/modules/RSConv/dense.py:202-397   (the `RSConv_MSN` benchmark model)
   RSConvMapper, SharedRSConv               torch_points3d/modules/RSConv/dense.py:18-104
   RSConvSharedMSGDown, RSConvMSGDown       torch_points3d/modules/RSConv/dense.py:107-199, 400-482
+  RSConv_MSN                               torch_points3d/models/segmentation/rsconv.py:14-124 over
+                                           conf/models/segmentation/rsconv.yaml:57-108 (the network the reference benchmarks)
   Convolution, RSConvDown                  torch_points3d/modules/RSConv/message_passing.py:10-60  (MESSAGE_PASSING format,
                                            the `RSConv_2LD` / `RSConv_4LD` models; edge gathers and per-target max of csrc/edges.cu)
 
@@ -25,7 +27,7 @@ import torch.nn.functional as F
 from . import ops
 from .message_passing import BaseConvolutionDown
 from .partial_dense import MLP
-from .pointnet2 import MLP2D, PointNetMSGDown
+from .pointnet2 import Conv1D, DenseFPModule, GlobalDenseBaseModule, MLP2D, PointNetMSGDown
 from .spatial_ops import DenseFPSSampler, DenseRadiusNeighbourFinder, FPSSampler, RadiusNeighbourFinder
 
 
@@ -262,3 +264,54 @@ class RSConvDown(BaseConvolutionDown):
 
     def conv(self, x, pos, edge_index, batch):
         return self._conv(x, pos, edge_index)
+
+
+class RSConv_MSN(nn.Module):
+    """The multi-scale-neighbourhood RSConv segmentation network: RSConvLogicModel (models/segmentation/rsconv.py:14-124)
+    with its architecture entry `RSConv_MSN` (conf/models/segmentation/rsconv.yaml:57-108) written out.  Four
+    RSConvOriginalMSGDown levels (1024 / 256 / 64 / 16 centres, three radii each), two global modules (mean over the
+    points of the last and of the second-to-last level), four feature-propagation levels back to the input points
+    (the fifth `up_conv` entry of the file is empty and never called: kept, parameter-free), and a head over
+    [propagated features, both global vectors broadcast to every point].  Module names follow
+    UnwrappedUnetBasedModel (`down_modules`, `inner_modules`, `up_modules`, `FC_layer`).
+
+    forward(pos [B,N,3] with N >= 1024, x [B,N,FEAT]) returns the [B*N, classes] logits of rsconv.py:104; `loss` is
+    its cross-entropy with the ignore label (:110-112)."""
+
+    def __init__(self, feat_dim=3, num_classes=50, **kwargs):
+        super().__init__()
+        levels = [  # npoint, radii, nsample, relation MLP (+ feature lift on the first level), channel raising
+            (1024, [0.075, 0.1, 0.125], [16, 32, 48], [[10, 64 // 2, 16], [feat_dim + 3, 16]], [16, 64]),
+            (256, [0.1, 0.15, 0.2], [16, 48, 64], [10, 128 // 4, 64 * 3 + 3], [64 * 3 + 3, 128]),
+            (64, [0.2, 0.3, 0.4], [16, 32, 48], [10, 256 // 4, 128 * 3 + 3], [128 * 3 + 3, 256]),
+            (16, [0.4, 0.6, 0.8], [16, 24, 32], [10, 512 // 4, 256 * 3 + 3], [256 * 3 + 3, 512])]
+        self.down_modules = nn.ModuleList(
+            RSConvOriginalMSGDown(npoint=n, radii=r, nsample=k, down_conv_nn=d, channel_raising_nn=c, index=i, **kwargs)
+            for i, (n, r, k, d, c) in enumerate(levels))
+        self.inner_modules = nn.ModuleList([GlobalDenseBaseModule([512 * 3 + 3, 128], aggr="mean"),
+                                            GlobalDenseBaseModule([256 * 3 + 3, 128], aggr="mean")])
+        self.up_modules = nn.ModuleList(DenseFPModule(up_conv_nn=w, bn=True, bias=False, skip=True, index=i) for i, w in enumerate(
+            [[512 * 3 + 256 * 3, 512, 512], [128 * 3 + 512, 512, 512], [64 * 3 + 512, 256, 256],
+             [256 + feat_dim, 128, 128], []]))
+        self.FC_layer = nn.Sequential(Conv1D(128 * 2 + 2 * 64, 128, bn=True, bias=False),
+                                      Conv1D(128, num_classes, activation=None, bias=True, bn=False))
+        self._num_classes = num_classes
+
+    def forward(self, pos, x):
+        from types import SimpleNamespace
+        data = SimpleNamespace(pos=pos, x=None if x is None else x.transpose(1, 2).contiguous())
+        skips = [data]
+        for module in self.down_modules[:-1]:
+            data = module(data)
+            skips.append(data)
+        data = self.down_modules[-1](data)
+        whole = self.inner_modules[0](data)                  # mean over the 16 points of the last level
+        coarse = self.inner_modules[1](skips[3])             # mean over the 64 points of the level above
+        for module in self.up_modules[:-1]:
+            data = module((data, skips.pop()))
+        n = data.x.shape[-1]
+        last = torch.cat([data.x, whole.x.repeat(1, 1, n), coarse.x.repeat(1, 1, n)], dim=1)
+        return self.FC_layer(last).transpose(1, 2).contiguous().view((-1, self._num_classes))
+
+    def loss(self, logits, labels):
+        return F.cross_entropy(logits, torch.flatten(labels).long(), ignore_index=-1)
