@@ -102,3 +102,32 @@ def test_rsconv_message_passing_down_module():
     out.x.square().mean().backward()
     assert float(x.grad.abs().sum()) > 0 and all(p.grad is not None for p in down.parameters())
     assert _cabi.launch_count() > before, "no kernel of libp3d_b200.so was launched"
+
+
+def test_rsconv_msn_network_step():
+    """one training step of the whole RSConv_MSN network on the device (its arithmetic is pinned on the CPU against the
+    reference's own network code, tests/test_reference_rsconv_net.py): shapes, finite logits, a gradient for every
+    parameter, the fused and the op-by-op grouping paths agree."""
+    import __graft_entry__
+    __graft_entry__.build()
+    before = _cabi.launch_count()
+    torch.manual_seed(0)
+    B, n = 2, 2048
+    pos = T(synthetic.surface_clouds(B, n, seed=78))
+    x = torch.randn(B, n, 3, device=DEV)
+    y = torch.randint(0, 50, (B, n), device=DEV)
+    y[:, ::31] = -1
+    model = rsconv.RSConv_MSN(3, 50).to(DEV)
+    logits = model(pos, x)
+    assert logits.shape == (B * n, 50) and torch.isfinite(logits).all()
+    loss = model.loss(logits, y)
+    loss.backward()
+    assert torch.isfinite(loss) and all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+    model.eval()
+    with torch.no_grad():
+        fused = model(pos, x)
+        for m in model.down_modules:
+            m.fused_grouping = False
+        plain = model(pos, x)
+    assert torch.allclose(fused, plain, rtol=1e-4, atol=1e-4 * float(plain.abs().max()))
+    assert _cabi.launch_count() > before, "no kernel of libp3d_b200.so was launched"
