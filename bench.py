@@ -463,6 +463,7 @@ def run_b200(args):
     section("operators", lambda: bench_operators(dev))
     section("c1", lambda: bench_c1(dev))
     section("c2_model", lambda: bench_c2_model(dev, line["ms_per_step"]))
+    section("rsconv_model", lambda: bench_rsconv_model(dev))   # written after the last GPU session: first run at round end
     line["cpu_baseline"] = None
     section("cpu_baseline", lambda: cpu_baseline(max_seconds=12.0))
     dog.cancel()
@@ -1053,6 +1054,48 @@ def bench_c2_model(dev, chain_ms):
             "published_reference": {"iteration_s": 0.231, "clouds_per_s": round(16 / 0.231, 1), "hardware": "not stated",
                                     "source": "benchmark/shapenet/pointnet2_charlesmsg.md:211"},
             "speedup_vs_published_iteration": round(231.0 / ms, 1)}
+
+
+def bench_rsconv_model(dev):
+    """The RSConv segmentation network the reference benchmarks (`RSConv_MSN`, conf/models/segmentation/rsconv.yaml:57-108;
+    models/segmentation/rsconv.py:14-124): forward + cross-entropy on 50 classes + backward + Adam, batch 12 x 2048
+    points with 3 normals -- the batch size of the published run (`iteration=0.133 s`, benchmark/shapenet/rscnn_original.md,
+    hardware not stated).  Same operators as the C2 chain (FPS, multi-radius ball query, fused grouping, three_nn /
+    three_interpolate); 1x1 convolutions / BatchNorm stock cuDNN as in the reference."""
+    import torch
+    from torch_points3d_b200 import rsconv, synthetic
+    torch.manual_seed(13)
+    clouds = 12
+    pos = torch.from_numpy(synthetic.surface_clouds(clouds, N_PTS, 1003)).to(dev)
+    nrm = pos / (pos.norm(dim=-1, keepdim=True) + 1e-12)
+    labels = torch.randint(0, 50, (clouds, N_PTS), device=dev)
+    model = rsconv.RSConv_MSN(feat_dim=3, num_classes=50).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = model.loss(model(pos, nrm), labels)
+        loss.backward()
+        opt.step()
+        return loss.detach()
+
+    losses = [float(step()) for _ in range(5)]
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"workload": "RSConv_MSN full model: fwd + cross-entropy + bwd + Adam, batch 12 x 2048 (eager)",
+            "ms_per_step": round(ms, 3), "clouds_per_s": round(clouds / (ms * 1e-3), 1),
+            "parameters": int(sum(p.numel() for p in model.parameters())),
+            "loss_first": round(losses[0], 4), "loss_fifth": round(losses[-1], 4),
+            "published_reference": {"iteration_s": 0.133, "clouds_per_s": round(12 / 0.133, 1), "hardware": "not stated",
+                                    "source": "benchmark/shapenet/rscnn_original.md"},
+            "speedup_vs_published_iteration": round(133.0 / ms, 1)}
 
 
 # ------------------------------------------------------------ CPU arm (oracle port) -----------
